@@ -1,0 +1,78 @@
+"""ark_bulletproofs_b200 -- B200-native hot path of ark-bulletproofs behind a C ABI.
+
+Python is only the test/bench harness over libbp_b200.so (include/bp_b200.h); the host-side
+mirror of the reference's Rust API lives in C++ inside the library."""
+import ctypes
+
+from . import _lib, codec
+from ._lib import BpError
+
+
+class Context:
+    """bp_ctx: one curve on one GPU (include/bp_b200.h)."""
+
+    def __init__(self, curve: str = "secq256k1", device: int = 0):
+        self.lib = _lib.load()
+        self.curve = curve
+        h = ctypes.c_void_p()
+        rc = self.lib.bp_ctx_create(codec.CURVE_IDS[curve], device, ctypes.byref(h))
+        if rc != 0:
+            raise BpError(rc, "bp_ctx_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BpError(rc, (self.lib.bp_last_error(self.h) or b"").decode())
+
+    @property
+    def stream_ptr(self) -> int:
+        return self.lib.bp_ctx_stream(self.h)
+
+    @property
+    def launches(self) -> int:
+        return self.lib.bp_ctx_launch_count(self.h)
+
+    def sync(self):
+        self._check(self.lib.bp_ctx_sync(self.h))
+
+    def set_window(self, c: int):
+        self._check(self.lib.bp_msm_set_window(self.h, c))
+
+    def msm_bytes(self, bases: bytes, scalars: bytes, n: int):
+        """bp_msm over host buffers; returns (64-byte affine, is_identity)."""
+        out = ctypes.create_string_buffer(64)
+        ident = ctypes.c_int(0)
+        self._check(self.lib.bp_msm(self.h, bases, scalars, n, out, ctypes.byref(ident)))
+        return out.raw, bool(ident.value)
+
+    def msm(self, points, scalars):
+        """Sum s_i * P_i for Python-int affine points / scalars (test helper)."""
+        assert len(points) == len(scalars)
+        raw, ident = self.msm_bytes(codec.enc_points(points, self.curve), codec.enc_scalars(scalars, self.curve), len(points))
+        return None if ident else codec.dec_point(raw, self.curve)
+
+    def msm_device(self, d_bases: int, d_scalars: int, n: int):
+        out = ctypes.create_string_buffer(64)
+        ident = ctypes.c_int(0)
+        self._check(self.lib.bp_msm_device(self.h, d_bases, d_scalars, n, out, ctypes.byref(ident)))
+        return out.raw, bool(ident.value)
+
+    def points_sum(self, points):
+        out = ctypes.create_string_buffer(64)
+        ident = ctypes.c_int(0)
+        self._check(self.lib.bp_points_sum(self.h, codec.enc_points(points, self.curve), len(points), out, ctypes.byref(ident)))
+        return None if ident.value else codec.dec_point(out.raw, self.curve)
+
+    def synth_points_device(self, d_out: int, n: int, start: int = 0):
+        self._check(self.lib.bp_synth_points_device(self.h, d_out, n, start))

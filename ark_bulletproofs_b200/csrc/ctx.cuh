@@ -1,0 +1,62 @@
+// Context: one curve on one GPU, one stream, a grow-only scratch arena.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include "../../include/bp_b200.h"
+#include "ec.cuh"
+
+namespace bp {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace bp
+
+struct bp_ctx {
+    int curve = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int force_c = 0;
+    int sm_count = 148;
+    // MSM scratch
+    bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;
+    bp::DevBuf stage_bases, stage_scalars;
+    void* h_result = nullptr;   // pinned, 256 B
+};
+
+#define BP_CUDA_TRY(ctx, expr)                                                                       \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                         \
+            return BP_ERR_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+#define BP_LAUNCH_CHECK(ctx)                                                                         \
+    do {                                                                                             \
+        (ctx)->launches++;                                                                           \
+        BP_CUDA_TRY(ctx, cudaGetLastError());                                                        \
+    } while (0)

@@ -1,0 +1,198 @@
+// Short-Weierstrass group law for the bucket / fold kernels (secq256k1: a = 0; zorro: a = 6).
+//
+// Replaces ark-ec `short_weierstrass::{Affine,Projective}` arithmetic that the reference
+// reaches through `G::Group::msm`, `mul_bigint`, `into_affine` (SURVEY.md 8(a) rows a1, a11;
+// src/generators.rs:39-44, src/inner_product_proof.rs:104-156). Only the *values* matter for
+// parity (results are canonicalised to affine before they are hashed or serialised), so the
+// coordinates are chosen for the GPU: XYZZ (x = X/ZZ, y = Y/ZZZ) for accumulation --
+// mixed add 8M+2S, full add 12M+2S -- and affine (x,y) Montgomery pairs in HBM (64 B).
+//
+// Identity encodings: XYZZ with ZZ == 0; affine (0,0) (never on a curve with b != 0).
+#pragma once
+#include "fp.cuh"
+
+namespace bp {
+
+struct alignas(16) affine { fe x, y; };
+struct alignas(16) xyzz { fe x, y, zz, zzz; };
+
+template <class C>
+struct SW {
+    using F = Fp<typename C::Fq>;
+
+    BP_HD static bool is_identity(const affine& p) { return F::is_zero(p.x) && F::is_zero(p.y); }
+    BP_HD static bool is_identity(const xyzz& p) { return F::is_zero(p.zz); }
+    BP_HD static xyzz identity() {
+        xyzz r;
+        r.x = F::zero(); r.y = F::zero(); r.zz = F::zero(); r.zzz = F::zero();
+        return r;
+    }
+    BP_HD static affine affine_identity() {
+        affine r;
+        r.x = F::zero(); r.y = F::zero();
+        return r;
+    }
+    BP_HD static xyzz from_affine(const affine& p) {
+        xyzz r;
+        if (is_identity(p)) return identity();
+        r.x = p.x; r.y = p.y; r.zz = F::one(); r.zzz = F::one();
+        return r;
+    }
+    BP_HD static affine neg(const affine& p) {
+        affine r;
+        r.x = p.x; r.y = F::neg(p.y);
+        return r;
+    }
+    BP_HD static xyzz neg(const xyzz& p) {
+        xyzz r = p;
+        r.y = F::neg(p.y);
+        return r;
+    }
+    BP_HD static fe mul_a(const fe& t) { return F::mul_small(t, C::A_SMALL); }
+
+    // 2*(x,y) -> XYZZ   [mdbl-2008-s-1]
+    BP_HD static xyzz dbl_affine(const affine& p) {
+        if (is_identity(p) || F::is_zero(p.y)) return identity();
+        xyzz r;
+        fe U = F::dbl(p.y);
+        fe V = F::sqr(U);
+        fe W = F::mul(U, V);
+        fe S = F::mul(p.x, V);
+        fe M = F::mul3(F::sqr(p.x));
+        if (C::A_SMALL != 0) M = F::add(M, F::from_u32(C::A_SMALL));
+        r.x = F::sub(F::sqr(M), F::dbl(S));
+        r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+        r.zz = V;
+        r.zzz = W;
+        return r;
+    }
+
+    // 2*P, XYZZ   [dbl-2008-s-1]
+    BP_HD static xyzz dbl(const xyzz& p) {
+        if (is_identity(p) || F::is_zero(p.y)) return identity();
+        xyzz r;
+        fe U = F::dbl(p.y);
+        fe V = F::sqr(U);
+        fe W = F::mul(U, V);
+        fe S = F::mul(p.x, V);
+        fe M = F::mul3(F::sqr(p.x));
+        if (C::A_SMALL != 0) M = F::add(M, mul_a(F::sqr(p.zz)));
+        r.x = F::sub(F::sqr(M), F::dbl(S));
+        r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+        r.zz = F::mul(V, p.zz);
+        r.zzz = F::mul(W, p.zzz);
+        return r;
+    }
+
+    // acc += (x2,y2)   [madd-2008-s], all special cases handled
+    BP_HD static void madd(xyzz& acc, const affine& q) {
+        if (is_identity(q)) return;
+        if (is_identity(acc)) { acc = from_affine(q); return; }
+        fe U2 = F::mul(q.x, acc.zz);
+        fe S2 = F::mul(q.y, acc.zzz);
+        fe P = F::sub(U2, acc.x);
+        fe R = F::sub(S2, acc.y);
+        if (F::is_zero(P)) {
+            if (F::is_zero(R)) acc = dbl_affine(q);
+            else acc = identity();
+            return;
+        }
+        fe PP = F::sqr(P);
+        fe PPP = F::mul(P, PP);
+        fe Q = F::mul(acc.x, PP);
+        fe X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+        fe Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(acc.y, PPP));
+        acc.x = X3;
+        acc.y = Y3;
+        acc.zz = F::mul(acc.zz, PP);
+        acc.zzz = F::mul(acc.zzz, PPP);
+    }
+
+    // acc += q, both XYZZ   [add-2008-s]
+    BP_HD static void add(xyzz& acc, const xyzz& q) {
+        if (is_identity(q)) return;
+        if (is_identity(acc)) { acc = q; return; }
+        fe U1 = F::mul(acc.x, q.zz);
+        fe U2 = F::mul(q.x, acc.zz);
+        fe S1 = F::mul(acc.y, q.zzz);
+        fe S2 = F::mul(q.y, acc.zzz);
+        fe P = F::sub(U2, U1);
+        fe R = F::sub(S2, S1);
+        if (F::is_zero(P)) {
+            if (F::is_zero(R)) acc = dbl(acc);
+            else acc = identity();
+            return;
+        }
+        fe PP = F::sqr(P);
+        fe PPP = F::mul(P, PP);
+        fe Q = F::mul(U1, PP);
+        fe X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+        fe Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(S1, PPP));
+        acc.x = X3;
+        acc.y = Y3;
+        acc.zz = F::mul(F::mul(acc.zz, q.zz), PP);
+        acc.zzz = F::mul(F::mul(acc.zzz, q.zzz), PPP);
+    }
+
+    // XYZZ -> affine with one field inversion (x = X/ZZ, y = Y/ZZZ)
+    BP_HD_NOINL static affine to_affine(const xyzz& p) {
+        if (is_identity(p)) return affine_identity();
+        // 1/ZZZ, then 1/ZZ = (1/ZZZ)^2 * ZZ^2 ... simpler: invert ZZ*ZZZ once
+        fe t = F::mul(p.zz, p.zzz);
+        fe ti = F::inv(t);
+        affine r;
+        r.x = F::mul(p.x, F::mul(ti, p.zzz));
+        r.y = F::mul(p.y, F::mul(ti, p.zz));
+        return r;
+    }
+
+    // k*P for a small non-negative k (double-and-add, MSB first); used by the bucket reduction
+    BP_HD_NOINL static xyzz mul_u32(const xyzz& p, uint32_t k) {
+        xyzz acc = identity();
+        for (int bit = 31; bit >= 0; bit--) {
+            acc = dbl(acc);
+            if ((k >> bit) & 1u) add(acc, p);
+        }
+        return acc;
+    }
+
+    // s*P for a canonical (non-Montgomery) 256-bit scalar given as 8 LE limbs
+    BP_HD_NOINL static xyzz mul_scalar(const affine& p, const uint32_t* s) {
+        xyzz acc = identity();
+        for (int i = 7; i >= 0; i--) {
+            for (int bit = 31; bit >= 0; bit--) {
+                acc = dbl(acc);
+                if ((s[i] >> bit) & 1u) madd(acc, p);
+            }
+        }
+        return acc;
+    }
+
+    BP_HD static bool on_curve(const affine& p) {
+        if (is_identity(p)) return true;
+        fe b;
+        for (int i = 0; i < 8; i++) b.v[i] = C::b(i);
+        fe rhs = F::add(F::mul(F::sqr(p.x), p.x), b);
+        if (C::A_SMALL != 0) rhs = F::add(rhs, mul_a(p.x));
+        return F::eq(F::sqr(p.y), rhs);
+    }
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ affine ld_affine(const affine* p) {
+    affine r;
+    r.x = ld_fe(&p->x);
+    r.y = ld_fe(&p->y);
+    return r;
+}
+__device__ __forceinline__ void st_xyzz(xyzz* p, const xyzz& v) {
+    st_fe(&p->x, v.x); st_fe(&p->y, v.y); st_fe(&p->zz, v.zz); st_fe(&p->zzz, v.zzz);
+}
+__device__ __forceinline__ xyzz ld_xyzz(const xyzz* p) {
+    xyzz r;
+    r.x = ld_fe_rw(&p->x); r.y = ld_fe_rw(&p->y); r.zz = ld_fe_rw(&p->zz); r.zzz = ld_fe_rw(&p->zzz);
+    return r;
+}
+#endif
+
+}  // namespace bp

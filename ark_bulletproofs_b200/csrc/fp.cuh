@@ -1,0 +1,284 @@
+// 256-bit Montgomery prime-field arithmetic for sm_100a (8 x 32-bit limbs, R = 2^256).
+//
+// Replaces ark-ff `Fp256<MontBackend<_,4>>` (reference: Cargo.toml:28-35; zorro
+// Fq at src/curve/zorro/fq.rs:3-7) for the five moduli of SURVEY.md App. A.1.
+// Memory layout is identical to ark-ff's ([u64;4] little-endian limbs holding
+// value*2^256 mod m), so buffers cross the C ABI without conversion.
+//
+// The multiplier is an even/odd-column CIOS: every 32x32 product is issued as an
+// adjacent (mad.lo.cc, madc.hi.cc) pair on a 64-bit column, which ptxas fuses into one
+// IMAD.WIDE.U32(.X) with predicate carries -- 128 wide multiplies + 8 for the quotients per
+// modmul (checked with cuobjdump; see profiles/).
+//
+// Every value handed between functions is fully reduced (< m): the secq256k1
+// moduli are within 2^129 of 2^256, so there are no spare bits for lazy reduction.
+//
+// The carry primitives have a host emulation (a thread-local carry flag) so that the very
+// same templates run in the CPU unit tests and in the O(log n) host-side glue; the bulk
+// paths only ever run on the device.
+#pragma once
+#include <cstdint>
+#include "consts.cuh"
+
+#if defined(__CUDACC__)
+#define BP_HD __host__ __device__ __forceinline__
+#define BP_HD_NOINL __host__ __device__
+#else
+#define BP_HD inline
+#define BP_HD_NOINL inline
+#endif
+
+namespace bp {
+
+struct alignas(16) fe { uint32_t v[8]; };
+
+#if !defined(__CUDA_ARCH__)
+namespace hostcc {
+inline uint32_t& cc() { static thread_local uint32_t c = 0; return c; }
+inline uint32_t addx(uint32_t a, uint32_t b, uint32_t cin, bool setcc) {
+    uint64_t s = (uint64_t)a + b + cin;
+    if (setcc) cc() = (uint32_t)(s >> 32);
+    return (uint32_t)s;
+}
+inline uint32_t subx(uint32_t a, uint32_t b, uint32_t bin, bool setcc) {
+    uint64_t s = (uint64_t)a - b - bin;
+    if (setcc) cc() = (uint32_t)((s >> 32) & 1);
+    return (uint32_t)s;
+}
+}  // namespace hostcc
+#endif
+
+// ---- carry-chain primitives -------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define BP_ASM2(name, ins) \
+    __device__ __forceinline__ uint32_t name(uint32_t a, uint32_t b) { uint32_t r; asm volatile(ins " %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BP_ASM2(add_cc, "add.cc.u32")
+BP_ASM2(addc_cc, "addc.cc.u32")
+BP_ASM2(addc, "addc.u32")
+BP_ASM2(sub_cc, "sub.cc.u32")
+BP_ASM2(subc_cc, "subc.cc.u32")
+BP_ASM2(subc, "subc.u32")
+#undef BP_ASM2
+// 64-bit column (hi:lo) += a*b, starting a carry chain
+__device__ __forceinline__ void wmad_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("mad.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (hi:lo) += a*b + carry, continuing the chain
+__device__ __forceinline__ void wmadc_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (dhi:dlo) = a*b + (shi:slo) + carry
+__device__ __forceinline__ void wmadc_to_cc(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b, uint32_t slo, uint32_t shi) {
+    asm volatile("madc.lo.cc.u32 %0,%2,%3,%4; madc.hi.cc.u32 %1,%2,%3,%5;" : "=r"(dlo), "=r"(dhi) : "r"(a), "r"(b), "r"(slo), "r"(shi));
+}
+#else
+inline uint32_t add_cc(uint32_t a, uint32_t b) { return hostcc::addx(a, b, 0, true); }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { return hostcc::addx(a, b, hostcc::cc(), true); }
+inline uint32_t addc(uint32_t a, uint32_t b) { return hostcc::addx(a, b, hostcc::cc(), false); }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { return hostcc::subx(a, b, 0, true); }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { return hostcc::subx(a, b, hostcc::cc(), true); }
+inline uint32_t subc(uint32_t a, uint32_t b) { return hostcc::subx(a, b, hostcc::cc(), false); }
+inline void wmad_impl(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b, uint32_t slo, uint32_t shi, uint32_t cin) {
+    unsigned __int128 t = (unsigned __int128)((uint64_t)a * b) + (((uint64_t)shi << 32) | slo) + cin;
+    dlo = (uint32_t)t;
+    dhi = (uint32_t)(t >> 32);
+    hostcc::cc() = (uint32_t)(t >> 64);
+}
+inline void wmad_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { wmad_impl(lo, hi, a, b, lo, hi, 0); }
+inline void wmadc_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { wmad_impl(lo, hi, a, b, lo, hi, hostcc::cc()); }
+inline void wmadc_to_cc(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b, uint32_t slo, uint32_t shi) {
+    wmad_impl(dlo, dhi, a, b, slo, shi, hostcc::cc());
+}
+#endif
+
+template <class M>
+struct Fp {
+    using Mod = M;
+    // r = t - m if t >= m, where t carries a possible 257th bit `top`
+    BP_HD static void final_sub(fe& r, const uint32_t* t, uint32_t top) {
+        uint32_t s[8];
+        s[0] = sub_cc(t[0], M::m(0));
+#pragma unroll
+        for (int i = 1; i < 8; i++) s[i] = subc_cc(t[i], M::m(i));
+        uint32_t borrow = subc(top, 0u);   // negative iff t < m
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = ((int32_t)borrow < 0) ? t[i] : s[i];
+    }
+
+    BP_HD static fe add(const fe& a, const fe& b) {
+        uint32_t t[8];
+        t[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) t[i] = addc_cc(a.v[i], b.v[i]);
+        uint32_t top = addc(0u, 0u);
+        fe r;
+        final_sub(r, t, top);
+        return r;
+    }
+
+    BP_HD static fe sub(const fe& a, const fe& b) {
+        uint32_t t[8];
+        t[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) t[i] = subc_cc(a.v[i], b.v[i]);
+        uint32_t borrow = subc(0u, 0u);    // 0xFFFFFFFF if a < b
+        fe r;
+        r.v[0] = add_cc(t[0], borrow & M::m(0));
+#pragma unroll
+        for (int i = 1; i < 7; i++) r.v[i] = addc_cc(t[i], borrow & M::m(i));
+        r.v[7] = addc(t[7], borrow & M::m(7));
+        return r;
+    }
+
+    BP_HD static fe zero() {
+        fe r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = 0;
+        return r;
+    }
+    BP_HD static bool is_zero(const fe& a) {
+        uint32_t o = a.v[0];
+#pragma unroll
+        for (int i = 1; i < 8; i++) o |= a.v[i];
+        return o == 0;
+    }
+    BP_HD static bool eq(const fe& a, const fe& b) {
+        uint32_t o = a.v[0] ^ b.v[0];
+#pragma unroll
+        for (int i = 1; i < 8; i++) o |= a.v[i] ^ b.v[i];
+        return o == 0;
+    }
+    BP_HD static fe neg(const fe& a) { return is_zero(a) ? a : sub(zero(), a); }
+    BP_HD static fe dbl(const fe& a) { return add(a, a); }
+    BP_HD static fe mul3(const fe& a) { return add(dbl(a), a); }
+    BP_HD static fe mul_small(const fe& a, int k) {   // k in {0..8}, by additions
+        fe r = zero();
+        fe p = a;
+        for (int bit = 0; bit < 4; bit++) {
+            if ((k >> bit) & 1) r = add(r, p);
+            p = dbl(p);
+        }
+        return r;
+    }
+
+    // Montgomery product a*b*2^-256 mod m.
+    // Running total T = X + 2^32*Y. Each round adds a*b_k and q*m (even-indexed limbs of
+    // a / m into the aligned array, odd-indexed into the offset array), then divides by
+    // 2^32 by swapping roles: X' = Y + X[1] (carry handed to Y'), Y' = X >> 64.
+    // Bounds: T < 2^33*m inside a round, so Y < 2m < 2^257 and X < 2^259: 9 limbs each.
+    BP_HD static fe mul(const fe& a, const fe& b) {
+        uint32_t X[10], Y[10];
+#pragma unroll
+        for (int i = 0; i < 10; i++) { X[i] = 0; Y[i] = 0; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t bk = b.v[k];
+            uint32_t Xn[10], Yn[10];
+            Xn[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+            for (int j = 1; j < 9; j++) Xn[j] = Y[j];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) wmadc_to_cc(Yn[j], Yn[j + 1], a.v[j + 1], bk, X[j + 2], X[j + 3]);
+            Yn[8] = addc(0u, 0u);
+            wmad_cc(Xn[0], Xn[1], a.v[0], bk);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Xn[j], Xn[j + 1], a.v[j], bk);
+            Xn[8] = addc(Xn[8], 0u);
+            const uint32_t q = Xn[0] * M::INV32;
+            wmad_cc(Yn[0], Yn[1], q, M::m(1));
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Yn[j], Yn[j + 1], q, M::m(j + 1));
+            Yn[8] = addc(Yn[8], 0u);
+            wmad_cc(Xn[0], Xn[1], q, M::m(0));
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Xn[j], Xn[j + 1], q, M::m(j));
+            Xn[8] = addc(Xn[8], 0u);
+#pragma unroll
+            for (int j = 0; j < 9; j++) { X[j] = Xn[j]; Y[j] = Yn[j]; }
+            X[9] = 0; Y[9] = 0;
+        }
+        uint32_t r[9];
+        r[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+        for (int j = 1; j < 8; j++) r[j] = addc_cc(Y[j], X[j + 1]);
+        r[8] = addc(Y[8], 0u);
+        fe o;
+        final_sub(o, r, r[8]);
+        return o;
+    }
+    BP_HD static fe sqr(const fe& a) { return mul(a, a); }
+
+    BP_HD static fe one() {
+        fe r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = M::one(i);
+        return r;
+    }
+    BP_HD static fe r2() {
+        fe r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = M::r2(i);
+        return r;
+    }
+    BP_HD static fe to_mont(const fe& a) { return mul(a, r2()); }
+    BP_HD static fe from_mont(const fe& a) {
+        fe o = zero();
+        o.v[0] = 1;
+        return mul(a, o);
+    }
+    BP_HD static fe from_u32(uint32_t x) {
+        fe o = zero();
+        o.v[0] = x;
+        return to_mont(o);
+    }
+
+    // a^e, e as 8 little-endian limbs (square-and-multiply, MSB first)
+    BP_HD_NOINL static fe pow(const fe& a, const uint32_t* e) {
+        fe r = one();
+        bool started = false;
+        for (int i = 7; i >= 0; i--) {
+            for (int bit = 31; bit >= 0; bit--) {
+                if (started) r = sqr(r);
+                if ((e[i] >> bit) & 1u) {
+                    r = started ? mul(r, a) : a;
+                    started = true;
+                }
+            }
+        }
+        return r;
+    }
+
+    // Fermat inverse a^(m-2); inv(0) = 0
+    BP_HD_NOINL static fe inv(const fe& a) {
+        uint32_t e[8];
+        e[0] = M::m(0) - 2u;   // all five moduli have low limb >= 2: no borrow
+        for (int i = 1; i < 8; i++) e[i] = M::m(i);
+        return pow(a, e);
+    }
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ fe ld_fe(const void* p) {   // read-only path (inputs never written by the same kernel)
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    fe r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ fe ld_fe_rw(const void* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    fe r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fe(void* p, const fe& r) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+#endif
+
+}  // namespace bp

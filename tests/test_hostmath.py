@@ -1,0 +1,101 @@
+"""CPU unit tests of the device math templates (csrc/fp.cuh, csrc/ec.cuh) compiled for the
+host (carry primitives emulated) against the Python oracle's big-integer arithmetic."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+import bp_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+R = 1 << 256
+FIELDS = [O.SECP_N, O.SECP_P, O.ZORRO.q, 2**255 - 19, O.CURVE25519.r]
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("hm") / "libhostmath.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-x", "c++",
+                           os.path.join(HERE, "native", "hostmath.cpp"), "-o", str(out)])
+    return ctypes.CDLL(str(out))
+
+
+def _b(v):
+    return (ctypes.c_uint32 * 8).from_buffer_copy(v.to_bytes(32, "little"))
+
+
+def _fp(lib, field, op, a, b=0):
+    out = (ctypes.c_uint32 * 8)()
+    assert lib.hm_fp_op(field, op, _b(a), _b(b), out) == 0
+    return int.from_bytes(bytes(out), "little")
+
+
+@pytest.mark.parametrize("field", range(5))
+def test_field_ops(lib, field):
+    m = FIELDS[field]
+    rnd = random.Random(1234 + field)
+    edge = [0, 1, 2, m - 1, m - 2, (1 << 255) % m, R % m, (m - 1) // 2, 0xFFFFFFFF, (1 << 224) - 1]
+    vals = edge + [rnd.randrange(m) for _ in range(40)]
+    rinv = pow(R, -1, m)
+    for a in vals:
+        for b in rnd.sample(vals, 8) + [m - 1, a]:
+            assert _fp(lib, field, 0, a, b) == a * b * rinv % m
+            assert _fp(lib, field, 1, a, b) == (a + b) % m
+            assert _fp(lib, field, 2, a, b) == (a - b) % m
+        assert _fp(lib, field, 4, a) == a * rinv % m
+        assert _fp(lib, field, 5, a) == a * R % m
+        assert _fp(lib, field, 6, a) == (-a) % m
+        assert _fp(lib, field, 7, a) == a * a * rinv % m
+    for a in vals[:12]:
+        am = a * R % m
+        inv = _fp(lib, field, 3, am)
+        if a == 0:
+            assert inv == 0
+        else:
+            assert inv == pow(a, -1, m) * R % m
+
+
+def _pt(cv, P):
+    if P is None:
+        return (ctypes.c_uint32 * 16)()
+    x, y = P
+    return (ctypes.c_uint32 * 16).from_buffer_copy((x * R % cv.q).to_bytes(32, "little") + (y * R % cv.q).to_bytes(32, "little"))
+
+
+def _unpt(cv, buf):
+    raw = bytes(buf)
+    x = int.from_bytes(raw[:32], "little") * pow(R, -1, cv.q) % cv.q
+    y = int.from_bytes(raw[32:], "little") * pow(R, -1, cv.q) % cv.q
+    return None if (x == 0 and y == 0) else (x, y)
+
+
+def _ec(lib, cid, cv, op, P, Q, s=0):
+    out = (ctypes.c_uint32 * 16)()
+    rc = lib.hm_ec_op(cid, op, _pt(cv, P), _pt(cv, Q), _b(s), out)
+    assert rc == 0
+    return _unpt(cv, out)
+
+
+@pytest.mark.parametrize("cid,cv", [(0, O.SECQ256K1), (1, O.ZORRO)])
+def test_curve_ops(lib, cid, cv):
+    rnd = random.Random(99 + cid)
+    G = cv.G
+    pts = [O.pt_mul(cv, rnd.randrange(1, cv.r), G) for _ in range(4)]
+    add, mul, neg = (lambda a, b: O.pt_add(cv, a, b)), (lambda k, a: O.pt_mul(cv, k, a)), (lambda a: O.pt_neg(cv, a))
+    cases = [(P, Q) for P in pts[:2] for Q in pts[2:]] + [(pts[0], pts[0]), (pts[0], neg(pts[0])), (pts[0], None), (None, pts[1]), (None, None)]
+    for P, Q in cases:
+        assert _ec(lib, cid, cv, 0, P, Q) == add(P, Q)
+        assert _ec(lib, cid, cv, 1, P, Q) == add(mul(2, P), mul(2, Q))
+        assert _ec(lib, cid, cv, 5, P, Q) == add(mul(2, P), mul(2, Q))
+        assert _ec(lib, cid, cv, 2, P, Q) == mul(4, P)
+        assert _ec(lib, cid, cv, 4, P, Q) == add(mul(2, P), Q)
+    # 2P + Q with Q = 2P (mixed add hitting the doubling branch) and Q = -2P
+    P = pts[0]
+    assert _ec(lib, cid, cv, 4, P, mul(2, P)) == mul(4, P)
+    assert _ec(lib, cid, cv, 4, P, neg(mul(2, P))) is None
+    for s in [0, 1, 2, cv.r - 1, rnd.randrange(cv.r), rnd.randrange(cv.r)]:
+        assert _ec(lib, cid, cv, 3, P, None, s) == mul(s, P)
+    for k in [0, 1, 5, 65535, 0xFFFFFFFF]:
+        assert _ec(lib, cid, cv, 6, P, None, k) == mul(2 * k, P)

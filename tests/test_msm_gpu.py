@@ -1,0 +1,101 @@
+"""GPU parity: bp_msm (C ABI, csrc/msm.cu) vs the CPU oracle on the same inputs.
+Covers SURVEY.md section 7 step 4's cases: N = 1,2,3,31,32,33,2^k+-1, zero scalars, repeated
+points, identity bases, all-equal scalars, p-1."""
+import random
+
+import pytest
+
+import bp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ark_bulletproofs_b200 import Context
+    return Context("secq256k1", 0)
+
+
+def _points(cv, n, rnd):
+    base = O.pt_mul(cv, rnd.randrange(1, cv.r), cv.G)
+    pts, P = [], None
+    for _ in range(n):
+        P = O.pt_add(cv, P, base)
+        pts.append(P)
+    return pts
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 127, 128, 129, 1000, 4097])
+def test_msm_random(ctx, n):
+    cv = O.SECQ256K1
+    rnd = random.Random(n)
+    pts = _points(cv, n, rnd)
+    sc = [rnd.randrange(cv.r) for _ in range(n)]
+    assert ctx.msm(pts, sc) == O.msm(cv, pts, sc)
+
+
+@pytest.mark.parametrize("c", [3, 4, 7, 8, 11, 13, 16])
+def test_msm_windows(ctx, c):
+    cv = O.SECQ256K1
+    rnd = random.Random(100 + c)
+    n = 257
+    pts = _points(cv, n, rnd)
+    sc = [rnd.randrange(cv.r) for _ in range(n)]
+    ctx.set_window(c)
+    try:
+        assert ctx.msm(pts, sc) == O.msm(cv, pts, sc)
+    finally:
+        ctx.set_window(0)
+
+
+def test_msm_edge_scalars(ctx):
+    cv = O.SECQ256K1
+    rnd = random.Random(5)
+    n = 200
+    pts = _points(cv, n, rnd)
+    for sc in ([0] * n, [1] * n, [cv.r - 1] * n, [rnd.randrange(cv.r)] * n,
+               [0 if i % 2 else rnd.randrange(cv.r) for i in range(n)],
+               [(1 << 255)] * n, [(1 << 256) - (1 << 32) - 978] * n, [2**128 - 1] * n):
+        got = ctx.msm(pts, sc)
+        assert got == O.msm(cv, pts, sc)
+
+
+def test_msm_edge_points(ctx):
+    cv = O.SECQ256K1
+    rnd = random.Random(6)
+    n = 150
+    pts = _points(cv, n, rnd)
+    sc = [rnd.randrange(cv.r) for _ in range(n)]
+    # identity bases (verifier.rs:582-584: A_I2.. may be the identity), repeated points, P and -P
+    pts2 = list(pts)
+    for i in range(0, n, 7):
+        pts2[i] = None
+    pts2[1] = pts2[2] = pts2[3]
+    pts2[4] = O.pt_neg(cv, pts2[5])
+    assert ctx.msm(pts2, sc) == O.msm(cv, pts2, sc)
+    # all the same point and all the same scalar: one bucket, every add is a doubling at first
+    same = [pts[0]] * n
+    assert ctx.msm(same, [3] * n) == O.pt_mul(cv, 3 * n, pts[0])
+    # sum that cancels to the identity
+    assert ctx.msm([pts[0], O.pt_neg(cv, pts[0])], [5, 5]) is None
+    assert ctx.msm([], []) is None
+
+
+def test_points_sum(ctx):
+    cv = O.SECQ256K1
+    pts = _points(cv, 9, random.Random(1)) + [None]
+    want = None
+    for P in pts:
+        want = O.pt_add(cv, want, P)
+    assert ctx.points_sum(pts) == want
+
+
+def test_zorro_msm():
+    from ark_bulletproofs_b200 import Context
+    cv = O.ZORRO
+    ctx = Context("zorro", 0)
+    rnd = random.Random(77)
+    n = 300
+    pts = _points(cv, n, rnd)
+    sc = [rnd.randrange(cv.r) for _ in range(n)]
+    assert ctx.msm(pts, sc) == O.msm(cv, pts, sc)
