@@ -4,7 +4,7 @@
 
 namespace bp {
 int msm_dispatch(bp_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, uint8_t out_xy[64], int* out_is_identity);
-int points_sum_dispatch(bp_ctx* ctx, const void* d_pts, size_t n, uint8_t out_xy[64], int* out_is_identity);
+int host_points_sum(int curve, const uint8_t* pts_xy, size_t n, uint8_t out_xy[64], int* out_is_identity);
 int synth_points_dispatch(bp_ctx* ctx, void* d_out, size_t n, uint64_t start);
 }  // namespace bp
 
@@ -24,7 +24,7 @@ int bp_ctx_create(int curve, int device, bp_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost(&ctx->h_result, 4096) != cudaSuccess) {
+        cudaMallocHost(&ctx->h_result, 16384) != cudaSuccess) {
         delete ctx;
         return BP_ERR_CUDA;
     }
@@ -81,10 +81,8 @@ int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t 
 
 int bp_points_sum(bp_ctx* ctx, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity) {
     if (!ctx || !out_xy || (n && !points_xy)) return BP_ERR_ARG;
-    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    BP_CUDA_TRY(ctx, ctx->stage_bases.reserve(n * 64 + 64));
-    if (n) BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_bases.p, points_xy, n * 64, cudaMemcpyHostToDevice, ctx->stream));
-    return bp::points_sum_dispatch(ctx, ctx->stage_bases.p, n, out_xy, out_is_identity);
+    // a handful of points (one per GPU): serial adds + one inversion, done on the host (host_tail.cpp)
+    return bp::host_points_sum(ctx->curve, points_xy, n, out_xy, out_is_identity);
 }
 
 int bp_synth_points_device(bp_ctx* ctx, void* d_out_xy, size_t n, uint64_t start) {

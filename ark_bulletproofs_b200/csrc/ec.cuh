@@ -16,9 +16,9 @@ namespace bp {
 struct alignas(16) affine { fe x, y; };
 struct alignas(16) xyzz { fe x, y, zz, zzz; };
 
-template <class C>
+template <class C, class F_ = Fp<typename C::Fq>>
 struct SW {
-    using F = Fp<typename C::Fq>;
+    using F = F_;
 
     BP_HD static bool is_identity(const affine& p) { return F::is_zero(p.x) && F::is_zero(p.y); }
     BP_HD static bool is_identity(const xyzz& p) { return F::is_zero(p.zz); }
@@ -149,7 +149,9 @@ struct SW {
     // k*P for a small non-negative k (double-and-add, MSB first); used by the bucket reduction
     BP_HD_NOINL static xyzz mul_u32(const xyzz& p, uint32_t k) {
         xyzz acc = identity();
-        for (int bit = 31; bit >= 0; bit--) {
+        int top = 31;
+        while (top >= 0 && !((k >> top) & 1u)) top--;
+        for (int bit = top; bit >= 0; bit--) {
             acc = dbl(acc);
             if ((k >> bit) & 1u) add(acc, p);
         }

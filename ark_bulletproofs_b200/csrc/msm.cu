@@ -1,339 +1,13 @@
-// Pippenger variable-base MSM for sm_100a.
-//
-// Replaces ark-ec `VariableBaseMSM::msm` at the 17 call sites of SURVEY.md 8(a) row a1
-// (src/inner_product_proof.rs:104,124,187,202; src/r1cs/prover.rs:516-559,607-648;
-// src/r1cs/verifier.rs:574,685). Only the value of the sum is observable, so the algorithm is
-// chosen for the GPU:
-//   1. digits      : scalar (Montgomery) -> canonical -> signed c-bit digits; emits one
-//                    (bucket key, point index | sign) pair per window          [HBM-bound]
-//   2. sort        : radix sort of the pairs by key (cub::DeviceRadixSort)      [HBM-bound]
-//   3. accumulate  : every thread walks a fixed-length chunk of the sorted pairs, gathers
-//                    the 64-byte affine points (128-bit loads, next point prefetched during
-//                    the current add) and sums runs in XYZZ; runs closed inside the chunk
-//                    are stored straight to their bucket, runs cut by a chunk edge go to a
-//                    partial list                                               [IMAD-bound]
-//   4. partials    : partial sums of one bucket are adjacent; the first one folds the rest
-//   5. reduce      : per window, sum_b (b+1)*B_b by per-thread running sums over bucket
-//                    segments + a short double-and-add for the segment offset   [IMAD-bound]
-//   6. window sums : block tree-reduction of the segment results
-//   7. combine     : Horner over the windows (c doublings each) + to-affine
-//
-// Chunking by entries (not by bucket) keeps the work per thread constant for any scalar
-// distribution (all-equal scalars, 50% zeros, ...) -- SURVEY.md 8(d) config 1's adversarial sets.
-#include <cub/device/device_radix_sort.cuh>
+// Curve dispatch for the MSM entry points (kernels: msm_kernels.cuh).
 #include "ctx.cuh"
 
 namespace bp {
-
-static constexpr uint32_t INVALID_KEY = 0xFFFFFFFFu;
-
-struct MsmPlan {
-    int c;            // window width in bits
-    int W;            // number of windows
-    uint32_t nb;      // buckets per window = 2^(c-1); bucket b holds digit magnitude b+1
-    int key_bits;     // radix-sort end bit
-    size_t entries;   // n * W
-    int L;            // sorted entries per accumulate thread
-    size_t T;         // accumulate threads
-    uint32_t seg;     // buckets per reduce thread
-    uint32_t nseg;    // segments per window
-};
-
-static MsmPlan make_plan(size_t n, int force_c, int sm_count) {
-    MsmPlan p;
-    int best_c = 4;
-    double best = 1e300;
-    for (int c = 3; c <= 20; c++) {
-        int W = 256 / c + 1;
-        double nb = (double)(1u << (c - 1));
-        double cost = W * (10.0 * (double)n + 45.0 * nb);   // modmul-equivalents
-        if (cost < best) { best = cost; best_c = c; }
-    }
-    p.c = force_c > 0 ? force_c : best_c;
-    p.W = 256 / p.c + 1;
-    p.nb = 1u << (p.c - 1);
-    uint64_t nkeys = (uint64_t)p.W * p.nb;
-    p.key_bits = 1;
-    while ((1ull << p.key_bits) <= nkeys) p.key_bits++;
-    p.entries = n * (size_t)p.W;
-    size_t per = p.entries / ((size_t)sm_count * 256);
-    p.L = (int)(per < 8 ? 8 : per > 64 ? 64 : per);
-    p.T = (p.entries + p.L - 1) / p.L;
-    uint32_t seg = p.nb / 1024;
-    p.seg = seg < 4 ? 4 : seg > 32 ? 32 : seg;
-    if (p.seg > p.nb) p.seg = p.nb;
-    p.nseg = (p.nb + p.seg - 1) / p.seg;
-    return p;
-}
-
-// ---- 1. digits -------------------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(256) msm_digits_kernel(const fe* __restrict__ scalars, size_t n, int c, int W,
-                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    fe s = Fp<typename C::Fr>::from_mont(ld_fe(scalars + i));
-    const uint32_t half = 1u << (c - 1);
-    const uint32_t mask = (1u << c) - 1u;
-    uint32_t carry = 0;
-    for (int w = 0; w < W; w++) {
-        int bit = w * c;
-        int limb = bit >> 5, sh = bit & 31;
-        uint32_t lo = limb < 8 ? s.v[limb] : 0u;
-        uint32_t hi = (limb + 1) < 8 ? s.v[limb + 1] : 0u;
-        uint32_t d = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & mask;
-        d += carry;
-        uint32_t neg = 0;
-        if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else carry = 0;
-        uint32_t key = d ? (((uint32_t)w << (c - 1)) | (d - 1u)) : INVALID_KEY;
-        keys[(size_t)w * n + i] = key;
-        vals[(size_t)w * n + i] = (uint32_t)i | (neg << 31);
-    }
-}
-
-// ---- 3. accumulate ---------------------------------------------------------------------------
-template <class C>
-__device__ __forceinline__ affine gather_point(const affine* __restrict__ pts, uint32_t v) {
-    affine p = ld_affine(pts + (v & 0x7FFFFFFFu));
-    if (v >> 31) p.y = Fp<typename C::Fq>::neg(p.y);
-    return p;
-}
-
-template <class C>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                             size_t M, int L, size_t T, const affine* __restrict__ pts,
-                                                             xyzz* __restrict__ buckets, uint32_t* __restrict__ part_keys,
-                                                             xyzz* __restrict__ part_pts) {
-    using E = SW<C>;
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    size_t s = t * (size_t)L;
-    size_t e = s + L < M ? s + L : M;
-    uint32_t pk[2] = {INVALID_KEY, INVALID_KEY};
-    int nparts = 0;
-    uint32_t cur = keys[s];
-    if (cur != INVALID_KEY) {
-        bool open_left = s > 0 && keys[s - 1] == cur;
-        xyzz acc = E::identity();
-        affine p = gather_point<C>(pts, vals[s]);
-        size_t i = s;
-        while (true) {
-            size_t j = i + 1;
-            uint32_t knext = INVALID_KEY;
-            affine pnext;
-            if (j < M) knext = keys[j];
-            bool have_next = j < e && knext != INVALID_KEY;
-            if (have_next) pnext = gather_point<C>(pts, vals[j]);   // in flight during the add below
-            E::madd(acc, p);
-            if (j >= e || knext != cur) {
-                bool open_right = j >= e && knext == cur;
-                if (!open_left && !open_right) {
-                    st_xyzz(buckets + cur, acc);
-                } else {
-                    pk[nparts] = cur;
-                    st_xyzz(part_pts + 2 * t + nparts, acc);
-                    nparts++;
-                }
-                if (!have_next) break;
-                cur = knext;
-                acc = E::identity();
-                open_left = false;
-            }
-            p = pnext;
-            i = j;
-        }
-    }
-    part_keys[2 * t] = pk[0];
-    part_keys[2 * t + 1] = pk[1];
-}
-
-// ---- 4. partials -----------------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(128) msm_partials_kernel(const uint32_t* __restrict__ part_keys, const xyzz* __restrict__ part_pts,
-                                                           size_t nslots, xyzz* __restrict__ buckets) {
-    using E = SW<C>;
-    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nslots) return;
-    uint32_t k = part_keys[p];
-    if (k == INVALID_KEY) return;
-    // first partial of this key?
-    for (size_t q = p; q-- > 0;) {
-        uint32_t kq = part_keys[q];
-        if (kq == INVALID_KEY) continue;
-        if (kq == k) return;
-        break;
-    }
-    xyzz acc = ld_xyzz(part_pts + p);
-    for (size_t q = p + 1; q < nslots; q++) {
-        uint32_t kq = part_keys[q];
-        if (kq == INVALID_KEY) continue;
-        if (kq != k) break;
-        xyzz o = ld_xyzz(part_pts + q);
-        E::add(acc, o);
-    }
-    st_xyzz(buckets + k, acc);
-}
-
-// ---- 5. bucket reduction ---------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz* __restrict__ buckets, uint32_t nb, uint32_t seg, uint32_t nseg,
-                                                         int W, xyzz* __restrict__ seg_out) {
-    using E = SW<C>;
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)W * nseg) return;
-    uint32_t w = (uint32_t)(t / nseg), sg = (uint32_t)(t % nseg);
-    uint32_t lo = sg * seg;
-    uint32_t hi = lo + seg < nb ? lo + seg : nb;
-    const xyzz* B = buckets + (size_t)w * nb;
-    xyzz run = E::identity(), acc = E::identity();
-    for (uint32_t b = hi; b-- > lo;) {
-        xyzz v = ld_xyzz(B + b);
-        E::add(run, v);
-        E::add(acc, run);
-    }
-    // acc = sum (b - lo + 1) B_b ; weights are b + 1  ->  add lo * run
-    if (lo != 0 && !E::is_identity(run)) {
-        xyzz m = E::mul_u32(run, lo);
-        E::add(acc, m);
-    }
-    st_xyzz(seg_out + t, acc);
-}
-
-// ---- 6. window sums --------------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(128) msm_window_sum_kernel(const xyzz* __restrict__ seg_out, uint32_t nseg, xyzz* __restrict__ win_out) {
-    using E = SW<C>;
-    __shared__ xyzz sh[128];
-    uint32_t w = blockIdx.x;
-    xyzz acc = E::identity();
-    for (uint32_t s = threadIdx.x; s < nseg; s += blockDim.x) {
-        xyzz v = ld_xyzz(seg_out + (size_t)w * nseg + s);
-        E::add(acc, v);
-    }
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int stride = 64; stride > 0; stride >>= 1) {
-        if ((int)threadIdx.x < stride) {
-            xyzz a = sh[threadIdx.x];
-            xyzz b = sh[threadIdx.x + stride];
-            E::add(a, b);
-            sh[threadIdx.x] = a;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) st_xyzz(win_out + w, sh[0]);
-}
-
-// ---- 7. combine ------------------------------------------------------------------------------
-// out[0] = affine result (64 B), out flag word at byte 64: 1 if identity
-template <class C>
-__global__ void msm_combine_kernel(const xyzz* __restrict__ win, int W, int c, uint32_t* __restrict__ out) {
-    using E = SW<C>;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    xyzz acc = ld_xyzz(win + (W - 1));
-    for (int w = W - 2; w >= 0; w--) {
-        for (int k = 0; k < c; k++) acc = E::dbl(acc);
-        xyzz v = ld_xyzz(win + w);
-        E::add(acc, v);
-    }
-    affine a = E::to_affine(acc);
-    for (int i = 0; i < 8; i++) { out[i] = a.x.v[i]; out[8 + i] = a.y.v[i]; }
-    out[16] = E::is_identity(acc) ? 1u : 0u;
-}
-
-// sum of n affine points -> out (same layout as combine)
-template <class C>
-__global__ void points_sum_kernel(const affine* __restrict__ pts, size_t n, uint32_t* __restrict__ out) {
-    using E = SW<C>;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    xyzz acc = E::identity();
-    for (size_t i = 0; i < n; i++) {
-        affine p = ld_affine(pts + i);
-        E::madd(acc, p);
-    }
-    affine a = E::to_affine(acc);
-    for (int i = 0; i < 8; i++) { out[i] = a.x.v[i]; out[8 + i] = a.y.v[i]; }
-    out[16] = E::is_identity(acc) ? 1u : 0u;
-}
-
-// synthetic workload: out[i] = (start + i + 1) * G
-template <class C>
-__global__ void __launch_bounds__(128) synth_points_kernel(affine* __restrict__ out, size_t n, uint64_t start) {
-    using E = SW<C>;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    affine g;
-    for (int k = 0; k < 8; k++) { g.x.v[k] = C::gx(k); g.y.v[k] = C::gy(k); }
-    uint64_t k = start + i + 1;
-    uint32_t s[8] = {(uint32_t)k, (uint32_t)(k >> 32), 0, 0, 0, 0, 0, 0};
-    xyzz acc = E::identity();
-    for (int bit = 63; bit >= 0; bit--) {
-        acc = E::dbl(acc);
-        if ((s[bit >> 5] >> (bit & 31)) & 1u) E::madd(acc, g);
-    }
-    affine a = E::to_affine(acc);
-    st_fe(&out[i].x, a.x);
-    st_fe(&out[i].y, a.y);
-}
-
-// ---- host driver -----------------------------------------------------------------------------
-template <class C>
-static int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) {
-    cudaStream_t st = ctx->stream;
-    uint32_t* d_res = nullptr;
-    BP_CUDA_TRY(ctx, ctx->result.reserve(256));
-    d_res = ctx->result.as<uint32_t>();
-    if (n == 0) {
-        memset(out_xy, 0, 64);
-        if (out_is_identity) *out_is_identity = 1;
-        return BP_OK;
-    }
-    if (n >= (1ull << 31)) return BP_ERR_LEN;
-    MsmPlan p = make_plan(n, ctx->force_c, ctx->sm_count);
-    BP_CUDA_TRY(ctx, ctx->keys_a.reserve(p.entries * 4));
-    BP_CUDA_TRY(ctx, ctx->keys_b.reserve(p.entries * 4));
-    BP_CUDA_TRY(ctx, ctx->vals_a.reserve(p.entries * 4));
-    BP_CUDA_TRY(ctx, ctx->vals_b.reserve(p.entries * 4));
-    size_t nbuckets = (size_t)p.W * p.nb;
-    BP_CUDA_TRY(ctx, ctx->buckets.reserve(nbuckets * sizeof(xyzz)));
-    BP_CUDA_TRY(ctx, ctx->part_keys.reserve(2 * p.T * 4));
-    BP_CUDA_TRY(ctx, ctx->part_pts.reserve(2 * p.T * sizeof(xyzz)));
-    BP_CUDA_TRY(ctx, ctx->seg_out.reserve((size_t)p.W * p.nseg * sizeof(xyzz)));
-    BP_CUDA_TRY(ctx, ctx->win_out.reserve((size_t)p.W * sizeof(xyzz)));
-    size_t tmp_bytes = 0;
-    BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->keys_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(),
-                                                     ctx->vals_a.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, 0,
-                                                     p.key_bits, st));
-    BP_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
-
-    msm_digits_kernel<C><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scalars, n, p.c, p.W, ctx->keys_a.as<uint32_t>(),
-                                                                     ctx->vals_a.as<uint32_t>());
-    BP_LAUNCH_CHECK(ctx);
-    BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->keys_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(),
-                                                     ctx->vals_a.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, 0,
-                                                     p.key_bits, st));
-    BP_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, nbuckets * sizeof(xyzz), st));
-    msm_accumulate_kernel<C><<<(unsigned)((p.T + 127) / 128), 128, 0, st>>>(
-        ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, p.L, p.T, d_bases, ctx->buckets.as<xyzz>(),
-        ctx->part_keys.as<uint32_t>(), ctx->part_pts.as<xyzz>());
-    BP_LAUNCH_CHECK(ctx);
-    msm_partials_kernel<C><<<(unsigned)((2 * p.T + 127) / 128), 128, 0, st>>>(ctx->part_keys.as<uint32_t>(), ctx->part_pts.as<xyzz>(),
-                                                                              2 * p.T, ctx->buckets.as<xyzz>());
-    BP_LAUNCH_CHECK(ctx);
-    size_t rt = (size_t)p.W * p.nseg;
-    msm_reduce_kernel<C><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, p.W,
-                                                                       ctx->seg_out.as<xyzz>());
-    BP_LAUNCH_CHECK(ctx);
-    msm_window_sum_kernel<C><<<p.W, 128, 0, st>>>(ctx->seg_out.as<xyzz>(), p.nseg, ctx->win_out.as<xyzz>());
-    BP_LAUNCH_CHECK(ctx);
-    msm_combine_kernel<C><<<1, 32, 0, st>>>(ctx->win_out.as<xyzz>(), p.W, p.c, d_res);
-    BP_LAUNCH_CHECK(ctx);
-    BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_result, d_res, 68, cudaMemcpyDeviceToHost, st));
-    BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    memcpy(out_xy, ctx->h_result, 64);
-    if (out_is_identity) *out_is_identity = (int)reinterpret_cast<uint32_t*>(ctx->h_result)[16];
-    return BP_OK;
-}
+template <class C> int msm_run(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);
+template <class C> int synth_points_run(bp_ctx*, void*, size_t, uint64_t);
+extern template int msm_run<Secq256k1>(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);
+extern template int msm_run<Zorro>(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);
+extern template int synth_points_run<Secq256k1>(bp_ctx*, void*, size_t, uint64_t);
+extern template int synth_points_run<Zorro>(bp_ctx*, void*, size_t, uint64_t);
 
 int msm_dispatch(bp_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) {
     switch (ctx->curve) {
@@ -347,37 +21,12 @@ int msm_dispatch(bp_ctx* ctx, const void* d_bases, const void* d_scalars, size_t
     }
 }
 
-template <class C>
-static int points_sum_run(bp_ctx* ctx, const affine* d_pts, size_t n, uint8_t out_xy[64], int* out_is_identity) {
-    BP_CUDA_TRY(ctx, ctx->result.reserve(256));
-    uint32_t* d_res = ctx->result.as<uint32_t>();
-    points_sum_kernel<C><<<1, 32, 0, ctx->stream>>>(d_pts, n, d_res);
-    BP_LAUNCH_CHECK(ctx);
-    BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_result, d_res, 68, cudaMemcpyDeviceToHost, ctx->stream));
-    BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(out_xy, ctx->h_result, 64);
-    if (out_is_identity) *out_is_identity = (int)reinterpret_cast<uint32_t*>(ctx->h_result)[16];
-    return BP_OK;
-}
-
-int points_sum_dispatch(bp_ctx* ctx, const void* d_pts, size_t n, uint8_t out_xy[64], int* out_is_identity) {
-    switch (ctx->curve) {
-        case BP_CURVE_SECQ256K1: return points_sum_run<Secq256k1>(ctx, (const affine*)d_pts, n, out_xy, out_is_identity);
-        case BP_CURVE_ZORRO: return points_sum_run<Zorro>(ctx, (const affine*)d_pts, n, out_xy, out_is_identity);
-        default: ctx->err = "curve not supported"; return BP_ERR_UNSUPPORTED;
-    }
-}
-
 int synth_points_dispatch(bp_ctx* ctx, void* d_out, size_t n, uint64_t start) {
-    if (n == 0) return BP_OK;
-    unsigned grid = (unsigned)((n + 127) / 128);
     switch (ctx->curve) {
-        case BP_CURVE_SECQ256K1: synth_points_kernel<Secq256k1><<<grid, 128, 0, ctx->stream>>>((affine*)d_out, n, start); break;
-        case BP_CURVE_ZORRO: synth_points_kernel<Zorro><<<grid, 128, 0, ctx->stream>>>((affine*)d_out, n, start); break;
+        case BP_CURVE_SECQ256K1: return synth_points_run<Secq256k1>(ctx, d_out, n, start);
+        case BP_CURVE_ZORRO: return synth_points_run<Zorro>(ctx, d_out, n, start);
         default: ctx->err = "curve not supported"; return BP_ERR_UNSUPPORTED;
     }
-    BP_LAUNCH_CHECK(ctx);
-    return BP_OK;
 }
 
 }  // namespace bp

@@ -1,0 +1,6 @@
+// secq256k1 instantiation of the MSM kernels (one curve per translation unit keeps nvcc parallel).
+#include "msm_kernels.cuh"
+namespace bp {
+template int msm_run<Secq256k1>(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);
+template int synth_points_run<Secq256k1>(bp_ctx*, void*, size_t, uint64_t);
+}  // namespace bp

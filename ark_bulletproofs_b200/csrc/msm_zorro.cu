@@ -1,0 +1,6 @@
+// zorro (src/curve/zorro/g1.rs) instantiation of the MSM kernels.
+#include "msm_kernels.cuh"
+namespace bp {
+template int msm_run<Zorro>(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);
+template int synth_points_run<Zorro>(bp_ctx*, void*, size_t, uint64_t);
+}  // namespace bp

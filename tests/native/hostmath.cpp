@@ -3,10 +3,10 @@
 // algorithms that run in the kernels are checked here against the Python oracle.
 #include <cstring>
 #include "../../ark_bulletproofs_b200/csrc/ec.cuh"
+#include "../../ark_bulletproofs_b200/csrc/host/fp_host.hpp"
 using namespace bp;
 
-template <class M> static int fp_op_t(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
-    using F = Fp<M>;
+template <class F> static int fp_op_t(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     fe x, y, r;
     memcpy(x.v, a, 32);
     memcpy(y.v, b, 32);
@@ -26,18 +26,22 @@ template <class M> static int fp_op_t(int op, const uint32_t* a, const uint32_t*
 }
 extern "C" int hm_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     switch (field) {
-        case 0: return fp_op_t<SecqFq>(op, a, b, out);
-        case 1: return fp_op_t<SecqFr>(op, a, b, out);
-        case 2: return fp_op_t<ZorroFq>(op, a, b, out);
-        case 3: return fp_op_t<Fp25519>(op, a, b, out);
-        case 4: return fp_op_t<Fr25519>(op, a, b, out);
+        case 0: return fp_op_t<Fp<SecqFq>>(op, a, b, out);
+        case 1: return fp_op_t<Fp<SecqFr>>(op, a, b, out);
+        case 2: return fp_op_t<Fp<ZorroFq>>(op, a, b, out);
+        case 3: return fp_op_t<Fp<Fp25519>>(op, a, b, out);
+        case 4: return fp_op_t<Fp<Fr25519>>(op, a, b, out);
+        case 10: return fp_op_t<HostFp<SecqFq>>(op, a, b, out);
+        case 11: return fp_op_t<HostFp<SecqFr>>(op, a, b, out);
+        case 12: return fp_op_t<HostFp<ZorroFq>>(op, a, b, out);
+        case 13: return fp_op_t<HostFp<Fp25519>>(op, a, b, out);
+        case 14: return fp_op_t<HostFp<Fr25519>>(op, a, b, out);
     }
     return -1;
 }
 
 // points cross as affine (x,y) Montgomery, (0,0) = identity
-template <class C> static int ec_op_t(int op, const uint32_t* p, const uint32_t* q, const uint32_t* s, uint32_t* out) {
-    using E = SW<C>;
+template <class E> static int ec_op_t(int op, const uint32_t* p, const uint32_t* q, const uint32_t* s, uint32_t* out) {
     affine P, Q;
     memcpy(&P, p, 64);
     memcpy(&Q, q, 64);
@@ -58,8 +62,10 @@ template <class C> static int ec_op_t(int op, const uint32_t* p, const uint32_t*
 }
 extern "C" int hm_ec_op(int curve, int op, const uint32_t* p, const uint32_t* q, const uint32_t* s, uint32_t* out) {
     switch (curve) {
-        case 0: return ec_op_t<Secq256k1>(op, p, q, s, out);
-        case 1: return ec_op_t<Zorro>(op, p, q, s, out);
+        case 0: return ec_op_t<SW<Secq256k1>>(op, p, q, s, out);
+        case 1: return ec_op_t<SW<Zorro>>(op, p, q, s, out);
+        case 10: return ec_op_t<SW<Secq256k1, HostFp<SecqFq>>>(op, p, q, s, out);
+        case 11: return ec_op_t<SW<Zorro, HostFp<ZorroFq>>>(op, p, q, s, out);
     }
     return -1;
 }
