@@ -46,6 +46,16 @@ class Context:
     def sync(self):
         self._check(self.lib.bp_ctx_sync(self.h))
 
+    def set_timing(self, enable: bool):
+        self._check(self.lib.bp_ctx_set_timing(self.h, 1 if enable else 0))
+
+    def last_phases(self):
+        ph = (ctypes.c_float * 8)()
+        c, w, e = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_uint64(0)
+        self._check(self.lib.bp_msm_last_phases(self.h, ph, ctypes.byref(c), ctypes.byref(w), ctypes.byref(e)))
+        names = ["digits", "sort", "accumulate", "partials", "reduce"]
+        return {"ms": {n: ph[i] for i, n in enumerate(names)}, "c": c.value, "windows": w.value, "entries": e.value}
+
     def set_window(self, c: int):
         self._check(self.lib.bp_msm_set_window(self.h, c))
 

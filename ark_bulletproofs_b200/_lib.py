@@ -43,6 +43,8 @@ def load():
         "bp_msm": (i32, [vp, vp, vp, sz, vp, pi32]),
         "bp_msm_device": (i32, [vp, vp, vp, sz, vp, pi32]),
         "bp_msm_set_window": (i32, [vp, i32]),
+        "bp_ctx_set_timing": (i32, [vp, i32]),
+        "bp_msm_last_phases": (i32, [vp, ctypes.POINTER(ctypes.c_float), pi32, pi32, ctypes.POINTER(u64)]),
         "bp_points_sum": (i32, [vp, vp, sz, vp, pi32]),
         "bp_synth_points_device": (i32, [vp, vp, sz, u64]),
     }
@@ -56,5 +58,5 @@ def load():
 
 EXPORTED_SYMBOLS = [
     "bp_ctx_create", "bp_ctx_destroy", "bp_last_error", "bp_ctx_stream", "bp_ctx_sync", "bp_ctx_launch_count",
-    "bp_msm", "bp_msm_device", "bp_msm_set_window", "bp_points_sum", "bp_synth_points_device",
+    "bp_msm", "bp_msm_device", "bp_msm_set_window", "bp_ctx_set_timing", "bp_msm_last_phases", "bp_points_sum", "bp_synth_points_device",
 ]

@@ -40,6 +40,7 @@ void bp_ctx_destroy(bp_ctx* ctx) {
                           &ctx->part_pts, &ctx->seg_out, &ctx->win_out, &ctx->result, &ctx->stage_bases, &ctx->stage_scalars};
     for (auto* b : bufs) b->release();
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -52,6 +53,24 @@ int bp_ctx_sync(bp_ctx* ctx) {
     if (!ctx) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BP_OK;
+}
+
+int bp_ctx_set_timing(bp_ctx* ctx, int enable) {
+    if (!ctx) return BP_ERR_ARG;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (enable && !ctx->ev[0])
+        for (int i = 0; i < 8; i++) BP_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i]));
+    ctx->timing = enable != 0;
+    return BP_OK;
+}
+
+int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* windows, uint64_t* entries) {
+    if (!ctx || !phase_ms) return BP_ERR_ARG;
+    for (int i = 0; i < 8; i++) phase_ms[i] = ctx->phase_ms[i];
+    if (c) *c = ctx->last_c;
+    if (windows) *windows = ctx->last_W;
+    if (entries) *entries = ctx->last_entries;
     return BP_OK;
 }
 

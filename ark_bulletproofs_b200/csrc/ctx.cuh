@@ -43,7 +43,13 @@ struct bp_ctx {
     // MSM scratch
     bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;
     bp::DevBuf stage_bases, stage_scalars;
-    void* h_result = nullptr;   // pinned, 256 B
+    void* h_result = nullptr;   // pinned, 16 KiB
+    // optional per-phase timing of the last MSM (cudaEvents on `stream`)
+    bool timing = false;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int last_c = 0, last_W = 0;
+    size_t last_entries = 0;
 };
 
 #define BP_CUDA_TRY(ctx, expr)                                                                       \

@@ -320,18 +320,24 @@ int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, u
                                                      p.key_bits, st));
     BP_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
 
+    ctx->last_c = p.c; ctx->last_W = p.W; ctx->last_entries = p.entries;
+    auto mark = [&](int i) { if (ctx->timing) cudaEventRecord(ctx->ev[i], st); };
+    mark(0);
     msm_digits_kernel<C><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scalars, n, p.c, p.W, ctx->keys_a.as<uint32_t>(),
                                                                      ctx->vals_a.as<uint32_t>());
     BP_LAUNCH_CHECK(ctx);
+    mark(7);
     BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->keys_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(),
                                                      ctx->vals_a.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, 0,
                                                      p.key_bits, st));
+    mark(1);
     BP_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, nbuckets * sizeof(xyzz), st));
     uint32_t* pk = ctx->part_keys.as<uint32_t>();
     xyzz* pp = ctx->part_pts.as<xyzz>();
     msm_accumulate_kernel<C><<<(unsigned)((p.T + 127) / 128), 128, 0, st>>>(ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(),
                                                                             p.entries, p.L, p.T, d_bases, ctx->buckets.as<xyzz>(), pk, pp);
     BP_LAUNCH_CHECK(ctx);
+    mark(2);
     // hierarchical reduction of the boundary partials (ping-pong inside the two regions)
     size_t nslots = slots1;
     uint32_t* in_k = pk;
@@ -349,16 +355,26 @@ int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, u
     }
     msm_partials_final_kernel<C><<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(in_k, in_p, nslots, ctx->buckets.as<xyzz>());
     BP_LAUNCH_CHECK(ctx);
+    mark(3);
     size_t rt = (size_t)p.W * p.nseg;
     msm_reduce_kernel<C><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, p.W,
                                                                        ctx->seg_out.as<xyzz>());
     BP_LAUNCH_CHECK(ctx);
     msm_window_sum_kernel<C><<<p.W, 128, 0, st>>>(ctx->seg_out.as<xyzz>(), p.nseg, ctx->win_out.as<xyzz>());
     BP_LAUNCH_CHECK(ctx);
+    mark(4);
     // The Horner combination over windows is 256 dependent doublings: 1.35 ms on one GPU
     // thread (measured), ~0.1 ms on a host core. The W window sums (W*128 B) go to the host.
     BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_result, ctx->win_out.p, (size_t)p.W * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
     BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (ctx->timing) {
+        // phases: 0 digits, 1 sort, 2 memset+accumulate, 3 partial levels, 4 bucket reduce + window sums
+        cudaEventElapsedTime(&ctx->phase_ms[0], ctx->ev[0], ctx->ev[7]);
+        cudaEventElapsedTime(&ctx->phase_ms[1], ctx->ev[7], ctx->ev[1]);
+        cudaEventElapsedTime(&ctx->phase_ms[2], ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&ctx->phase_ms[3], ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&ctx->phase_ms[4], ctx->ev[3], ctx->ev[4]);
+    }
     return host_combine(ctx->curve, ctx->h_result, p.W, p.c, out_xy, out_is_identity);
 }
 

@@ -1,0 +1,293 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native ark-bulletproofs hot path.
+
+Metric (BASELINE.json): secq256k1 variable-base MSM throughput in Mpoints/s (configs[1]:
+"standalone secq256k1 MSM sweep 2^12-2^24 random points/scalars on 1 B200 vs ark-ec
+VariableBaseMSM on host cores"); the workload is the 2^24-point MSM of the north star.
+
+  python bench.py --gpus N --steps K --warmup W            # this framework
+  python bench.py --impl reference ...                     # the reference's CPU algorithm
+                                                           # (oracle port; the Rust crate itself
+                                                           #  cannot be built in this image)
+One step = one MSM over one batch of synthetic points/scalars. With N > 1 (torchrun) every
+rank runs its own 2^lg_n-point shard and the 64-byte partial sums are all-gathered over NCCL
+and added; value = total points / max-over-ranks time ("weak" scaling).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CURVE = "secq256k1"
+METRIC = "secq256k1_msm_mpoints_per_s"
+UNIT = "Mpoints/s"
+MODMUL_IMAD = 136        # one 256-bit modmul = 136 32x32->64 multiply-adds
+MADD_MODMUL = 10         # XYZZ mixed add 8M + 2S
+
+
+def imad_peak():
+    """Measured integer-multiply peak of this pool's B200 (tools/microbench, committed under
+    profiles/); MEASURED_PEAKS.json has only HBM and bf16 figures."""
+    p = os.path.join(ROOT, "profiles", "imad_peak.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["imad_per_s"], "measured: " + d.get("how", "tools/microbench")
+    return 148 * 64 * 1.965e9, "nominal 148 SM x 64 IMAD/clk x 1.965 GHz (no measurement found)"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "MEASURED_PEAKS.json"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                mx = float(f[1])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[0]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(lg_sample, steps, warmup, threads=None):
+    """The reference algorithm on host cores: ark-style wNAF Pippenger (oracle/c/bp_ref.c)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
+    import c_oracle
+    from ark_bulletproofs_b200 import codec
+    import bp_oracle as O
+
+    threads = threads or c_oracle.num_threads()
+    n = 1 << lg_sample
+    pts = c_oracle.synth_points(0, codec.enc_point(O.SECQ256K1.G, CURVE), n, 0)
+    rng = np.random.default_rng(2)
+    sc = rng.integers(0, 256, size=n * 32, dtype=np.uint8)
+    sc.reshape(n, 32)[:, 31] &= 0x7F
+    scb = sc.tobytes()
+    ptb = bytes(pts)
+    for _ in range(warmup):
+        c_oracle.msm_bytes(0, ptb, scb, n, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c_oracle.msm_bytes(0, ptb, scb, n, threads)
+    dt = (time.perf_counter() - t0) / steps
+    return n / dt / 1e6, dt * 1e3, threads
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lg-n", type=int, default=24, help="log2 of the MSM size per GPU")
+    ap.add_argument("--cpu-lg-n", type=int, default=0, help="log2 of the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    workload = "secq256k1 variable-base MSM, 2^%d points per GPU, uniform 255-bit scalars" % args.lg_n
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ncores = os.cpu_count() or 1
+        lg = args.cpu_lg_n or (20 if ncores >= 16 else 18)
+        val, ms, threads = cpu_reference_run(lg, args.steps, warmup)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u256 (Montgomery, 4x64-bit limbs)", "data": "synthetic",
+            "config": {"workload": workload, "sample": "2^%d-point MSM per step (bounded sample of the workload)" % lg},
+            "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "oracle/c/bp_ref.c ark-style wNAF Pippenger (windows over OpenMP threads, the analogue of "
+                                       "feature `parallel`), 2^%d points; the Rust crate cannot be built here (no cargo/rustc)" % lg},
+            "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from ark_bulletproofs_b200 import Context
+
+    ctx = Context(CURVE, local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+    n = 1 << args.lg_n
+    pts = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    ctx.synth_points_device(pts.data_ptr(), n, rank * n)
+    ctx.sync()
+    g = torch.Generator(device="cuda").manual_seed(2 + rank)
+    sc = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device="cuda", generator=g)
+    sc.view(-1, 32)[:, 31] &= 0x7F            # 255-bit raw Montgomery residues: uniform scalars < r
+    torch.cuda.synchronize()
+    h_pts = torch.empty(n * 64, dtype=torch.uint8, pin_memory=True)
+    h_sc = torch.empty(n * 32, dtype=torch.uint8, pin_memory=True)
+    h_pts.copy_(pts)
+    h_sc.copy_(sc)
+    torch.cuda.synchronize()
+    gather_buf = [torch.empty(68, dtype=torch.uint8, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def combine(raw, ident):
+        """all-gather the per-GPU partial points, add them on every rank."""
+        if world == 1:
+            return raw, ident
+        mine = torch.frombuffer(bytearray(raw + bytes([1 if ident else 0, 0, 0, 0])), dtype=torch.uint8).cuda()
+        dist.all_gather(gather_buf, mine)
+        allb = b"".join(bytes(t.cpu().numpy().tobytes()[:64]) for t in gather_buf)
+        out = ctypes.create_string_buffer(64)
+        idn = ctypes.c_int(0)
+        ctx._check(ctx.lib.bp_points_sum(ctx.h, allb, world, out, ctypes.byref(idn)))
+        return out.raw, bool(idn.value)
+
+    def step_device():
+        return combine(*ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n))
+
+    def step_e2e():
+        out = ctypes.create_string_buffer(64)
+        idn = ctypes.c_int(0)
+        ctx._check(ctx.lib.bp_msm(ctx.h, h_pts.data_ptr(), h_sc.data_ptr(), n, out, ctypes.byref(idn)))
+        return combine(out.raw, bool(idn.value))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        e0.record(stream)
+        for _ in range(steps):
+            res = fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res, t0, t1
+
+    ctx.set_timing(True)
+    for _ in range(warmup):
+        ref = step_device()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = ctx.launches
+    ms, res, t0, t1 = timed(step_device, args.steps)
+    launches = ctx.launches - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    assert res == ref, "MSM result changed between steps"
+    phases = ctx.last_phases()
+    ms_per_step = ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    step_e2e()
+    ms_e2e, res_e2e, _, _ = timed(step_e2e, args.steps)
+    assert res_e2e == ref, "host-buffer path disagrees with the device-resident path"
+    e2e_val = world * n / (ms_e2e / args.steps * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # roofline of the dominant kernel (msm_accumulate: integer-multiply bound)
+    acc_ms = phases["ms"]["accumulate"]
+    alg_imad = phases["entries"] * MADD_MODMUL * MODMUL_IMAD
+    peak, peak_src = imad_peak()
+    achieved = alg_imad / (acc_ms * 1e-3)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "accumulate_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch_lg%d" % args.lg_n)
+    hbm, hbm_src = hbm_peak()
+    sort_bytes = phases["entries"] * 8 * 2 * ((phases["c"] - 1 + max(1, (phases["windows"] - 1).bit_length()) + 7) // 8)
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u256 (Montgomery, 8x32-bit limbs, IMAD.WIDE)", "data": "synthetic",
+        "config": {"workload": workload, "curve": CURVE, "window_bits": phases["c"], "windows": phases["windows"],
+                   "l2": "inputs (%.2f GB) exceed the 126 MB L2; no flush needed" % (n * 96 / 1e9),
+                   "parallelism": "msm-shard x%d + all-gather of 64 B partial points" % world},
+        "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 64 + phases["windows"] * 128,
+                "ms_per_step": round(ms_e2e / args.steps, 4), "api": "bp_msm (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": round(achieved / 1e12, 4), "peak": round(peak / 1e12, 4),
+                     "unit": "TIMAD/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                     "algorithmic": "%d bucket additions x 10 modmul x 136 IMAD" % phases["entries"], "peak_source": peak_src,
+                     "launch_ms": round(acc_ms, 4)},
+        "roofline_hbm": {"bound": "hbm", "kernel": "cub radix sort of (bucket, point) pairs", "achieved": round(sort_bytes / (phases["ms"]["sort"] * 1e-3) / 1e9, 1),
+                         "peak": hbm, "unit": "GB/s", "frac": round(sort_bytes / (phases["ms"]["sort"] * 1e-3) / 1e9 / hbm, 4),
+                         "peak_source": hbm_src, "launch_ms": round(phases["ms"]["sort"], 4)},
+        "phases_ms": {k: round(v, 4) for k, v in phases["ms"].items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ncores = os.cpu_count() or 1
+        lg = args.cpu_lg_n or (20 if ncores >= 16 else 18)
+        val, cms, threads = cpu_reference_run(lg, 1, 0)
+        line["cpu_baseline"] = {"value": round(val, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "one 2^%d-point MSM, oracle/c/bp_ref.c (ark-style wNAF Pippenger), %.1f s" % (lg, cms / 1e3)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -68,6 +68,11 @@ int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t 
 /* Same, with bases and scalars already resident in this context's GPU memory. */
 int bp_msm_device(bp_ctx* ctx, const void* d_bases_xy, const void* d_scalars, size_t n, uint8_t out_xy[64],
                   int* out_is_identity);
+/* Per-phase device timing of the last MSM (cudaEvents on the context's stream), for the roofline
+ * numbers in bench.py: phase_ms[0..4] = digits, sort, accumulate, partial reduction, bucket
+ * reduction + window sums; *c / *windows / *entries describe the Pippenger plan that ran. */
+int bp_ctx_set_timing(bp_ctx* ctx, int enable);
+int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* windows, uint64_t* entries);
 /* Force the Pippenger window width (0 = automatic); for parity tests and tuning. */
 int bp_msm_set_window(bp_ctx* ctx, int c);
 
