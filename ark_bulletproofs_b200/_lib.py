@@ -33,8 +33,11 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     vp, sz, i32, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
     pi32 = ctypes.POINTER(ctypes.c_int)
+    pu64 = ctypes.POINTER(u64)
+    psz = ctypes.POINTER(sz)
+    pvp = ctypes.POINTER(vp)
     sigs = {
-        "bp_ctx_create": (i32, [i32, i32, ctypes.POINTER(vp)]),
+        "bp_ctx_create": (i32, [i32, i32, pvp]),
         "bp_ctx_destroy": (None, [vp]),
         "bp_last_error": (ctypes.c_char_p, [vp]),
         "bp_ctx_stream": (vp, [vp]),
@@ -44,10 +47,62 @@ def load():
         "bp_msm_device": (i32, [vp, vp, vp, sz, vp, pi32]),
         "bp_msm_set_window": (i32, [vp, i32]),
         "bp_ctx_set_timing": (i32, [vp, i32]),
-        "bp_msm_last_phases": (i32, [vp, ctypes.POINTER(ctypes.c_float), pi32, pi32, ctypes.POINTER(u64)]),
+        "bp_msm_last_phases": (i32, [vp, ctypes.POINTER(ctypes.c_float), pi32, pi32, pu64]),
         "bp_points_sum": (i32, [vp, vp, sz, vp, pi32]),
         "bp_synth_points_device": (i32, [vp, vp, sz, u64]),
+        "bp_transcript_new": (vp, [vp, sz]),
+        "bp_transcript_clone": (vp, [vp]),
+        "bp_transcript_free": (None, [vp]),
+        "bp_transcript_append_message": (None, [vp, vp, sz, vp, sz]),
+        "bp_transcript_append_u64": (None, [vp, vp, sz, u64]),
+        "bp_transcript_challenge_bytes": (None, [vp, vp, sz, vp, sz]),
+        "bp_transcript_challenge_scalar": (i32, [i32, vp, vp, sz, vp]),
+        "bp_rng_chacha20": (vp, [vp]),
+        "bp_rng_from_callbacks": (vp, [vp, vp, vp, vp]),
+        "bp_rng_free": (None, [vp]),
+        "bp_rng_words_used": (u64, [vp]),
+        "bp_rng_scalar": (i32, [i32, vp, vp]),
+        "bp_scalar_to_bytes": (i32, [i32, vp, vp]),
+        "bp_scalar_from_bytes": (i32, [i32, vp, vp]),
+        "bp_point_compress": (i32, [i32, vp, vp]),
+        "bp_point_serialize_uncompressed": (i32, [i32, vp, vp]),
+        "bp_point_decompress": (i32, [i32, vp, vp]),
+        "bp_gens_generate_host": (i32, [i32, sz, vp, vp, vp, vp]),
+        "bp_gens_create": (i32, [vp, sz, pvp]),
+        "bp_gens_from_points": (i32, [vp, vp, vp, vp, vp, sz, pvp]),
+        "bp_gens_free": (None, [vp]),
+        "bp_gens_capacity": (sz, [vp]),
+        "bp_gens_export": (i32, [vp, i32, sz, sz, vp]),
+        "bp_pedersen_commit": (i32, [vp, vp, vp, vp]),
+        "bp_cs_multiply": (i32, [vp, vp, sz, vp, sz, vp]),
+        "bp_cs_allocate": (i32, [vp, vp, vp]),
+        "bp_cs_allocate_multiplier": (i32, [vp, vp, vp, vp]),
+        "bp_cs_constrain": (i32, [vp, vp, sz]),
+        "bp_cs_multipliers_len": (sz, [vp]),
+        "bp_cs_specify_randomized_constraints": (i32, [vp, vp, vp]),
+        "bp_cs_challenge_scalar": (i32, [vp, vp, sz, vp]),
+        "bp_prover_new": (i32, [vp, vp, vp, pvp]),
+        "bp_prover_free": (None, [vp]),
+        "bp_prover_cs": (vp, [vp]),
+        "bp_prover_commit": (i32, [vp, vp, vp, vp, vp]),
+        "bp_prover_prove": (i32, [vp, vp, pvp]),
+        "bp_verifier_new": (i32, [vp, vp, pvp]),
+        "bp_verifier_free": (None, [vp]),
+        "bp_verifier_cs": (vp, [vp]),
+        "bp_verifier_commit": (i32, [vp, vp, vp]),
+        "bp_verifier_verify": (i32, [vp, vp, vp]),
+        "bp_batch_verify": (i32, [vp, vp, vp, vp, sz, vp]),
+        "bp_proof_free": (None, [vp]),
+        "bp_proof_to_bytes": (i32, [vp, vp, sz, psz]),
+        "bp_proof_from_bytes": (i32, [i32, vp, sz, pvp]),
+        "bp_proof_clone": (vp, [vp]),
+        "bp_proof_get_field": (i32, [vp, i32, vp]),
+        "bp_proof_set_field": (i32, [vp, i32, vp]),
+        "bp_proof_rounds": (sz, [vp]),
+        "bp_ipa_create": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]),
     }
+    global EXPORTED_SYMBOLS
+    EXPORTED_SYMBOLS = sorted(sigs)
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
         fn.restype = res
@@ -56,7 +111,4 @@ def load():
     return lib
 
 
-EXPORTED_SYMBOLS = [
-    "bp_ctx_create", "bp_ctx_destroy", "bp_last_error", "bp_ctx_stream", "bp_ctx_sync", "bp_ctx_launch_count",
-    "bp_msm", "bp_msm_device", "bp_msm_set_window", "bp_ctx_set_timing", "bp_msm_last_phases", "bp_points_sum", "bp_synth_points_device",
-]
+EXPORTED_SYMBOLS = []   # filled by load()

@@ -1,0 +1,179 @@
+// Per-curve implementation of the handle-based C ABI (include/bp_b200.h), instantiated once per
+// curve in api_<curve>.cu and reached from capi.cu through a table of function pointers.
+#pragma once
+#include "api_types.hpp"
+#include "r1cs.cuh"
+
+namespace bp {
+
+template <class C>
+struct ApiImpl {
+    using HC = HostCurve<C>;
+    using Fr = HostFp<typename C::Fr>;
+
+    static fe ld(const uint8_t* p) { fe r; memcpy(r.v, p, 32); return r; }
+    static affine ldp(const uint8_t* p) { affine r; memcpy(&r, p, 64); return r; }
+
+    // ---- generators -----------------------------------------------------------------------
+    static int gens_upload(bp_ctx* ctx, const affine& B, const affine& Bb, const affine* G, const affine* H, size_t cap, GensDev** out) {
+        std::unique_ptr<GensDev> g(new GensDev());
+        g->ctx = ctx;
+        g->capacity = cap;
+        g->B = B;
+        g->B_blinding = Bb;
+        BP_CUDA_TRY(ctx, g->G.reserve((cap + 1) * sizeof(affine)));
+        BP_CUDA_TRY(ctx, g->H.reserve((cap + 1) * sizeof(affine)));
+        BP_CUDA_TRY(ctx, g->pc.reserve(2 * sizeof(affine)));
+        affine pc[2] = {B, Bb};
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(g->pc.p, pc, sizeof(pc), cudaMemcpyHostToDevice, ctx->stream));
+        if (cap) {
+            BP_CUDA_TRY(ctx, cudaMemcpyAsync(g->G.p, G, cap * sizeof(affine), cudaMemcpyHostToDevice, ctx->stream));
+            BP_CUDA_TRY(ctx, cudaMemcpyAsync(g->H.p, H, cap * sizeof(affine), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        *out = g.release();
+        return BP_OK;
+    }
+    static int gens_generate_host(size_t cap, uint8_t* G, uint8_t* H, uint8_t* B, uint8_t* Bb) {
+        affine b, bb;
+        GensHost<C>::pedersen_default(b, bb);
+        if (B) memcpy(B, &b, 64);
+        if (Bb) memcpy(Bb, &bb, 64);
+        if (cap && G && H) GensHost<C>::bulletproof_gens(cap, reinterpret_cast<affine*>(G), reinterpret_cast<affine*>(H));
+        return BP_OK;
+    }
+    static int gens_create(bp_ctx* ctx, size_t cap, GensDev** out) {
+        std::vector<affine> G(cap), H(cap);
+        affine b, bb;
+        GensHost<C>::pedersen_default(b, bb);
+        GensHost<C>::bulletproof_gens(cap, G.data(), H.data());
+        return gens_upload(ctx, b, bb, G.data(), H.data(), cap, out);
+    }
+    static int gens_from_points(bp_ctx* ctx, const uint8_t* B, const uint8_t* Bb, const uint8_t* G, const uint8_t* H, size_t cap, GensDev** out) {
+        return gens_upload(ctx, ldp(B), ldp(Bb), reinterpret_cast<const affine*>(G), reinterpret_cast<const affine*>(H), cap, out);
+    }
+    static int pedersen_commit(const GensDev* g, const uint8_t* v, const uint8_t* blind, uint8_t* out) {
+        affine r = HC::add(HC::mul(g->B, ld(v)), HC::mul(g->B_blinding, ld(blind)));
+        memcpy(out, &r, 64);
+        return BP_OK;
+    }
+
+    // ---- scalars / points ---------------------------------------------------------------------
+    static int challenge_scalar(Transcript* t, const char* label, uint8_t* out) {
+        fe s = TP<C>::challenge_scalar(*t, label);
+        memcpy(out, s.v, 32);
+        return BP_OK;
+    }
+    static int rng_scalar(Rng* rng, uint8_t* out) {
+        fe s = HC::scalar_rand(*rng);
+        memcpy(out, s.v, 32);
+        return BP_OK;
+    }
+    static int scalar_to_bytes(const uint8_t* mont, uint8_t* out) { HC::scalar_to_bytes(ld(mont), out); return BP_OK; }
+    static int scalar_from_bytes(const uint8_t* in, uint8_t* mont) {
+        fe s;
+        if (!HC::scalar_from_bytes(in, s)) return BP_ERR_FORMAT;
+        memcpy(mont, s.v, 32);
+        return BP_OK;
+    }
+    static int point_compress(const uint8_t* xy, uint8_t* out) { HC::point_compressed(ldp(xy), out); return BP_OK; }
+    static int point_uncompressed(const uint8_t* xy, uint8_t* out) { HC::point_uncompressed(ldp(xy), out); return BP_OK; }
+    static int point_decompress(const uint8_t* in, uint8_t* xy) {
+        affine p;
+        if (!HC::point_from_compressed(in, p)) return BP_ERR_FORMAT;
+        memcpy(xy, &p, 64);
+        return BP_OK;
+    }
+
+    // ---- prover / verifier / proof ------------------------------------------------------------------
+    static void* prover_new(bp_ctx* ctx, const GensDev* g, Transcript* t) { return new ProverT<C>(ctx, g, t); }
+    static void prover_free(void* p) { delete static_cast<ProverT<C>*>(p); }
+    static ConstraintSystemBase* prover_cs(void* p) { return static_cast<ProverT<C>*>(p); }
+    static int prover_commit(void* p, const uint8_t* v, const uint8_t* blind, uint8_t* out_V, Variable* var) {
+        affine V;
+        int rc = static_cast<ProverT<C>*>(p)->commit(ld(v), ld(blind), V, *var);
+        memcpy(out_V, &V, 64);
+        return rc;
+    }
+    static int prover_prove(void* p, Rng* rng, void** out_proof) {
+        std::unique_ptr<ProofT<C>> pr(new ProofT<C>());
+        int rc = static_cast<ProverT<C>*>(p)->prove(*rng, *pr);
+        if (rc == BP_OK) *out_proof = pr.release();
+        return rc;
+    }
+    static void* verifier_new(bp_ctx* ctx, Transcript* t) { return new VerifierT<C>(ctx, t); }
+    static void verifier_free(void* p) { delete static_cast<VerifierT<C>*>(p); }
+    static ConstraintSystemBase* verifier_cs(void* p) { return static_cast<VerifierT<C>*>(p); }
+    static int verifier_commit(void* p, const uint8_t* V, Variable* var) { return static_cast<VerifierT<C>*>(p)->commit(ldp(V), *var); }
+    static int verifier_verify(void* p, const void* proof, const GensDev* g) {
+        return static_cast<VerifierT<C>*>(p)->verify(*static_cast<const ProofT<C>*>(proof), *g);
+    }
+    static int batch_verify(bp_ctx* ctx, Rng* rng, void** verifiers, const void** proofs, size_t n, const GensDev* g) {
+        std::vector<VerifierT<C>*> vs(n);
+        std::vector<const ProofT<C>*> ps(n);
+        for (size_t i = 0; i < n; i++) { vs[i] = static_cast<VerifierT<C>*>(verifiers[i]); ps[i] = static_cast<const ProofT<C>*>(proofs[i]); }
+        return batch_verify_t<C>(ctx, *rng, vs, ps, *g);
+    }
+    static void proof_free(void* p) { delete static_cast<ProofT<C>*>(p); }
+    static int proof_to_bytes(const void* p, std::vector<uint8_t>& out) { out = static_cast<const ProofT<C>*>(p)->to_bytes(); return BP_OK; }
+    static int proof_from_bytes(const uint8_t* d, size_t len, void** out) {
+        std::unique_ptr<ProofT<C>> pr(new ProofT<C>());
+        int rc = ProofT<C>::from_bytes(d, len, *pr);
+        if (rc == BP_OK) *out = pr.release();
+        return rc;
+    }
+    static void* proof_clone(const void* p) { return new ProofT<C>(*static_cast<const ProofT<C>*>(p)); }
+    // field access for tamper tests: which = 0 t_x, 1 t_x_blinding, 2 e_blinding, 3 a, 4 b (scalars);
+    // 10.. = points A_I1,A_O1,S1,A_I2,A_O2,S2,T_1,T_3,T_4,T_5,T_6 ; 100+j = L_j ; 200+j = R_j
+    static int proof_field(void* p, int which, uint8_t* buf, int set) {
+        ProofT<C>* pr = static_cast<ProofT<C>*>(p);
+        fe* s = nullptr;
+        affine* a = nullptr;
+        affine* pts[11] = {&pr->A_I1, &pr->A_O1, &pr->S1, &pr->A_I2, &pr->A_O2, &pr->S2, &pr->T_1, &pr->T_3, &pr->T_4, &pr->T_5, &pr->T_6};
+        if (which == 0) s = &pr->t_x; else if (which == 1) s = &pr->t_x_blinding; else if (which == 2) s = &pr->e_blinding;
+        else if (which == 3) s = &pr->a; else if (which == 4) s = &pr->b;
+        else if (which >= 10 && which < 21) a = pts[which - 10];
+        else if (which >= 100 && which < 100 + (int)pr->L_vec.size()) a = &pr->L_vec[which - 100];
+        else if (which >= 200 && which < 200 + (int)pr->R_vec.size()) a = &pr->R_vec[which - 200];
+        else return BP_ERR_ARG;
+        if (s) { if (set) memcpy(s->v, buf, 32); else memcpy(buf, s->v, 32); }
+        else { if (set) memcpy(a, buf, 64); else memcpy(buf, a, 64); }
+        return BP_OK;
+    }
+    static size_t proof_rounds(const void* p) { return static_cast<const ProofT<C>*>(p)->L_vec.size(); }
+
+    // ---- InnerProductProof::create over host buffers --------------------------------------------
+    static int ipa_create_host(bp_ctx* ctx, Transcript* t, const uint8_t* Q, const uint8_t* Gf, const uint8_t* Hf, const uint8_t* G,
+                               const uint8_t* H, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out_L, uint8_t* out_R,
+                               uint8_t* out_a, uint8_t* out_b) {
+        if (n == 0 || (n & (n - 1))) return BP_ERR_POW2;
+        DevBuf dG, dH, dGf, dHf, da, db;
+        struct Guard { DevBuf* b[6]; ~Guard() { for (auto* x : b) x->release(); } } guard{{&dG, &dH, &dGf, &dHf, &da, &db}};
+        BP_CUDA_TRY(ctx, dG.reserve(n * 64)); BP_CUDA_TRY(ctx, dH.reserve(n * 64));
+        BP_CUDA_TRY(ctx, dGf.reserve(n * 32)); BP_CUDA_TRY(ctx, dHf.reserve(n * 32));
+        BP_CUDA_TRY(ctx, da.reserve(n * 32)); BP_CUDA_TRY(ctx, db.reserve(n * 32));
+        using D = Dev<C>;
+        D::upload(ctx, dG.p, G, n * 64); D::upload(ctx, dH.p, H, n * 64); D::upload(ctx, dGf.p, Gf, n * 32);
+        D::upload(ctx, dHf.p, Hf, n * 32); D::upload(ctx, da.p, a, n * 32);
+        if (int rc = D::upload(ctx, db.p, b, n * 32)) return rc;
+        std::vector<affine> L, R;
+        fe ao, bo;
+        int rc = ipa_create<C>(ctx, *t, ldp(Q), dGf.as<fe>(), dHf.as<fe>(), dG.as<affine>(), dH.as<affine>(), da.as<fe>(), db.as<fe>(), n, L, R, ao, bo);
+        if (rc) return rc;
+        if (!L.empty()) { memcpy(out_L, L.data(), L.size() * 64); memcpy(out_R, R.data(), R.size() * 64); }
+        memcpy(out_a, ao.v, 32);
+        memcpy(out_b, bo.v, 32);
+        return BP_OK;
+    }
+
+    static const CurveApi* table() {
+        static const CurveApi api = {
+            gens_generate_host, gens_create, gens_from_points, pedersen_commit, challenge_scalar, rng_scalar, scalar_to_bytes, scalar_from_bytes,
+            point_compress, point_uncompressed, point_decompress, prover_new, prover_free, prover_cs, prover_commit, prover_prove, verifier_new,
+            verifier_free, verifier_cs, verifier_commit, verifier_verify, batch_verify, proof_free, proof_to_bytes, proof_from_bytes, proof_clone,
+            proof_field, proof_rounds, ipa_create_host};
+        return &api;
+    }
+};
+
+}  // namespace bp

@@ -24,7 +24,7 @@ int bp_ctx_create(int curve, int device, bp_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost(&ctx->h_result, 16384) != cudaSuccess) {
+        cudaMallocHost(&ctx->h_result, BP_HOST_RESULT_BYTES) != cudaSuccess) {
         delete ctx;
         return BP_ERR_CUDA;
     }
@@ -36,9 +36,7 @@ void bp_ctx_destroy(bp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    bp::DevBuf* bufs[] = {&ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->cub_tmp, &ctx->buckets, &ctx->part_keys,
-                          &ctx->part_pts, &ctx->seg_out, &ctx->win_out, &ctx->result, &ctx->stage_bases, &ctx->stage_scalars};
-    for (auto* b : bufs) b->release();
+    ctx->for_each_buf([](bp::DevBuf* b) { b->release(); });
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
@@ -108,6 +106,312 @@ int bp_synth_points_device(bp_ctx* ctx, void* d_out_xy, size_t n, uint64_t start
     if (!ctx || (n && !d_out_xy)) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return bp::synth_points_dispatch(ctx, d_out_xy, n, start);
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// Handle-based API: transcript, RNG, generators, constraint systems, prover, verifier, proofs, IPA.
+// =====================================================================================================
+#include <memory>
+#include <string>
+#include "api_types.hpp"
+
+#include "r1cs_types.hpp"
+
+struct bp_transcript { bp::Transcript t; };
+struct bp_rng { std::unique_ptr<bp::Rng> r; bp::ChaCha20Rng* chacha = nullptr; };
+struct bp_gens { int curve; bp::GensDev* g; };
+struct bp_cs { int curve; bp::ConstraintSystemBase* cs; };
+struct bp_prover { int curve; bp_ctx* ctx; void* impl; bp_cs cs; };
+struct bp_verifier { int curve; bp_ctx* ctx; void* impl; bp_cs cs; };
+struct bp_proof { int curve; void* impl; };
+
+namespace {
+struct CallbackRng : bp::Rng {
+    void* user;
+    uint64_t (*f64)(void*);
+    uint32_t (*f32)(void*);
+    void (*ffill)(void*, uint8_t*, size_t);
+    uint32_t next_u32() override { return f32(user); }
+    uint64_t next_u64() override { return f64(user); }
+    void fill_bytes(uint8_t* out, size_t n) override { ffill(user, out, n); }
+};
+inline std::string lbl(const uint8_t* l, size_t n) { return std::string(reinterpret_cast<const char*>(l), n); }
+inline void split_terms(const bp_term* t, size_t n, std::vector<bp::Variable>& v, std::vector<bp::fe>& c) {
+    v.resize(n);
+    c.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        v[i].kind = t[i].var.kind;
+        v[i].idx = t[i].var.index;
+        memcpy(c[i].v, t[i].coeff, 32);
+    }
+}
+inline void put_var(bp_var* o, const bp::Variable& v) { o->kind = v.kind; o->reserved = 0; o->index = v.idx; }
+}  // namespace
+
+extern "C" {
+
+// ---- transcript (merlin::Transcript) ----
+bp_transcript* bp_transcript_new(const uint8_t* label, size_t len) {
+    bp_transcript* t = new bp_transcript();
+    t->t = bp::Transcript(label, len);
+    return t;
+}
+bp_transcript* bp_transcript_clone(const bp_transcript* t) { return t ? new bp_transcript(*t) : nullptr; }
+void bp_transcript_free(bp_transcript* t) { delete t; }
+void bp_transcript_append_message(bp_transcript* t, const uint8_t* label, size_t llen, const uint8_t* msg, size_t mlen) {
+    t->t.append_message_l(label, llen, msg, mlen);
+}
+void bp_transcript_append_u64(bp_transcript* t, const uint8_t* label, size_t llen, uint64_t v) {
+    uint8_t b[8];
+    for (int i = 0; i < 8; i++) b[i] = (uint8_t)(v >> (8 * i));
+    t->t.append_message_l(label, llen, b, 8);
+}
+void bp_transcript_challenge_bytes(bp_transcript* t, const uint8_t* label, size_t llen, uint8_t* out, size_t n) {
+    t->t.challenge_bytes_l(label, llen, out, n);
+}
+int bp_transcript_challenge_scalar(int curve, bp_transcript* t, const uint8_t* label, size_t llen, uint8_t out[32]) {
+    const bp::CurveApi* api = bp::curve_api(curve);
+    if (!api || !t) return BP_ERR_ARG;
+    return api->challenge_scalar(&t->t, lbl(label, llen).c_str(), out);
+}
+
+// ---- RNG (rand_core::RngCore) ----
+bp_rng* bp_rng_chacha20(const uint8_t seed[32]) {
+    bp_rng* r = new bp_rng();
+    r->chacha = new bp::ChaCha20Rng(seed);
+    r->r.reset(r->chacha);
+    return r;
+}
+bp_rng* bp_rng_from_callbacks(void* user, uint64_t (*next_u64)(void*), uint32_t (*next_u32)(void*), void (*fill_bytes)(void*, uint8_t*, size_t)) {
+    CallbackRng* c = new CallbackRng();
+    c->user = user; c->f64 = next_u64; c->f32 = next_u32; c->ffill = fill_bytes;
+    bp_rng* r = new bp_rng();
+    r->r.reset(c);
+    return r;
+}
+void bp_rng_free(bp_rng* r) { delete r; }
+uint64_t bp_rng_words_used(const bp_rng* r) { return r && r->chacha ? r->chacha->words_used : 0; }
+int bp_rng_scalar(int curve, bp_rng* r, uint8_t out[32]) {
+    const bp::CurveApi* api = bp::curve_api(curve);
+    if (!api || !r) return BP_ERR_ARG;
+    return api->rng_scalar(r->r.get(), out);
+}
+
+// ---- serialisation helpers (ark-serialize) ----
+int bp_scalar_to_bytes(int curve, const uint8_t mont[32], uint8_t out[32]) { auto a = bp::curve_api(curve); return a ? a->scalar_to_bytes(mont, out) : BP_ERR_ARG; }
+int bp_scalar_from_bytes(int curve, const uint8_t in[32], uint8_t mont[32]) { auto a = bp::curve_api(curve); return a ? a->scalar_from_bytes(in, mont) : BP_ERR_ARG; }
+int bp_point_compress(int curve, const uint8_t xy[64], uint8_t out[33]) { auto a = bp::curve_api(curve); return a ? a->point_compress(xy, out) : BP_ERR_ARG; }
+int bp_point_serialize_uncompressed(int curve, const uint8_t xy[64], uint8_t out[65]) { auto a = bp::curve_api(curve); return a ? a->point_uncompressed(xy, out) : BP_ERR_ARG; }
+int bp_point_decompress(int curve, const uint8_t in[33], uint8_t xy[64]) { auto a = bp::curve_api(curve); return a ? a->point_decompress(in, xy) : BP_ERR_ARG; }
+
+// ---- generators ----
+int bp_gens_generate_host(int curve, size_t capacity, uint8_t* G_xy, uint8_t* H_xy, uint8_t B[64], uint8_t B_blinding[64]) {
+    auto a = bp::curve_api(curve);
+    return a ? a->gens_generate_host(capacity, G_xy, H_xy, B, B_blinding) : BP_ERR_ARG;
+}
+int bp_gens_create(bp_ctx* ctx, size_t capacity, bp_gens** out) {
+    if (!ctx || !out) return BP_ERR_ARG;
+    auto a = bp::curve_api(ctx->curve);
+    if (!a) return BP_ERR_UNSUPPORTED;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    bp::GensDev* g = nullptr;
+    int rc = a->gens_create(ctx, capacity, &g);
+    if (rc) return rc;
+    *out = new bp_gens{ctx->curve, g};
+    return BP_OK;
+}
+int bp_gens_from_points(bp_ctx* ctx, const uint8_t B[64], const uint8_t B_blinding[64], const uint8_t* G_xy, const uint8_t* H_xy, size_t capacity,
+                        bp_gens** out) {
+    if (!ctx || !out || !B || !B_blinding || (capacity && (!G_xy || !H_xy))) return BP_ERR_ARG;
+    auto a = bp::curve_api(ctx->curve);
+    if (!a) return BP_ERR_UNSUPPORTED;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    bp::GensDev* g = nullptr;
+    int rc = a->gens_from_points(ctx, B, B_blinding, G_xy, H_xy, capacity, &g);
+    if (rc) return rc;
+    *out = new bp_gens{ctx->curve, g};
+    return BP_OK;
+}
+void bp_gens_free(bp_gens* g) { if (g) { delete g->g; delete g; } }
+size_t bp_gens_capacity(const bp_gens* g) { return g ? g->g->capacity : 0; }
+int bp_gens_export(const bp_gens* g, int which, size_t offset, size_t count, uint8_t* out_xy) {
+    if (!g || !out_xy) return BP_ERR_ARG;
+    bp_ctx* ctx = g->g->ctx;
+    const bp::DevBuf& b = which == 0 ? g->g->G : which == 1 ? g->g->H : g->g->pc;
+    size_t lim = which == 2 ? 2 : g->g->capacity;
+    if (offset + count > lim) return BP_ERR_LEN;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    BP_CUDA_TRY(ctx, cudaMemcpyAsync(out_xy, b.as<uint8_t>() + offset * 64, count * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BP_OK;
+}
+int bp_pedersen_commit(const bp_gens* g, const uint8_t value[32], const uint8_t blinding[32], uint8_t out_xy[64]) {
+    if (!g) return BP_ERR_ARG;
+    return bp::curve_api(g->curve)->pedersen_commit(g->g, value, blinding, out_xy);
+}
+
+// ---- constraint system (trait ConstraintSystem / RandomizableConstraintSystem) ----
+int bp_cs_multiply(bp_cs* cs, const bp_term* left, size_t nl, const bp_term* right, size_t nr, bp_var out[3]) {
+    if (!cs || !out) return BP_ERR_ARG;
+    std::vector<bp::Variable> lv, rv;
+    std::vector<bp::fe> lc, rc;
+    split_terms(left, nl, lv, lc);
+    split_terms(right, nr, rv, rc);
+    bp::Variable o[3];
+    int r = cs->cs->multiply(lv.data(), lc.data(), nl, rv.data(), rc.data(), nr, o);
+    for (int i = 0; i < 3; i++) put_var(&out[i], o[i]);
+    return r;
+}
+int bp_cs_allocate(bp_cs* cs, const uint8_t* assignment, bp_var* out) {
+    if (!cs || !out) return BP_ERR_ARG;
+    bp::fe a;
+    if (assignment) memcpy(a.v, assignment, 32);
+    bp::Variable o{0, 0};
+    int r = cs->cs->allocate(assignment ? &a : nullptr, &o);
+    put_var(out, o);
+    return r;
+}
+int bp_cs_allocate_multiplier(bp_cs* cs, const uint8_t* left, const uint8_t* right, bp_var out[3]) {
+    if (!cs || !out) return BP_ERR_ARG;
+    bp::fe l, r;
+    if (left) memcpy(l.v, left, 32);
+    if (right) memcpy(r.v, right, 32);
+    bp::Variable o[3] = {{0, 0}, {0, 0}, {0, 0}};
+    int rc = cs->cs->allocate_multiplier(left ? &l : nullptr, right ? &r : nullptr, o);
+    for (int i = 0; i < 3; i++) put_var(&out[i], o[i]);
+    return rc;
+}
+int bp_cs_constrain(bp_cs* cs, const bp_term* terms, size_t n) {
+    if (!cs) return BP_ERR_ARG;
+    std::vector<bp::Variable> v;
+    std::vector<bp::fe> c;
+    split_terms(terms, n, v, c);
+    return cs->cs->constrain(v.data(), c.data(), n);
+}
+size_t bp_cs_multipliers_len(const bp_cs* cs) { return cs ? cs->cs->multipliers_len() : 0; }
+int bp_cs_specify_randomized_constraints(bp_cs* cs, bp_randomized_cb cb, void* user) {
+    if (!cs || !cb) return BP_ERR_ARG;
+    int curve = cs->curve;
+    return cs->cs->specify_randomized_constraints([cb, user, curve](bp::ConstraintSystemBase& inner) {
+        bp_cs h{curve, &inner};
+        return cb(&h, user);
+    });
+}
+int bp_cs_challenge_scalar(bp_cs* cs, const uint8_t* label, size_t llen, uint8_t out[32]) {
+    if (!cs || !out) return BP_ERR_ARG;
+    bp::fe s;
+    int rc = cs->cs->challenge_scalar(lbl(label, llen).c_str(), &s);
+    if (rc == BP_OK) memcpy(out, s.v, 32);
+    return rc;
+}
+
+// ---- prover ----
+int bp_prover_new(bp_ctx* ctx, const bp_gens* pc_gens, bp_transcript* transcript, bp_prover** out) {
+    if (!ctx || !pc_gens || !transcript || !out) return BP_ERR_ARG;
+    auto a = bp::curve_api(ctx->curve);
+    if (!a || pc_gens->curve != ctx->curve) return BP_ERR_UNSUPPORTED;
+    bp_prover* p = new bp_prover{ctx->curve, ctx, a->prover_new(ctx, pc_gens->g, &transcript->t), {ctx->curve, nullptr}};
+    p->cs.cs = a->prover_cs(p->impl);
+    *out = p;
+    return BP_OK;
+}
+void bp_prover_free(bp_prover* p) { if (p) { bp::curve_api(p->curve)->prover_free(p->impl); delete p; } }
+bp_cs* bp_prover_cs(bp_prover* p) { return p ? &p->cs : nullptr; }
+int bp_prover_commit(bp_prover* p, const uint8_t value[32], const uint8_t blinding[32], uint8_t out_commitment[64], bp_var* out_var) {
+    if (!p || !value || !blinding || !out_commitment || !out_var) return BP_ERR_ARG;
+    bp::Variable v{0, 0};
+    int rc = bp::curve_api(p->curve)->prover_commit(p->impl, value, blinding, out_commitment, &v);
+    put_var(out_var, v);
+    return rc;
+}
+int bp_prover_prove(bp_prover* p, bp_rng* rng, bp_proof** out) {
+    if (!p || !rng || !out) return BP_ERR_ARG;
+    BP_CUDA_TRY(p->ctx, cudaSetDevice(p->ctx->device));
+    void* pr = nullptr;
+    int rc = bp::curve_api(p->curve)->prover_prove(p->impl, rng->r.get(), &pr);
+    if (rc) return rc;
+    *out = new bp_proof{p->curve, pr};
+    return BP_OK;
+}
+
+// ---- verifier ----
+int bp_verifier_new(bp_ctx* ctx, bp_transcript* transcript, bp_verifier** out) {
+    if (!ctx || !transcript || !out) return BP_ERR_ARG;
+    auto a = bp::curve_api(ctx->curve);
+    if (!a) return BP_ERR_UNSUPPORTED;
+    bp_verifier* v = new bp_verifier{ctx->curve, ctx, a->verifier_new(ctx, &transcript->t), {ctx->curve, nullptr}};
+    v->cs.cs = a->verifier_cs(v->impl);
+    *out = v;
+    return BP_OK;
+}
+void bp_verifier_free(bp_verifier* v) { if (v) { bp::curve_api(v->curve)->verifier_free(v->impl); delete v; } }
+bp_cs* bp_verifier_cs(bp_verifier* v) { return v ? &v->cs : nullptr; }
+int bp_verifier_commit(bp_verifier* v, const uint8_t commitment[64], bp_var* out_var) {
+    if (!v || !commitment || !out_var) return BP_ERR_ARG;
+    bp::Variable var{0, 0};
+    int rc = bp::curve_api(v->curve)->verifier_commit(v->impl, commitment, &var);
+    put_var(out_var, var);
+    return rc;
+}
+int bp_verifier_verify(bp_verifier* v, const bp_proof* proof, const bp_gens* gens) {
+    if (!v || !proof || !gens) return BP_ERR_ARG;
+    if (proof->curve != v->curve || gens->curve != v->curve) return BP_ERR_ARG;
+    BP_CUDA_TRY(v->ctx, cudaSetDevice(v->ctx->device));
+    return bp::curve_api(v->curve)->verifier_verify(v->impl, proof->impl, gens->g);
+}
+int bp_batch_verify(bp_ctx* ctx, bp_rng* rng, bp_verifier* const* verifiers, const bp_proof* const* proofs, size_t n, const bp_gens* gens) {
+    if (!ctx || !rng || !gens || (n && (!verifiers || !proofs))) return BP_ERR_ARG;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<void*> vs(n);
+    std::vector<const void*> ps(n);
+    for (size_t i = 0; i < n; i++) {
+        if (!verifiers[i] || !proofs[i] || verifiers[i]->curve != ctx->curve || proofs[i]->curve != ctx->curve) return BP_ERR_ARG;
+        vs[i] = verifiers[i]->impl;
+        ps[i] = proofs[i]->impl;
+    }
+    return bp::curve_api(ctx->curve)->batch_verify(ctx, rng->r.get(), vs.data(), ps.data(), n, gens->g);
+}
+
+// ---- proofs ----
+void bp_proof_free(bp_proof* p) { if (p) { bp::curve_api(p->curve)->proof_free(p->impl); delete p; } }
+int bp_proof_to_bytes(const bp_proof* p, uint8_t* out, size_t cap, size_t* len) {
+    if (!p || !len) return BP_ERR_ARG;
+    std::vector<uint8_t> b;
+    bp::curve_api(p->curve)->proof_to_bytes(p->impl, b);
+    *len = b.size();
+    if (!out) return BP_OK;
+    if (cap < b.size()) return BP_ERR_LEN;
+    memcpy(out, b.data(), b.size());
+    return BP_OK;
+}
+int bp_proof_from_bytes(int curve, const uint8_t* data, size_t len, bp_proof** out) {
+    auto a = bp::curve_api(curve);
+    if (!a || !data || !out) return BP_ERR_ARG;
+    void* pr = nullptr;
+    int rc = a->proof_from_bytes(data, len, &pr);
+    if (rc) return rc;
+    *out = new bp_proof{curve, pr};
+    return BP_OK;
+}
+bp_proof* bp_proof_clone(const bp_proof* p) { return p ? new bp_proof{p->curve, bp::curve_api(p->curve)->proof_clone(p->impl)} : nullptr; }
+int bp_proof_get_field(const bp_proof* p, int which, uint8_t* buf) { return p && buf ? bp::curve_api(p->curve)->proof_field(p->impl, which, buf, 0) : BP_ERR_ARG; }
+int bp_proof_set_field(bp_proof* p, int which, const uint8_t* buf) {
+    return p && buf ? bp::curve_api(p->curve)->proof_field(p->impl, which, const_cast<uint8_t*>(buf), 1) : BP_ERR_ARG;
+}
+size_t bp_proof_rounds(const bp_proof* p) { return p ? bp::curve_api(p->curve)->proof_rounds(p->impl) : 0; }
+
+// ---- InnerProductProof::create ----
+int bp_ipa_create(bp_ctx* ctx, bp_transcript* transcript, const uint8_t Q[64], const uint8_t* G_factors, const uint8_t* H_factors,
+                  const uint8_t* G_xy, const uint8_t* H_xy, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out_L, uint8_t* out_R,
+                  uint8_t out_a[32], uint8_t out_b[32]) {
+    if (!ctx || !transcript || !Q || !G_factors || !H_factors || !G_xy || !H_xy || !a || !b || !out_a || !out_b) return BP_ERR_ARG;
+    if (n > 1 && (!out_L || !out_R)) return BP_ERR_ARG;
+    auto api = bp::curve_api(ctx->curve);
+    if (!api) return BP_ERR_UNSUPPORTED;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return api->ipa_create_host(ctx, &transcript->t, Q, G_factors, H_factors, G_xy, H_xy, a, b, n, out_L, out_R, out_a, out_b);
 }
 
 }  // extern "C"

@@ -27,10 +27,12 @@ struct DevBuf {
         p = nullptr;
         cap = 0;
     }
-    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
 }  // namespace bp
+
+static constexpr size_t BP_HOST_RESULT_BYTES = 128 * 1024;
 
 struct bp_ctx {
     int curve = 0;
@@ -43,7 +45,16 @@ struct bp_ctx {
     // MSM scratch
     bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;
     bp::DevBuf stage_bases, stage_scalars;
-    void* h_result = nullptr;   // pinned, 16 KiB
+    // IPA / prover / verifier work buffers (r1cs.cuh)
+    bp::DevBuf ipa_G, ipa_H, ipa_s, ipa_parts, small;
+    bp::DevBuf p_aL, p_aR, p_aO, p_sL, p_sR, p_wL, p_wR, p_wO, p_ypow, p_yinv, p_l, p_r, p_Gf, p_Hf, v_pts, v_sc;
+    template <class F> void for_each_buf(F f) {
+        bp::DevBuf* all[] = {&keys_a, &keys_b, &vals_a, &vals_b, &cub_tmp, &buckets, &part_keys, &part_pts, &seg_out, &win_out, &result,
+                             &stage_bases, &stage_scalars, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
+                             &p_wL, &p_wR, &p_wO, &p_ypow, &p_yinv, &p_l, &p_r, &p_Gf, &p_Hf, &v_pts, &v_sc};
+        for (auto* b : all) f(b);
+    }
+    void* h_result = nullptr;   // pinned, BP_HOST_RESULT_BYTES
     // optional per-phase timing of the last MSM (cudaEvents on `stream`)
     bool timing = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

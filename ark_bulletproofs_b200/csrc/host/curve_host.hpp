@@ -1,0 +1,185 @@
+// Host-side restatement of the arkworks value semantics the reference relies on
+// (SURVEY.md App. A.3, A.5): `Fp::rand`, `Affine::rand`, canonical (de)serialisation, plus
+// small host group operations (single scalar multiplications for Pedersen commitments and
+// Q = w*B, src/generators.rs:39-44, src/r1cs/prover.rs:779).
+#pragma once
+#include <algorithm>
+#include <stdexcept>
+#include <vector>
+#include "../ec.cuh"
+#include "fp_host.hpp"
+#include "merlin.hpp"
+
+namespace bp {
+
+template <class C>
+struct HostCurve {
+    using Fq = HostFp<typename C::Fq>;
+    using Fr = HostFp<typename C::Fr>;
+    using E = SW<C, Fq>;
+    static constexpr int POINT_COMPRESSED = 33, POINT_UNCOMPRESSED = 65;
+
+    // ---- ark-ff Fp::rand: 4 x next_u64, shave, accept iff < modulus; raw = Montgomery repr ----
+    template <class M>
+    static fe fp_rand(Rng& rng) {
+        const int shave = 256 - M::BITS;
+        const uint64_t mask = shave == 64 ? 0 : (~0ull >> shave);
+        while (true) {
+            uint64_t l[4];
+            for (int i = 0; i < 4; i++) l[i] = rng.next_u64();
+            l[3] &= mask;
+            if (!HostFp<M>::geq_m(l)) return HostFp<M>::put(l);
+        }
+    }
+    static fe scalar_rand(Rng& rng) { return fp_rand<typename C::Fr>(rng); }
+
+    // ---- canonical little-endian bytes -----------------------------------------------------
+    template <class F>
+    static void fe_to_bytes(const fe& a, uint8_t out[32]) {
+        fe c = F::from_mont(a);
+        memcpy(out, c.v, 32);
+    }
+    template <class F>
+    static bool fe_from_bytes(const uint8_t in[32], fe& out) {   // false if >= modulus
+        uint64_t l[4];
+        memcpy(l, in, 32);
+        if (F::geq_m(l)) return false;
+        out = F::to_mont(F::put(l));
+        return true;
+    }
+    static void scalar_to_bytes(const fe& a, uint8_t out[32]) { fe_to_bytes<Fr>(a, out); }
+    static bool scalar_from_bytes(const uint8_t in[32], fe& out) { return fe_from_bytes<Fr>(in, out); }
+
+    // y > -y as canonical integers (ark SWFlags::from_y_coordinate)
+    static bool y_is_larger(const fe& y) {
+        fe yc = Fq::from_mont(y), nc = Fq::from_mont(Fq::neg(y));
+        return Fq::canonical_lt(nc, yc);
+    }
+    static void point_uncompressed(const affine& p, uint8_t out[65]) {   // src/transcript.rs:75-79
+        if (E::is_identity(p)) { memset(out, 0, 65); out[64] = 0x40; return; }
+        fe_to_bytes<Fq>(p.x, out);
+        fe_to_bytes<Fq>(p.y, out + 32);
+        out[64] = y_is_larger(p.y) ? 0x80 : 0;
+    }
+    static void point_compressed(const affine& p, uint8_t out[33]) {     // src/r1cs/proof.rs:74-78
+        if (E::is_identity(p)) { memset(out, 0, 33); out[32] = 0x40; return; }
+        fe_to_bytes<Fq>(p.x, out);
+        out[32] = y_is_larger(p.y) ? 0x80 : 0;
+    }
+
+    static fe curve_b() { fe b; for (int i = 0; i < 8; i++) b.v[i] = C::b(i); return b; }
+    static affine generator() {
+        affine g;
+        for (int i = 0; i < 8; i++) { g.x.v[i] = C::gx(i); g.y.v[i] = C::gy(i); }
+        return g;
+    }
+    static fe rhs(const fe& x) {
+        fe r = Fq::add(Fq::mul(Fq::sqr(x), x), curve_b());
+        if (C::A_SMALL != 0) r = Fq::add(r, Fq::mul_small(x, C::A_SMALL));
+        return r;
+    }
+
+    // Tonelli-Shanks; returns false for non-residues
+    static bool fq_sqrt(const fe& a, fe& out) {
+        struct TS { int s; uint32_t t[8]; uint32_t t1h[8]; fe z; uint32_t half[8]; };
+        static const TS ts = [] {
+            TS r;
+            uint32_t e[8];
+            for (int i = 0; i < 8; i++) e[i] = C::Fq::m(i);
+            e[0] -= 1;   // q - 1
+            // (q-1)/2 for Euler's criterion
+            for (int i = 0; i < 8; i++) r.half[i] = (e[i] >> 1) | (i < 7 ? (e[i + 1] << 31) : 0);
+            r.s = 0;
+            while (!(e[0] & 1)) {
+                for (int i = 0; i < 8; i++) e[i] = (e[i] >> 1) | (i < 7 ? (e[i + 1] << 31) : 0);
+                r.s++;
+            }
+            memcpy(r.t, e, 32);
+            // (t+1)/2 = (t >> 1) + 1 for odd t
+            uint32_t h[8];
+            for (int i = 0; i < 8; i++) h[i] = (e[i] >> 1) | (i < 7 ? (e[i + 1] << 31) : 0);
+            uint64_t c = 1;
+            for (int i = 0; i < 8; i++) { c += h[i]; h[i] = (uint32_t)c; c >>= 32; }
+            memcpy(r.t1h, h, 32);
+            // a non-residue z, then z^t
+            fe one = Fq::one();
+            for (uint32_t k = 2;; k++) {
+                fe cand = Fq::from_u32(k);
+                fe l = Fq::pow(cand, r.half);
+                if (!Fq::eq(l, one) && !Fq::is_zero(l)) { r.z = Fq::pow(cand, r.t); break; }
+            }
+            return r;
+        }();
+        if (Fq::is_zero(a)) { out = a; return true; }
+        fe one = Fq::one();
+        if (!Fq::eq(Fq::pow(a, ts.half), one)) return false;
+        int m = ts.s;
+        fe c = ts.z, t = Fq::pow(a, ts.t), r = Fq::pow(a, ts.t1h);
+        while (!Fq::eq(t, one)) {
+            int i = 0;
+            fe t2 = t;
+            while (!Fq::eq(t2, one)) { t2 = Fq::sqr(t2); i++; }
+            fe b = c;
+            for (int k = 0; k < m - i - 1; k++) b = Fq::sqr(b);
+            m = i;
+            c = Fq::sqr(b);
+            t = Fq::mul(t, c);
+            r = Fq::mul(r, b);
+        }
+        out = r;
+        return true;
+    }
+
+    // ark-ec get_point_from_x_unchecked(x, greatest)
+    static bool point_from_x(const fe& x, bool greatest, affine& out) {
+        fe y;
+        if (!fq_sqrt(rhs(x), y)) return false;
+        fe ny = Fq::neg(y);
+        bool y_larger = y_is_larger(y);
+        out.x = x;
+        out.y = (greatest == y_larger) ? y : ny;
+        return true;
+    }
+
+    // ark-ec `Affine::rand` for short Weierstrass (cofactor 1): x = Fq::rand, greatest = top bit
+    // of next_u32, retry until x^3+ax+b is a square (src/generators.rs:63,99,115)
+    static affine affine_rand(Rng& rng) {
+        while (true) {
+            fe x = fp_rand<typename C::Fq>(rng);
+            bool greatest = (rng.next_u32() >> 31) & 1;
+            affine p;
+            if (point_from_x(x, greatest, p)) return p;
+        }
+    }
+
+    // deserialize_compressed with validation (on curve; cofactor 1 => subgroup trivial)
+    static bool point_from_compressed(const uint8_t in[33], affine& out) {
+        uint8_t flags = in[32];
+        if (flags & 0x3F) return false;
+        uint64_t l[4];
+        memcpy(l, in, 32);
+        if (Fq::geq_m(l)) return false;
+        if (flags & 0x40) {
+            if (flags & 0x80) return false;
+            if (l[0] | l[1] | l[2] | l[3]) return false;
+            out = E::affine_identity();
+            return true;
+        }
+        fe x = Fq::to_mont(Fq::put(l));
+        return point_from_x(x, (flags & 0x80) != 0, out);
+    }
+
+    // k*P with k a Montgomery-form scalar (mul_bigint(k.into_bigint())) -> affine
+    static affine mul(const affine& p, const fe& k_mont) {
+        fe k = Fr::from_mont(k_mont);
+        xyzz acc = E::mul_scalar(p, k.v);
+        return E::to_affine(acc);
+    }
+    static affine add(const affine& a, const affine& b) {
+        xyzz acc = E::from_affine(a);
+        E::madd(acc, b);
+        return E::to_affine(acc);
+    }
+};
+
+}  // namespace bp

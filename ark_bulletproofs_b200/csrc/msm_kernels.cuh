@@ -41,20 +41,21 @@ struct MsmPlan {
     uint32_t nseg;    // segments per window
 };
 
-static inline MsmPlan make_plan(size_t n, int force_c, int sm_count) {
+static inline MsmPlan make_plan(size_t n, int nmsm, int force_c, int sm_count) {
+    // n = total number of (point, scalar) terms over all nmsm batched MSMs
     MsmPlan p;
     int best_c = 4;
     double best = 1e300;
     for (int c = 3; c <= 20; c++) {
         int W = 256 / c + 1;
         double nb = (double)(1u << (c - 1));
-        double cost = W * (10.0 * (double)n + 45.0 * nb);   // modmul-equivalents
+        double cost = W * (10.0 * (double)n + 45.0 * nb * nmsm);   // modmul-equivalents
         if (cost < best) { best = cost; best_c = c; }
     }
     p.c = force_c > 0 ? force_c : best_c;
     p.W = 256 / p.c + 1;
     p.nb = 1u << (p.c - 1);
-    uint64_t nkeys = (uint64_t)p.W * p.nb;
+    uint64_t nkeys = (uint64_t)nmsm * p.W * p.nb;
     p.key_bits = 1;
     while ((1ull << p.key_bits) <= nkeys) p.key_bits++;
     p.entries = n * (size_t)p.W;
@@ -68,15 +69,47 @@ static inline MsmPlan make_plan(size_t n, int force_c, int sm_count) {
     return p;
 }
 
+// A batch of up to MSM_MAX_BATCH independent MSMs given as up to MSM_MAX_SEGS segments; each
+// segment pairs `count` scalars with `count` affine bases from its own array and belongs to one
+// MSM of the batch. (A_I = <a_L,G> + <a_R,H> + i_bl*B_blinding is three segments of one MSM;
+// the L and R of an IPA round are two MSMs of three segments each.)
+static constexpr int MSM_MAX_SEGS = 8;
+static constexpr int MSM_MAX_BATCH = 8;
+static constexpr uint32_t MSM_IDX_MASK = 0x0FFFFFFFu;   // val = sign<<31 | seg<<28 | index
+struct MsmJob {
+    int nseg = 0;
+    int nmsm = 1;
+    const affine* bases[MSM_MAX_SEGS];
+    const fe* scalars[MSM_MAX_SEGS];
+    uint32_t count[MSM_MAX_SEGS];
+    uint32_t start[MSM_MAX_SEGS + 1];   // prefix sums of count
+    uint32_t msm[MSM_MAX_SEGS];
+    void add(const affine* b, const fe* s, size_t n, int m) {
+        bases[nseg] = b; scalars[nseg] = s; count[nseg] = (uint32_t)n; msm[nseg] = (uint32_t)m;
+        start[nseg] = nseg ? start[nseg - 1] + count[nseg - 1] : 0;
+        nseg++;
+        start[nseg] = start[nseg - 1] + (uint32_t)n;
+        if (m + 1 > nmsm) nmsm = m + 1;
+    }
+    size_t total() const { return nseg ? start[nseg] : 0; }
+};
+
 // ---- 1. digits -------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(256) msm_digits_kernel(const fe* __restrict__ scalars, size_t n, int c, int W,
+__global__ void __launch_bounds__(256) msm_digits_kernel(const __grid_constant__ MsmJob job, size_t n, int c, int W,
                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fe s = Fp<typename C::Fr>::from_mont(ld_fe(scalars + i));
+    int sg = 0;
+#pragma unroll
+    for (int k = 1; k < MSM_MAX_SEGS; k++)
+        if (k < job.nseg && i >= job.start[k]) sg = k;
+    uint32_t local = (uint32_t)i - job.start[sg];
+    fe s = Fp<typename C::Fr>::from_mont(ld_fe(job.scalars[sg] + local));
     const uint32_t half = 1u << (c - 1);
     const uint32_t mask = (1u << c) - 1u;
+    const uint32_t wbase = job.msm[sg] * (uint32_t)W;
+    const uint32_t vbase = ((uint32_t)sg << 28) | local;
     uint32_t carry = 0;
     for (int w = 0; w < W; w++) {
         int bit = w * c;
@@ -87,16 +120,16 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const fe* __restrict__ 
         d += carry;
         uint32_t neg = 0;
         if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else carry = 0;
-        uint32_t key = d ? (((uint32_t)w << (c - 1)) | (d - 1u)) : INVALID_KEY;
+        uint32_t key = d ? (((wbase + (uint32_t)w) << (c - 1)) | (d - 1u)) : INVALID_KEY;
         keys[(size_t)w * n + i] = key;
-        vals[(size_t)w * n + i] = (uint32_t)i | (neg << 31);
+        vals[(size_t)w * n + i] = vbase | (neg << 31);
     }
 }
 
 // ---- 3. accumulate ---------------------------------------------------------------------------
 template <class C>
-__device__ __forceinline__ affine gather_point(const affine* __restrict__ pts, uint32_t v) {
-    affine p = ld_affine(pts + (v & 0x7FFFFFFFu));
+__device__ __forceinline__ affine gather_point(const MsmJob& job, uint32_t v) {
+    affine p = ld_affine(job.bases[(v >> 28) & 7u] + (v & MSM_IDX_MASK));
     if (v >> 31) p.y = Fp<typename C::Fq>::neg(p.y);
     return p;
 }
@@ -137,7 +170,7 @@ struct RunSink {
 // level 1: sorted (key, point index|sign) pairs -> run sums of gathered affine points
 template <class C>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                             size_t M, int L, size_t T, const affine* __restrict__ pts,
+                                                             size_t M, int L, size_t T, const __grid_constant__ MsmJob job,
                                                              xyzz* __restrict__ buckets, uint32_t* __restrict__ out_keys,
                                                              xyzz* __restrict__ out_pts) {
     using E = SW<C>;
@@ -149,7 +182,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
     uint32_t cur = keys[s];
     if (cur == INVALID_KEY) { sink.empty(); return; }
     xyzz acc = E::identity();
-    affine p = gather_point<C>(pts, vals[s]);
+    affine p = gather_point<C>(job, vals[s]);
     size_t i = s;
     while (true) {
         size_t j = i + 1;
@@ -157,7 +190,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
         affine pnext;
         if (j < e) knext = keys[j];
         bool have_next = knext != INVALID_KEY;
-        if (have_next) pnext = gather_point<C>(pts, vals[j]);   // in flight during the add below
+        if (have_next) pnext = gather_point<C>(job, vals[j]);   // in flight during the add below
         E::madd(acc, p);
         if (knext != cur) {
             sink.flush(cur, acc, !have_next);
@@ -290,21 +323,25 @@ __global__ void __launch_bounds__(128) synth_points_kernel(affine* __restrict__ 
 // ---- host driver -----------------------------------------------------------------------------
 int host_combine(int curve, const void* win, int W, int c, uint8_t out_xy[64], int* out_is_identity);
 
+// Runs the batch; out_xy / out_is_identity have job.nmsm entries.
 template <class C>
-int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) {
+int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_is_identity) {
     cudaStream_t st = ctx->stream;
+    size_t n = job.total();
     if (n == 0) {
-        memset(out_xy, 0, 64);
-        if (out_is_identity) *out_is_identity = 1;
+        for (int m = 0; m < job.nmsm; m++) { memset(out_xy[m], 0, 64); if (out_is_identity) out_is_identity[m] = 1; }
         return BP_OK;
     }
+    for (int k = 0; k < job.nseg; k++)
+        if (job.count[k] > MSM_IDX_MASK) return BP_ERR_LEN;
     if (n >= (1ull << 31)) return BP_ERR_LEN;
-    MsmPlan p = make_plan(n, ctx->force_c, ctx->sm_count);
+    MsmPlan p = make_plan(n, job.nmsm, ctx->force_c, ctx->sm_count);
+    const int NW = job.nmsm * p.W;   // windows over the whole batch
     BP_CUDA_TRY(ctx, ctx->keys_a.reserve(p.entries * 4));
     BP_CUDA_TRY(ctx, ctx->keys_b.reserve(p.entries * 4));
     BP_CUDA_TRY(ctx, ctx->vals_a.reserve(p.entries * 4));
     BP_CUDA_TRY(ctx, ctx->vals_b.reserve(p.entries * 4));
-    size_t nbuckets = (size_t)p.W * p.nb;
+    size_t nbuckets = (size_t)NW * p.nb;
     BP_CUDA_TRY(ctx, ctx->buckets.reserve(nbuckets * sizeof(xyzz)));
     // partial slot lists: level 1 has 2T slots, every further level shrinks by PL/2
     const int PL = 16;
@@ -312,8 +349,9 @@ int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, u
     size_t slots2 = 2 * ((slots1 + PL - 1) / PL);
     BP_CUDA_TRY(ctx, ctx->part_keys.reserve((slots1 + slots2 + 64) * 4));
     BP_CUDA_TRY(ctx, ctx->part_pts.reserve((slots1 + slots2 + 64) * sizeof(xyzz)));
-    BP_CUDA_TRY(ctx, ctx->seg_out.reserve((size_t)p.W * p.nseg * sizeof(xyzz)));
-    BP_CUDA_TRY(ctx, ctx->win_out.reserve((size_t)p.W * sizeof(xyzz)));
+    BP_CUDA_TRY(ctx, ctx->seg_out.reserve((size_t)NW * p.nseg * sizeof(xyzz)));
+    BP_CUDA_TRY(ctx, ctx->win_out.reserve((size_t)NW * sizeof(xyzz)));
+    if ((size_t)NW * sizeof(xyzz) > BP_HOST_RESULT_BYTES) return BP_ERR_LEN;
     size_t tmp_bytes = 0;
     BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->keys_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(),
                                                      ctx->vals_a.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, 0,
@@ -323,7 +361,7 @@ int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, u
     ctx->last_c = p.c; ctx->last_W = p.W; ctx->last_entries = p.entries;
     auto mark = [&](int i) { if (ctx->timing) cudaEventRecord(ctx->ev[i], st); };
     mark(0);
-    msm_digits_kernel<C><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scalars, n, p.c, p.W, ctx->keys_a.as<uint32_t>(),
+    msm_digits_kernel<C><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(job, n, p.c, p.W, ctx->keys_a.as<uint32_t>(),
                                                                      ctx->vals_a.as<uint32_t>());
     BP_LAUNCH_CHECK(ctx);
     mark(7);
@@ -335,7 +373,7 @@ int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, u
     uint32_t* pk = ctx->part_keys.as<uint32_t>();
     xyzz* pp = ctx->part_pts.as<xyzz>();
     msm_accumulate_kernel<C><<<(unsigned)((p.T + 127) / 128), 128, 0, st>>>(ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(),
-                                                                            p.entries, p.L, p.T, d_bases, ctx->buckets.as<xyzz>(), pk, pp);
+                                                                            p.entries, p.L, p.T, job, ctx->buckets.as<xyzz>(), pk, pp);
     BP_LAUNCH_CHECK(ctx);
     mark(2);
     // hierarchical reduction of the boundary partials (ping-pong inside the two regions)
@@ -356,16 +394,16 @@ int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, u
     msm_partials_final_kernel<C><<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(in_k, in_p, nslots, ctx->buckets.as<xyzz>());
     BP_LAUNCH_CHECK(ctx);
     mark(3);
-    size_t rt = (size_t)p.W * p.nseg;
-    msm_reduce_kernel<C><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, p.W,
+    size_t rt = (size_t)NW * p.nseg;
+    msm_reduce_kernel<C><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, NW,
                                                                        ctx->seg_out.as<xyzz>());
     BP_LAUNCH_CHECK(ctx);
-    msm_window_sum_kernel<C><<<p.W, 128, 0, st>>>(ctx->seg_out.as<xyzz>(), p.nseg, ctx->win_out.as<xyzz>());
+    msm_window_sum_kernel<C><<<NW, 128, 0, st>>>(ctx->seg_out.as<xyzz>(), p.nseg, ctx->win_out.as<xyzz>());
     BP_LAUNCH_CHECK(ctx);
     mark(4);
     // The Horner combination over windows is 256 dependent doublings: 1.35 ms on one GPU
     // thread (measured), ~0.1 ms on a host core. The W window sums (W*128 B) go to the host.
-    BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_result, ctx->win_out.p, (size_t)p.W * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
+    BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_result, ctx->win_out.p, (size_t)NW * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
     BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (ctx->timing) {
         // phases: 0 digits, 1 sort, 2 memset+accumulate, 3 partial levels, 4 bucket reduce + window sums
@@ -375,9 +413,27 @@ int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, u
         cudaEventElapsedTime(&ctx->phase_ms[3], ctx->ev[2], ctx->ev[3]);
         cudaEventElapsedTime(&ctx->phase_ms[4], ctx->ev[3], ctx->ev[4]);
     }
-    return host_combine(ctx->curve, ctx->h_result, p.W, p.c, out_xy, out_is_identity);
+    for (int m = 0; m < job.nmsm; m++) {
+        int rc = host_combine(ctx->curve, (const xyzz*)ctx->h_result + (size_t)m * p.W, p.W, p.c, out_xy[m],
+                              out_is_identity ? &out_is_identity[m] : nullptr);
+        if (rc != BP_OK) return rc;
+    }
+    return BP_OK;
 }
 
+template <class C>
+int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) {
+    if (n > MSM_IDX_MASK) return BP_ERR_LEN;
+    MsmJob job;
+    if (n) job.add(d_bases, d_scalars, n, 0);
+    uint8_t out[1][64];
+    int ident[1] = {0};
+    int rc = msm_run_job<C>(ctx, job, out, ident);
+    if (rc != BP_OK) return rc;
+    memcpy(out_xy, out[0], 64);
+    if (out_is_identity) *out_is_identity = ident[0];
+    return BP_OK;
+}
 
 template <class C>
 int synth_points_run(bp_ctx* ctx, void* d_out, size_t n, uint64_t start) {

@@ -2,5 +2,6 @@
 #include "msm_kernels.cuh"
 namespace bp {
 template int msm_run<Zorro>(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);
+template int msm_run_job<Zorro>(bp_ctx*, const MsmJob&, uint8_t (*)[64], int*);
 template int synth_points_run<Zorro>(bp_ctx*, void*, size_t, uint64_t);
 }  // namespace bp

@@ -1,0 +1,762 @@
+// C++ host mirror of the reference's proving / verification API, driving the CUDA kernels.
+//
+//   InnerProductProof::create          src/inner_product_proof.rs:37-239     -> ipa_create()
+//   Prover {commit, multiply, allocate, allocate_multiplier, constrain,
+//           specify_randomized_constraints, prove}   src/r1cs/prover.rs:96-831 -> ProverT<C>
+//   Verifier {commit, ..., verification_scalars, verify}  src/r1cs/verifier.rs:69-600 -> VerifierT<C>
+//   batch_verify                        src/r1cs/verifier.rs:604-691          -> batch_verify_t()
+//   R1CSProof::{to_bytes,from_bytes}    src/r1cs/proof.rs:25-91               -> ProofT<C>
+//
+// Same names, argument meaning and error behaviour as the Rust crate (Rust itself is absent from
+// this image). The transcript schedule, RNG draw order and wire format are the reference's, so
+// proofs are byte-identical to the CPU oracle; all O(n) arithmetic runs in the kernels of
+// msm_kernels.cuh / vec_kernels.cuh on the context's stream.
+#pragma once
+#include <functional>
+#include <memory>
+#include <vector>
+#include "host/gens_host.hpp"
+#include "r1cs_types.hpp"
+#include "msm_kernels.cuh"
+#include "vec_kernels.cuh"
+
+namespace bp {
+
+template <class C>
+struct ProofT : ProofBase {
+    using HC = HostCurve<C>;
+    affine A_I1, A_O1, S1, A_I2, A_O2, S2, T_1, T_3, T_4, T_5, T_6;
+    fe t_x, t_x_blinding, e_blinding;
+    std::vector<affine> L_vec, R_vec;
+    fe a, b;
+
+    std::vector<uint8_t> to_bytes() const override {                     // proof.rs:74-78
+        std::vector<uint8_t> out;
+        auto pt = [&](const affine& p) { uint8_t buf[33]; HC::point_compressed(p, buf); out.insert(out.end(), buf, buf + 33); };
+        auto sc = [&](const fe& s) { uint8_t buf[32]; HC::scalar_to_bytes(s, buf); out.insert(out.end(), buf, buf + 32); };
+        auto u64 = [&](uint64_t v) { for (int i = 0; i < 8; i++) out.push_back((uint8_t)(v >> (8 * i))); };
+        const affine* pts[11] = {&A_I1, &A_O1, &S1, &A_I2, &A_O2, &S2, &T_1, &T_3, &T_4, &T_5, &T_6};
+        for (auto p : pts) pt(*p);
+        sc(t_x); sc(t_x_blinding); sc(e_blinding);
+        u64(L_vec.size()); for (auto& p : L_vec) pt(p);
+        u64(R_vec.size()); for (auto& p : R_vec) pt(p);
+        sc(a); sc(b);
+        return out;
+    }
+    static int from_bytes(const uint8_t* d, size_t len, ProofT& pr) {     // proof.rs:83-91 (FormatError)
+        size_t off = 0;
+        auto pt = [&](affine& p) { if (off + 33 > len) return false; bool ok = HC::point_from_compressed(d + off, p); off += 33; return ok; };
+        auto sc = [&](fe& s) { if (off + 32 > len) return false; bool ok = HC::scalar_from_bytes(d + off, s); off += 32; return ok; };
+        affine* pts[11] = {&pr.A_I1, &pr.A_O1, &pr.S1, &pr.A_I2, &pr.A_O2, &pr.S2, &pr.T_1, &pr.T_3, &pr.T_4, &pr.T_5, &pr.T_6};
+        for (auto p : pts) if (!pt(*p)) return BP_ERR_FORMAT;
+        if (!sc(pr.t_x) || !sc(pr.t_x_blinding) || !sc(pr.e_blinding)) return BP_ERR_FORMAT;
+        for (int v = 0; v < 2; v++) {
+            if (off + 8 > len) return BP_ERR_FORMAT;
+            uint64_t cnt = 0;
+            for (int i = 0; i < 8; i++) cnt |= (uint64_t)d[off + i] << (8 * i);
+            off += 8;
+            if (cnt > (len - off) / 33) return BP_ERR_FORMAT;
+            auto& vec = v == 0 ? pr.L_vec : pr.R_vec;
+            vec.resize(cnt);
+            for (auto& p : vec) if (!pt(p)) return BP_ERR_FORMAT;
+        }
+        if (!sc(pr.a) || !sc(pr.b)) return BP_ERR_FORMAT;
+        return BP_OK;
+    }
+};
+
+// ---- transcript protocol (src/transcript.rs:45-101) -------------------------------------------------
+template <class C>
+struct TP {
+    using HC = HostCurve<C>;
+    static void append_scalar(Transcript& t, const char* label, const fe& s) { uint8_t b[32]; HC::scalar_to_bytes(s, b); t.append_message(label, b, 32); }
+    static void append_point(Transcript& t, const char* label, const affine& p) { uint8_t b[65]; HC::point_uncompressed(p, b); t.append_message(label, b, 65); }
+    static int validate_and_append_point(Transcript& t, const char* label, const affine& p) {
+        if (HC::E::is_identity(p)) return BP_ERR_VERIFY;
+        append_point(t, label, p);
+        return BP_OK;
+    }
+    static fe challenge_scalar(Transcript& t, const char* label) {
+        uint8_t buf[32];
+        t.challenge_bytes(label, buf, 32);
+        ChaCha20Rng rng(buf);
+        return HC::scalar_rand(rng);
+    }
+};
+
+// ---- device helpers -----------------------------------------------------------------------------
+template <class C>
+struct Dev {
+    using Fr = HostFp<typename C::Fr>;
+    static PowTable pow_table(const fe& base) {
+        PowTable t;
+        t.p[0] = base;
+        for (int k = 1; k < 32; k++) t.p[k] = Fr::sqr(t.p[k - 1]);
+        return t;
+    }
+    static int pow_vec(bp_ctx* ctx, const fe& base, fe* d_out, size_t n) {
+        if (!n) return BP_OK;
+        vec_pow_kernel<C><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pow_table(base), d_out, n);
+        BP_LAUNCH_CHECK(ctx);
+        return BP_OK;
+    }
+    static int upload(bp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+        if (bytes) BP_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return BP_OK;
+    }
+    static int download(bp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+        if (bytes) BP_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return BP_OK;
+    }
+    static ScalarBits bits(const fe& mont) {
+        fe c = Fr::from_mont(mont);
+        ScalarBits b;
+        for (int i = 0; i < 8; i++) b.w[i] = c.v[i];
+        return b;
+    }
+};
+
+// ---- InnerProductProof::create on the device (inner_product_proof.rs:37-239) ------------------------
+// d_G, d_H: generators (read-only); d_Gf, d_Hf: factor vectors; d_a, d_b: overwritten.
+template <class C>
+int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, const fe* d_Hf, const affine* d_G, const affine* d_H,
+               fe* d_a, fe* d_b, size_t n, std::vector<affine>& L_vec, std::vector<affine>& R_vec, fe& a_out, fe& b_out) {
+    using Fr = HostFp<typename C::Fr>;
+    using D = Dev<C>;
+    if (n == 0 || (n & (n - 1))) return BP_ERR_POW2;                     // assert at :66
+    t.append_message("dom-sep", (const uint8_t*)"ipp v1", 6);            // transcript.rs:52-55
+    t.append_u64("n", n);
+    L_vec.clear();
+    R_vec.clear();
+    cudaStream_t st = ctx->stream;
+    size_t half = n / 2;
+    BP_CUDA_TRY(ctx, ctx->ipa_G.reserve((half + 1) * sizeof(affine)));
+    BP_CUDA_TRY(ctx, ctx->ipa_H.reserve((half + 1) * sizeof(affine)));
+    BP_CUDA_TRY(ctx, ctx->ipa_s.reserve((4 * half + 8) * sizeof(fe)));
+    const int PREP_BLOCKS = 296;
+    BP_CUDA_TRY(ctx, ctx->ipa_parts.reserve((size_t)(2 * PREP_BLOCKS + 8) * sizeof(fe)));
+    BP_CUDA_TRY(ctx, ctx->small.reserve(4096));
+    affine* wG = ctx->ipa_G.as<affine>();
+    affine* wH = ctx->ipa_H.as<affine>();
+    fe* s_all = ctx->ipa_s.as<fe>();
+    fe* parts = ctx->ipa_parts.as<fe>();
+    fe* d_c = ctx->small.as<fe>();                      // [cL, cR]
+    affine* d_Q = reinterpret_cast<affine*>(ctx->small.as<uint8_t>() + 256);
+    if (int rc = D::upload(ctx, d_Q, &Q, sizeof(affine))) return rc;
+
+    const affine* curG = d_G;
+    const affine* curH = d_H;
+    fe fG = Fr::one(), fH = Fr::one();
+    bool first = true;
+    while (n != 1) {
+        size_t h = n / 2;
+        fe *sLG = s_all, *sLH = s_all + h, *sRG = s_all + 2 * h, *sRH = s_all + 3 * h;
+        int blocks = (int)((h + 127) / 128);
+        if (blocks > PREP_BLOCKS) blocks = PREP_BLOCKS;
+        ipa_prep_kernel<C><<<blocks, 128, 0, st>>>(d_a, d_b, h, first ? d_Gf : nullptr, first ? d_Hf : nullptr, fG, fH, sLG, sLH, sRG, sRH, parts);
+        BP_LAUNCH_CHECK(ctx);
+        vec_reduce_partials_kernel<C, 2><<<1, 128, 0, st>>>(parts, blocks, d_c);
+        BP_LAUNCH_CHECK(ctx);
+        // L = <a_L*gR, G_R> + <b_R*hL, H_L> + c_L*Q ; R = <a_R*gL, G_L> + <b_L*hR, H_R> + c_R*Q
+        MsmJob job;
+        job.add(curG + h, sLG, h, 0);
+        job.add(curH, sLH, h, 0);
+        job.add(d_Q, d_c, 1, 0);
+        job.add(curG, sRG, h, 1);
+        job.add(curH + h, sRH, h, 1);
+        job.add(d_Q, d_c + 1, 1, 1);
+        uint8_t out[2][64];
+        int ident[2];
+        if (int rc = msm_run_job<C>(ctx, job, out, ident)) return rc;
+        affine Lp, Rp;
+        memcpy(&Lp, out[0], 64);
+        memcpy(&Rp, out[1], 64);
+        L_vec.push_back(Lp);
+        R_vec.push_back(Rp);
+        TP<C>::append_point(t, "L", Lp);
+        TP<C>::append_point(t, "R", Rp);
+        fe u = TP<C>::challenge_scalar(t, "u");
+        fe uinv = Fr::inv(u);                                            // u.inverse().unwrap()
+        ipa_fold_scalars_kernel<C><<<(unsigned)((h + 255) / 256), 256, 0, st>>>(d_a, d_b, h, u, uinv);
+        BP_LAUNCH_CHECK(ctx);
+        unsigned fgrid = (unsigned)((2 * h + 127) / 128);
+        if (first) {
+            // factors folded into the points (inner_product_proof.rs:143-155)
+            ipa_fold_points_joint_kernel<C><<<fgrid, 128, 0, st>>>(curG, d_Gf, uinv, u, wG, curH, d_Hf, u, uinv, wH, h);
+            BP_LAUNCH_CHECK(ctx);
+        } else {
+            // u^-1*G_L + u*G_R = u^-1*(G_L + u^2*G_R): the common factor moves into fG (resp. fH)
+            fe u2 = Fr::sqr(u), ui2 = Fr::sqr(uinv);
+            ipa_fold_points_uniform_kernel<C><<<fgrid, 128, 0, st>>>(curG, curG + h, wG, curH, curH + h, wH, h, D::bits(u2), D::bits(ui2));
+            BP_LAUNCH_CHECK(ctx);
+            fG = Fr::mul(fG, uinv);
+            fH = Fr::mul(fH, u);
+        }
+        curG = wG;
+        curH = wH;
+        first = false;
+        n = h;
+    }
+    fe ab[2];
+    if (int rc = D::download(ctx, &ab[0], d_a, sizeof(fe))) return rc;
+    if (int rc = D::download(ctx, &ab[1], d_b, sizeof(fe))) return rc;
+    a_out = ab[0];
+    b_out = ab[1];
+    return BP_OK;
+}
+
+// ---- constraint storage shared by prover and verifier -----------------------------------------------
+struct ConstraintStore {
+    std::vector<uint8_t> kind;
+    std::vector<uint64_t> idx;
+    std::vector<fe> coeff;
+    std::vector<size_t> start;   // constraint q covers terms [start[q], start[q+1])
+    ConstraintStore() { start.push_back(0); }
+    void push(const Variable* v, const fe* c, size_t n, const Variable* extra_v = nullptr, const fe* extra_c = nullptr) {
+        for (size_t i = 0; i < n; i++) { kind.push_back((uint8_t)v[i].kind); idx.push_back(v[i].idx); coeff.push_back(c[i]); }
+        if (extra_v) { kind.push_back((uint8_t)extra_v->kind); idx.push_back(extra_v->idx); coeff.push_back(*extra_c); }
+        start.push_back(kind.size());
+    }
+    size_t count() const { return start.size() - 1; }
+};
+
+// flattened_constraints (prover.rs:354-397 / verifier.rs:304-349): host sparse scatter
+template <class C>
+static void flatten(const ConstraintStore& cs, const fe& z, size_t n, size_t m, std::vector<fe>& wL, std::vector<fe>& wR,
+                    std::vector<fe>& wO, std::vector<fe>& wV, fe* wc) {
+    using Fr = HostFp<typename C::Fr>;
+    wL.assign(n, Fr::zero()); wR.assign(n, Fr::zero()); wO.assign(n, Fr::zero()); wV.assign(m, Fr::zero());
+    if (wc) *wc = Fr::zero();
+    fe exp_z = z;
+    for (size_t q = 0; q < cs.count(); q++) {
+        for (size_t k = cs.start[q]; k < cs.start[q + 1]; k++) {
+            fe term = Fr::mul(exp_z, cs.coeff[k]);
+            size_t i = cs.idx[k];
+            switch (cs.kind[k]) {
+                case VAR_MUL_LEFT: wL[i] = Fr::add(wL[i], term); break;
+                case VAR_MUL_RIGHT: wR[i] = Fr::add(wR[i], term); break;
+                case VAR_MUL_OUT: wO[i] = Fr::add(wO[i], term); break;
+                case VAR_COMMITTED: wV[i] = Fr::sub(wV[i], term); break;
+                case VAR_ONE: if (wc) *wc = Fr::sub(*wc, term); break;
+            }
+        }
+        exp_z = Fr::mul(exp_z, z);
+    }
+}
+
+static inline size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }   // 0 -> 1 like Rust
+
+// ---- Prover (src/r1cs/prover.rs) ----------------------------------------------------------------
+template <class C>
+struct ProverT : ConstraintSystemBase {
+    using HC = HostCurve<C>;
+    using Fr = HostFp<typename C::Fr>;
+    using D = Dev<C>;
+    bp_ctx* ctx;
+    const GensDev* gens;
+    Transcript* transcript;
+    std::vector<fe> v, v_blinding, a_L, a_R, a_O;
+    ConstraintStore cs;
+    std::vector<std::function<int(ConstraintSystemBase&)>> deferred;
+    bool has_pending = false, randomizing = false;
+    size_t pending = 0;
+
+    ProverT(bp_ctx* c, const GensDev* g, Transcript* t) : ctx(c), gens(g), transcript(t) {     // prover.rs:291-308
+        t->append_message("dom-sep", (const uint8_t*)"r1cs v1", 7);
+    }
+    fe eval(const Variable* vars, const fe* coeffs, size_t n) const {                          // prover.rs:399-414
+        fe tot = Fr::zero();
+        for (size_t k = 0; k < n; k++) {
+            fe val;
+            switch (vars[k].kind) {
+                case VAR_MUL_LEFT: val = a_L[vars[k].idx]; break;
+                case VAR_MUL_RIGHT: val = a_R[vars[k].idx]; break;
+                case VAR_MUL_OUT: val = a_O[vars[k].idx]; break;
+                case VAR_COMMITTED: val = v[vars[k].idx]; break;
+                case VAR_ONE: val = Fr::one(); break;
+                default: val = Fr::zero();
+            }
+            tot = Fr::add(tot, Fr::mul(coeffs[k], val));
+        }
+        return tot;
+    }
+    int multiply(const Variable* lv, const fe* lc, size_t ln, const Variable* rv, const fe* rc, size_t rn, Variable out[3]) override {   // :103-133
+        fe l = eval(lv, lc, ln), r = eval(rv, rc, rn);
+        fe o = Fr::mul(l, r);
+        uint64_t i = a_L.size();
+        out[0] = {VAR_MUL_LEFT, i}; out[1] = {VAR_MUL_RIGHT, i}; out[2] = {VAR_MUL_OUT, i};
+        a_L.push_back(l); a_R.push_back(r); a_O.push_back(o);
+        fe minus_one = Fr::neg(Fr::one());
+        cs.push(lv, lc, ln, &out[0], &minus_one);
+        cs.push(rv, rc, rn, &out[1], &minus_one);
+        return BP_OK;
+    }
+    int allocate(const fe* assignment, Variable* out) override {                               // :135-157
+        if (!assignment) return BP_ERR_MISSING;
+        if (!has_pending) {
+            uint64_t i = a_L.size();
+            has_pending = true; pending = i;
+            a_L.push_back(*assignment); a_R.push_back(Fr::zero()); a_O.push_back(Fr::zero());
+            *out = {VAR_MUL_LEFT, i};
+        } else {
+            has_pending = false;
+            a_R[pending] = *assignment;
+            a_O[pending] = Fr::mul(a_L[pending], a_R[pending]);
+            *out = {VAR_MUL_RIGHT, pending};
+        }
+        return BP_OK;
+    }
+    int allocate_multiplier(const fe* l, const fe* r, Variable out[3]) override {               // :159-183
+        if (!l || !r) return BP_ERR_MISSING;
+        uint64_t i = a_L.size();
+        out[0] = {VAR_MUL_LEFT, i}; out[1] = {VAR_MUL_RIGHT, i}; out[2] = {VAR_MUL_OUT, i};
+        a_L.push_back(*l); a_R.push_back(*r); a_O.push_back(Fr::mul(*l, *r));
+        return BP_OK;
+    }
+    int constrain(const Variable* vv, const fe* c, size_t n) override { cs.push(vv, c, n); return BP_OK; }   // :189-193
+    size_t multipliers_len() const override { return a_L.size(); }
+    int challenge_scalar(const char* label, fe* out) override {                                 // :262-267
+        if (!randomizing) return BP_ERR_ARG;
+        *out = TP<C>::challenge_scalar(*transcript, label);
+        return BP_OK;
+    }
+    int specify_randomized_constraints(std::function<int(ConstraintSystemBase&)> cb) override { deferred.push_back(std::move(cb)); return BP_OK; }
+    // commit (prover.rs:327-341): V = v*B + v_blinding*B_blinding
+    int commit(const fe& val, const fe& blind, affine& V, Variable& var) {
+        uint64_t i = v.size();
+        v.push_back(val);
+        v_blinding.push_back(blind);
+        V = HC::add(HC::mul(gens->B, val), HC::mul(gens->B_blinding, blind));                   // generators.rs:39-44
+        TP<C>::append_point(*transcript, "V", V);
+        var = {VAR_COMMITTED, i};
+        return BP_OK;
+    }
+    int create_randomized_constraints() {                                                       // :418-441
+        has_pending = false;
+        if (deferred.empty()) {
+            transcript->append_message("dom-sep", (const uint8_t*)"r1cs-1phase", 11);
+        } else {
+            transcript->append_message("dom-sep", (const uint8_t*)"r1cs-2phase", 11);
+            auto cbs = std::move(deferred);
+            deferred.clear();
+            randomizing = true;
+            for (auto& cb : cbs)
+                if (int rc = cb(*this)) { randomizing = false; return rc; }
+            randomizing = false;
+        }
+        return BP_OK;
+    }
+
+    // three vector commitments over generators [off, off+cnt) in one batched MSM (prover.rs:516-559 / 604-649)
+    int commit_phase(size_t off, size_t cnt, const fe bl[3], const fe* d_aL, const fe* d_aR, const fe* d_aO, const fe* d_sL, const fe* d_sR,
+                     affine out[3]) {
+        fe* d_bl = ctx->small.as<fe>() + 16;
+        if (int rc = D::upload(ctx, d_bl, bl, 3 * sizeof(fe))) return rc;
+        const affine* Bb = gens->pc.template as<affine>() + 1;
+        const affine* G = gens->G.template as<affine>() + off;
+        const affine* H = gens->H.template as<affine>() + off;
+        MsmJob job;
+        job.add(Bb, d_bl, 1, 0); job.add(G, d_aL, cnt, 0); job.add(H, d_aR, cnt, 0);   // A_I
+        job.add(Bb, d_bl + 1, 1, 1); job.add(G, d_aO, cnt, 1);                          // A_O
+        job.add(Bb, d_bl + 2, 1, 2); job.add(G, d_sL, cnt, 2); job.add(H, d_sR, cnt, 2);   // S
+        uint8_t o[3][64];
+        int id[3];
+        if (int rc = msm_run_job<C>(ctx, job, o, id)) return rc;
+        for (int k = 0; k < 3; k++) memcpy(&out[k], o[k], 64);
+        return BP_OK;
+    }
+
+    // prove_and_return_transcript (prover.rs:454-831)
+    int prove(Rng& prng, ProofT<C>& proof) {
+        Transcript& t = *transcript;
+        cudaStream_t st = ctx->stream;
+        t.append_u64("m", v.size());                                                            // :466
+        std::vector<std::vector<uint8_t>> wit;
+        for (auto& vb : v_blinding) { std::vector<uint8_t> b(32); HC::scalar_to_bytes(vb, b.data()); wit.push_back(b); }
+        TranscriptRng rng = t.make_rng("v_blinding", wit, prng);                                // :483-494
+        size_t n1 = a_L.size();
+        if (gens->capacity < n1) return BP_ERR_GENS;                                            // :499-501
+        fe bl1[3];
+        for (int k = 0; k < 3; k++) bl1[k] = HC::scalar_rand(rng);                              // :506-508
+        std::vector<fe> s_L(n1), s_R(n1);
+        for (size_t i = 0; i < n1; i++) s_L[i] = HC::scalar_rand(rng);                          // :510-513
+        for (size_t i = 0; i < n1; i++) s_R[i] = HC::scalar_rand(rng);
+        BP_CUDA_TRY(ctx, ctx->small.reserve(4096));
+        // device vectors sized for phase 1; grown after the randomised phase
+        auto need = [&](size_t n_) -> int {
+            DevBuf* bufs[] = {&ctx->p_aL, &ctx->p_aR, &ctx->p_aO, &ctx->p_sL, &ctx->p_sR};
+            for (auto* b : bufs) BP_CUDA_TRY(ctx, b->reserve((n_ + 1) * sizeof(fe)));
+            return BP_OK;
+        };
+        if (int rc = need(n1)) return rc;
+        fe *d_aL = ctx->p_aL.as<fe>(), *d_aR = ctx->p_aR.as<fe>(), *d_aO = ctx->p_aO.as<fe>(), *d_sL = ctx->p_sL.as<fe>(), *d_sR = ctx->p_sR.as<fe>();
+        D::upload(ctx, d_aL, a_L.data(), n1 * sizeof(fe)); D::upload(ctx, d_aR, a_R.data(), n1 * sizeof(fe));
+        D::upload(ctx, d_aO, a_O.data(), n1 * sizeof(fe)); D::upload(ctx, d_sL, s_L.data(), n1 * sizeof(fe));
+        if (int rc = D::upload(ctx, d_sR, s_R.data(), n1 * sizeof(fe))) return rc;
+        affine c1[3];
+        if (int rc = commit_phase(0, n1, bl1, d_aL, d_aR, d_aO, d_sL, d_sR, c1)) return rc;
+        proof.A_I1 = c1[0]; proof.A_O1 = c1[1]; proof.S1 = c1[2];
+        TP<C>::append_point(t, "A_I1", proof.A_I1);                                             // :561-564
+        TP<C>::append_point(t, "A_O1", proof.A_O1);
+        TP<C>::append_point(t, "S1", proof.S1);
+        if (int rc = create_randomized_constraints()) return rc;                                // :567
+        size_t n = a_L.size(), n2 = n - n1, padded_n = next_pow2(n), pad = padded_n - n;
+        if (gens->capacity < padded_n) return BP_ERR_GENS;                                      // :577-579
+        fe bl2[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
+        if (n2 > 0) for (int k = 0; k < 3; k++) bl2[k] = HC::scalar_rand(rng);                   // :585-597
+        s_L.resize(n); s_R.resize(n);
+        for (size_t i = n1; i < n; i++) s_L[i] = HC::scalar_rand(rng);                          // :599-602
+        for (size_t i = n1; i < n; i++) s_R[i] = HC::scalar_rand(rng);
+        if (n2 > 0) {
+            // grow (contents of phase 1 are re-uploaded: the arena may move)
+            if (int rc = need(n)) return rc;
+            d_aL = ctx->p_aL.as<fe>(); d_aR = ctx->p_aR.as<fe>(); d_aO = ctx->p_aO.as<fe>(); d_sL = ctx->p_sL.as<fe>(); d_sR = ctx->p_sR.as<fe>();
+            D::upload(ctx, d_aL, a_L.data(), n * sizeof(fe)); D::upload(ctx, d_aR, a_R.data(), n * sizeof(fe));
+            D::upload(ctx, d_aO, a_O.data(), n * sizeof(fe)); D::upload(ctx, d_sL, s_L.data(), n * sizeof(fe));
+            if (int rc = D::upload(ctx, d_sR, s_R.data(), n * sizeof(fe))) return rc;
+            affine c2[3];
+            if (int rc = commit_phase(n1, n2, bl2, d_aL + n1, d_aR + n1, d_aO + n1, d_sL + n1, d_sR + n1, c2)) return rc;
+            proof.A_I2 = c2[0]; proof.A_O2 = c2[1]; proof.S2 = c2[2];
+        } else {
+            proof.A_I2 = proof.A_O2 = proof.S2 = HC::E::affine_identity();                      // :651-655
+        }
+        TP<C>::append_point(t, "A_I2", proof.A_I2);                                             // :658-661
+        TP<C>::append_point(t, "A_O2", proof.A_O2);
+        TP<C>::append_point(t, "S2", proof.S2);
+        fe y = TP<C>::challenge_scalar(t, "y"), z = TP<C>::challenge_scalar(t, "z");            // :665-667
+        std::vector<fe> wL, wR, wO, wV;
+        flatten<C>(cs, z, n, v.size(), wL, wR, wO, wV, nullptr);                                // :669
+        fe y_inv = Fr::inv(y);                                                                  // :675
+        // device: w vectors, power tables, l/r/t
+        DevBuf* wb[] = {&ctx->p_wL, &ctx->p_wR, &ctx->p_wO};
+        for (auto* b : wb) BP_CUDA_TRY(ctx, b->reserve((n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->p_ypow.reserve((padded_n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->p_yinv.reserve((padded_n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->p_l.reserve((padded_n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->p_r.reserve((padded_n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->p_Gf.reserve((padded_n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->p_Hf.reserve((padded_n + 1) * sizeof(fe)));
+        const int TP_BLOCKS = 296;
+        BP_CUDA_TRY(ctx, ctx->ipa_parts.reserve((size_t)(6 * TP_BLOCKS + 8) * sizeof(fe)));
+        D::upload(ctx, ctx->p_wL.p, wL.data(), n * sizeof(fe)); D::upload(ctx, ctx->p_wR.p, wR.data(), n * sizeof(fe));
+        if (int rc = D::upload(ctx, ctx->p_wO.p, wO.data(), n * sizeof(fe))) return rc;
+        if (int rc = D::pow_vec(ctx, y, ctx->p_ypow.as<fe>(), padded_n)) return rc;              // exp_iter(y), util.rs:35-58
+        if (int rc = D::pow_vec(ctx, y_inv, ctx->p_yinv.as<fe>(), padded_n)) return rc;          // :676-678
+        LrInputs in{d_aL, d_aR, d_aO, d_sL, d_sR, ctx->p_wL.as<fe>(), ctx->p_wR.as<fe>(), ctx->p_wO.as<fe>(), ctx->p_ypow.as<fe>(), ctx->p_yinv.as<fe>()};
+        fe tc[6];
+        for (auto& x : tc) x = Fr::zero();
+        if (n > 0) {
+            int blocks = (int)((n + 127) / 128);
+            if (blocks > TP_BLOCKS) blocks = TP_BLOCKS;
+            r1cs_tpoly_kernel<C><<<blocks, 128, 0, st>>>(in, n, ctx->ipa_parts.as<fe>());       // :684-703
+            BP_LAUNCH_CHECK(ctx);
+            fe* d_t = ctx->small.as<fe>() + 32;
+            vec_reduce_partials_kernel<C, 6><<<1, 128, 0, st>>>(ctx->ipa_parts.as<fe>(), blocks, d_t);
+            BP_LAUNCH_CHECK(ctx);
+            if (int rc = D::download(ctx, tc, d_t, 6 * sizeof(fe))) return rc;
+        }
+        fe tb[6];
+        tb[0] = HC::scalar_rand(rng);                                                           // t_1_blinding :705
+        for (int k = 2; k < 6; k++) tb[k] = HC::scalar_rand(rng);                               // t_3..t_6   :706-709
+        // T_i = t_i*B + tb_i*B_blinding for i in {1,3,4,5,6}: five 2-term MSMs in one batch (:711-715)
+        {
+            fe sc[10];
+            const int ids[5] = {0, 2, 3, 4, 5};
+            for (int k = 0; k < 5; k++) { sc[2 * k] = tc[ids[k]]; sc[2 * k + 1] = tb[ids[k]]; }
+            fe* d_sc = ctx->small.as<fe>() + 48;
+            if (int rc = D::upload(ctx, d_sc, sc, sizeof(sc))) return rc;
+            MsmJob job;
+            for (int k = 0; k < 5; k++) job.add(gens->pc.template as<affine>(), d_sc + 2 * k, 2, k);
+            uint8_t o[5][64];
+            int id[5];
+            if (int rc = msm_run_job<C>(ctx, job, o, id)) return rc;
+            affine* Ts[5] = {&proof.T_1, &proof.T_3, &proof.T_4, &proof.T_5, &proof.T_6};
+            for (int k = 0; k < 5; k++) memcpy(Ts[k], o[k], 64);
+        }
+        TP<C>::append_point(t, "T_1", proof.T_1); TP<C>::append_point(t, "T_3", proof.T_3);     // :717-722
+        TP<C>::append_point(t, "T_4", proof.T_4); TP<C>::append_point(t, "T_5", proof.T_5);
+        TP<C>::append_point(t, "T_6", proof.T_6);
+        fe u = TP<C>::challenge_scalar(t, "u"), x = TP<C>::challenge_scalar(t, "x");            // :724-725
+        tb[1] = Fr::zero();                                                                     // t_2_blinding :729-733
+        for (size_t i = 0; i < wV.size(); i++) tb[1] = Fr::add(tb[1], Fr::mul(v_blinding[i], wV[i]));
+        auto poly6 = [&](const fe* c) {                                                         // util.rs:107-109
+            fe acc = c[5];
+            for (int k = 4; k >= 0; k--) acc = Fr::add(c[k], Fr::mul(x, acc));
+            return Fr::mul(x, acc);
+        };
+        proof.t_x = poly6(tc);                                                                  // :744-745
+        proof.t_x_blinding = poly6(tb);
+        r1cs_lr_eval_kernel<C><<<(unsigned)((padded_n + 255) / 256), 256, 0, st>>>(in, n, padded_n, n1, x, u, ctx->p_l.as<fe>(), ctx->p_r.as<fe>(),
+                                                                                  ctx->p_Gf.as<fe>(), ctx->p_Hf.as<fe>());   // :746-756, :781-789
+        BP_LAUNCH_CHECK(ctx);
+        (void)pad;
+        fe i_bl = Fr::add(bl1[0], Fr::mul(u, bl2[0])), o_bl = Fr::add(bl1[1], Fr::mul(u, bl2[1])), s_bl = Fr::add(bl1[2], Fr::mul(u, bl2[2]));
+        proof.e_blinding = Fr::mul(x, Fr::add(i_bl, Fr::mul(x, Fr::add(o_bl, Fr::mul(x, s_bl)))));   // :758-762
+        TP<C>::append_scalar(t, "t_x", proof.t_x);                                              // :764-774
+        TP<C>::append_scalar(t, "t_x_blinding", proof.t_x_blinding);
+        TP<C>::append_scalar(t, "e_blinding", proof.e_blinding);
+        fe w = TP<C>::challenge_scalar(t, "w");                                                 // :777-779
+        affine Q = HC::mul(gens->B, w);
+        int rc = ipa_create<C>(ctx, t, Q, ctx->p_Gf.as<fe>(), ctx->p_Hf.as<fe>(), gens->G.template as<affine>(), gens->H.template as<affine>(),
+                               ctx->p_l.as<fe>(), ctx->p_r.as<fe>(), padded_n, proof.L_vec, proof.R_vec, proof.a, proof.b);   // :791-800
+        // secrets: zero the device copies (mirrors prover.rs:74-94,805-812)
+        DevBuf* sec[] = {&ctx->p_aL, &ctx->p_aR, &ctx->p_aO, &ctx->p_sL, &ctx->p_sR, &ctx->p_l, &ctx->p_r};
+        for (auto* b : sec) if (b->p) cudaMemsetAsync(b->p, 0, b->cap, st);
+        for (auto& s : s_L) s = Fr::zero();
+        for (auto& s : s_R) s = Fr::zero();
+        return rc;
+    }
+};
+
+// ---- Verifier (src/r1cs/verifier.rs) ------------------------------------------------------------
+template <class C>
+struct VerifierT : ConstraintSystemBase {
+    using HC = HostCurve<C>;
+    using Fr = HostFp<typename C::Fr>;
+    using D = Dev<C>;
+    bp_ctx* ctx;
+    Transcript* transcript;
+    size_t num_vars = 0;
+    std::vector<affine> V;
+    ConstraintStore cs;
+    std::vector<std::function<int(ConstraintSystemBase&)>> deferred;
+    bool has_pending = false, randomizing = false;
+    size_t pending = 0;
+
+    VerifierT(bp_ctx* c, Transcript* t) : ctx(c), transcript(t) { t->append_message("dom-sep", (const uint8_t*)"r1cs v1", 7); }   // :252-263
+    int multiply(const Variable* lv, const fe* lc, size_t ln, const Variable* rv, const fe* rc, size_t rn, Variable out[3]) override {   // :74-98
+        uint64_t i = num_vars++;
+        out[0] = {VAR_MUL_LEFT, i}; out[1] = {VAR_MUL_RIGHT, i}; out[2] = {VAR_MUL_OUT, i};
+        fe minus_one = Fr::neg(Fr::one());
+        cs.push(lv, lc, ln, &out[0], &minus_one);
+        cs.push(rv, rc, rn, &out[1], &minus_one);
+        return BP_OK;
+    }
+    int allocate(const fe*, Variable* out) override {                                           // :100-116
+        if (!has_pending) { uint64_t i = num_vars++; has_pending = true; pending = i; *out = {VAR_MUL_LEFT, i}; }
+        else { has_pending = false; *out = {VAR_MUL_RIGHT, pending}; }
+        return BP_OK;
+    }
+    int allocate_multiplier(const fe*, const fe*, Variable out[3]) override {                   // :118-137
+        uint64_t i = num_vars++;
+        out[0] = {VAR_MUL_LEFT, i}; out[1] = {VAR_MUL_RIGHT, i}; out[2] = {VAR_MUL_OUT, i};
+        return BP_OK;
+    }
+    int constrain(const Variable* vv, const fe* c, size_t n) override { cs.push(vv, c, n); return BP_OK; }
+    size_t multipliers_len() const override { return num_vars; }
+    int challenge_scalar(const char* label, fe* out) override {
+        if (!randomizing) return BP_ERR_ARG;
+        *out = TP<C>::challenge_scalar(*transcript, label);
+        return BP_OK;
+    }
+    int specify_randomized_constraints(std::function<int(ConstraintSystemBase&)> cb) override { deferred.push_back(std::move(cb)); return BP_OK; }
+    int commit(const affine& commitment, Variable& var) {                                       // :279-287
+        uint64_t i = V.size();
+        V.push_back(commitment);
+        TP<C>::append_point(*transcript, "V", commitment);
+        var = {VAR_COMMITTED, i};
+        return BP_OK;
+    }
+    int create_randomized_constraints() {                                                       // :353-376
+        has_pending = false;
+        if (deferred.empty()) {
+            transcript->append_message("dom-sep", (const uint8_t*)"r1cs-1phase", 11);
+        } else {
+            transcript->append_message("dom-sep", (const uint8_t*)"r1cs-2phase", 11);
+            auto cbs = std::move(deferred);
+            deferred.clear();
+            randomizing = true;
+            for (auto& cb : cbs)
+                if (int rc = cb(*this)) { randomizing = false; return rc; }
+            randomizing = false;
+        }
+        return BP_OK;
+    }
+
+    // Result of verification_scalars (verifier.rs:394-541): g/h scalars stay on the device
+    // (d_g, d_h, padded_n each); head = [B, B_blinding] scalars; tail = scalars of
+    // A_I1..S2, V, T_1..T_6, L, R in the reference's order.
+    struct Scalars {
+        size_t padded_n = 0;
+        fe head[2];
+        std::vector<fe> tail;
+        DevBuf g, h;
+        ~Scalars() { g.release(); h.release(); }
+    };
+
+    int verification_scalars(const ProofT<C>& proof, const GensDev& gens, Scalars& out) {
+        Transcript& t = *transcript;
+        cudaStream_t st = ctx->stream;
+        t.append_u64("m", V.size());                                                            // :404
+        size_t n1 = num_vars;
+        if (TP<C>::validate_and_append_point(t, "A_I1", proof.A_I1)) return BP_ERR_VERIFY;      // :407-409
+        if (TP<C>::validate_and_append_point(t, "A_O1", proof.A_O1)) return BP_ERR_VERIFY;
+        if (TP<C>::validate_and_append_point(t, "S1", proof.S1)) return BP_ERR_VERIFY;
+        if (int rc = create_randomized_constraints()) return rc;                                // :412
+        size_t n = num_vars, padded_n = next_pow2(n);
+        if (gens.capacity < padded_n) return BP_ERR_GENS;                                       // :425-427
+        TP<C>::append_point(t, "A_I2", proof.A_I2);                                             // :430-432
+        TP<C>::append_point(t, "A_O2", proof.A_O2);
+        TP<C>::append_point(t, "S2", proof.S2);
+        fe y = TP<C>::challenge_scalar(t, "y"), z = TP<C>::challenge_scalar(t, "z");            // :434-436
+        if (TP<C>::validate_and_append_point(t, "T_1", proof.T_1)) return BP_ERR_VERIFY;        // :438-442
+        if (TP<C>::validate_and_append_point(t, "T_3", proof.T_3)) return BP_ERR_VERIFY;
+        if (TP<C>::validate_and_append_point(t, "T_4", proof.T_4)) return BP_ERR_VERIFY;
+        if (TP<C>::validate_and_append_point(t, "T_5", proof.T_5)) return BP_ERR_VERIFY;
+        if (TP<C>::validate_and_append_point(t, "T_6", proof.T_6)) return BP_ERR_VERIFY;
+        fe u = TP<C>::challenge_scalar(t, "u"), x = TP<C>::challenge_scalar(t, "x");            // :444-445
+        TP<C>::append_scalar(t, "t_x", proof.t_x);                                              // :447-457
+        TP<C>::append_scalar(t, "t_x_blinding", proof.t_x_blinding);
+        TP<C>::append_scalar(t, "e_blinding", proof.e_blinding);
+        fe w = TP<C>::challenge_scalar(t, "w");                                                 // :459
+        std::vector<fe> wL, wR, wO, wV;
+        fe wc;
+        flatten<C>(cs, z, n, V.size(), wL, wR, wO, wV, &wc);                                    // :462
+        // InnerProductProof::verification_scalars (inner_product_proof.rs:244-314), host part
+        size_t lg_n = proof.L_vec.size();
+        if (lg_n >= 32 || proof.R_vec.size() != lg_n || padded_n != ((size_t)1 << lg_n)) return BP_ERR_VERIFY;   // :256-264
+        t.append_message("dom-sep", (const uint8_t*)"ipp v1", 6);
+        t.append_u64("n", padded_n);
+        std::vector<fe> ch(lg_n), ch_inv(lg_n);
+        for (size_t j = 0; j < lg_n; j++) {                                                     // :271-277
+            if (TP<C>::validate_and_append_point(t, "L", proof.L_vec[j])) return BP_ERR_VERIFY;
+            if (TP<C>::validate_and_append_point(t, "R", proof.R_vec[j])) return BP_ERR_VERIFY;
+            ch[j] = TP<C>::challenge_scalar(t, "u");
+        }
+        fe allinv = Fr::one();
+        for (size_t j = 0; j < lg_n; j++) {                                                     // batch_inversion leaves zeros (:283-288)
+            ch_inv[j] = Fr::is_zero(ch[j]) ? ch[j] : Fr::inv(ch[j]);
+            if (!Fr::is_zero(ch_inv[j])) allinv = Fr::mul(allinv, ch_inv[j]);
+        }
+        VerifyInputs vin;
+        for (size_t j = 0; j < lg_n; j++) { ch[j] = Fr::sqr(ch[j]); ch_inv[j] = Fr::sqr(ch_inv[j]); vin.usq[j] = ch[j]; }   // :292-296
+        const fe& a = proof.a;
+        const fe& b = proof.b;
+        fe y_inv = Fr::inv(y);                                                                  // :473
+        // device part: y^-i, g_scalars, h_scalars, delta
+        DevBuf* wb[] = {&ctx->p_wL, &ctx->p_wR, &ctx->p_wO};
+        for (auto* bf : wb) BP_CUDA_TRY(ctx, bf->reserve((n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->p_yinv.reserve((padded_n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, out.g.reserve((padded_n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, out.h.reserve((padded_n + 1) * sizeof(fe)));
+        const int VB = 296;
+        BP_CUDA_TRY(ctx, ctx->ipa_parts.reserve((size_t)(VB + 8) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->small.reserve(4096));
+        D::upload(ctx, ctx->p_wL.p, wL.data(), n * sizeof(fe)); D::upload(ctx, ctx->p_wR.p, wR.data(), n * sizeof(fe));
+        if (int rc = D::upload(ctx, ctx->p_wO.p, wO.data(), n * sizeof(fe))) return rc;
+        if (int rc = D::pow_vec(ctx, y_inv, ctx->p_yinv.as<fe>(), padded_n)) return rc;          // :474-476
+        vin.wL = ctx->p_wL.as<fe>(); vin.wR = ctx->p_wR.as<fe>(); vin.wO = ctx->p_wO.as<fe>(); vin.yinvpow = ctx->p_yinv.as<fe>();
+        vin.allinv = allinv; vin.x = x; vin.a = a; vin.b = b; vin.u = u; vin.lg_n = (int)lg_n;
+        int blocks = (int)((padded_n + 127) / 128);
+        if (blocks > VB) blocks = VB;
+        r1cs_verify_scalars_kernel<C><<<blocks, 128, 0, st>>>(vin, n, padded_n, n1, out.g.template as<fe>(), out.h.template as<fe>(), ctx->ipa_parts.as<fe>());
+        BP_LAUNCH_CHECK(ctx);
+        fe* d_delta = ctx->small.as<fe>() + 40;
+        vec_reduce_partials_kernel<C, 1><<<1, 128, 0, st>>>(ctx->ipa_parts.as<fe>(), blocks, d_delta);
+        BP_LAUNCH_CHECK(ctx);
+        fe delta;
+        if (int rc = D::download(ctx, &delta, d_delta, sizeof(fe))) return rc;
+        // r: challenge on a CLONE of the transcript (verifier.rs:516-519)
+        Transcript tc = t;
+        fe r = TP<C>::challenge_scalar(tc, "r");
+        fe xx = Fr::sqr(x), rxx = Fr::mul(r, xx), xxx = Fr::mul(x, xx);
+        out.padded_n = padded_n;
+        // scalars[0], scalars[1]  (:529-530)
+        out.head[0] = Fr::add(Fr::mul(w, Fr::sub(proof.t_x, Fr::mul(a, b))), Fr::mul(r, Fr::sub(Fr::mul(xx, Fr::add(wc, delta)), proof.t_x)));
+        out.head[1] = Fr::sub(Fr::neg(proof.e_blinding), Fr::mul(r, proof.t_x_blinding));
+        out.tail.clear();
+        out.tail.push_back(x); out.tail.push_back(xx); out.tail.push_back(xxx);                 // :533
+        out.tail.push_back(Fr::mul(u, x)); out.tail.push_back(Fr::mul(u, xx)); out.tail.push_back(Fr::mul(u, xxx));
+        for (auto& wVi : wV) out.tail.push_back(Fr::mul(wVi, rxx));                             // :534-536
+        out.tail.push_back(Fr::mul(r, x)); out.tail.push_back(Fr::mul(rxx, x)); out.tail.push_back(Fr::mul(rxx, xx));   // T_scalars :526
+        out.tail.push_back(Fr::mul(rxx, xxx)); out.tail.push_back(Fr::mul(Fr::mul(rxx, xx), xx));
+        for (auto& s : ch) out.tail.push_back(s);                                               // u_sq      :538
+        for (auto& s : ch_inv) out.tail.push_back(s);                                           // u_inv_sq  :539
+        return BP_OK;
+    }
+
+    void tail_points(const ProofT<C>& proof, std::vector<affine>& pts) const {                  // verifier.rs:579-588
+        const affine* p6[6] = {&proof.A_I1, &proof.A_O1, &proof.S1, &proof.A_I2, &proof.A_O2, &proof.S2};
+        for (auto p : p6) pts.push_back(*p);
+        for (auto& p : V) pts.push_back(p);
+        const affine* p5[5] = {&proof.T_1, &proof.T_3, &proof.T_4, &proof.T_5, &proof.T_6};
+        for (auto p : p5) pts.push_back(*p);
+        for (auto& p : proof.L_vec) pts.push_back(p);
+        for (auto& p : proof.R_vec) pts.push_back(p);
+    }
+
+    // verify_and_return_transcript (verifier.rs:559-600): one mega-MSM, accept iff identity
+    int verify(const ProofT<C>& proof, const GensDev& gens) {
+        Scalars sc;
+        if (int rc = verification_scalars(proof, gens, sc)) return rc;
+        std::vector<affine> pts;
+        tail_points(proof, pts);
+        const fe* dg = sc.g.template as<fe>();
+        const fe* dh = sc.h.template as<fe>();
+        return mega_check(ctx, gens, sc.head, dg, dh, sc.padded_n, pts, sc.tail);
+    }
+
+    static int mega_check(bp_ctx* ctx, const GensDev& gens, const fe head[2], const fe* d_g, const fe* d_h, size_t np,
+                          const std::vector<affine>& pts, const std::vector<fe>& tail) {
+        if (pts.size() != tail.size()) return BP_ERR_LEN;
+        BP_CUDA_TRY(ctx, ctx->v_pts.reserve((pts.size() + 1) * sizeof(affine)));
+        BP_CUDA_TRY(ctx, ctx->v_sc.reserve((tail.size() + 4) * sizeof(fe)));
+        fe* d_sc = ctx->v_sc.as<fe>();
+        D::upload(ctx, d_sc, head, 2 * sizeof(fe));
+        D::upload(ctx, d_sc + 2, tail.data(), tail.size() * sizeof(fe));
+        if (int rc = D::upload(ctx, ctx->v_pts.p, pts.data(), pts.size() * sizeof(affine))) return rc;
+        MsmJob job;
+        job.add(gens.pc.template as<affine>(), d_sc, 2, 0);
+        job.add(gens.G.template as<affine>(), d_g, np, 0);
+        job.add(gens.H.template as<affine>(), d_h, np, 0);
+        job.add(ctx->v_pts.as<affine>(), d_sc + 2, pts.size(), 0);
+        uint8_t o[1][64];
+        int id[1] = {0};
+        if (int rc = msm_run_job<C>(ctx, job, o, id)) return rc;
+        return id[0] ? BP_OK : BP_ERR_VERIFY;                                                   // :595-597
+    }
+};
+
+// ---- batch_verify (src/r1cs/verifier.rs:604-691) -------------------------------------------------
+template <class C>
+int batch_verify_t(bp_ctx* ctx, Rng& prng, std::vector<VerifierT<C>*>& verifiers, std::vector<const ProofT<C>*>& proofs, const GensDev& gens) {
+    using Fr = HostFp<typename C::Fr>;
+    using HC = HostCurve<C>;
+    using D = Dev<C>;
+    size_t k = verifiers.size();
+    if (proofs.size() != k) return BP_ERR_LEN;
+    std::vector<std::unique_ptr<typename VerifierT<C>::Scalars>> sc(k);
+    size_t max_n = 0;
+    for (size_t p = 0; p < k; p++) {                                                            // :617-627
+        sc[p].reset(new typename VerifierT<C>::Scalars());
+        if (int rc = verifiers[p]->verification_scalars(*proofs[p], gens, *sc[p])) return rc;
+        if (sc[p]->padded_n > max_n) max_n = sc[p]->padded_n;
+    }
+    DevBuf acc_g, acc_h;
+    struct Guard { DevBuf &a, &b; ~Guard() { a.release(); b.release(); } } guard{acc_g, acc_h};
+    BP_CUDA_TRY(ctx, acc_g.reserve((max_n + 1) * sizeof(fe)));
+    BP_CUDA_TRY(ctx, acc_h.reserve((max_n + 1) * sizeof(fe)));
+    BP_CUDA_TRY(ctx, cudaMemsetAsync(acc_g.p, 0, max_n * sizeof(fe), ctx->stream));             // :631-633
+    BP_CUDA_TRY(ctx, cudaMemsetAsync(acc_h.p, 0, max_n * sizeof(fe), ctx->stream));
+    fe head[2] = {Fr::zero(), Fr::zero()};
+    std::vector<affine> pts;
+    std::vector<fe> tail;
+    for (size_t p = 0; p < k; p++) {
+        fe alpha = HC::scalar_rand(prng);                                                       // :649
+        head[0] = Fr::add(head[0], Fr::mul(alpha, sc[p]->head[0]));                             // :652-653
+        head[1] = Fr::add(head[1], Fr::mul(alpha, sc[p]->head[1]));
+        size_t np = sc[p]->padded_n;
+        unsigned grid = (unsigned)((np + 255) / 256);
+        vec_scale_accum_kernel<C><<<grid, 256, 0, ctx->stream>>>(sc[p]->g.template as<fe>(), alpha, acc_g.as<fe>(), np);   // :655-664
+        BP_LAUNCH_CHECK(ctx);
+        vec_scale_accum_kernel<C><<<grid, 256, 0, ctx->stream>>>(sc[p]->h.template as<fe>(), alpha, acc_h.as<fe>(), np);
+        BP_LAUNCH_CHECK(ctx);
+        for (auto& s : sc[p]->tail) tail.push_back(Fr::mul(alpha, s));                          // :666-668
+        verifiers[p]->tail_points(*proofs[p], pts);                                             // :669-682
+    }
+    (void)sizeof(D);
+    return VerifierT<C>::mega_check(ctx, gens, head, acc_g.as<fe>(), acc_h.as<fe>(), max_n, pts, tail);   // :685-690
+}
+
+}  // namespace bp

@@ -1,0 +1,37 @@
+// Types shared by the templated host layer (r1cs.cuh) and the C ABI glue (capi.cu).
+#pragma once
+#include <functional>
+#include <vector>
+#include "ctx.cuh"
+
+namespace bp {
+
+enum VarKind : uint32_t { VAR_COMMITTED = 0, VAR_MUL_LEFT = 1, VAR_MUL_RIGHT = 2, VAR_MUL_OUT = 3, VAR_ONE = 4 };
+struct Variable { uint32_t kind; uint64_t idx; };
+
+// ---- device-resident generators (BulletproofGens share 0 + PedersenGens) ------------------------
+struct GensDev {
+    bp_ctx* ctx = nullptr;
+    size_t capacity = 0;
+    DevBuf G, H, pc;          // pc = [B, B_blinding]
+    affine B, B_blinding;
+    ~GensDev() { G.release(); H.release(); pc.release(); }
+};
+
+// ---- abstract interfaces for the C ABI ------------------------------------------------------------
+struct ProofBase {
+    virtual ~ProofBase() {}
+    virtual std::vector<uint8_t> to_bytes() const = 0;
+};
+struct ConstraintSystemBase {
+    virtual ~ConstraintSystemBase() {}
+    virtual int multiply(const Variable* lv, const fe* lc, size_t ln, const Variable* rv, const fe* rc, size_t rn, Variable out[3]) = 0;
+    virtual int allocate(const fe* assignment, Variable* out) = 0;
+    virtual int allocate_multiplier(const fe* l, const fe* r, Variable out[3]) = 0;
+    virtual int constrain(const Variable* v, const fe* c, size_t n) = 0;
+    virtual size_t multipliers_len() const = 0;
+    virtual int challenge_scalar(const char* label, fe* out) = 0;
+    virtual int specify_randomized_constraints(std::function<int(ConstraintSystemBase&)> cb) = 0;
+};
+
+}  // namespace bp

@@ -1,0 +1,297 @@
+// Scalar-vector and IPA kernels.
+//
+// Replaces the serial loops of the reference:
+//   src/inner_product_proof.rs:83-84,139-156,171-172,216-225  (inner products, a/b fold, G/H fold)
+//   src/inner_product_proof.rs:302-311                        (s-vector)
+//   src/r1cs/prover.rs:674-701,746-756,781-789                (l(x), r(x), t-poly, factors)
+//   src/r1cs/verifier.rs:473-514                              (verification scalars)
+//   src/util.rs:35-110                                        (exp_iter, VecPoly3, Poly6)
+// Scalars are Fr elements in Montgomery form (8 x u32), vectors are plain arrays in HBM.
+#pragma once
+#include "ctx.cuh"
+
+namespace bp {
+
+struct PowTable { fe p[32]; };   // p[k] = base^(2^k)
+
+template <class F>
+__device__ __forceinline__ fe pow_from_table(const PowTable& t, uint32_t e) {
+    fe r = F::one();
+    for (int k = 0; k < 32 && (e >> k); k++)
+        if ((e >> k) & 1u) r = F::mul(r, t.p[k]);
+    return r;
+}
+
+// out[i] = base^i
+template <class C>
+__global__ void __launch_bounds__(256) vec_pow_kernel(const __grid_constant__ PowTable t, fe* __restrict__ out, size_t n) {
+    using F = Fp<typename C::Fr>;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_fe(out + i, pow_from_table<F>(t, (uint32_t)i));
+}
+
+// block-wide sum of NV field elements per thread -> thread 0 holds the totals
+template <class F, int NV, int BLOCK>
+__device__ __forceinline__ void block_sum(fe (&v)[NV], fe* smem /* NV * BLOCK */) {
+    for (int k = 0; k < NV; k++) smem[k * BLOCK + threadIdx.x] = v[k];
+    __syncthreads();
+    for (int stride = BLOCK / 2; stride > 0; stride >>= 1) {
+        if ((int)threadIdx.x < stride)
+            for (int k = 0; k < NV; k++)
+                smem[k * BLOCK + threadIdx.x] = F::add(smem[k * BLOCK + threadIdx.x], smem[k * BLOCK + threadIdx.x + stride]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int k = 0; k < NV; k++) v[k] = smem[k * BLOCK];
+}
+
+// second stage: sums `nparts` rows of NV partials -> out[NV]
+template <class C, int NV>
+__global__ void __launch_bounds__(128) vec_reduce_partials_kernel(const fe* __restrict__ parts, int nparts, fe* __restrict__ out) {
+    using F = Fp<typename C::Fr>;
+    __shared__ fe sm[NV * 128];
+    fe v[NV];
+    for (int k = 0; k < NV; k++) v[k] = F::zero();
+    for (int r = threadIdx.x; r < nparts; r += 128)
+        for (int k = 0; k < NV; k++) v[k] = F::add(v[k], ld_fe_rw(parts + (size_t)r * NV + k));
+    block_sum<F, NV, 128>(v, sm);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < NV; k++) st_fe(out + k, v[k]);
+}
+
+// ---- IPA round preparation (inner_product_proof.rs:83-122 / 171-200) -----------------------------
+// With h = n/2:  sLG[i] = a[i]*gR_i, sLH[i] = b[h+i]*hL_i, sRG[i] = a[h+i]*gL_i, sRH[i] = b[i]*hR_i,
+// where (gL,gR,hL,hR) are Gf[i],Gf[h+i],Hf[i],Hf[h+i] in the first round and the uniform deferred
+// factors fG,fH afterwards; block partials of c_L = <a_L,b_R>, c_R = <a_R,b_L>.
+template <class C>
+__global__ void __launch_bounds__(128) ipa_prep_kernel(const fe* __restrict__ a, const fe* __restrict__ b, size_t h,
+                                                       const fe* __restrict__ Gf, const fe* __restrict__ Hf, fe fG, fe fH,
+                                                       fe* __restrict__ sLG, fe* __restrict__ sLH, fe* __restrict__ sRG,
+                                                       fe* __restrict__ sRH, fe* __restrict__ parts) {
+    using F = Fp<typename C::Fr>;
+    __shared__ fe sm[2 * 128];
+    fe acc[2] = {F::zero(), F::zero()};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < h; i += (size_t)gridDim.x * blockDim.x) {
+        fe aL = ld_fe_rw(a + i), aR = ld_fe_rw(a + h + i), bL = ld_fe_rw(b + i), bR = ld_fe_rw(b + h + i);
+        fe gL = fG, gR = fG, hL = fH, hR = fH;
+        if (Gf) { gL = ld_fe_rw(Gf + i); gR = ld_fe_rw(Gf + h + i); hL = ld_fe_rw(Hf + i); hR = ld_fe_rw(Hf + h + i); }
+        st_fe(sLG + i, F::mul(aL, gR));
+        st_fe(sLH + i, F::mul(bR, hL));
+        st_fe(sRG + i, F::mul(aR, gL));
+        st_fe(sRH + i, F::mul(bL, hR));
+        acc[0] = F::add(acc[0], F::mul(aL, bR));
+        acc[1] = F::add(acc[1], F::mul(aR, bL));
+    }
+    block_sum<F, 2, 128>(acc, sm);
+    if (threadIdx.x == 0) { st_fe(parts + 2 * blockIdx.x, acc[0]); st_fe(parts + 2 * blockIdx.x + 1, acc[1]); }
+}
+
+// a[i] = a[i]*u + uinv*a[h+i] ; b[i] = b[i]*uinv + u*b[h+i]      (inner_product_proof.rs:140-141)
+template <class C>
+__global__ void __launch_bounds__(256) ipa_fold_scalars_kernel(fe* __restrict__ a, fe* __restrict__ b, size_t h, fe u, fe uinv) {
+    using F = Fp<typename C::Fr>;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h) return;
+    fe aL = ld_fe_rw(a + i), aR = ld_fe_rw(a + h + i), bL = ld_fe_rw(b + i), bR = ld_fe_rw(b + h + i);
+    st_fe(a + i, F::add(F::mul(aL, u), F::mul(uinv, aR)));
+    st_fe(b + i, F::add(F::mul(bL, uinv), F::mul(u, bR)));
+}
+
+struct ScalarBits { uint32_t w[8]; };   // canonical (non-Montgomery) little-endian limbs
+
+// Generator fold with one scalar shared by every thread (uniform control flow):
+//   out[i] = L[i] + kappa * R[i]   -> affine.
+// The deferred-factor form of inner_product_proof.rs:219-224: the reference computes
+// u^-1*G_L + u*G_R = u^-1 * (G_L + u^2*G_R); the common factor is carried as a scalar
+// (fG, fH) into the MSM scalars of the next round, so only one scalar multiplication per output
+// point remains. Threads [0,count) fold (L0,R0) with kappa0, threads [count,2*count) fold (L1,R1)
+// with kappa1 (G and H in one launch).
+template <class C>
+__global__ void __launch_bounds__(128) ipa_fold_points_uniform_kernel(const affine* __restrict__ L0, const affine* __restrict__ R0,
+                                                                      affine* __restrict__ out0, const affine* __restrict__ L1,
+                                                                      const affine* __restrict__ R1, affine* __restrict__ out1,
+                                                                      size_t count, const __grid_constant__ ScalarBits k0,
+                                                                      const __grid_constant__ ScalarBits k1) {
+    using E = SW<C>;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * count) return;
+    const bool second = t >= count;   // count is a multiple of the block size or the block is split; either way correct
+    size_t i = second ? t - count : t;
+    const affine* L = second ? L1 : L0;
+    const affine* R = second ? R1 : R0;
+    affine* out = second ? out1 : out0;
+    const ScalarBits& k = second ? k1 : k0;
+    affine pr = ld_affine(R + i);
+    xyzz acc = E::identity();
+    for (int limb = 7; limb >= 0; limb--) {
+        uint32_t w = k.w[limb];
+        for (int bit = 31; bit >= 0; bit--) {
+            acc = E::dbl(acc);
+            if ((w >> bit) & 1u) E::madd(acc, pr);
+        }
+    }
+    affine pl = ld_affine(L + i);
+    E::madd(acc, pl);
+    affine r = E::to_affine(acc);
+    st_fe(&out[i].x, r.x);
+    st_fe(&out[i].y, r.y);
+}
+
+// First-round fold with per-element factors (inner_product_proof.rs:143-155):
+//   out[i] = (cL*f[i]) * P[i] + (cR*f[h+i]) * P[h+i]      (joint double-and-add)
+// Threads [0,h) handle (P0,f0,cL0,cR0) = (G, G_factors, u^-1, u); threads [h,2h) handle H with
+// (H_factors, u, u^-1).
+template <class C>
+__global__ void __launch_bounds__(128) ipa_fold_points_joint_kernel(const affine* __restrict__ P0, const fe* __restrict__ f0, fe cL0, fe cR0,
+                                                                    affine* __restrict__ out0, const affine* __restrict__ P1,
+                                                                    const fe* __restrict__ f1, fe cL1, fe cR1, affine* __restrict__ out1,
+                                                                    size_t h) {
+    using E = SW<C>;
+    using Fr = Fp<typename C::Fr>;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * h) return;
+    const bool second = t >= h;
+    size_t i = second ? t - h : t;
+    const affine* P = second ? P1 : P0;
+    const fe* f = second ? f1 : f0;
+    affine* out = second ? out1 : out0;
+    fe sl = Fr::from_mont(Fr::mul(second ? cL1 : cL0, ld_fe_rw(f + i)));
+    fe sr = Fr::from_mont(Fr::mul(second ? cR1 : cR0, ld_fe_rw(f + h + i)));
+    affine pl = ld_affine(P + i), pr = ld_affine(P + h + i);
+    xyzz both = E::from_affine(pl);
+    E::madd(both, pr);
+    xyzz xl = E::from_affine(pl), xr = E::from_affine(pr);
+    xyzz acc = E::identity();
+    for (int limb = 7; limb >= 0; limb--) {
+        uint32_t wl = sl.v[limb], wr = sr.v[limb];
+        for (int bit = 31; bit >= 0; bit--) {
+            acc = E::dbl(acc);
+            uint32_t sel = ((wl >> bit) & 1u) | (((wr >> bit) & 1u) << 1);
+            if (sel) {
+                xyzz q = sel == 1 ? xl : sel == 2 ? xr : both;
+                E::add(acc, q);
+            }
+        }
+    }
+    affine r = E::to_affine(acc);
+    st_fe(&out[i].x, r.x);
+    st_fe(&out[i].y, r.y);
+}
+
+// ---- R1CS prover vector kernels (prover.rs:674-756) ----------------------------------------------
+struct LrInputs {
+    const fe *aL, *aR, *aO, *sL, *sR, *wL, *wR, *wO;   // length n
+    const fe *ypow, *yinvpow;                          // y^i, y^-i, length padded_n
+};
+
+// t-polynomial coefficients (util.rs:75-93): block partials of t1..t6
+template <class C>
+__global__ void __launch_bounds__(128) r1cs_tpoly_kernel(const __grid_constant__ LrInputs in, size_t n, fe* __restrict__ parts) {
+    using F = Fp<typename C::Fr>;
+    __shared__ fe sm[6 * 128];
+    fe t[6];
+    for (int k = 0; k < 6; k++) t[k] = F::zero();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        fe yp = ld_fe_rw(in.ypow + i), yi = ld_fe_rw(in.yinvpow + i);
+        fe l1 = F::add(ld_fe_rw(in.aL + i), F::mul(yi, ld_fe_rw(in.wR + i)));     // prover.rs:687
+        fe l2 = ld_fe_rw(in.aO + i);                                               // :689
+        fe l3 = ld_fe_rw(in.sL + i);                                               // :691
+        fe r0 = F::sub(ld_fe_rw(in.wO + i), yp);                                   // :693
+        fe r1 = F::add(F::mul(yp, ld_fe_rw(in.aR + i)), ld_fe_rw(in.wL + i));      // :695
+        fe r3 = F::mul(yp, ld_fe_rw(in.sR + i));                                   // :698
+        t[0] = F::add(t[0], F::mul(l1, r0));
+        t[1] = F::add(t[1], F::add(F::mul(l1, r1), F::mul(l2, r0)));
+        t[2] = F::add(t[2], F::add(F::mul(l2, r1), F::mul(l3, r0)));
+        t[3] = F::add(t[3], F::add(F::mul(l1, r3), F::mul(l3, r1)));
+        t[4] = F::add(t[4], F::mul(l2, r3));
+        t[5] = F::add(t[5], F::mul(l3, r3));
+    }
+    block_sum<F, 6, 128>(t, sm);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 6; k++) st_fe(parts + 6 * blockIdx.x + k, t[k]);
+}
+
+// l_vec = l(x), r_vec = r(x) with padding (util.rs:95-102, prover.rs:746-756), and the IPA factor
+// vectors G_factors = 1^{n1} || u^{..}, H_factors = y^-i * G_factors (prover.rs:781-789).
+template <class C>
+__global__ void __launch_bounds__(256) r1cs_lr_eval_kernel(const __grid_constant__ LrInputs in, size_t n, size_t padded_n, size_t n1,
+                                                           fe x, fe u, fe* __restrict__ l_vec, fe* __restrict__ r_vec,
+                                                           fe* __restrict__ Gf, fe* __restrict__ Hf) {
+    using F = Fp<typename C::Fr>;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= padded_n) return;
+    fe yp = ld_fe_rw(in.ypow + i), yi = ld_fe_rw(in.yinvpow + i);
+    fe l, r;
+    if (i < n) {
+        fe l1 = F::add(ld_fe_rw(in.aL + i), F::mul(yi, ld_fe_rw(in.wR + i)));
+        fe l2 = ld_fe_rw(in.aO + i);
+        fe l3 = ld_fe_rw(in.sL + i);
+        fe r0 = F::sub(ld_fe_rw(in.wO + i), yp);
+        fe r1 = F::add(F::mul(yp, ld_fe_rw(in.aR + i)), ld_fe_rw(in.wL + i));
+        fe r3 = F::mul(yp, ld_fe_rw(in.sR + i));
+        l = F::mul(x, F::add(l1, F::mul(x, F::add(l2, F::mul(x, l3)))));
+        r = F::add(r0, F::mul(x, F::add(r1, F::mul(x, F::mul(x, r3)))));
+    } else {
+        l = F::zero();
+        r = F::neg(yp);
+    }
+    st_fe(l_vec + i, l);
+    st_fe(r_vec + i, r);
+    fe g = i < n1 ? F::one() : u;
+    st_fe(Gf + i, g);
+    st_fe(Hf + i, F::mul(yi, g));
+}
+
+// ---- verifier scalars (verifier.rs:473-514, inner_product_proof.rs:302-311) -----------------------
+struct VerifyInputs {
+    const fe *wL, *wR, *wO;     // length n
+    const fe* yinvpow;          // length padded_n
+    fe usq[32];                 // u_j^2 in creation order (challenges_sq)
+    fe allinv, x, a, b, u;
+    int lg_n;
+};
+
+// s_i = allinv * prod_{j: bit j of i set} u_sq[lg_n-1-j]
+template <class F>
+__device__ __forceinline__ fe s_value(const VerifyInputs& in, uint32_t i) {
+    fe s = in.allinv;
+    for (int j = 0; j < in.lg_n; j++)
+        if ((i >> j) & 1u) s = F::mul(s, in.usq[in.lg_n - 1 - j]);
+    return s;
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) r1cs_verify_scalars_kernel(const __grid_constant__ VerifyInputs in, size_t n, size_t padded_n,
+                                                                  size_t n1, fe* __restrict__ g_scalars, fe* __restrict__ h_scalars,
+                                                                  fe* __restrict__ delta_parts) {
+    using F = Fp<typename C::Fr>;
+    __shared__ fe sm[128];
+    fe acc[1] = {F::zero()};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded_n; i += (size_t)gridDim.x * blockDim.x) {
+        fe yi = ld_fe_rw(in.yinvpow + i);
+        fe wl = F::zero(), wr = F::zero(), wo = F::zero();
+        if (i < n) { wl = ld_fe_rw(in.wL + i); wr = ld_fe_rw(in.wR + i); wo = ld_fe_rw(in.wO + i); }
+        fe yneg_wr = F::mul(wr, yi);                                                         // verifier.rs:477-482
+        acc[0] = F::add(acc[0], F::mul(yneg_wr, wl));                                         // delta, :484
+        fe si = s_value<F>(in, (uint32_t)i);
+        fe sinv = s_value<F>(in, (uint32_t)(padded_n - 1 - i));                               // 1/s_i = s_{n-1-i}
+        fe g = F::sub(F::mul(in.x, yneg_wr), F::mul(in.a, si));                               // :496
+        fe hh = F::sub(F::mul(yi, F::sub(F::add(F::mul(in.x, wl), wo), F::mul(in.b, sinv))), F::one());   // :512
+        if (i >= n1) { g = F::mul(in.u, g); hh = F::mul(in.u, hh); }
+        st_fe(g_scalars + i, g);
+        st_fe(h_scalars + i, hh);
+    }
+    block_sum<F, 1, 128>(acc, sm);
+    if (threadIdx.x == 0) st_fe(delta_parts + blockIdx.x, acc[0]);
+}
+
+// out[i] = alpha * in[i]  (+ accumulate into acc[i] if acc != nullptr)      (verifier.rs:650-664)
+template <class C>
+__global__ void __launch_bounds__(256) vec_scale_accum_kernel(const fe* __restrict__ in, fe alpha, fe* __restrict__ acc, size_t n) {
+    using F = Fp<typename C::Fr>;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_fe(acc + i, F::add(ld_fe_rw(acc + i), F::mul(alpha, ld_fe_rw(in + i))));
+}
+
+}  // namespace bp

@@ -84,6 +84,112 @@ int bp_points_sum(bp_ctx* ctx, const uint8_t* points_xy, size_t n, uint8_t out_x
  * synthetic MSM workloads. */
 int bp_synth_points_device(bp_ctx* ctx, void* d_out_xy, size_t n, uint64_t start);
 
+
+/* =====================================================================================================
+ * Handle-based mirror of the crate's public API. A Rust shim keeps its `Prover` / `Verifier` /
+ * `BulletproofGens` types as thin wrappers around these handles.
+ * ===================================================================================================== */
+typedef struct bp_transcript bp_transcript; /* merlin::Transcript */
+typedef struct bp_rng bp_rng;               /* rand_core::RngCore + CryptoRng */
+typedef struct bp_gens bp_gens;             /* PedersenGens + BulletproofGens (party 0), resident in HBM */
+typedef struct bp_cs bp_cs;                 /* trait ConstraintSystem (src/r1cs/constraint_system.rs:19-135) */
+typedef struct bp_prover bp_prover;         /* r1cs::Prover   (src/r1cs/prover.rs:30-45) */
+typedef struct bp_verifier bp_verifier;     /* r1cs::Verifier (src/r1cs/verifier.rs:34-58) */
+typedef struct bp_proof bp_proof;           /* r1cs::R1CSProof (src/r1cs/proof.rs:25-59) */
+
+/* r1cs::Variable (src/r1cs/linear_combination.rs:14-27) */
+enum bp_var_kind { BP_VAR_COMMITTED = 0, BP_VAR_MUL_LEFT = 1, BP_VAR_MUL_RIGHT = 2, BP_VAR_MUL_OUT = 3, BP_VAR_ONE = 4 };
+typedef struct { uint32_t kind; uint32_t reserved; uint64_t index; } bp_var;
+/* one (Variable, coeff) term of a LinearCombination (src/r1cs/linear_combination.rs:85-88) */
+typedef struct { bp_var var; uint8_t coeff[32]; } bp_term;
+
+/* ---- merlin::Transcript (same STROBE schedule; src/transcript.rs uses append_message / challenge_bytes) */
+bp_transcript* bp_transcript_new(const uint8_t* label, size_t len);
+bp_transcript* bp_transcript_clone(const bp_transcript* t);
+void bp_transcript_free(bp_transcript* t);
+void bp_transcript_append_message(bp_transcript* t, const uint8_t* label, size_t llen, const uint8_t* msg, size_t mlen);
+void bp_transcript_append_u64(bp_transcript* t, const uint8_t* label, size_t llen, uint64_t v);
+void bp_transcript_challenge_bytes(bp_transcript* t, const uint8_t* label, size_t llen, uint8_t* out, size_t n);
+/* TranscriptProtocol::challenge_scalar (src/transcript.rs:95-101); out = Montgomery scalar */
+int bp_transcript_challenge_scalar(int curve, bp_transcript* t, const uint8_t* label, size_t llen, uint8_t out[32]);
+
+/* ---- RNGs: rand_chacha::ChaCha20Rng::from_seed, or the caller's own RngCore through callbacks */
+bp_rng* bp_rng_chacha20(const uint8_t seed[32]);
+bp_rng* bp_rng_from_callbacks(void* user, uint64_t (*next_u64)(void*), uint32_t (*next_u32)(void*),
+                              void (*fill_bytes)(void*, uint8_t*, size_t));
+void bp_rng_free(bp_rng* r);
+uint64_t bp_rng_words_used(const bp_rng* r);
+/* `ScalarField::rand(rng)` (ark-ff UniformRand); out = Montgomery scalar */
+int bp_rng_scalar(int curve, bp_rng* r, uint8_t out[32]);
+
+/* ---- ark-serialize canonical forms (src/transcript.rs:69-79, src/r1cs/proof.rs:74-91) */
+int bp_scalar_to_bytes(int curve, const uint8_t mont[32], uint8_t out[32]);
+int bp_scalar_from_bytes(int curve, const uint8_t in[32], uint8_t mont[32]);
+int bp_point_compress(int curve, const uint8_t xy[64], uint8_t out[33]);
+int bp_point_serialize_uncompressed(int curve, const uint8_t xy[64], uint8_t out[65]);
+int bp_point_decompress(int curve, const uint8_t in[33], uint8_t xy[64]);
+
+/* ---- generators: PedersenGens::default() + BulletproofGens::new(capacity, 1)
+ * (src/generators.rs:47-66,174-221). bp_gens_generate_host needs no GPU (pure host generation);
+ * bp_gens_create generates and uploads; bp_gens_from_points uploads tables the caller already has
+ * (a Rust shim passes the crate's own G_vec[0] / H_vec[0]). */
+int bp_gens_generate_host(int curve, size_t capacity, uint8_t* G_xy, uint8_t* H_xy, uint8_t B[64], uint8_t B_blinding[64]);
+int bp_gens_create(bp_ctx* ctx, size_t capacity, bp_gens** out);
+int bp_gens_from_points(bp_ctx* ctx, const uint8_t B[64], const uint8_t B_blinding[64], const uint8_t* G_xy, const uint8_t* H_xy,
+                        size_t capacity, bp_gens** out);
+void bp_gens_free(bp_gens* g);
+size_t bp_gens_capacity(const bp_gens* g);
+/* which: 0 = G, 1 = H, 2 = [B, B_blinding] */
+int bp_gens_export(const bp_gens* g, int which, size_t offset, size_t count, uint8_t* out_xy);
+/* PedersenGens::commit (src/generators.rs:39-44) */
+int bp_pedersen_commit(const bp_gens* g, const uint8_t value[32], const uint8_t blinding[32], uint8_t out_xy[64]);
+
+/* ---- ConstraintSystem / RandomizableConstraintSystem / RandomizedConstraintSystem
+ * (src/r1cs/constraint_system.rs:19-135; prover.rs:96-268; verifier.rs:69-240).
+ * Assignments are Montgomery scalars; pass NULL where the verifier passes None. */
+int bp_cs_multiply(bp_cs* cs, const bp_term* left, size_t nl, const bp_term* right, size_t nr, bp_var out[3]);
+int bp_cs_allocate(bp_cs* cs, const uint8_t* assignment, bp_var* out);
+int bp_cs_allocate_multiplier(bp_cs* cs, const uint8_t* left, const uint8_t* right, bp_var out[3]);
+int bp_cs_constrain(bp_cs* cs, const bp_term* terms, size_t n);
+size_t bp_cs_multipliers_len(const bp_cs* cs);
+typedef int (*bp_randomized_cb)(bp_cs* cs, void* user);
+int bp_cs_specify_randomized_constraints(bp_cs* cs, bp_randomized_cb cb, void* user);
+int bp_cs_challenge_scalar(bp_cs* cs, const uint8_t* label, size_t llen, uint8_t out[32]);
+
+/* ---- Prover::new / commit / prove (src/r1cs/prover.rs:291,327,444) */
+int bp_prover_new(bp_ctx* ctx, const bp_gens* pc_gens, bp_transcript* transcript, bp_prover** out);
+void bp_prover_free(bp_prover* p);
+bp_cs* bp_prover_cs(bp_prover* p);
+int bp_prover_commit(bp_prover* p, const uint8_t value[32], const uint8_t blinding[32], uint8_t out_commitment[64], bp_var* out_var);
+/* Consumes the constraint system like `Prover::prove(self, prng, bp_gens)`; bp_gens are the ones
+ * given to bp_prover_new. BP_ERR_GENS when gens_capacity < padded multipliers. */
+int bp_prover_prove(bp_prover* p, bp_rng* prng, bp_proof** out);
+
+/* ---- Verifier::new / commit / verify (src/r1cs/verifier.rs:252,279,549) and batch_verify (:604) */
+int bp_verifier_new(bp_ctx* ctx, bp_transcript* transcript, bp_verifier** out);
+void bp_verifier_free(bp_verifier* v);
+bp_cs* bp_verifier_cs(bp_verifier* v);
+int bp_verifier_commit(bp_verifier* v, const uint8_t commitment[64], bp_var* out_var);
+int bp_verifier_verify(bp_verifier* v, const bp_proof* proof, const bp_gens* gens);
+int bp_batch_verify(bp_ctx* ctx, bp_rng* prng, bp_verifier* const* verifiers, const bp_proof* const* proofs, size_t n, const bp_gens* gens);
+
+/* ---- R1CSProof::{to_bytes, from_bytes} (src/r1cs/proof.rs:74-91). With out == NULL only *len is set. */
+void bp_proof_free(bp_proof* p);
+int bp_proof_to_bytes(const bp_proof* p, uint8_t* out, size_t cap, size_t* len);
+int bp_proof_from_bytes(int curve, const uint8_t* data, size_t len, bp_proof** out);
+bp_proof* bp_proof_clone(const bp_proof* p);
+/* Field access (tamper tests). which: 0 t_x, 1 t_x_blinding, 2 e_blinding, 3 ipp.a, 4 ipp.b (32 B, Montgomery);
+ * 10..20 = A_I1,A_O1,S1,A_I2,A_O2,S2,T_1,T_3,T_4,T_5,T_6; 100+j = L_j; 200+j = R_j (64 B affine). */
+int bp_proof_get_field(const bp_proof* p, int which, uint8_t* buf);
+int bp_proof_set_field(bp_proof* p, int which, const uint8_t* buf);
+size_t bp_proof_rounds(const bp_proof* p);
+
+/* ---- InnerProductProof::create (src/inner_product_proof.rs:37-239) over host buffers; n a power of two.
+ * out_L / out_R receive log2(n) affine points each. */
+int bp_ipa_create(bp_ctx* ctx, bp_transcript* transcript, const uint8_t Q[64], const uint8_t* G_factors, const uint8_t* H_factors,
+                  const uint8_t* G_xy, const uint8_t* H_xy, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out_L, uint8_t* out_R,
+                  uint8_t out_a[32], uint8_t out_b[32]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,3 +58,78 @@ def range_verifier(cv, com, nbits):
     var = v.commit(com)
     O.range_proof_gadget(v, var, None, nbits)
     return v
+
+
+# ---- deterministic case table shared by tests/golden/make_golden.py and the GPU parity tests ----
+def shuffle_values(k, seed):
+    import random
+    rnd = random.Random(seed)
+    inp = [rnd.randrange(1 << 64) for _ in range(k)]
+    out = list(inp)
+    rnd.shuffle(out)
+    return inp, out
+
+
+def prove_chain(cv, pc, bp, N, rng=None):
+    rng = rng or seed_a_rng()
+    x0, ks = O.chain_circuit_witness(cv, N)
+    p = O.Prover(cv, pc, O.Transcript(b"ChainCircuit"))
+    com, var = p.commit(x0, O.scalar_rand(cv, rng))
+    O.chain_circuit(p, var, N, ks, x0, cv.r)
+    return p.prove(rng, bp), com, ks
+
+
+def chain_verifier(cv, com, N, ks):
+    v = O.Verifier(cv, O.Transcript(b"ChainCircuit"))
+    var = v.commit(com)
+    O.chain_circuit(v, var, N, ks, None, cv.r)
+    return v
+
+
+GOLDEN_CASES = [
+    # (name, curve, kind, params)
+    ("v1_example", "secq256k1", "example", {}),
+    ("v2_shuffle3", "secq256k1", "shuffle_fixed", {"inp": [5, 9, 2], "out": [2, 5, 9]}),
+    ("v3_range8", "secq256k1", "range", {"value": 0xA5, "bits": 8}),
+    ("shuffle4", "secq256k1", "shuffle", {"k": 4, "seed": 4}),
+    ("shuffle7", "secq256k1", "shuffle", {"k": 7, "seed": 7}),
+    ("shuffle24", "secq256k1", "shuffle", {"k": 24, "seed": 24}),
+    ("shuffle42", "secq256k1", "shuffle", {"k": 42, "seed": 42}),
+    ("range63", "secq256k1", "range", {"value": (1 << 63) - 12345, "bits": 63}),
+    ("chain5", "secq256k1", "chain", {"N": 5}),
+    ("chain100", "secq256k1", "chain", {"N": 100}),
+    ("chain1000", "secq256k1", "chain", {"N": 1000}),
+    ("zorro_example", "zorro", "example", {}),
+    ("zorro_shuffle3", "zorro", "shuffle_fixed", {"inp": [5, 9, 2], "out": [2, 5, 9]}),
+    ("zorro_chain20", "zorro", "chain", {"N": 20}),
+]
+
+
+def oracle_prove_case(kind, params, cv, pc, bp):
+    """Returns (proof, [commitments])."""
+    if kind == "example":
+        proof, coms = prove_example(cv, pc, bp, 9)
+        return proof, coms
+    if kind in ("shuffle", "shuffle_fixed"):
+        inp, out = (params["inp"], params["out"]) if kind == "shuffle_fixed" else shuffle_values(params["k"], params["seed"])
+        proof, ic, oc = prove_shuffle(cv, pc, bp, inp, out)
+        return proof, ic + oc
+    if kind == "range":
+        proof, com = prove_range(cv, pc, bp, params["value"], params["bits"])
+        return proof, [com]
+    if kind == "chain":
+        proof, com, _ = prove_chain(cv, pc, bp, params["N"])
+        return proof, [com]
+    raise ValueError(kind)
+
+
+def gens_capacity(kind, params):
+    if kind == "example":
+        return 1
+    if kind == "shuffle_fixed":
+        return 8
+    if kind == "shuffle":
+        return 1 << (2 * params["k"] - 1).bit_length()
+    if kind == "range":
+        return 1 << (params["bits"] - 1).bit_length()
+    return 1 << (params["N"] - 1).bit_length()

@@ -1,0 +1,276 @@
+"""GPU parity of the IPA / R1CS prover / verifier / batch verifier (C ABI -> C++ host -> CUDA)
+against the CPU oracle: byte-identical proofs under the SEED-A RNG convention, proofs verify under
+the oracle's verifier, and accept/reject decisions match on valid and tampered proofs.
+Mirrors tests/r1cs_secq256k1.rs:131-475 and src/inner_product_proof.rs:407-553."""
+import hashlib
+import json
+import os
+import random
+
+import pytest
+
+import bp_oracle as O
+import oracle_cases as C
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "proofs.json")))
+
+
+@pytest.fixture(scope="module")
+def env():
+    from ark_bulletproofs_b200 import Context
+    from ark_bulletproofs_b200 import r1cs as R
+    ctxs, gens = {}, {}
+
+    def get(curve, cap):
+        if curve not in ctxs:
+            ctxs[curve] = Context(curve, 0)
+        key = (curve, cap)
+        if key not in gens:
+            gens[key] = R.Gens(ctxs[curve], cap)
+        return ctxs[curve], gens[key]
+    return get
+
+
+def seed_a():
+    from ark_bulletproofs_b200 import r1cs as R
+    return R.ChaChaRng(bytes(range(32)))
+
+
+def gpu_prove_case(R, ctx, gens, kind, params, curve):
+    cv = O.CURVES[curve]
+    rng = seed_a()
+    if kind == "example":
+        p = R.Prover(ctx, gens, R.Transcript(b"R1CSExampleGadget"))
+        cvs = [p.commit(v, rng.scalar(curve)) for v in (3, 4, 6, 1, 40)]
+        R.example_gadget(p, *[v for _, v in cvs], 9)
+        return p.prove(rng), [V for V, _ in cvs]
+    if kind in ("shuffle", "shuffle_fixed"):
+        inp, out = (params["inp"], params["out"]) if kind == "shuffle_fixed" else C.shuffle_values(params["k"], params["seed"])
+        t = R.Transcript(b"ShuffleProofTest")
+        t.append_message(b"dom-sep", b"ShuffleProof")
+        t.append_u64(b"k", len(inp))
+        p = R.Prover(ctx, gens, t)
+        ic = [p.commit(v, rng.scalar(curve)) for v in inp]
+        oc = [p.commit(v, rng.scalar(curve)) for v in out]
+        R.shuffle_gadget(p, [v for _, v in ic], [v for _, v in oc])
+        return p.prove(rng), [V for V, _ in ic] + [V for V, _ in oc]
+    if kind == "range":
+        p = R.Prover(ctx, gens, R.Transcript(b"RangeProofTest"))
+        com, var = p.commit(params["value"], rng.scalar(curve))
+        R.range_proof_gadget(p, var, params["value"], params["bits"])
+        return p.prove(rng), [com]
+    if kind == "chain":
+        x0, ks = O.chain_circuit_witness(cv, params["N"])
+        p = R.Prover(ctx, gens, R.Transcript(b"ChainCircuit"))
+        com, var = p.commit(x0, rng.scalar(curve))
+        R.chain_circuit(p, var, params["N"], ks, x0, cv.r)
+        return p.prove(rng), [com]
+    raise ValueError(kind)
+
+
+def gpu_verifier(R, ctx, kind, params, curve, coms):
+    cv = O.CURVES[curve]
+    if kind == "example":
+        v = R.Verifier(ctx, R.Transcript(b"R1CSExampleGadget"))
+        vs = [v.commit(V) for V in coms]
+        R.example_gadget(v, *vs, params.get("c2", 9))
+        return v
+    if kind in ("shuffle", "shuffle_fixed"):
+        k = len(coms) // 2
+        t = R.Transcript(b"ShuffleProofTest")
+        t.append_message(b"dom-sep", b"ShuffleProof")
+        t.append_u64(b"k", k)
+        v = R.Verifier(ctx, t)
+        iv = [v.commit(V) for V in coms[:k]]
+        ov = [v.commit(V) for V in coms[k:]]
+        R.shuffle_gadget(v, iv, ov)
+        return v
+    if kind == "range":
+        v = R.Verifier(ctx, R.Transcript(b"RangeProofTest"))
+        var = v.commit(coms[0])
+        R.range_proof_gadget(v, var, None, params["bits"])
+        return v
+    if kind == "chain":
+        _, ks = O.chain_circuit_witness(cv, params["N"])
+        v = R.Verifier(ctx, R.Transcript(b"ChainCircuit"))
+        var = v.commit(coms[0])
+        R.chain_circuit(v, var, params["N"], ks, None, cv.r)
+        return v
+    raise ValueError(kind)
+
+
+def oracle_verifier(kind, params, curve, coms):
+    cv = O.CURVES[curve]
+    if kind == "example":
+        v = O.Verifier(cv, O.Transcript(b"R1CSExampleGadget"))
+        vs = [v.commit(V) for V in coms]
+        O.example_gadget(v, *vs, params.get("c2", 9))
+        return v
+    if kind in ("shuffle", "shuffle_fixed"):
+        k = len(coms) // 2
+        return C.shuffle_verifier(cv, coms[:k], coms[k:])
+    if kind == "range":
+        return C.range_verifier(cv, coms[0], params["bits"])
+    _, ks = O.chain_circuit_witness(cv, params["N"])
+    return C.chain_verifier(cv, coms[0], params["N"], ks)
+
+
+def test_generators_on_device(env):
+    from ark_bulletproofs_b200 import r1cs as R
+    ctx, gens = env("secq256k1", 128)
+    cv = O.SECQ256K1
+    bp = O.BulletproofGens(cv, 128, 1)
+    pc = O.PedersenGens(cv)
+    assert gens.export(0, 0, 128) == bp.G(128) and gens.export(1, 0, 128) == bp.H(128)
+    assert gens.export(2, 0, 2) == [pc.B, pc.B_blinding]
+    assert gens.commit(5, 7) == pc.commit(5, 7)
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 32, 64])
+@pytest.mark.parametrize("factors", ["ones_geometric", "random"])
+def test_ipa_create_matches_oracle(env, n, factors):
+    from ark_bulletproofs_b200 import r1cs as R
+    cv = O.SECQ256K1
+    ctx, _ = env("secq256k1", 128)
+    bp = O.BulletproofGens(cv, 64, 1)
+    rnd = random.Random(n * 3 + len(factors))
+    Q = O.affine_rand(cv, O.ChaCha20Rng(hashlib.sha3_512(b"test point").digest()[:32]))   # inner_product_proof.rs:422-433
+    a = [rnd.randrange(cv.r) for _ in range(n)]
+    b = [rnd.randrange(cv.r) for _ in range(n)]
+    y_inv = rnd.randrange(1, cv.r)
+    if factors == "random":
+        Gf = [rnd.randrange(1, cv.r) for _ in range(n)]
+        Hf = [rnd.randrange(1, cv.r) for _ in range(n)]
+    else:
+        Gf = [1] * n
+        Hf = [pow(y_inv, i, cv.r) for i in range(n)]
+    want = O.ipa_create(cv, O.Transcript(b"innerproducttest"), Q, Gf, Hf, bp.G(n), bp.H(n), a, b)
+    L, Rv, ao, bo = R.ipa_create(ctx, R.Transcript(b"innerproducttest"), Q, Gf, Hf, bp.G(n), bp.H(n), a, b)
+    assert (L, Rv, ao, bo) == (want.L_vec, want.R_vec, want.a, want.b)
+    # and the proof verifies (make_ipp_*): P = <a,G> + <b*Hf,H> + <a,b>Q with Gf applied
+    c = O.inner_product(cv, a, b)
+    P = O.msm(cv, bp.G(n) + bp.H(n) + [Q], [x * g % cv.r for x, g in zip(a, Gf)] + [x * h % cv.r for x, h in zip(b, Hf)] + [c])
+    O.ipa_verify(cv, O.InnerProductProof(L, Rv, ao, bo), n, O.Transcript(b"innerproducttest"), Gf, Hf, P, Q, bp.G(n), bp.H(n))
+
+
+@pytest.mark.parametrize("name", [c[0] for c in C.GOLDEN_CASES])
+def test_golden_proofs_byte_identical(env, name):
+    from ark_bulletproofs_b200 import r1cs as R
+    g = GOLDEN[name]
+    curve, kind, params = g["curve"], g["kind"], g["params"]
+    cv = O.CURVES[curve]
+    ctx, gens = env(curve, max(g["gens_capacity"], 1))
+    proof, coms = gpu_prove_case(R, ctx, gens, kind, params, curve)
+    b = proof.to_bytes()
+    assert [O.ser_point(cv, V, True).hex() for V in coms] == g["commitments_hex"]
+    assert hashlib.sha256(b).hexdigest() == g["sha256"], "GPU proof bytes differ from the oracle's"
+    assert b.hex() == g["proof_hex"]
+    # the GPU verifier accepts it, also after a to_bytes/from_bytes round trip (tests/r1cs_secq256k1.rs:335-356)
+    gpu_verifier(R, ctx, kind, params, curve, coms).verify(proof, gens)
+    gpu_verifier(R, ctx, kind, params, curve, coms).verify(R.Proof.from_bytes(curve, b), gens)
+    # and the oracle's verifier accepts the GPU proof (small cases; pure Python)
+    if g["gens_capacity"] <= 128:
+        pc, bp = O.PedersenGens(cv), O.BulletproofGens(cv, max(g["gens_capacity"], 1), 1)
+        oracle_verifier(kind, params, curve, coms).verify(O.R1CSProof.from_bytes(cv, b), pc, bp)
+
+
+def test_appendix_b_hashes(env):
+    assert GOLDEN["v1_example"]["sha256"] == "765eaf6d94e0cd313db2691a02e39583483aa765bea4250d1b8032be830a83d5"
+    assert GOLDEN["v2_shuffle3"]["sha256"] == "a51ae53f5e0fac5dc5bb9d5f520615763e3e845b66b6c4179645b8c01ee32151"
+    assert GOLDEN["v3_range8"]["sha256"] == "d54cb874f445db631163dd4ce11056658f7bfdea5f9f88783af266c73bee658e"
+
+
+def test_reject_matrix(env):
+    """Wrong statements and tampered proofs are rejected exactly where the oracle rejects."""
+    from ark_bulletproofs_b200 import r1cs as R
+    curve = "secq256k1"
+    cv = O.SECQ256K1
+    ctx, gens = env(curve, 128)
+    # example gadget with the wrong constant (tests/r1cs_secq256k1.rs:347)
+    proof, coms = gpu_prove_case(R, ctx, gens, "example", {}, curve)
+    with pytest.raises(R.BpError) as e:
+        gpu_verifier(R, ctx, "example", {"c2": 10}, curve, coms).verify(proof, gens)
+    assert e.value.code == -7
+    # 4-bit range proof of 16 (tests/r1cs_secq256k1.rs:409)
+    proof, coms = gpu_prove_case(R, ctx, gens, "range", {"value": 16, "bits": 4}, curve)
+    with pytest.raises(R.BpError):
+        gpu_verifier(R, ctx, "range", {"bits": 4}, curve, coms).verify(proof, gens)
+    # tampering with every kind of field of a 2-phase proof
+    kind, params = "shuffle", {"k": 4, "seed": 4}
+    proof, coms = gpu_prove_case(R, ctx, gens, kind, params, curve)
+    gpu_verifier(R, ctx, kind, params, curve, coms).verify(proof, gens)
+    pc, bp = O.PedersenGens(cv), O.BulletproofGens(cv, 8, 1)
+    for which in (0, 1, 2, 3, 4):
+        bad = proof.clone()
+        bad.set_scalar(which, (bad.get_scalar(which) + 1) % cv.r)
+        with pytest.raises(R.BpError) as e:
+            gpu_verifier(R, ctx, kind, params, curve, coms).verify(bad, gens)
+        assert e.value.code == -7
+        with pytest.raises(O.R1CSError):
+            oracle_verifier(kind, params, curve, coms).verify(O.R1CSProof.from_bytes(cv, bad.to_bytes()), pc, bp)
+    other = O.pt_mul(cv, 999, cv.G)
+    for which in (10, 13, 16, 100, 201):
+        bad = proof.clone()
+        bad.set_point(which, other)
+        with pytest.raises(R.BpError):
+            gpu_verifier(R, ctx, kind, params, curve, coms).verify(bad, gens)
+    for which in (10, 16, 100):           # identity -> validate_and_append_point error (transcript.rs:81-93)
+        bad = proof.clone()
+        bad.set_point(which, None)
+        with pytest.raises(R.BpError):
+            gpu_verifier(R, ctx, kind, params, curve, coms).verify(bad, gens)
+    # insufficient generators -> InvalidGeneratorsLength (prover.rs:577-579, verifier.rs:425-427)
+    _, small = env(curve, 4)
+    with pytest.raises(R.BpError) as e:
+        gpu_verifier(R, ctx, kind, params, curve, coms).verify(proof, small)
+    assert e.value.code == -4
+    with pytest.raises(R.BpError) as e:
+        gpu_prove_case(R, ctx, small, kind, params, curve)
+    assert e.value.code == -4
+
+
+def test_batch_verify(env):
+    """tests/r1cs_secq256k1.rs:447-475: mixed sizes; any invalid member rejects the batch."""
+    from ark_bulletproofs_b200 import r1cs as R
+    curve = "secq256k1"
+    cv = O.SECQ256K1
+    ctx, gens = env(curve, 128)
+
+    def make(vals):
+        inst = []
+        for v, n in vals:
+            proof, coms = gpu_prove_case(R, ctx, gens, "range", {"value": v, "bits": n}, curve)
+            inst.append((gpu_verifier(R, ctx, "range", {"bits": n}, curve, coms), proof, coms, n))
+        return inst
+    good = [(0, 16), (3, 16), ((1 << 16) - 1, 16), (1 << 16, 32), (1 << 63, 64)]
+    inst = make(good)
+    R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), [(v, p) for v, p, _, _ in inst], gens)
+    # same decision as the oracle's batch_verify on the GPU-made proofs
+    pc, bp = O.PedersenGens(cv), O.BulletproofGens(cv, 64, 1)
+    oinst = [(C.range_verifier(cv, coms[0], n), O.R1CSProof.from_bytes(cv, p.to_bytes())) for _, p, coms, n in inst]
+    O.batch_verify(cv, O.ChaCha20Rng(bytes([5] * 32)), oinst, pc, bp)
+    bad = [(0, 16), (3, 16), (1 << 16, 16), (1 << 16, 32)]
+    inst = make(bad)
+    with pytest.raises(R.BpError) as e:
+        R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), [(v, p) for v, p, _, _ in inst], gens)
+    assert e.value.code == -7
+    R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), [], gens)     # empty batch: MSM of zero scalars -> accept
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 6])
+def test_kshuffle_sizes(env, k):
+    """tests/r1cs_secq256k1.rs:172-215 (k = 4,7,24,42 are golden cases above)."""
+    from ark_bulletproofs_b200 import r1cs as R
+    curve = "secq256k1"
+    cv = O.SECQ256K1
+    cap = 1 << (2 * k - 1).bit_length()
+    ctx, gens = env(curve, cap)
+    params = {"k": k, "seed": 100 + k}
+    proof, coms = gpu_prove_case(R, ctx, gens, "shuffle", params, curve)
+    gpu_verifier(R, ctx, "shuffle", params, curve, coms).verify(proof, gens)
+    pc, bp = O.PedersenGens(cv), O.BulletproofGens(cv, cap, 1)
+    inp, out = C.shuffle_values(k, 100 + k)
+    want, _, _ = C.prove_shuffle(cv, pc, bp, inp, out)
+    assert proof.to_bytes() == want.to_bytes(cv)
