@@ -56,6 +56,13 @@ class Context:
         names = ["digits", "sort", "accumulate", "partials", "reduce"]
         return {"ms": {n: ph[i] for i, n in enumerate(names)}, "c": c.value, "windows": w.value, "entries": e.value}
 
+    STAGES = ["rng", "commit", "flatten", "vec", "t_commit", "ipa", "ipa_msm", "ipa_fold", "ipa_host", "verify_scalars", "verify_msm", "upload"]
+
+    def last_stage_ms(self):
+        out = (ctypes.c_double * 16)()
+        self._check(self.lib.bp_ctx_last_stage_ms(self.h, out))
+        return {n: round(out[i], 4) for i, n in enumerate(self.STAGES)}
+
     def set_window(self, c: int):
         self._check(self.lib.bp_msm_set_window(self.h, c))
 

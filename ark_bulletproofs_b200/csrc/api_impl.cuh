@@ -142,6 +142,27 @@ struct ApiImpl {
     }
     static size_t proof_rounds(const void* p) { return static_cast<const ProofT<C>*>(p)->L_vec.size(); }
 
+    static int chain_circuit(ConstraintSystemBase* cs, const Variable* v0, size_t n, const uint8_t* ks, const uint8_t* x0) {
+        fe x = Fr::zero();
+        if (x0) x = ld(x0);
+        const fe one = Fr::one(), neg1 = Fr::neg(Fr::one());
+        Variable prev_o{0, 0};
+        for (size_t i = 0; i < n; i++) {
+            fe k = ld(ks + 32 * i);
+            Variable o[3];
+            if (int rc = cs->allocate_multiplier(x0 ? &x : nullptr, x0 ? &k : nullptr, o)) return rc;
+            Variable v2[2] = {o[1], {VAR_ONE, 0}};
+            fe c2[2] = {one, Fr::neg(k)};
+            if (int rc = cs->constrain(v2, c2, 2)) return rc;                 // R_i - k_i
+            Variable v3[2] = {o[0], i == 0 ? *v0 : prev_o};
+            fe c3[2] = {one, neg1};
+            if (int rc = cs->constrain(v3, c3, 2)) return rc;                 // L_i - (V | O_{i-1})
+            prev_o = o[2];
+            if (x0) x = Fr::mul(x, k);
+        }
+        return BP_OK;
+    }
+
     // ---- InnerProductProof::create over host buffers --------------------------------------------
     static int ipa_create_host(bp_ctx* ctx, Transcript* t, const uint8_t* Q, const uint8_t* Gf, const uint8_t* Hf, const uint8_t* G,
                                const uint8_t* H, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out_L, uint8_t* out_R,
@@ -171,7 +192,7 @@ struct ApiImpl {
             gens_generate_host, gens_create, gens_from_points, pedersen_commit, challenge_scalar, rng_scalar, scalar_to_bytes, scalar_from_bytes,
             point_compress, point_uncompressed, point_decompress, prover_new, prover_free, prover_cs, prover_commit, prover_prove, verifier_new,
             verifier_free, verifier_cs, verifier_commit, verifier_verify, batch_verify, proof_free, proof_to_bytes, proof_from_bytes, proof_clone,
-            proof_field, proof_rounds, ipa_create_host};
+            proof_field, proof_rounds, chain_circuit, ipa_create_host};
         return &api;
     }
 };

@@ -41,6 +41,7 @@ struct CurveApi {
     void* (*proof_clone)(const void*);
     int (*proof_field)(void*, int which, uint8_t* buf, int set);
     size_t (*proof_rounds)(const void*);
+    int (*chain_circuit)(ConstraintSystemBase*, const Variable* v0, size_t n, const uint8_t* ks, const uint8_t* x0);
     int (*ipa_create_host)(bp_ctx*, Transcript*, const uint8_t* Q, const uint8_t* Gf, const uint8_t* Hf, const uint8_t* G, const uint8_t* H,
                            const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out_L, uint8_t* out_R, uint8_t* out_a, uint8_t* out_b);
 };

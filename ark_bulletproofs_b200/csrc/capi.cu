@@ -72,6 +72,12 @@ int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* window
     return BP_OK;
 }
 
+int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]) {
+    if (!ctx || !out) return BP_ERR_ARG;
+    for (int i = 0; i < 16; i++) out[i] = ctx->stage_ms[i];
+    return BP_OK;
+}
+
 int bp_msm_set_window(bp_ctx* ctx, int c) {
     if (!ctx || c < 0 || c > 20 || c == 1 || c == 2) return BP_ERR_ARG;
     ctx->force_c = c;
@@ -193,6 +199,12 @@ bp_rng* bp_rng_from_callbacks(void* user, uint64_t (*next_u64)(void*), uint32_t 
 }
 void bp_rng_free(bp_rng* r) { delete r; }
 uint64_t bp_rng_words_used(const bp_rng* r) { return r && r->chacha ? r->chacha->words_used : 0; }
+int bp_rng_scalars(int curve, bp_rng* r, size_t n, uint8_t* out) {
+    const bp::CurveApi* api = bp::curve_api(curve);
+    if (!api || !r || (n && !out)) return BP_ERR_ARG;
+    for (size_t i = 0; i < n; i++) api->rng_scalar(r->r.get(), out + 32 * i);
+    return BP_OK;
+}
 int bp_rng_scalar(int curve, bp_rng* r, uint8_t out[32]) {
     const bp::CurveApi* api = bp::curve_api(curve);
     if (!api || !r) return BP_ERR_ARG;
@@ -305,6 +317,15 @@ int bp_cs_challenge_scalar(bp_cs* cs, const uint8_t* label, size_t llen, uint8_t
     int rc = cs->cs->challenge_scalar(lbl(label, llen).c_str(), &s);
     if (rc == BP_OK) memcpy(out, s.v, 32);
     return rc;
+}
+
+// Synthetic measurement circuit of SURVEY.md 8(d) config 2(i): the one-phase public-multiplier chain.
+//   (L_i,R_i,O_i) = allocate_multiplier((x_i,k_i)); constrain(R_i - k_i); constrain(L_0 - V) / constrain(L_i - O_{i-1}).
+// x0 == NULL builds the verifier's side. ks: n Montgomery scalars.
+int bp_cs_chain_circuit(bp_cs* cs, const bp_var* v0, size_t n, const uint8_t* ks, const uint8_t* x0) {
+    if (!cs || !v0 || (n && !ks)) return BP_ERR_ARG;
+    bp::Variable v{v0->kind, v0->index};
+    return bp::curve_api(cs->curve)->chain_circuit(cs->cs, &v, n, ks, x0);
 }
 
 // ---- prover ----

@@ -59,6 +59,8 @@ struct bp_ctx {
     bool timing = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // host wall-clock split of the last prove / verify (ms); see bp_ctx_last_stage_ms
+    double stage_ms[16] = {0};
     int last_c = 0, last_W = 0;
     size_t last_entries = 0;
 };

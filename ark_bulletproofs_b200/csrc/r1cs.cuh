@@ -12,6 +12,7 @@
 // proofs are byte-identical to the CPU oracle; all O(n) arithmetic runs in the kernels of
 // msm_kernels.cuh / vec_kernels.cuh on the context's stream.
 #pragma once
+#include <chrono>
 #include <functional>
 #include <memory>
 #include <vector>
@@ -84,6 +85,19 @@ struct TP {
     }
 };
 
+struct StageTimer {
+    bp_ctx* ctx;
+    std::chrono::steady_clock::time_point t0;
+    explicit StageTimer(bp_ctx* c) : ctx(c), t0(std::chrono::steady_clock::now()) { for (auto& x : c->stage_ms) x = 0; }
+    void lap(int i) {
+        auto t1 = std::chrono::steady_clock::now();
+        ctx->stage_ms[i] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+    }
+};
+enum { ST_RNG = 0, ST_COMMIT = 1, ST_FLATTEN = 2, ST_VEC = 3, ST_TCOMMIT = 4, ST_IPA = 5, ST_IPA_MSM = 6, ST_IPA_FOLD = 7, ST_IPA_HOST = 8,
+       ST_VSCALARS = 9, ST_VMSM = 10, ST_UPLOAD = 11 };
+
 // ---- device helpers -----------------------------------------------------------------------------
 template <class C>
 struct Dev {
@@ -149,7 +163,10 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
     const affine* curH = d_H;
     fe fG = Fr::one(), fH = Fr::one();
     bool first = true;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     while (n != 1) {
+        auto t_a = now();
         size_t h = n / 2;
         fe *sLG = s_all, *sLH = s_all + h, *sRG = s_all + 2 * h, *sRH = s_all + 3 * h;
         int blocks = (int)((h + 127) / 128);
@@ -169,6 +186,8 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
         uint8_t out[2][64];
         int ident[2];
         if (int rc = msm_run_job<C>(ctx, job, out, ident)) return rc;
+        auto t_b = now();
+        ctx->stage_ms[ST_IPA_MSM] += ms(t_a, t_b);
         affine Lp, Rp;
         memcpy(&Lp, out[0], 64);
         memcpy(&Rp, out[1], 64);
@@ -178,6 +197,8 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
         TP<C>::append_point(t, "R", Rp);
         fe u = TP<C>::challenge_scalar(t, "u");
         fe uinv = Fr::inv(u);                                            // u.inverse().unwrap()
+        auto t_c = now();
+        ctx->stage_ms[ST_IPA_HOST] += ms(t_b, t_c);
         ipa_fold_scalars_kernel<C><<<(unsigned)((h + 255) / 256), 256, 0, st>>>(d_a, d_b, h, u, uinv);
         BP_LAUNCH_CHECK(ctx);
         unsigned fgrid = (unsigned)((2 * h + 127) / 128);
@@ -193,6 +214,7 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
             fG = Fr::mul(fG, uinv);
             fH = Fr::mul(fH, u);
         }
+        if (ctx->timing) { cudaStreamSynchronize(st); ctx->stage_ms[ST_IPA_FOLD] += ms(t_c, now()); }
         curG = wG;
         curH = wH;
         first = false;
@@ -371,6 +393,7 @@ struct ProverT : ConstraintSystemBase {
     int prove(Rng& prng, ProofT<C>& proof) {
         Transcript& t = *transcript;
         cudaStream_t st = ctx->stream;
+        StageTimer tm(ctx);
         t.append_u64("m", v.size());                                                            // :466
         std::vector<std::vector<uint8_t>> wit;
         for (auto& vb : v_blinding) { std::vector<uint8_t> b(32); HC::scalar_to_bytes(vb, b.data()); wit.push_back(b); }
@@ -382,6 +405,7 @@ struct ProverT : ConstraintSystemBase {
         std::vector<fe> s_L(n1), s_R(n1);
         for (size_t i = 0; i < n1; i++) s_L[i] = HC::scalar_rand(rng);                          // :510-513
         for (size_t i = 0; i < n1; i++) s_R[i] = HC::scalar_rand(rng);
+        tm.lap(ST_RNG);
         BP_CUDA_TRY(ctx, ctx->small.reserve(4096));
         // device vectors sized for phase 1; grown after the randomised phase
         auto need = [&](size_t n_) -> int {
@@ -394,8 +418,10 @@ struct ProverT : ConstraintSystemBase {
         D::upload(ctx, d_aL, a_L.data(), n1 * sizeof(fe)); D::upload(ctx, d_aR, a_R.data(), n1 * sizeof(fe));
         D::upload(ctx, d_aO, a_O.data(), n1 * sizeof(fe)); D::upload(ctx, d_sL, s_L.data(), n1 * sizeof(fe));
         if (int rc = D::upload(ctx, d_sR, s_R.data(), n1 * sizeof(fe))) return rc;
+        tm.lap(ST_UPLOAD);
         affine c1[3];
         if (int rc = commit_phase(0, n1, bl1, d_aL, d_aR, d_aO, d_sL, d_sR, c1)) return rc;
+        tm.lap(ST_COMMIT);
         proof.A_I1 = c1[0]; proof.A_O1 = c1[1]; proof.S1 = c1[2];
         TP<C>::append_point(t, "A_I1", proof.A_I1);                                             // :561-564
         TP<C>::append_point(t, "A_O1", proof.A_O1);
@@ -408,6 +434,7 @@ struct ProverT : ConstraintSystemBase {
         s_L.resize(n); s_R.resize(n);
         for (size_t i = n1; i < n; i++) s_L[i] = HC::scalar_rand(rng);                          // :599-602
         for (size_t i = n1; i < n; i++) s_R[i] = HC::scalar_rand(rng);
+        tm.lap(ST_RNG);
         if (n2 > 0) {
             // grow (contents of phase 1 are re-uploaded: the arena may move)
             if (int rc = need(n)) return rc;
@@ -418,6 +445,7 @@ struct ProverT : ConstraintSystemBase {
             affine c2[3];
             if (int rc = commit_phase(n1, n2, bl2, d_aL + n1, d_aR + n1, d_aO + n1, d_sL + n1, d_sR + n1, c2)) return rc;
             proof.A_I2 = c2[0]; proof.A_O2 = c2[1]; proof.S2 = c2[2];
+            tm.lap(ST_COMMIT);
         } else {
             proof.A_I2 = proof.A_O2 = proof.S2 = HC::E::affine_identity();                      // :651-655
         }
@@ -427,6 +455,7 @@ struct ProverT : ConstraintSystemBase {
         fe y = TP<C>::challenge_scalar(t, "y"), z = TP<C>::challenge_scalar(t, "z");            // :665-667
         std::vector<fe> wL, wR, wO, wV;
         flatten<C>(cs, z, n, v.size(), wL, wR, wO, wV, nullptr);                                // :669
+        tm.lap(ST_FLATTEN);
         fe y_inv = Fr::inv(y);                                                                  // :675
         // device: w vectors, power tables, l/r/t
         DevBuf* wb[] = {&ctx->p_wL, &ctx->p_wR, &ctx->p_wO};
@@ -456,6 +485,7 @@ struct ProverT : ConstraintSystemBase {
             BP_LAUNCH_CHECK(ctx);
             if (int rc = D::download(ctx, tc, d_t, 6 * sizeof(fe))) return rc;
         }
+        tm.lap(ST_VEC);
         fe tb[6];
         tb[0] = HC::scalar_rand(rng);                                                           // t_1_blinding :705
         for (int k = 2; k < 6; k++) tb[k] = HC::scalar_rand(rng);                               // t_3..t_6   :706-709
@@ -474,6 +504,7 @@ struct ProverT : ConstraintSystemBase {
             affine* Ts[5] = {&proof.T_1, &proof.T_3, &proof.T_4, &proof.T_5, &proof.T_6};
             for (int k = 0; k < 5; k++) memcpy(Ts[k], o[k], 64);
         }
+        tm.lap(ST_TCOMMIT);
         TP<C>::append_point(t, "T_1", proof.T_1); TP<C>::append_point(t, "T_3", proof.T_3);     // :717-722
         TP<C>::append_point(t, "T_4", proof.T_4); TP<C>::append_point(t, "T_5", proof.T_5);
         TP<C>::append_point(t, "T_6", proof.T_6);
@@ -498,8 +529,12 @@ struct ProverT : ConstraintSystemBase {
         TP<C>::append_scalar(t, "e_blinding", proof.e_blinding);
         fe w = TP<C>::challenge_scalar(t, "w");                                                 // :777-779
         affine Q = HC::mul(gens->B, w);
+        tm.lap(ST_VEC);
+        double ipa_sub[3] = {ctx->stage_ms[ST_IPA_MSM], ctx->stage_ms[ST_IPA_FOLD], ctx->stage_ms[ST_IPA_HOST]};
+        (void)ipa_sub;
         int rc = ipa_create<C>(ctx, t, Q, ctx->p_Gf.as<fe>(), ctx->p_Hf.as<fe>(), gens->G.template as<affine>(), gens->H.template as<affine>(),
                                ctx->p_l.as<fe>(), ctx->p_r.as<fe>(), padded_n, proof.L_vec, proof.R_vec, proof.a, proof.b);   // :791-800
+        tm.lap(ST_IPA);
         // secrets: zero the device copies (mirrors prover.rs:74-94,805-812)
         DevBuf* sec[] = {&ctx->p_aL, &ctx->p_aR, &ctx->p_aO, &ctx->p_sL, &ctx->p_sR, &ctx->p_l, &ctx->p_r};
         for (auto* b : sec) if (b->p) cudaMemsetAsync(b->p, 0, b->cap, st);
@@ -688,13 +723,17 @@ struct VerifierT : ConstraintSystemBase {
 
     // verify_and_return_transcript (verifier.rs:559-600): one mega-MSM, accept iff identity
     int verify(const ProofT<C>& proof, const GensDev& gens) {
+        StageTimer tm(ctx);
         Scalars sc;
         if (int rc = verification_scalars(proof, gens, sc)) return rc;
+        tm.lap(ST_VSCALARS);
         std::vector<affine> pts;
         tail_points(proof, pts);
         const fe* dg = sc.g.template as<fe>();
         const fe* dh = sc.h.template as<fe>();
-        return mega_check(ctx, gens, sc.head, dg, dh, sc.padded_n, pts, sc.tail);
+        int rc = mega_check(ctx, gens, sc.head, dg, dh, sc.padded_n, pts, sc.tail);
+        tm.lap(ST_VMSM);
+        return rc;
     }
 
     static int mega_check(bp_ctx* ctx, const GensDev& gens, const fe head[2], const fe* d_g, const fe* d_h, size_t np,

@@ -114,6 +114,12 @@ class ChaChaRng:
         _chk(self.lib.bp_rng_scalar(codec.CURVE_IDS[curve], self.h, out))
         return codec.dec_fe(out.raw, codec.MODULI[curve][1])
 
+    def scalars_raw(self, curve: str, n: int) -> bytes:
+        """n successive ScalarField::rand draws as Montgomery bytes (32 B each)."""
+        out = ctypes.create_string_buffer(32 * max(n, 1))
+        _chk(self.lib.bp_rng_scalars(codec.CURVE_IDS[curve], self.h, n, out))
+        return out.raw[:32 * n]
+
     def __del__(self):
         if getattr(self, "h", None):
             self.lib.bp_rng_free(self.h)
@@ -202,6 +208,11 @@ class _CS:
         out = ctypes.create_string_buffer(32)
         _chk(self.lib.bp_cs_challenge_scalar(self.cs, label, len(label), out), "challenge_scalar")
         return codec.dec_fe(out.raw, self.r)
+
+    def chain_circuit_raw(self, v0, n: int, ks_raw: bytes, x0_raw=None):
+        """Native builder of the synthetic chain circuit (bp_cs_chain_circuit)."""
+        var = BpVar(v0[0], 0, v0[1])
+        _chk(self.lib.bp_cs_chain_circuit(self.cs, ctypes.byref(var), n, ks_raw, x0_raw), "chain_circuit")
 
     def specify_randomized_constraints(self, fn):
         outer = self

@@ -73,6 +73,11 @@ int bp_msm_device(bp_ctx* ctx, const void* d_bases_xy, const void* d_scalars, si
  * reduction + window sums; *c / *windows / *entries describe the Pippenger plan that ran. */
 int bp_ctx_set_timing(bp_ctx* ctx, int enable);
 int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* windows, uint64_t* entries);
+/* Host wall-clock split (ms) of the last bp_prover_prove / bp_verifier_verify on this context:
+ * 0 rng (TranscriptRng draws), 1 vector commitments, 2 flatten constraints, 3 l/r/t vector kernels,
+ * 4 T commitments, 5 IPA total, 6 IPA MSMs, 7 IPA folds (only with timing enabled), 8 IPA host
+ * (transcript, challenge inverse), 9 verification scalars, 10 mega-MSM, 11 uploads. */
+int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]);
 /* Force the Pippenger window width (0 = automatic); for parity tests and tuning. */
 int bp_msm_set_window(bp_ctx* ctx, int c);
 
@@ -121,6 +126,7 @@ void bp_rng_free(bp_rng* r);
 uint64_t bp_rng_words_used(const bp_rng* r);
 /* `ScalarField::rand(rng)` (ark-ff UniformRand); out = Montgomery scalar */
 int bp_rng_scalar(int curve, bp_rng* r, uint8_t out[32]);
+int bp_rng_scalars(int curve, bp_rng* r, size_t n, uint8_t* out); /* n successive ScalarField::rand draws */
 
 /* ---- ark-serialize canonical forms (src/transcript.rs:69-79, src/r1cs/proof.rs:74-91) */
 int bp_scalar_to_bytes(int curve, const uint8_t mont[32], uint8_t out[32]);
@@ -155,6 +161,10 @@ size_t bp_cs_multipliers_len(const bp_cs* cs);
 typedef int (*bp_randomized_cb)(bp_cs* cs, void* user);
 int bp_cs_specify_randomized_constraints(bp_cs* cs, bp_randomized_cb cb, void* user);
 int bp_cs_challenge_scalar(bp_cs* cs, const uint8_t* label, size_t llen, uint8_t out[32]);
+/* Synthetic measurement circuit: one-phase public-multiplier chain of n
+ * multipliers over the committed variable v0; ks = n Montgomery scalars; x0 = the prover's witness for
+ * v0 (NULL on the verifier's side). Equivalent to n allocate_multiplier + 2n constrain calls. */
+int bp_cs_chain_circuit(bp_cs* cs, const bp_var* v0, size_t n, const uint8_t* ks, const uint8_t* x0);
 
 /* ---- Prover::new / commit / prove (src/r1cs/prover.rs:291,327,444) */
 int bp_prover_new(bp_ctx* ctx, const bp_gens* pc_gens, bp_transcript* transcript, bp_prover** out);
