@@ -49,6 +49,7 @@ def load():
         "bp_ctx_set_timing": (i32, [vp, i32]),
         "bp_msm_last_phases": (i32, [vp, ctypes.POINTER(ctypes.c_float), pi32, pi32, pu64]),
         "bp_points_sum": (i32, [vp, vp, sz, vp, pi32]),
+        "bp_points_sum_curve": (i32, [i32, vp, sz, vp, pi32]),
         "bp_synth_points_device": (i32, [vp, vp, sz, u64]),
         "bp_transcript_new": (vp, [vp, sz]),
         "bp_transcript_clone": (vp, [vp]),

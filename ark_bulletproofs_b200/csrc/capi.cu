@@ -108,6 +108,11 @@ int bp_points_sum(bp_ctx* ctx, const uint8_t* points_xy, size_t n, uint8_t out_x
     return bp::host_points_sum(ctx->curve, points_xy, n, out_xy, out_is_identity);
 }
 
+int bp_points_sum_curve(int curve, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity) {
+    if (!out_xy || (n && !points_xy)) return BP_ERR_ARG;
+    return bp::host_points_sum(curve, points_xy, n, out_xy, out_is_identity);
+}
+
 int bp_synth_points_device(bp_ctx* ctx, void* d_out_xy, size_t n, uint64_t start) {
     if (!ctx || (n && !d_out_xy)) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));

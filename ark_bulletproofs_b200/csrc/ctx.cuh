@@ -47,11 +47,11 @@ struct bp_ctx {
     bp::DevBuf stage_bases, stage_scalars;
     // IPA / prover / verifier work buffers (r1cs.cuh)
     bp::DevBuf ipa_G, ipa_H, ipa_s, ipa_parts, small;
-    bp::DevBuf p_aL, p_aR, p_aO, p_sL, p_sR, p_wL, p_wR, p_wO, p_ypow, p_yinv, p_l, p_r, p_Gf, p_Hf, v_pts, v_sc;
+    bp::DevBuf p_aL, p_aR, p_aO, p_sL, p_sR, p_wL, p_wR, p_wO, p_ypow, p_yinv, p_l, p_r, p_Gf, p_Hf, v_pts, v_sc, v_g, v_h, v_accg, v_acch;
     template <class F> void for_each_buf(F f) {
         bp::DevBuf* all[] = {&keys_a, &keys_b, &vals_a, &vals_b, &cub_tmp, &buckets, &part_keys, &part_pts, &seg_out, &win_out, &result,
                              &stage_bases, &stage_scalars, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
-                             &p_wL, &p_wR, &p_wO, &p_ypow, &p_yinv, &p_l, &p_r, &p_Gf, &p_Hf, &v_pts, &v_sc};
+                             &p_wL, &p_wR, &p_wO, &p_ypow, &p_yinv, &p_l, &p_r, &p_Gf, &p_Hf, &v_pts, &v_sc, &v_g, &v_h, &v_accg, &v_acch};
         for (auto* b : all) f(b);
     }
     void* h_result = nullptr;   // pinned, BP_HOST_RESULT_BYTES

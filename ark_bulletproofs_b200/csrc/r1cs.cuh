@@ -616,8 +616,7 @@ struct VerifierT : ConstraintSystemBase {
         size_t padded_n = 0;
         fe head[2];
         std::vector<fe> tail;
-        DevBuf g, h;
-        ~Scalars() { g.release(); h.release(); }
+        fe *g = nullptr, *h = nullptr;   // context-owned device buffers (valid until the next verification_scalars)
     };
 
     int verification_scalars(const ProofT<C>& proof, const GensDev& gens, Scalars& out) {
@@ -673,8 +672,10 @@ struct VerifierT : ConstraintSystemBase {
         DevBuf* wb[] = {&ctx->p_wL, &ctx->p_wR, &ctx->p_wO};
         for (auto* bf : wb) BP_CUDA_TRY(ctx, bf->reserve((n + 1) * sizeof(fe)));
         BP_CUDA_TRY(ctx, ctx->p_yinv.reserve((padded_n + 1) * sizeof(fe)));
-        BP_CUDA_TRY(ctx, out.g.reserve((padded_n + 1) * sizeof(fe)));
-        BP_CUDA_TRY(ctx, out.h.reserve((padded_n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->v_g.reserve((padded_n + 1) * sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->v_h.reserve((padded_n + 1) * sizeof(fe)));
+        out.g = ctx->v_g.as<fe>();
+        out.h = ctx->v_h.as<fe>();
         const int VB = 296;
         BP_CUDA_TRY(ctx, ctx->ipa_parts.reserve((size_t)(VB + 8) * sizeof(fe)));
         BP_CUDA_TRY(ctx, ctx->small.reserve(4096));
@@ -685,7 +686,7 @@ struct VerifierT : ConstraintSystemBase {
         vin.allinv = allinv; vin.x = x; vin.a = a; vin.b = b; vin.u = u; vin.lg_n = (int)lg_n;
         int blocks = (int)((padded_n + 127) / 128);
         if (blocks > VB) blocks = VB;
-        r1cs_verify_scalars_kernel<C><<<blocks, 128, 0, st>>>(vin, n, padded_n, n1, out.g.template as<fe>(), out.h.template as<fe>(), ctx->ipa_parts.as<fe>());
+        r1cs_verify_scalars_kernel<C><<<blocks, 128, 0, st>>>(vin, n, padded_n, n1, out.g, out.h, ctx->ipa_parts.as<fe>());
         BP_LAUNCH_CHECK(ctx);
         fe* d_delta = ctx->small.as<fe>() + 40;
         vec_reduce_partials_kernel<C, 1><<<1, 128, 0, st>>>(ctx->ipa_parts.as<fe>(), blocks, d_delta);
@@ -729,9 +730,7 @@ struct VerifierT : ConstraintSystemBase {
         tm.lap(ST_VSCALARS);
         std::vector<affine> pts;
         tail_points(proof, pts);
-        const fe* dg = sc.g.template as<fe>();
-        const fe* dh = sc.h.template as<fe>();
-        int rc = mega_check(ctx, gens, sc.head, dg, dh, sc.padded_n, pts, sc.tail);
+        int rc = mega_check(ctx, gens, sc.head, sc.g, sc.h, sc.padded_n, pts, sc.tail);
         tm.lap(ST_VMSM);
         return rc;
     }
@@ -762,40 +761,54 @@ template <class C>
 int batch_verify_t(bp_ctx* ctx, Rng& prng, std::vector<VerifierT<C>*>& verifiers, std::vector<const ProofT<C>*>& proofs, const GensDev& gens) {
     using Fr = HostFp<typename C::Fr>;
     using HC = HostCurve<C>;
-    using D = Dev<C>;
     size_t k = verifiers.size();
     if (proofs.size() != k) return BP_ERR_LEN;
-    std::vector<std::unique_ptr<typename VerifierT<C>::Scalars>> sc(k);
-    size_t max_n = 0;
-    for (size_t p = 0; p < k; p++) {                                                            // :617-627
-        sc[p].reset(new typename VerifierT<C>::Scalars());
-        if (int rc = verifiers[p]->verification_scalars(*proofs[p], gens, *sc[p])) return rc;
-        if (sc[p]->padded_n > max_n) max_n = sc[p]->padded_n;
-    }
-    DevBuf acc_g, acc_h;
-    struct Guard { DevBuf &a, &b; ~Guard() { a.release(); b.release(); } } guard{acc_g, acc_h};
-    BP_CUDA_TRY(ctx, acc_g.reserve((max_n + 1) * sizeof(fe)));
-    BP_CUDA_TRY(ctx, acc_h.reserve((max_n + 1) * sizeof(fe)));
-    BP_CUDA_TRY(ctx, cudaMemsetAsync(acc_g.p, 0, max_n * sizeof(fe), ctx->stream));             // :631-633
-    BP_CUDA_TRY(ctx, cudaMemsetAsync(acc_h.p, 0, max_n * sizeof(fe), ctx->stream));
+    // The shared G/H accumulators need max_n_padded up front (:613-627); it only depends on the
+    // constraint systems, not on the proofs' scalars, and the randomised phase can still add
+    // multipliers, so a first pass computes every proof's scalars exactly like the reference and
+    // the accumulators are grown on demand (a smaller proof simply leaves the tail untouched).
     fe head[2] = {Fr::zero(), Fr::zero()};
     std::vector<affine> pts;
     std::vector<fe> tail;
+    size_t max_n = 0, acc_n = 0;
     for (size_t p = 0; p < k; p++) {
-        fe alpha = HC::scalar_rand(prng);                                                       // :649
-        head[0] = Fr::add(head[0], Fr::mul(alpha, sc[p]->head[0]));                             // :652-653
-        head[1] = Fr::add(head[1], Fr::mul(alpha, sc[p]->head[1]));
-        size_t np = sc[p]->padded_n;
+        typename VerifierT<C>::Scalars sc;
+        if (int rc = verifiers[p]->verification_scalars(*proofs[p], gens, sc)) return rc;           // :619
+        size_t np = sc.padded_n;
+        if (np > max_n) max_n = np;
+        if (np > acc_n) {
+            // grow the accumulators, keeping what is already summed, zero-extending (:631-633)
+            size_t want = np;
+            DevBuf ng, nh;
+            BP_CUDA_TRY(ctx, ng.reserve((want + 1) * sizeof(fe)));
+            BP_CUDA_TRY(ctx, nh.reserve((want + 1) * sizeof(fe)));
+            BP_CUDA_TRY(ctx, cudaMemsetAsync(ng.p, 0, want * sizeof(fe), ctx->stream));
+            BP_CUDA_TRY(ctx, cudaMemsetAsync(nh.p, 0, want * sizeof(fe), ctx->stream));
+            if (acc_n) {
+                BP_CUDA_TRY(ctx, cudaMemcpyAsync(ng.p, ctx->v_accg.p, acc_n * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+                BP_CUDA_TRY(ctx, cudaMemcpyAsync(nh.p, ctx->v_acch.p, acc_n * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->v_accg.release(); ctx->v_acch.release();
+            ctx->v_accg = ng; ctx->v_acch = nh;
+            acc_n = want;
+        }
+        fe alpha = HC::scalar_rand(prng);                                                       // :649 (same draw order)
+        head[0] = Fr::add(head[0], Fr::mul(alpha, sc.head[0]));                                 // :652-653
+        head[1] = Fr::add(head[1], Fr::mul(alpha, sc.head[1]));
         unsigned grid = (unsigned)((np + 255) / 256);
-        vec_scale_accum_kernel<C><<<grid, 256, 0, ctx->stream>>>(sc[p]->g.template as<fe>(), alpha, acc_g.as<fe>(), np);   // :655-664
+        vec_scale_accum_kernel<C><<<grid, 256, 0, ctx->stream>>>(sc.g, alpha, ctx->v_accg.as<fe>(), np);   // :655-664
         BP_LAUNCH_CHECK(ctx);
-        vec_scale_accum_kernel<C><<<grid, 256, 0, ctx->stream>>>(sc[p]->h.template as<fe>(), alpha, acc_h.as<fe>(), np);
+        vec_scale_accum_kernel<C><<<grid, 256, 0, ctx->stream>>>(sc.h, alpha, ctx->v_acch.as<fe>(), np);
         BP_LAUNCH_CHECK(ctx);
-        for (auto& s : sc[p]->tail) tail.push_back(Fr::mul(alpha, s));                          // :666-668
+        for (auto& s : sc.tail) tail.push_back(Fr::mul(alpha, s));                              // :666-668
         verifiers[p]->tail_points(*proofs[p], pts);                                             // :669-682
     }
-    (void)sizeof(D);
-    return VerifierT<C>::mega_check(ctx, gens, head, acc_g.as<fe>(), acc_h.as<fe>(), max_n, pts, tail);   // :685-690
+    if (k == 0) {
+        BP_CUDA_TRY(ctx, ctx->v_accg.reserve(sizeof(fe)));
+        BP_CUDA_TRY(ctx, ctx->v_acch.reserve(sizeof(fe)));
+    }
+    return VerifierT<C>::mega_check(ctx, gens, head, ctx->v_accg.as<fe>(), ctx->v_acch.as<fe>(), max_n, pts, tail);   // :685-690
 }
 
 }  // namespace bp

@@ -117,6 +117,43 @@ def cpu_reference_run(lg_sample, steps, warmup, threads=None):
     return n / dt / 1e6, dt * 1e3, threads
 
 
+def r1cs_prove_verify(ctx, lg_n):
+    """Secondary metric of BASELINE.json: secq256k1 R1CS prove / verify ms on the synthetic one-phase
+    chain circuit with 2^lg_n multipliers, through the C ABI; the proof is
+    byte-identical to the CPU oracle's at the sizes the parity tests cover."""
+    from ark_bulletproofs_b200 import codec
+    from ark_bulletproofs_b200 import r1cs as R
+    N = 1 << lg_n
+    r = codec.MODULI[CURVE][1]
+    gens = R.Gens(ctx, N)
+    wit = R.ChaChaRng(bytes([3] * 32))
+    x0_raw = wit.scalars_raw(CURVE, 1)
+    ks_raw = wit.scalars_raw(CURVE, N)
+    best = None
+    for _ in range(3):
+        rng = R.ChaChaRng(bytes(range(32)))
+        p = R.Prover(ctx, gens, R.Transcript(b"ChainCircuit"))
+        com, var = p.commit(codec.dec_fe(x0_raw, r), rng.scalar(CURVE))
+        p.chain_circuit_raw(var, N, ks_raw, x0_raw)
+        t0 = time.perf_counter()
+        proof = p.prove(rng)
+        t_prove = (time.perf_counter() - t0) * 1e3
+        st_p = ctx.last_stage_ms()
+        v = R.Verifier(ctx, R.Transcript(b"ChainCircuit"))
+        vv = v.commit(com)
+        v.chain_circuit_raw(vv, N, ks_raw, None)
+        t0 = time.perf_counter()
+        v.verify(proof, gens)
+        t_verify = (time.perf_counter() - t0) * 1e3
+        st_v = ctx.last_stage_ms()
+        if best is None or t_prove < best["prove_ms"]:
+            best = {"circuit": "one-phase public-multiplier chain, 2^%d multipliers, m=1" % lg_n, "prove_ms": round(t_prove, 2),
+                    "verify_ms": round(t_verify, 2), "proof_bytes": len(proof.to_bytes()),
+                    "prove_stages_ms": {k: v_ for k, v_ in st_p.items() if v_}, "verify_stages_ms": {k: v_ for k, v_ in st_v.items() if v_},
+                    "note": "prove includes the serial TranscriptRng (8n Keccak-f on one host core, stage 'rng') that any byte-identical prover pays"}
+    return best
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -126,6 +163,7 @@ def main():
     ap.add_argument("--lg-n", type=int, default=24, help="log2 of the MSM size per GPU")
     ap.add_argument("--cpu-lg-n", type=int, default=0, help="log2 of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--r1cs-lg-n", type=int, default=16, help="log2 multipliers of the secondary R1CS prove/verify measurement (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,19 +215,13 @@ def main():
     h_pts.copy_(pts)
     h_sc.copy_(sc)
     torch.cuda.synchronize()
-    gather_buf = [torch.empty(68, dtype=torch.uint8, device="cuda") for _ in range(world)] if world > 1 else None
+    from ark_bulletproofs_b200.dist import allgather_sum_points
 
     def combine(raw, ident):
-        """all-gather the per-GPU partial points, add them on every rank."""
+        """all-gather the per-GPU partial points (NCCL), add them on every rank."""
         if world == 1:
             return raw, ident
-        mine = torch.frombuffer(bytearray(raw + bytes([1 if ident else 0, 0, 0, 0])), dtype=torch.uint8).cuda()
-        dist.all_gather(gather_buf, mine)
-        allb = b"".join(bytes(t.cpu().numpy().tobytes()[:64]) for t in gather_buf)
-        out = ctypes.create_string_buffer(64)
-        idn = ctypes.c_int(0)
-        ctx._check(ctx.lib.bp_points_sum(ctx.h, allb, world, out, ctypes.byref(idn)))
-        return out.raw, bool(idn.value)
+        return allgather_sum_points(CURVE, raw, ident, device=torch.device("cuda", local_rank))
 
     def step_device():
         return combine(*ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n))
@@ -277,6 +309,8 @@ def main():
                          "peak_source": hbm_src, "launch_ms": round(phases["ms"]["sort"], 4)},
         "phases_ms": {k: round(v, 4) for k, v in phases["ms"].items()},
     }
+    if world == 1 and args.r1cs_lg_n > 0:
+        line["r1cs"] = r1cs_prove_verify(ctx, args.r1cs_lg_n)
     if world == 1 and not args.no_cpu_baseline:
         ncores = os.cpu_count() or 1
         lg = args.cpu_lg_n or (20 if ncores >= 16 else 18)

@@ -84,6 +84,8 @@ int bp_msm_set_window(bp_ctx* ctx, int c);
 /* Sum of n affine points (host). Used to combine per-GPU partial MSM results after the
  * all-gather of SURVEY.md 8(e). */
 int bp_points_sum(bp_ctx* ctx, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity);
+/* Same without a context (pure host arithmetic on a handful of points). */
+int bp_points_sum_curve(int curve, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity);
 
 /* Fill d_out_xy (device, n*64 bytes) with the distinct points (start+i+1)*G, i < n, for
  * synthetic MSM workloads. */
