@@ -10,6 +10,10 @@
 // IMAD.WIDE.U32(.X) with predicate carries -- 128 wide multiplies + 8 for the quotients per
 // modmul (checked with cuobjdump; see profiles/).
 //
+// A 9 x 29-bit unsaturated variant (carry-free IMAD.WIDE into 64-bit columns, 135 multiplies) was
+// built and measured in round 1: 46 G modmul/s vs 66.5 for this one -- its ~250 ALU ops per
+// modmul saturate the ALU pipe, which on B200 is as narrow as the IMAD pipe.
+//
 // Every value handed between functions is fully reduced (< m): the secq256k1
 // moduli are within 2^129 of 2^256, so there are no spare bits for lazy reduction.
 //
@@ -206,6 +210,7 @@ struct Fp {
         final_sub(o, r, r[8]);
         return o;
     }
+
     BP_HD static fe sqr(const fe& a) { return mul(a, a); }
 
     BP_HD static fe one() {

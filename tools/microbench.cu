@@ -81,6 +81,15 @@ __global__ void k_fpmul(fe* out, const fe* in) {
     st_fe(out + blockIdx.x * blockDim.x + threadIdx.x, Fp<M>::add(x, y));
 }
 template <class M>
+__global__ void k_fpsqr(fe* out, const fe* in) {
+    fe x = ld_fe(in + threadIdx.x % 32), y = ld_fe(in + 32 + threadIdx.x % 32);
+    for (int i = 0; i < MITERS; i++) {
+        x = Fp<M>::sqr(x);
+        y = Fp<M>::sqr(y);
+    }
+    st_fe(out + blockIdx.x * blockDim.x + threadIdx.x, Fp<M>::add(x, y));
+}
+template <class M>
 __global__ void k_fpadd(fe* out, const fe* in) {
     fe x = ld_fe(in + threadIdx.x % 32), y = ld_fe(in + 32 + threadIdx.x % 32);
     for (int i = 0; i < MITERS * 8; i++) {
@@ -130,7 +139,7 @@ int main() {
     { affine h[64]; for (int i = 0; i < 64; i++) h[i] = g; cudaMemcpy(pin, h, sizeof(h), cudaMemcpyHostToDevice); }
     int blocks = sms * 8, threads = 256;
     double nthreads = (double)blocks * threads;
-    struct { const char* name; float ms; double ops; } r[16];
+    struct { const char* name; float ms; double ops; } r[24];
     int nr = 0;
     r[nr++] = {"imad_lo", timeit([&] { k_imad_lo<<<blocks, threads>>>((uint32_t*)out, 3, 5); }), nthreads * ITERS * 8};
     r[nr++] = {"imad_hi", timeit([&] { k_imad_hi<<<blocks, threads>>>((uint32_t*)out, 3, 5); }), nthreads * ITERS * 8};
@@ -145,6 +154,8 @@ int main() {
         r[nr] = {names[nr % 8], timeit([&] { k_fpmul<SecqFq><<<bl, t>>>((fe*)out, in); }), nt * MITERS * 2};
         nr++;
     }
+    r[nr++] = {"fpsqr_secqfq", timeit([&] { k_fpsqr<SecqFq><<<blocks, threads>>>((fe*)out, in); }), nthreads * MITERS * 2};
+    r[nr++] = {"fpmul_zorrofq", timeit([&] { k_fpmul<ZorroFq><<<blocks, threads>>>((fe*)out, in); }), nthreads * MITERS * 2};
     r[nr++] = {"fpmul_secqfr", timeit([&] { k_fpmul<SecqFr><<<blocks, threads>>>((fe*)out, in); }), nthreads * MITERS * 2};
     r[nr++] = {"fpaddsub_secqfq", timeit([&] { k_fpadd<SecqFq><<<blocks, threads>>>((fe*)out, in); }), nthreads * MITERS * 16};
     r[nr++] = {"madd_secq", timeit([&] { k_madd<<<sms * 8, 128>>>((xyzz*)out, pin); }), (double)sms * 8 * 128 * MITERS};
