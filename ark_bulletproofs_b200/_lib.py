@@ -96,6 +96,7 @@ def load():
         "bp_verifier_commit": (i32, [vp, vp, vp]),
         "bp_verifier_verify": (i32, [vp, vp, vp]),
         "bp_batch_verify": (i32, [vp, vp, vp, vp, sz, vp]),
+        "bp_batch_verify_partial": (i32, [vp, vp, vp, vp, sz, vp, vp, pi32]),
         "bp_proof_free": (None, [vp]),
         "bp_proof_to_bytes": (i32, [vp, vp, sz, psz]),
         "bp_proof_from_bytes": (i32, [i32, vp, sz, pvp]),

@@ -112,7 +112,25 @@ struct ApiImpl {
         std::vector<VerifierT<C>*> vs(n);
         std::vector<const ProofT<C>*> ps(n);
         for (size_t i = 0; i < n; i++) { vs[i] = static_cast<VerifierT<C>*>(verifiers[i]); ps[i] = static_cast<const ProofT<C>*>(proofs[i]); }
-        return batch_verify_t<C>(ctx, *rng, vs, ps, *g);
+        return batch_verify_t<C>(ctx, rng, nullptr, vs, ps, *g);
+    }
+    static int batch_verify_partial(bp_ctx* ctx, const uint8_t* alphas, void** verifiers, const void** proofs, size_t n, const GensDev* g,
+                                    uint8_t* out_xy, int* out_identity) {
+        std::vector<VerifierT<C>*> vs(n);
+        std::vector<const ProofT<C>*> ps(n);
+        std::vector<fe> al(n);
+        for (size_t i = 0; i < n; i++) {
+            vs[i] = static_cast<VerifierT<C>*>(verifiers[i]);
+            ps[i] = static_cast<const ProofT<C>*>(proofs[i]);
+            al[i] = ld(alphas + 32 * i);
+        }
+        affine sum;
+        int ident = 0;
+        int rc = batch_verify_t<C>(ctx, nullptr, al.data(), vs, ps, *g, &sum, &ident);
+        if (rc) return rc;
+        memcpy(out_xy, &sum, 64);
+        *out_identity = ident;
+        return BP_OK;
     }
     static void proof_free(void* p) { delete static_cast<ProofT<C>*>(p); }
     static int proof_to_bytes(const void* p, std::vector<uint8_t>& out) { out = static_cast<const ProofT<C>*>(p)->to_bytes(); return BP_OK; }
@@ -191,7 +209,7 @@ struct ApiImpl {
         static const CurveApi api = {
             gens_generate_host, gens_create, gens_from_points, pedersen_commit, challenge_scalar, rng_scalar, scalar_to_bytes, scalar_from_bytes,
             point_compress, point_uncompressed, point_decompress, prover_new, prover_free, prover_cs, prover_commit, prover_prove, verifier_new,
-            verifier_free, verifier_cs, verifier_commit, verifier_verify, batch_verify, proof_free, proof_to_bytes, proof_from_bytes, proof_clone,
+            verifier_free, verifier_cs, verifier_commit, verifier_verify, batch_verify, batch_verify_partial, proof_free, proof_to_bytes, proof_from_bytes, proof_clone,
             proof_field, proof_rounds, chain_circuit, ipa_create_host};
         return &api;
     }

@@ -35,6 +35,8 @@ struct CurveApi {
     int (*verifier_commit)(void*, const uint8_t* V, Variable* var);
     int (*verifier_verify)(void*, const void* proof, const GensDev*);
     int (*batch_verify)(bp_ctx*, Rng*, void** verifiers, const void** proofs, size_t n, const GensDev*);
+    int (*batch_verify_partial)(bp_ctx*, const uint8_t* alphas, void** verifiers, const void** proofs, size_t n, const GensDev*, uint8_t* out_xy,
+                                int* out_identity);
     void (*proof_free)(void*);
     int (*proof_to_bytes)(const void*, std::vector<uint8_t>& out);
     int (*proof_from_bytes)(const uint8_t*, size_t, void** out);
@@ -48,5 +50,6 @@ struct CurveApi {
 
 const CurveApi* curve_api_secq();
 const CurveApi* curve_api_zorro();
-inline const CurveApi* curve_api(int curve) { return curve == 0 ? curve_api_secq() : curve == 1 ? curve_api_zorro() : nullptr; }
+const CurveApi* curve_api_c25519();
+inline const CurveApi* curve_api(int curve) { return curve == 0 ? curve_api_secq() : curve == 1 ? curve_api_zorro() : curve == 2 ? curve_api_c25519() : nullptr; }
 }  // namespace bp

@@ -400,6 +400,20 @@ int bp_batch_verify(bp_ctx* ctx, bp_rng* rng, bp_verifier* const* verifiers, con
     return bp::curve_api(ctx->curve)->batch_verify(ctx, rng->r.get(), vs.data(), ps.data(), n, gens->g);
 }
 
+int bp_batch_verify_partial(bp_ctx* ctx, const uint8_t* alphas, bp_verifier* const* verifiers, const bp_proof* const* proofs, size_t n,
+                            const bp_gens* gens, uint8_t out_xy[64], int* out_is_identity) {
+    if (!ctx || !gens || !out_xy || !out_is_identity || (n && (!verifiers || !proofs || !alphas))) return BP_ERR_ARG;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<void*> vs(n);
+    std::vector<const void*> ps(n);
+    for (size_t i = 0; i < n; i++) {
+        if (!verifiers[i] || !proofs[i] || verifiers[i]->curve != ctx->curve || proofs[i]->curve != ctx->curve) return BP_ERR_ARG;
+        vs[i] = verifiers[i]->impl;
+        ps[i] = proofs[i]->impl;
+    }
+    return bp::curve_api(ctx->curve)->batch_verify_partial(ctx, alphas, vs.data(), ps.data(), n, gens->g, out_xy, out_is_identity);
+}
+
 // ---- proofs ----
 void bp_proof_free(bp_proof* p) { if (p) { bp::curve_api(p->curve)->proof_free(p->impl); delete p; } }
 int bp_proof_to_bytes(const bp_proof* p, uint8_t* out, size_t cap, size_t* len) {

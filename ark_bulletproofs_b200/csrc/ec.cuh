@@ -180,6 +180,121 @@ struct SW {
     }
 };
 
+// ---- twisted Edwards, a = -1 (curve25519 as instantiated by tests/r1cs_curve25519.rs) -----------------
+// Extended coordinates (X:Y:Z:T), x = X/Z, y = Y/Z, T = XY/Z, stored in the same 128-byte slot as
+// XYZZ (fields x, y, zz, zzz = X, Y, Z, T). The unified addition law (add-2008-hwcd-3) is complete
+// for a = -1 (a square) and d a non-square, so there are no exceptional cases; "all zero" (Z = 0)
+// is accepted as an additional encoding of the identity so zero-initialised buckets work unchanged.
+// ABI: affine (x,y); the identity is (0,1) and, on input, also (0,0).
+template <class C, class F_ = Fp<typename C::Fq>>
+struct TE {
+    using F = F_;
+    BP_HD static fe d2() { fe r; for (int i = 0; i < 8; i++) r.v[i] = C::d2(i); return r; }
+    BP_HD static fe dcoef() { fe r; for (int i = 0; i < 8; i++) r.v[i] = C::b(i); return r; }
+    BP_HD static bool is_identity(const affine& p) { return F::is_zero(p.x) && (F::is_zero(p.y) || F::eq(p.y, F::one())); }
+    BP_HD static bool is_identity(const xyzz& p) { return F::is_zero(p.zz) || (F::is_zero(p.x) && F::eq(p.y, p.zz)); }
+    BP_HD static xyzz identity() {
+        xyzz r;
+        r.x = F::zero(); r.y = F::zero(); r.zz = F::zero(); r.zzz = F::zero();
+        return r;
+    }
+    BP_HD static affine affine_identity() {
+        affine r;
+        r.x = F::zero(); r.y = F::zero();
+        return r;
+    }
+    BP_HD static xyzz from_affine(const affine& p) {
+        if (is_identity(p)) return identity();
+        xyzz r;
+        r.x = p.x; r.y = p.y; r.zz = F::one(); r.zzz = F::mul(p.x, p.y);
+        return r;
+    }
+    BP_HD static affine neg(const affine& p) {
+        affine r;
+        r.x = F::neg(p.x); r.y = p.y;
+        return r;
+    }
+    BP_HD static xyzz neg(const xyzz& p) {
+        xyzz r = p;
+        r.x = F::neg(p.x); r.zzz = F::neg(p.zzz);
+        return r;
+    }
+    // dbl-2008-hwcd with a = -1: 4M + 4S
+    BP_HD static xyzz dbl(const xyzz& p) {
+        if (F::is_zero(p.zz)) return identity();
+        fe A = F::sqr(p.x), B = F::sqr(p.y), Cc = F::dbl(F::sqr(p.zz));
+        fe D = F::neg(A);
+        fe E = F::sub(F::sub(F::sqr(F::add(p.x, p.y)), A), B);
+        fe G = F::add(D, B), Fv = F::sub(G, Cc), H = F::sub(D, B);
+        xyzz r;
+        r.x = F::mul(E, Fv); r.y = F::mul(G, H); r.zzz = F::mul(E, H); r.zz = F::mul(Fv, G);
+        return r;
+    }
+    BP_HD static xyzz dbl_affine(const affine& p) { return dbl(from_affine(p)); }
+    // acc += q (both extended): add-2008-hwcd-3, 8M + 1 (2d)
+    BP_HD static void add(xyzz& acc, const xyzz& q) {
+        if (F::is_zero(q.zz)) return;
+        if (F::is_zero(acc.zz)) { acc = q; return; }
+        fe A = F::mul(F::sub(acc.y, acc.x), F::sub(q.y, q.x));
+        fe B = F::mul(F::add(acc.y, acc.x), F::add(q.y, q.x));
+        fe Cc = F::mul(F::mul(acc.zzz, d2()), q.zzz);
+        fe D = F::dbl(F::mul(acc.zz, q.zz));
+        fe E = F::sub(B, A), Fv = F::sub(D, Cc), G = F::add(D, Cc), H = F::add(B, A);
+        acc.x = F::mul(E, Fv); acc.y = F::mul(G, H); acc.zzz = F::mul(E, H); acc.zz = F::mul(Fv, G);
+    }
+    // acc += affine q: 9M (T2 = x2*y2 computed on the fly)
+    BP_HD static void madd(xyzz& acc, const affine& q) {
+        if (is_identity(q)) return;
+        if (F::is_zero(acc.zz)) { acc = from_affine(q); return; }
+        fe A = F::mul(F::sub(acc.y, acc.x), F::sub(q.y, q.x));
+        fe B = F::mul(F::add(acc.y, acc.x), F::add(q.y, q.x));
+        fe Cc = F::mul(F::mul(acc.zzz, d2()), F::mul(q.x, q.y));
+        fe D = F::dbl(acc.zz);
+        fe E = F::sub(B, A), Fv = F::sub(D, Cc), G = F::add(D, Cc), H = F::add(B, A);
+        acc.x = F::mul(E, Fv); acc.y = F::mul(G, H); acc.zzz = F::mul(E, H); acc.zz = F::mul(Fv, G);
+    }
+    BP_HD_NOINL static affine to_affine(const xyzz& p) {
+        if (is_identity(p)) return affine_identity();
+        fe zi = F::inv(p.zz);
+        affine r;
+        r.x = F::mul(p.x, zi);
+        r.y = F::mul(p.y, zi);
+        return r;
+    }
+    BP_HD_NOINL static xyzz mul_u32(const xyzz& p, uint32_t k) {
+        xyzz acc = identity();
+        int top = 31;
+        while (top >= 0 && !((k >> top) & 1u)) top--;
+        for (int bit = top; bit >= 0; bit--) {
+            acc = dbl(acc);
+            if ((k >> bit) & 1u) add(acc, p);
+        }
+        return acc;
+    }
+    BP_HD_NOINL static xyzz mul_scalar(const affine& p, const uint32_t* s) {
+        xyzz acc = identity();
+        for (int i = 7; i >= 0; i--) {
+            for (int bit = 31; bit >= 0; bit--) {
+                acc = dbl(acc);
+                if ((s[i] >> bit) & 1u) madd(acc, p);
+            }
+        }
+        return acc;
+    }
+    BP_HD static bool on_curve(const affine& p) {
+        if (is_identity(p)) return true;
+        fe x2 = F::sqr(p.x), y2 = F::sqr(p.y);
+        fe lhs = F::sub(y2, x2);
+        fe rhs = F::add(F::one(), F::mul(dcoef(), F::mul(x2, y2)));
+        return F::eq(lhs, rhs);
+    }
+};
+
+// group law selected by the curve descriptor (consts.cuh: KIND 0 = short Weierstrass, 1 = twisted Edwards)
+template <class C, class F, int KIND> struct GroupLawSel { using type = SW<C, F>; };
+template <class C, class F> struct GroupLawSel<C, F, 1> { using type = TE<C, F>; };
+template <class C, class F = Fp<typename C::Fq>> using GroupLaw = typename GroupLawSel<C, F, C::KIND>::type;
+
 #if defined(__CUDACC__)
 __device__ __forceinline__ affine ld_affine(const affine* p) {
     affine r;

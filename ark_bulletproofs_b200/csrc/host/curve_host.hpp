@@ -16,8 +16,11 @@ template <class C>
 struct HostCurve {
     using Fq = HostFp<typename C::Fq>;
     using Fr = HostFp<typename C::Fr>;
-    using E = SW<C, Fq>;
-    static constexpr int POINT_COMPRESSED = 33, POINT_UNCOMPRESSED = 65;
+    using E = GroupLaw<C, Fq>;
+    static constexpr bool IS_TE = C::KIND == 1;
+    // ark-serialize sizes: SW 256-bit fields need a 33rd byte for the two flag bits; TE (255-bit field) packs
+    // its one flag into the top bit and has no flags in uncompressed form
+    static constexpr int POINT_COMPRESSED = IS_TE ? 32 : 33, POINT_UNCOMPRESSED = IS_TE ? 64 : 65;
 
     // ---- ark-ff Fp::rand: 4 x next_u64, shave, accept iff < modulus; raw = Montgomery repr ----
     template <class M>
@@ -50,21 +53,34 @@ struct HostCurve {
     static void scalar_to_bytes(const fe& a, uint8_t out[32]) { fe_to_bytes<Fr>(a, out); }
     static bool scalar_from_bytes(const uint8_t in[32], fe& out) { return fe_from_bytes<Fr>(in, out); }
 
-    // y > -y as canonical integers (ark SWFlags::from_y_coordinate)
+    // v > -v as canonical integers (ark SWFlags::from_y_coordinate / TEFlags::from_x_coordinate)
     static bool y_is_larger(const fe& y) {
         fe yc = Fq::from_mont(y), nc = Fq::from_mont(Fq::neg(y));
         return Fq::canonical_lt(nc, yc);
     }
-    static void point_uncompressed(const affine& p, uint8_t out[65]) {   // src/transcript.rs:75-79
-        if (E::is_identity(p)) { memset(out, 0, 65); out[64] = 0x40; return; }
-        fe_to_bytes<Fq>(p.x, out);
-        fe_to_bytes<Fq>(p.y, out + 32);
-        out[64] = y_is_larger(p.y) ? 0x80 : 0;
+    static affine te_identity() { affine r; r.x = Fq::zero(); r.y = Fq::one(); return r; }
+    static void point_uncompressed(const affine& p, uint8_t* out) {      // src/transcript.rs:75-79
+        if constexpr (IS_TE) {
+            affine q = E::is_identity(p) ? te_identity() : p;
+            fe_to_bytes<Fq>(q.x, out);
+            fe_to_bytes<Fq>(q.y, out + 32);
+        } else {
+            if (E::is_identity(p)) { memset(out, 0, 65); out[64] = 0x40; return; }
+            fe_to_bytes<Fq>(p.x, out);
+            fe_to_bytes<Fq>(p.y, out + 32);
+            out[64] = y_is_larger(p.y) ? 0x80 : 0;
+        }
     }
-    static void point_compressed(const affine& p, uint8_t out[33]) {     // src/r1cs/proof.rs:74-78
-        if (E::is_identity(p)) { memset(out, 0, 33); out[32] = 0x40; return; }
-        fe_to_bytes<Fq>(p.x, out);
-        out[32] = y_is_larger(p.y) ? 0x80 : 0;
+    static void point_compressed(const affine& p, uint8_t* out) {        // src/r1cs/proof.rs:74-78
+        if constexpr (IS_TE) {
+            affine q = E::is_identity(p) ? te_identity() : p;
+            fe_to_bytes<Fq>(q.y, out);
+            if (y_is_larger(q.x)) out[31] |= 0x80;
+        } else {
+            if (E::is_identity(p)) { memset(out, 0, 33); out[32] = 0x40; return; }
+            fe_to_bytes<Fq>(p.x, out);
+            out[32] = y_is_larger(p.y) ? 0x80 : 0;
+        }
     }
 
     static fe curve_b() { fe b; for (int i = 0; i < 8; i++) b.v[i] = C::b(i); return b; }
@@ -141,32 +157,74 @@ struct HostCurve {
         return true;
     }
 
-    // ark-ec `Affine::rand` for short Weierstrass (cofactor 1): x = Fq::rand, greatest = top bit
-    // of next_u32, retry until x^3+ax+b is a square (src/generators.rs:63,99,115)
+    // ark-ec TE get_point_from_y_unchecked(y, greatest): x^2 = (1 - y^2) / (a - d*y^2), a = -1
+    static bool point_from_y(const fe& y, bool greatest, affine& out) {
+        fe y2 = Fq::sqr(y);
+        fe num = Fq::sub(Fq::one(), y2);
+        fe den = Fq::sub(Fq::neg(Fq::one()), Fq::mul(curve_b(), y2));
+        if (Fq::is_zero(den)) return false;
+        fe x;
+        if (!fq_sqrt(Fq::mul(num, Fq::inv(den)), x)) return false;
+        fe nx = Fq::neg(x);
+        bool x_larger = y_is_larger(x);
+        out.x = (greatest == x_larger) ? x : nx;
+        out.y = y;
+        return true;
+    }
+
+    // ark-ec `Affine::rand`: SW: x = Fq::rand, greatest = top bit of next_u32, retry until on curve;
+    // TE: the same with y drawn and x recovered, then mul_by_cofactor (src/generators.rs:63,99,115)
     static affine affine_rand(Rng& rng) {
         while (true) {
-            fe x = fp_rand<typename C::Fq>(rng);
+            fe c0 = fp_rand<typename C::Fq>(rng);
             bool greatest = (rng.next_u32() >> 31) & 1;
             affine p;
-            if (point_from_x(x, greatest, p)) return p;
+            if constexpr (IS_TE) {
+                if (!point_from_y(c0, greatest, p)) continue;
+                xyzz acc = E::from_affine(p);
+                for (int k = 0; k < 3; k++) acc = E::dbl(acc);     // cofactor 8
+                affine r = E::to_affine(acc);
+                return E::is_identity(r) ? te_identity() : r;
+            } else {
+                if (point_from_x(c0, greatest, p)) return p;
+            }
         }
     }
 
-    // deserialize_compressed with validation (on curve; cofactor 1 => subgroup trivial)
-    static bool point_from_compressed(const uint8_t in[33], affine& out) {
-        uint8_t flags = in[32];
-        if (flags & 0x3F) return false;
-        uint64_t l[4];
-        memcpy(l, in, 32);
-        if (Fq::geq_m(l)) return false;
-        if (flags & 0x40) {
-            if (flags & 0x80) return false;
-            if (l[0] | l[1] | l[2] | l[3]) return false;
-            out = E::affine_identity();
+    // deserialize_compressed with validation (on curve, and in the prime-order subgroup for TE)
+    static bool point_from_compressed(const uint8_t* in, affine& out) {
+        if constexpr (IS_TE) {
+            uint8_t buf[32];
+            memcpy(buf, in, 32);
+            bool sign = (buf[31] & 0x80) != 0;
+            buf[31] &= 0x7F;
+            uint64_t l[4];
+            memcpy(l, buf, 32);
+            if (Fq::geq_m(l)) return false;
+            fe y = Fq::to_mont(Fq::put(l));
+            if (!point_from_y(y, sign, out)) return false;
+            // is_in_correct_subgroup_assuming_on_curve: r * P == 0
+            uint32_t rl[8];
+            for (int i = 0; i < 8; i++) rl[i] = C::Fr::m(i);
+            xyzz t = E::mul_scalar(out, rl);
+            if (!E::is_identity(t)) return false;
+            if (E::is_identity(out)) out = E::affine_identity();
             return true;
+        } else {
+            uint8_t flags = in[32];
+            if (flags & 0x3F) return false;
+            uint64_t l[4];
+            memcpy(l, in, 32);
+            if (Fq::geq_m(l)) return false;
+            if (flags & 0x40) {
+                if (flags & 0x80) return false;
+                if (l[0] | l[1] | l[2] | l[3]) return false;
+                out = E::affine_identity();
+                return true;
+            }
+            fe x = Fq::to_mont(Fq::put(l));
+            return point_from_x(x, (flags & 0x80) != 0, out);
         }
-        fe x = Fq::to_mont(Fq::put(l));
-        return point_from_x(x, (flags & 0x80) != 0, out);
     }
 
     // k*P with k a Montgomery-form scalar (mul_bigint(k.into_bigint())) -> affine

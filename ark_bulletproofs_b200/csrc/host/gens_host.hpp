@@ -85,10 +85,10 @@ struct GensHost {
     // PedersenGens::default()  (generators.rs:47-66)
     static void pedersen_default(affine& B, affine& B_blinding) {
         B = HC::generator();
-        uint8_t ser[65];
+        uint8_t ser[65] = {0};
         HC::point_uncompressed(B, ser);
         uint8_t h[64];
-        sha3_512(ser, 65, h);
+        sha3_512(ser, HC::POINT_UNCOMPRESSED, h);
         ChaCha20Rng rng(h);
         B_blinding = HC::affine_rand(rng);
     }

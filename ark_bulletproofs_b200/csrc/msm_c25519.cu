@@ -1,0 +1,7 @@
+// curve25519 (twisted Edwards; tests/r1cs_curve25519.rs) instantiation of the MSM kernels.
+#include "msm_kernels.cuh"
+namespace bp {
+template int msm_run<Curve25519>(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);
+template int msm_run_job<Curve25519>(bp_ctx*, const MsmJob&, uint8_t (*)[64], int*);
+template int synth_points_run<Curve25519>(bp_ctx*, void*, size_t, uint64_t);
+}  // namespace bp

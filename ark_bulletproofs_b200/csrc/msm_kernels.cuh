@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const __grid_constant__
 template <class C>
 __device__ __forceinline__ affine gather_point(const MsmJob& job, uint32_t v) {
     affine p = ld_affine(job.bases[(v >> 28) & 7u] + (v & MSM_IDX_MASK));
-    if (v >> 31) p.y = Fp<typename C::Fq>::neg(p.y);
+    if (v >> 31) p = GroupLaw<C>::neg(p);
     return p;
 }
 
@@ -139,7 +139,7 @@ __device__ __forceinline__ affine gather_point(const MsmJob& job, uint32_t v) {
 // A single-run chunk fills slot 1 with (key, identity) so the slot list stays dense and sorted.
 template <class C>
 struct RunSink {
-    using E = SW<C>;
+    using E = GroupLaw<C>;
     xyzz* buckets;
     uint32_t* out_keys;
     xyzz* out_pts;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
                                                              size_t M, int L, size_t T, const __grid_constant__ MsmJob job,
                                                              xyzz* __restrict__ buckets, uint32_t* __restrict__ out_keys,
                                                              xyzz* __restrict__ out_pts) {
-    using E = SW<C>;
+    using E = GroupLaw<C>;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     size_t s = t * (size_t)L;
@@ -208,7 +208,7 @@ template <class C>
 __global__ void __launch_bounds__(128) msm_partials_level_kernel(const uint32_t* __restrict__ in_keys, const xyzz* __restrict__ in_pts,
                                                                  size_t nslots, int L, size_t T, xyzz* __restrict__ buckets,
                                                                  uint32_t* __restrict__ out_keys, xyzz* __restrict__ out_pts) {
-    using E = SW<C>;
+    using E = GroupLaw<C>;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     size_t s = t * (size_t)L;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(128) msm_partials_level_kernel(const uint32_t*
 template <class C>
 __global__ void __launch_bounds__(128) msm_partials_final_kernel(const uint32_t* __restrict__ keys, const xyzz* __restrict__ pts,
                                                                  size_t nslots, xyzz* __restrict__ buckets) {
-    using E = SW<C>;
+    using E = GroupLaw<C>;
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nslots) return;
     uint32_t k = keys[p];
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(128) msm_partials_final_kernel(const uint32_t*
 template <class C>
 __global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz* __restrict__ buckets, uint32_t nb, uint32_t seg, uint32_t nseg,
                                                          int W, xyzz* __restrict__ seg_out) {
-    using E = SW<C>;
+    using E = GroupLaw<C>;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)W * nseg) return;
     uint32_t w = (uint32_t)(t / nseg), sg = (uint32_t)(t % nseg);
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz* __restrict_
 // ---- 6. window sums --------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(128) msm_window_sum_kernel(const xyzz* __restrict__ seg_out, uint32_t nseg, xyzz* __restrict__ win_out) {
-    using E = SW<C>;
+    using E = GroupLaw<C>;
     __shared__ xyzz sh[128];
     uint32_t w = blockIdx.x;
     xyzz acc = E::identity();
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(128) msm_window_sum_kernel(const xyzz* __restr
 // synthetic workload: out[i] = (start + i + 1) * G
 template <class C>
 __global__ void __launch_bounds__(128) synth_points_kernel(affine* __restrict__ out, size_t n, uint64_t start) {
-    using E = SW<C>;
+    using E = GroupLaw<C>;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     affine g;

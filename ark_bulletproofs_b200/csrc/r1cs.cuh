@@ -33,7 +33,8 @@ struct ProofT : ProofBase {
 
     std::vector<uint8_t> to_bytes() const override {                     // proof.rs:74-78
         std::vector<uint8_t> out;
-        auto pt = [&](const affine& p) { uint8_t buf[33]; HC::point_compressed(p, buf); out.insert(out.end(), buf, buf + 33); };
+        constexpr int PC = HC::POINT_COMPRESSED;
+        auto pt = [&](const affine& p) { uint8_t buf[33] = {0}; HC::point_compressed(p, buf); out.insert(out.end(), buf, buf + PC); };
         auto sc = [&](const fe& s) { uint8_t buf[32]; HC::scalar_to_bytes(s, buf); out.insert(out.end(), buf, buf + 32); };
         auto u64 = [&](uint64_t v) { for (int i = 0; i < 8; i++) out.push_back((uint8_t)(v >> (8 * i))); };
         const affine* pts[11] = {&A_I1, &A_O1, &S1, &A_I2, &A_O2, &S2, &T_1, &T_3, &T_4, &T_5, &T_6};
@@ -46,7 +47,8 @@ struct ProofT : ProofBase {
     }
     static int from_bytes(const uint8_t* d, size_t len, ProofT& pr) {     // proof.rs:83-91 (FormatError)
         size_t off = 0;
-        auto pt = [&](affine& p) { if (off + 33 > len) return false; bool ok = HC::point_from_compressed(d + off, p); off += 33; return ok; };
+        constexpr size_t PC = HC::POINT_COMPRESSED;
+        auto pt = [&](affine& p) { if (off + PC > len) return false; bool ok = HC::point_from_compressed(d + off, p); off += PC; return ok; };
         auto sc = [&](fe& s) { if (off + 32 > len) return false; bool ok = HC::scalar_from_bytes(d + off, s); off += 32; return ok; };
         affine* pts[11] = {&pr.A_I1, &pr.A_O1, &pr.S1, &pr.A_I2, &pr.A_O2, &pr.S2, &pr.T_1, &pr.T_3, &pr.T_4, &pr.T_5, &pr.T_6};
         for (auto p : pts) if (!pt(*p)) return BP_ERR_FORMAT;
@@ -56,7 +58,7 @@ struct ProofT : ProofBase {
             uint64_t cnt = 0;
             for (int i = 0; i < 8; i++) cnt |= (uint64_t)d[off + i] << (8 * i);
             off += 8;
-            if (cnt > (len - off) / 33) return BP_ERR_FORMAT;
+            if (cnt > (len - off) / PC) return BP_ERR_FORMAT;
             auto& vec = v == 0 ? pr.L_vec : pr.R_vec;
             vec.resize(cnt);
             for (auto& p : vec) if (!pt(p)) return BP_ERR_FORMAT;
@@ -71,7 +73,7 @@ template <class C>
 struct TP {
     using HC = HostCurve<C>;
     static void append_scalar(Transcript& t, const char* label, const fe& s) { uint8_t b[32]; HC::scalar_to_bytes(s, b); t.append_message(label, b, 32); }
-    static void append_point(Transcript& t, const char* label, const affine& p) { uint8_t b[65]; HC::point_uncompressed(p, b); t.append_message(label, b, 65); }
+    static void append_point(Transcript& t, const char* label, const affine& p) { uint8_t b[65] = {0}; HC::point_uncompressed(p, b); t.append_message(label, b, HC::POINT_UNCOMPRESSED); }
     static int validate_and_append_point(Transcript& t, const char* label, const affine& p) {
         if (HC::E::is_identity(p)) return BP_ERR_VERIFY;
         append_point(t, label, p);
@@ -737,6 +739,14 @@ struct VerifierT : ConstraintSystemBase {
 
     static int mega_check(bp_ctx* ctx, const GensDev& gens, const fe head[2], const fe* d_g, const fe* d_h, size_t np,
                           const std::vector<affine>& pts, const std::vector<fe>& tail) {
+        affine sum;
+        int ident = 0;
+        if (int rc = mega_msm(ctx, gens, head, d_g, d_h, np, pts, tail, sum, ident)) return rc;
+        return ident ? BP_OK : BP_ERR_VERIFY;                                                   // :595-597
+    }
+
+    static int mega_msm(bp_ctx* ctx, const GensDev& gens, const fe head[2], const fe* d_g, const fe* d_h, size_t np,
+                        const std::vector<affine>& pts, const std::vector<fe>& tail, affine& sum, int& is_identity) {
         if (pts.size() != tail.size()) return BP_ERR_LEN;
         BP_CUDA_TRY(ctx, ctx->v_pts.reserve((pts.size() + 1) * sizeof(affine)));
         BP_CUDA_TRY(ctx, ctx->v_sc.reserve((tail.size() + 4) * sizeof(fe)));
@@ -752,13 +762,16 @@ struct VerifierT : ConstraintSystemBase {
         uint8_t o[1][64];
         int id[1] = {0};
         if (int rc = msm_run_job<C>(ctx, job, o, id)) return rc;
-        return id[0] ? BP_OK : BP_ERR_VERIFY;                                                   // :595-597
+        memcpy(&sum, o[0], 64);
+        is_identity = id[0];
+        return BP_OK;
     }
 };
 
 // ---- batch_verify (src/r1cs/verifier.rs:604-691) -------------------------------------------------
 template <class C>
-int batch_verify_t(bp_ctx* ctx, Rng& prng, std::vector<VerifierT<C>*>& verifiers, std::vector<const ProofT<C>*>& proofs, const GensDev& gens) {
+int batch_verify_t(bp_ctx* ctx, Rng* prng, const fe* alphas, std::vector<VerifierT<C>*>& verifiers, std::vector<const ProofT<C>*>& proofs,
+                   const GensDev& gens, affine* partial_out = nullptr, int* partial_identity = nullptr) {
     using Fr = HostFp<typename C::Fr>;
     using HC = HostCurve<C>;
     size_t k = verifiers.size();
@@ -793,7 +806,7 @@ int batch_verify_t(bp_ctx* ctx, Rng& prng, std::vector<VerifierT<C>*>& verifiers
             ctx->v_accg = ng; ctx->v_acch = nh;
             acc_n = want;
         }
-        fe alpha = HC::scalar_rand(prng);                                                       // :649 (same draw order)
+        fe alpha = alphas ? alphas[p] : HC::scalar_rand(*prng);                                 // :649 (same draw order)
         head[0] = Fr::add(head[0], Fr::mul(alpha, sc.head[0]));                                 // :652-653
         head[1] = Fr::add(head[1], Fr::mul(alpha, sc.head[1]));
         unsigned grid = (unsigned)((np + 255) / 256);
@@ -807,6 +820,11 @@ int batch_verify_t(bp_ctx* ctx, Rng& prng, std::vector<VerifierT<C>*>& verifiers
     if (k == 0) {
         BP_CUDA_TRY(ctx, ctx->v_accg.reserve(sizeof(fe)));
         BP_CUDA_TRY(ctx, ctx->v_acch.reserve(sizeof(fe)));
+    }
+    if (partial_out) {
+        // multi-GPU batch verification: this rank's share of the final MSM; the caller
+        // all-gathers the partial points and accepts iff their sum is the identity
+        return VerifierT<C>::mega_msm(ctx, gens, head, ctx->v_accg.as<fe>(), ctx->v_acch.as<fe>(), max_n, pts, tail, *partial_out, *partial_identity);
     }
     return VerifierT<C>::mega_check(ctx, gens, head, ctx->v_accg.as<fe>(), ctx->v_acch.as<fe>(), max_n, pts, tail);   // :685-690
 }

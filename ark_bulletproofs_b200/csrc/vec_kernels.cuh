@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) ipa_fold_points_uniform_kernel(const affi
                                                                       const affine* __restrict__ R1, affine* __restrict__ out1,
                                                                       size_t count, const __grid_constant__ ScalarBits k0,
                                                                       const __grid_constant__ ScalarBits k1) {
-    using E = SW<C>;
+    using E = GroupLaw<C>;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * count) return;
     const bool second = t >= count;   // count is a multiple of the block size or the block is split; either way correct
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128) ipa_fold_points_joint_kernel(const affine
                                                                     affine* __restrict__ out0, const affine* __restrict__ P1,
                                                                     const fe* __restrict__ f1, fe cL1, fe cR1, affine* __restrict__ out1,
                                                                     size_t h) {
-    using E = SW<C>;
+    using E = GroupLaw<C>;
     using Fr = Fp<typename C::Fr>;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * h) return;

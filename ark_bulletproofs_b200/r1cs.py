@@ -327,6 +327,18 @@ def batch_verify(ctx, rng: ChaChaRng, instances, gens: Gens):
     ctx._check(ctx.lib.bp_batch_verify(ctx.h, rng.h, vs, ps, n, gens.h))
 
 
+def batch_verify_partial(ctx, alphas, instances, gens: Gens):
+    """This rank's share of a sharded batch verification: returns the partial MSM point (None = identity).
+    alphas: the Python-int alpha of each instance (drawn by the caller in global proof order)."""
+    n = len(instances)
+    vs = (ctypes.c_void_p * max(n, 1))(*[v.h for v, _ in instances])
+    ps = (ctypes.c_void_p * max(n, 1))(*[p.h for _, p in instances])
+    out = ctypes.create_string_buffer(64)
+    idn = ctypes.c_int(0)
+    ctx._check(ctx.lib.bp_batch_verify_partial(ctx.h, codec.enc_scalars(alphas, ctx.curve), vs, ps, n, gens.h, out, ctypes.byref(idn)))
+    return None if idn.value else codec.dec_point(out.raw, ctx.curve)
+
+
 def ipa_create(ctx, transcript: Transcript, Q, G_factors, H_factors, G, H, a, b):
     """InnerProductProof::create over Python-int inputs; returns (L_vec, R_vec, a, b)."""
     curve = ctx.curve

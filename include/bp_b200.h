@@ -185,6 +185,13 @@ int bp_verifier_commit(bp_verifier* v, const uint8_t commitment[64], bp_var* out
 int bp_verifier_verify(bp_verifier* v, const bp_proof* proof, const bp_gens* gens);
 int bp_batch_verify(bp_ctx* ctx, bp_rng* prng, bp_verifier* const* verifiers, const bp_proof* const* proofs, size_t n, const bp_gens* gens);
 
+/* Multi-GPU batch verification: proofs are sharded over ranks; every rank draws the
+ * same alpha sequence from the caller's RNG (verifier.rs:649), passes the alphas of ITS proofs here and
+ * gets its share of the final MSM (verifier.rs:685) as a point. The batch is accepted iff the sum of all
+ * ranks' points (all-gather + bp_points_sum_curve) is the identity. alphas: n Montgomery scalars. */
+int bp_batch_verify_partial(bp_ctx* ctx, const uint8_t* alphas, bp_verifier* const* verifiers, const bp_proof* const* proofs, size_t n,
+                            const bp_gens* gens, uint8_t out_xy[64], int* out_is_identity);
+
 /* ---- R1CSProof::{to_bytes, from_bytes} (src/r1cs/proof.rs:74-91). With out == NULL only *len is set. */
 void bp_proof_free(bp_proof* p);
 int bp_proof_to_bytes(const bp_proof* p, uint8_t* out, size_t cap, size_t* len);

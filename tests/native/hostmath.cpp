@@ -64,6 +64,8 @@ extern "C" int hm_ec_op(int curve, int op, const uint32_t* p, const uint32_t* q,
     switch (curve) {
         case 0: return ec_op_t<SW<Secq256k1>>(op, p, q, s, out);
         case 1: return ec_op_t<SW<Zorro>>(op, p, q, s, out);
+        case 2: return ec_op_t<TE<Curve25519>>(op, p, q, s, out);
+        case 12: return ec_op_t<TE<Curve25519, HostFp<Fp25519>>>(op, p, q, s, out);
         case 10: return ec_op_t<SW<Secq256k1, HostFp<SecqFq>>>(op, p, q, s, out);
         case 11: return ec_op_t<SW<Zorro, HostFp<ZorroFq>>>(op, p, q, s, out);
     }

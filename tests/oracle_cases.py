@@ -102,6 +102,10 @@ GOLDEN_CASES = [
     ("zorro_example", "zorro", "example", {}),
     ("zorro_shuffle3", "zorro", "shuffle_fixed", {"inp": [5, 9, 2], "out": [2, 5, 9]}),
     ("zorro_chain20", "zorro", "chain", {"N": 20}),
+    ("c25519_example", "curve25519", "example", {}),
+    ("c25519_shuffle3", "curve25519", "shuffle_fixed", {"inp": [5, 9, 2], "out": [2, 5, 9]}),
+    ("c25519_range8", "curve25519", "range", {"value": 0xA5, "bits": 8}),
+    ("c25519_chain20", "curve25519", "chain", {"N": 20}),
 ]
 
 

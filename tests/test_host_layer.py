@@ -34,7 +34,7 @@ def test_transcript_matches_oracle_long():
     assert a.challenge_bytes(b"z", 200) == b.challenge_bytes(b"z", 200)
 
 
-@pytest.mark.parametrize("curve", ["secq256k1", "zorro"])
+@pytest.mark.parametrize("curve", ["secq256k1", "zorro", "curve25519"])
 def test_challenge_scalar_and_rng(curve):
     c = O.CURVES[curve]
     t1, t2 = R.Transcript(b"kat"), O.Transcript(b"kat")
@@ -51,7 +51,7 @@ def test_kat_challenge_appendix_b():
     assert v.to_bytes(32, "little").hex() == "4d4c04d1ab63e641ff5fe0f5b50d61c58107288fb2a92ed3558d7cd9ec97692f"
 
 
-@pytest.mark.parametrize("curve,cap", [("secq256k1", 300), ("zorro", 20)])
+@pytest.mark.parametrize("curve,cap", [("secq256k1", 300), ("zorro", 20), ("curve25519", 12)])
 def test_generators_match_oracle(curve, cap):
     # cap = 300 exercises the threaded seek path on secq256k1 (count >= 256)
     c = O.CURVES[curve]
@@ -106,3 +106,28 @@ def test_proof_from_bytes_matches_oracle_bytes():
     corrupt[33 * 11 + 96] = 0xFF        # L length prefix -> huge
     with pytest.raises(R.BpError):
         R.Proof.from_bytes("secq256k1", bytes(corrupt))
+
+
+def test_curve25519_serialisation():
+    """TE points: 32-byte compressed (y + sign of x), 64-byte uncompressed, identity = (0,1); decompression
+    checks the curve equation and the prime-order subgroup."""
+    c = O.CURVE25519
+    lib = _lib.load()
+    P = O.pt_mul(c, 987654321, c.G)
+    for pt in (P, O.pt_neg(c, P), None):
+        out = ctypes.create_string_buffer(33)
+        assert lib.bp_point_compress(2, codec.enc_point(pt, "curve25519"), out) == 0
+        assert out.raw[:32] == O.ser_point(c, pt, True)
+        unc = ctypes.create_string_buffer(65)
+        assert lib.bp_point_serialize_uncompressed(2, codec.enc_point(pt, "curve25519"), unc) == 0
+        assert unc.raw[:64] == O.ser_point(c, pt, False)
+        back = ctypes.create_string_buffer(64)
+        assert lib.bp_point_decompress(2, out.raw[:32], back) == 0
+        assert codec.dec_point(back.raw, "curve25519") == pt
+    # a point of small order (order 8 component) must be rejected: (x, y) with y = 0 -> x^2 = -1... use a torsion point
+    # 8-torsion point of ed25519: y = 0x7a03ac9277fdc74ec6cc392cfa53202a0f67100d760b3cba4fd84d3d706a17c7 (order 8)
+    y8 = 0x7a03ac9277fdc74ec6cc392cfa53202a0f67100d760b3cba4fd84d3d706a17c7
+    raw = y8.to_bytes(32, "little")
+    assert lib.bp_point_decompress(2, raw, ctypes.create_string_buffer(64)) == -8
+    with pytest.raises(ValueError):
+        O.de_point_compressed(c, raw)

@@ -78,7 +78,7 @@ def _ec(lib, cid, cv, op, P, Q, s=0):
     return _unpt(cv, out)
 
 
-@pytest.mark.parametrize("cid,cv", [(0, O.SECQ256K1), (1, O.ZORRO), (10, O.SECQ256K1), (11, O.ZORRO)])
+@pytest.mark.parametrize("cid,cv", [(0, O.SECQ256K1), (1, O.ZORRO), (2, O.CURVE25519), (10, O.SECQ256K1), (11, O.ZORRO), (12, O.CURVE25519)])
 def test_curve_ops(lib, cid, cv):
     rnd = random.Random(99 + cid)
     G = cv.G

@@ -99,3 +99,21 @@ def test_zorro_msm():
     pts = _points(cv, n, rnd)
     sc = [rnd.randrange(cv.r) for _ in range(n)]
     assert ctx.msm(pts, sc) == O.msm(cv, pts, sc)
+
+
+def test_curve25519_msm():
+    from ark_bulletproofs_b200 import Context
+    cv = O.CURVE25519
+    ctx = Context("curve25519", 0)
+    rnd = random.Random(78)
+    n = 200
+    pts = _points(cv, n, rnd)
+    pts[5] = None                       # identity base
+    pts[7] = pts[8]                     # repeated point (the unified law has no doubling exception)
+    pts[9] = O.pt_neg(cv, pts[10])
+    sc = [rnd.randrange(cv.r) for _ in range(n)]
+    sc[0] = cv.r - 1
+    sc[1] = 0
+    assert ctx.msm(pts, sc) == O.msm(cv, pts, sc)
+    assert ctx.msm([pts[0], O.pt_neg(cv, pts[0])], [5, 5]) is None
+    assert ctx.msm([pts[0]] * 40, [3] * 40) == O.pt_mul(cv, 120, pts[0])

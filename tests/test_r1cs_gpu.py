@@ -274,3 +274,31 @@ def test_kshuffle_sizes(env, k):
     inp, out = C.shuffle_values(k, 100 + k)
     want, _, _ = C.prove_shuffle(cv, pc, bp, inp, out)
     assert proof.to_bytes() == want.to_bytes(cv)
+
+
+def test_batch_verify_sharded(env):
+    """batch verification sharded over ranks -- each rank's partial MSM point; the sum over
+    ranks is the identity iff the batch verifies. Emulated here with two shards on one GPU."""
+    from ark_bulletproofs_b200 import r1cs as R
+    curve = "secq256k1"
+    cv = O.SECQ256K1
+    ctx, gens = env(curve, 128)
+    vals = [(0, 16), (3, 16), ((1 << 16) - 1, 16), (1 << 16, 32), (1 << 63, 64), (77, 8)]
+
+    def run(vals):
+        proofs = [gpu_prove_case(R, ctx, gens, "range", {"value": v, "bits": n}, curve) for v, n in vals]
+        rng = R.ChaChaRng(bytes([5] * 32))
+        alphas = [rng.scalar(curve) for _ in vals]             # every rank draws the same sequence
+        parts = []
+        for rank in range(2):
+            idx = [i for i in range(len(vals)) if i % 2 == rank]
+            inst = [(gpu_verifier(R, ctx, "range", {"bits": vals[i][1]}, curve, proofs[i][1]), proofs[i][0]) for i in idx]
+            parts.append(R.batch_verify_partial(ctx, [alphas[i] for i in idx], inst, gens))
+        return parts
+    parts = run(vals)
+    assert all(P is not None for P in parts)                   # each share alone is not the identity...
+    assert O.pt_add(cv, parts[0], parts[1]) is None            # ...their sum is
+    bad = list(vals)
+    bad[2] = (1 << 16, 16)
+    parts = run(bad)
+    assert O.pt_add(cv, parts[0], parts[1]) is not None
