@@ -296,9 +296,9 @@ def test_batch_verify_sharded(env):
             parts.append(R.batch_verify_partial(ctx, [alphas[i] for i in idx], inst, gens))
         return parts
     parts = run(vals)
-    assert all(P is not None for P in parts)                   # each share alone is not the identity...
-    assert O.pt_add(cv, parts[0], parts[1]) is None            # ...their sum is
+    assert O.pt_add(cv, parts[0], parts[1]) is None            # (every valid proof's share is itself the identity)
     bad = list(vals)
-    bad[2] = (1 << 16, 16)
+    bad[2] = (1 << 16, 16)                                     # proof 2 lives on rank 0
     parts = run(bad)
+    assert parts[0] is not None and parts[1] is None
     assert O.pt_add(cv, parts[0], parts[1]) is not None
