@@ -19,6 +19,7 @@
 #include "host/gens_host.hpp"
 #include "r1cs_types.hpp"
 #include "msm_kernels.cuh"
+#include "flatten.cuh"
 #include "vec_kernels.cuh"
 
 namespace bp {
@@ -269,6 +270,66 @@ static void flatten(const ConstraintStore& cs, const fe& z, size_t n, size_t m, 
     }
 }
 
+// Device flatten: d_wL/d_wR/d_wO (n each, device) are filled; wV (m) and wc come back to the host.
+template <class C>
+int flatten_device(bp_ctx* ctx, const ConstraintStore& cs, const fe& z, size_t n, size_t m, fe* d_wL, fe* d_wR, fe* d_wO,
+                   std::vector<fe>& wV, fe* wc) {
+    using Fr = HostFp<typename C::Fr>;
+    using D = Dev<C>;
+    cudaStream_t st = ctx->stream;
+    size_t T = cs.kind.size(), Q = cs.count();
+    if (n >= (1u << 29) || m >= (1u << 29) || T >= (1ull << 32)) return BP_ERR_LEN;
+    wV.assign(m, Fr::zero());
+    if (wc) *wc = Fr::zero();
+    BP_CUDA_TRY(ctx, cudaMemsetAsync(d_wL, 0, n * sizeof(fe), st));
+    BP_CUDA_TRY(ctx, cudaMemsetAsync(d_wR, 0, n * sizeof(fe), st));
+    BP_CUDA_TRY(ctx, cudaMemsetAsync(d_wO, 0, n * sizeof(fe), st));
+    if (T == 0) return BP_OK;
+    BP_CUDA_TRY(ctx, ctx->f_kind.reserve(T));
+    BP_CUDA_TRY(ctx, ctx->f_idx.reserve(T * 8));
+    BP_CUDA_TRY(ctx, ctx->f_coeff.reserve(T * sizeof(fe)));
+    BP_CUDA_TRY(ctx, ctx->f_start.reserve((Q + 1) * 8));
+    BP_CUDA_TRY(ctx, ctx->f_keys.reserve(T * 4));
+    BP_CUDA_TRY(ctx, ctx->f_keys2.reserve(T * 4));
+    BP_CUDA_TRY(ctx, ctx->f_perm.reserve(T * 4));
+    BP_CUDA_TRY(ctx, ctx->f_perm2.reserve(T * 4));
+    BP_CUDA_TRY(ctx, ctx->f_contrib.reserve(T * sizeof(fe)));
+    BP_CUDA_TRY(ctx, ctx->f_sorted.reserve(T * sizeof(fe)));
+    BP_CUDA_TRY(ctx, ctx->f_ukeys.reserve(T * 4));
+    BP_CUDA_TRY(ctx, ctx->f_sums.reserve(T * sizeof(fe)));
+    BP_CUDA_TRY(ctx, ctx->f_wv.reserve((m + 2) * sizeof(fe) + 16));
+    D::upload(ctx, ctx->f_kind.p, cs.kind.data(), T);
+    D::upload(ctx, ctx->f_idx.p, cs.idx.data(), T * 8);
+    D::upload(ctx, ctx->f_coeff.p, cs.coeff.data(), T * sizeof(fe));
+    static_assert(sizeof(size_t) == 8, "64-bit host");
+    if (int rc = D::upload(ctx, ctx->f_start.p, cs.start.data(), (Q + 1) * 8)) return rc;
+    uint32_t *keys = ctx->f_keys.as<uint32_t>(), *keys2 = ctx->f_keys2.as<uint32_t>(), *perm = ctx->f_perm.as<uint32_t>(), *perm2 = ctx->f_perm2.as<uint32_t>();
+    flatten_contrib_kernel<C><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(ctx->f_kind.as<uint8_t>(), ctx->f_idx.as<uint64_t>(), ctx->f_coeff.as<fe>(),
+                                                                          ctx->f_start.as<uint64_t>(), Q, D::pow_table(z), keys, perm, ctx->f_contrib.as<fe>());
+    BP_LAUNCH_CHECK(ctx);
+    size_t tmp1 = 0, tmp2 = 0;
+    BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp1, keys, keys2, perm, perm2, T, 0, 32, st));
+    fe* d_wV = ctx->f_wv.as<fe>();
+    fe* d_wc = d_wV + m;
+    int* d_nruns = reinterpret_cast<int*>(d_wV + m + 1);
+    BP_CUDA_TRY(ctx, cub::DeviceReduce::ReduceByKey(nullptr, tmp2, keys2, ctx->f_ukeys.as<uint32_t>(), ctx->f_sorted.as<fe>(), ctx->f_sums.as<fe>(), d_nruns,
+                                                    FeAddOp<C>(), (int)T, st));
+    BP_CUDA_TRY(ctx, ctx->f_tmp.reserve(tmp1 > tmp2 ? tmp1 : tmp2));
+    BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->f_tmp.p, tmp1, keys, keys2, perm, perm2, T, 0, 32, st));
+    flatten_gather_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(ctx->f_contrib.as<fe>(), perm2, T, ctx->f_sorted.as<fe>());
+    BP_LAUNCH_CHECK(ctx);
+    BP_CUDA_TRY(ctx, cub::DeviceReduce::ReduceByKey(ctx->f_tmp.p, tmp2, keys2, ctx->f_ukeys.as<uint32_t>(), ctx->f_sorted.as<fe>(), ctx->f_sums.as<fe>(), d_nruns,
+                                                    FeAddOp<C>(), (int)T, st));
+    BP_CUDA_TRY(ctx, cudaMemsetAsync(d_wV, 0, (m + 1) * sizeof(fe), st));
+    flatten_scatter_kernel<C><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(ctx->f_ukeys.as<uint32_t>(), ctx->f_sums.as<fe>(), d_nruns, d_wL, d_wR, d_wO, d_wV, d_wc);
+    BP_LAUNCH_CHECK(ctx);
+    std::vector<fe> back(m + 1);
+    if (int rc = D::download(ctx, back.data(), d_wV, (m + 1) * sizeof(fe))) return rc;
+    for (size_t i = 0; i < m; i++) wV[i] = back[i];
+    if (wc) *wc = back[m];
+    return BP_OK;
+}
+
 static inline size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }   // 0 -> 1 like Rust
 
 // ---- Prover (src/r1cs/prover.rs) ----------------------------------------------------------------
@@ -455,8 +516,10 @@ struct ProverT : ConstraintSystemBase {
         TP<C>::append_point(t, "A_O2", proof.A_O2);
         TP<C>::append_point(t, "S2", proof.S2);
         fe y = TP<C>::challenge_scalar(t, "y"), z = TP<C>::challenge_scalar(t, "z");            // :665-667
-        std::vector<fe> wL, wR, wO, wV;
-        flatten<C>(cs, z, n, v.size(), wL, wR, wO, wV, nullptr);                                // :669
+        std::vector<fe> wV;
+        DevBuf* wb0[] = {&ctx->p_wL, &ctx->p_wR, &ctx->p_wO};
+        for (auto* b : wb0) BP_CUDA_TRY(ctx, b->reserve((n + 1) * sizeof(fe)));
+        if (int rc = flatten_device<C>(ctx, cs, z, n, v.size(), ctx->p_wL.as<fe>(), ctx->p_wR.as<fe>(), ctx->p_wO.as<fe>(), wV, nullptr)) return rc;   // :669
         tm.lap(ST_FLATTEN);
         fe y_inv = Fr::inv(y);                                                                  // :675
         // device: w vectors, power tables, l/r/t
@@ -470,8 +533,6 @@ struct ProverT : ConstraintSystemBase {
         BP_CUDA_TRY(ctx, ctx->p_Hf.reserve((padded_n + 1) * sizeof(fe)));
         const int TP_BLOCKS = 296;
         BP_CUDA_TRY(ctx, ctx->ipa_parts.reserve((size_t)(6 * TP_BLOCKS + 8) * sizeof(fe)));
-        D::upload(ctx, ctx->p_wL.p, wL.data(), n * sizeof(fe)); D::upload(ctx, ctx->p_wR.p, wR.data(), n * sizeof(fe));
-        if (int rc = D::upload(ctx, ctx->p_wO.p, wO.data(), n * sizeof(fe))) return rc;
         if (int rc = D::pow_vec(ctx, y, ctx->p_ypow.as<fe>(), padded_n)) return rc;              // exp_iter(y), util.rs:35-58
         if (int rc = D::pow_vec(ctx, y_inv, ctx->p_yinv.as<fe>(), padded_n)) return rc;          // :676-678
         LrInputs in{d_aL, d_aR, d_aO, d_sL, d_sR, ctx->p_wL.as<fe>(), ctx->p_wR.as<fe>(), ctx->p_wO.as<fe>(), ctx->p_ypow.as<fe>(), ctx->p_yinv.as<fe>()};
@@ -646,9 +707,11 @@ struct VerifierT : ConstraintSystemBase {
         TP<C>::append_scalar(t, "t_x_blinding", proof.t_x_blinding);
         TP<C>::append_scalar(t, "e_blinding", proof.e_blinding);
         fe w = TP<C>::challenge_scalar(t, "w");                                                 // :459
-        std::vector<fe> wL, wR, wO, wV;
+        std::vector<fe> wV;
         fe wc;
-        flatten<C>(cs, z, n, V.size(), wL, wR, wO, wV, &wc);                                    // :462
+        DevBuf* wb0[] = {&ctx->p_wL, &ctx->p_wR, &ctx->p_wO};
+        for (auto* bf : wb0) BP_CUDA_TRY(ctx, bf->reserve((n + 1) * sizeof(fe)));
+        if (int rc = flatten_device<C>(ctx, cs, z, n, V.size(), ctx->p_wL.as<fe>(), ctx->p_wR.as<fe>(), ctx->p_wO.as<fe>(), wV, &wc)) return rc;   // :462
         // InnerProductProof::verification_scalars (inner_product_proof.rs:244-314), host part
         size_t lg_n = proof.L_vec.size();
         if (lg_n >= 32 || proof.R_vec.size() != lg_n || padded_n != ((size_t)1 << lg_n)) return BP_ERR_VERIFY;   // :256-264
@@ -681,8 +744,6 @@ struct VerifierT : ConstraintSystemBase {
         const int VB = 296;
         BP_CUDA_TRY(ctx, ctx->ipa_parts.reserve((size_t)(VB + 8) * sizeof(fe)));
         BP_CUDA_TRY(ctx, ctx->small.reserve(4096));
-        D::upload(ctx, ctx->p_wL.p, wL.data(), n * sizeof(fe)); D::upload(ctx, ctx->p_wR.p, wR.data(), n * sizeof(fe));
-        if (int rc = D::upload(ctx, ctx->p_wO.p, wO.data(), n * sizeof(fe))) return rc;
         if (int rc = D::pow_vec(ctx, y_inv, ctx->p_yinv.as<fe>(), padded_n)) return rc;          // :474-476
         vin.wL = ctx->p_wL.as<fe>(); vin.wR = ctx->p_wR.as<fe>(); vin.wO = ctx->p_wO.as<fe>(); vin.yinvpow = ctx->p_yinv.as<fe>();
         vin.allinv = allinv; vin.x = x; vin.a = a; vin.b = b; vin.u = u; vin.lg_n = (int)lg_n;
