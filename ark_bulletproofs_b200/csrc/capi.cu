@@ -1,5 +1,6 @@
 // extern "C" surface of libbp_b200.so (declared in include/bp_b200.h).
 #include <cstring>
+#include <vector>
 #include "ctx.cuh"
 
 namespace bp {
@@ -24,6 +25,9 @@ int bp_ctx_create(int curve, int device, bp_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->copy_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->copy_ev[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost(&ctx->h_result, BP_HOST_RESULT_BYTES) != cudaSuccess) {
         delete ctx;
         return BP_ERR_CUDA;
@@ -40,6 +44,8 @@ void bp_ctx_destroy(bp_ctx* ctx) {
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; i++) if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
     delete ctx;
 }
 
@@ -78,6 +84,12 @@ int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]) {
     return BP_OK;
 }
 
+int bp_msm_set_chunk(bp_ctx* ctx, size_t points) {
+    if (!ctx || points == 0) return BP_ERR_ARG;
+    ctx->msm_chunk = points;
+    return BP_OK;
+}
+
 int bp_msm_set_window(bp_ctx* ctx, int c) {
     if (!ctx || c < 0 || c > 20 || c == 1 || c == 2) return BP_ERR_ARG;
     ctx->force_c = c;
@@ -93,13 +105,48 @@ int bp_msm_device(bp_ctx* ctx, const void* d_bases_xy, const void* d_scalars, si
 int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) {
     if (!ctx || !out_xy || (n && (!bases_xy || !scalars))) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (n) {
-        BP_CUDA_TRY(ctx, ctx->stage_bases.reserve(n * 64));
-        BP_CUDA_TRY(ctx, ctx->stage_scalars.reserve(n * 32));
-        BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_bases.p, bases_xy, n * 64, cudaMemcpyHostToDevice, ctx->stream));
-        BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    // Large host-resident inputs are processed in chunks: the H2D copy of chunk k+1 (copy stream) overlaps
+    // the MSM of chunk k (compute stream); the per-chunk partial points are added on the host. An MSM is a
+    // sum of independent terms, so chunking does not change the value.
+    const size_t CHUNK = ctx->msm_chunk;
+    if (n <= CHUNK + CHUNK / 2) {
+        if (n) {
+            BP_CUDA_TRY(ctx, ctx->stage_bases.reserve(n * 64));
+            BP_CUDA_TRY(ctx, ctx->stage_scalars.reserve(n * 32));
+            BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_bases.p, bases_xy, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+            BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        return bp::msm_dispatch(ctx, ctx->stage_bases.p, ctx->stage_scalars.p, n, out_xy, out_is_identity);
     }
-    return bp::msm_dispatch(ctx, ctx->stage_bases.p, ctx->stage_scalars.p, n, out_xy, out_is_identity);
+    size_t nchunks = (n + CHUNK - 1) / CHUNK;
+    bp::DevBuf* sb[2] = {&ctx->stage_bases, &ctx->stage2_bases};
+    bp::DevBuf* ss[2] = {&ctx->stage_scalars, &ctx->stage2_scalars};
+    for (int i = 0; i < 2; i++) {
+        BP_CUDA_TRY(ctx, sb[i]->reserve(CHUNK * 64));
+        BP_CUDA_TRY(ctx, ss[i]->reserve(CHUNK * 32));
+    }
+    auto issue_copy = [&](size_t k) -> int {
+        size_t lo = k * CHUNK, cnt = (lo + CHUNK <= n) ? CHUNK : n - lo;
+        int s = (int)(k & 1);
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(sb[s]->p, bases_xy + lo * 64, cnt * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(ss[s]->p, scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BP_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[s], ctx->copy_stream));
+        return BP_OK;
+    };
+    std::vector<uint8_t> partials(nchunks * 64);
+    if (int rc = issue_copy(0)) return rc;
+    for (size_t k = 0; k < nchunks; k++) {
+        if (k + 1 < nchunks)
+            if (int rc = issue_copy(k + 1)) return rc;       // buffer (k+1)&1 is free: the MSM of chunk k-1 has completed
+        int s = (int)(k & 1);
+        size_t lo = k * CHUNK, cnt = (lo + CHUNK <= n) ? CHUNK : n - lo;
+        BP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[s], 0));
+        int ident = 0;
+        int rc = bp::msm_dispatch(ctx, sb[s]->p, ss[s]->p, cnt, &partials[k * 64], &ident);
+        if (rc) return rc;
+        if (ident) memset(&partials[k * 64], 0, 64);
+    }
+    return bp::host_points_sum(ctx->curve, partials.data(), nchunks, out_xy, out_is_identity);
 }
 
 int bp_points_sum(bp_ctx* ctx, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity) {

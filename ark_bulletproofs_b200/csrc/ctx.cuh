@@ -38,9 +38,13 @@ struct bp_ctx {
     int curve = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // H2D of the next MSM chunk while the current one computes
+    cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+    bp::DevBuf stage2_bases, stage2_scalars;
     std::string err;
     uint64_t launches = 0;
     int force_c = 0;
+    size_t msm_chunk = (size_t)1 << 22;   // host-buffer MSMs above 1.5x this are chunked (copy/compute overlap)
     int sm_count = 148;
     // MSM scratch
     bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;
@@ -50,7 +54,7 @@ struct bp_ctx {
     bp::DevBuf p_aL, p_aR, p_aO, p_sL, p_sR, p_wL, p_wR, p_wO, p_ypow, p_yinv, p_l, p_r, p_Gf, p_Hf, v_pts, v_sc, v_g, v_h, v_accg, v_acch, f_kind, f_idx, f_coeff, f_start, f_keys, f_keys2, f_perm, f_perm2, f_contrib, f_sorted, f_ukeys, f_sums, f_tmp, f_wv;
     template <class F> void for_each_buf(F f) {
         bp::DevBuf* all[] = {&keys_a, &keys_b, &vals_a, &vals_b, &cub_tmp, &buckets, &part_keys, &part_pts, &seg_out, &win_out, &result,
-                             &stage_bases, &stage_scalars, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
+                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
                              &p_wL, &p_wR, &p_wO, &p_ypow, &p_yinv, &p_l, &p_r, &p_Gf, &p_Hf, &v_pts, &v_sc, &v_g, &v_h, &v_accg, &v_acch, &f_kind, &f_idx, &f_coeff, &f_start, &f_keys, &f_keys2, &f_perm, &f_perm2, &f_contrib, &f_sorted,
                              &f_ukeys, &f_sums, &f_tmp, &f_wv};
         for (auto* b : all) f(b);

@@ -28,6 +28,9 @@
 namespace bp {
 
 static constexpr uint32_t INVALID_KEY = 0xFFFFFFFFu;
+#ifndef BP_ACC_MIN_BLOCKS
+#define BP_ACC_MIN_BLOCKS 4
+#endif
 
 struct MsmPlan {
     int c;            // window width in bits
@@ -169,7 +172,7 @@ struct RunSink {
 
 // level 1: sorted (key, point index|sign) pairs -> run sums of gathered affine points
 template <class C>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+__global__ void __launch_bounds__(128, BP_ACC_MIN_BLOCKS) msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                              size_t M, int L, size_t T, const __grid_constant__ MsmJob job,
                                                              xyzz* __restrict__ buckets, uint32_t* __restrict__ out_keys,
                                                              xyzz* __restrict__ out_pts) {

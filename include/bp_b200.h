@@ -78,6 +78,9 @@ int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* window
  * 4 T commitments, 5 IPA total, 6 IPA MSMs, 7 IPA folds (only with timing enabled), 8 IPA host
  * (transcript, challenge inverse), 9 verification scalars, 10 mega-MSM, 11 uploads. */
 int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]);
+/* bp_msm over host buffers larger than 1.5x `points` is split into chunks of `points` whose H2D copies
+ * overlap the previous chunk's kernels (default 2^22); exposed for tests and tuning. */
+int bp_msm_set_chunk(bp_ctx* ctx, size_t points);
 /* Force the Pippenger window width (0 = automatic); for parity tests and tuning. */
 int bp_msm_set_window(bp_ctx* ctx, int c);
 

@@ -117,3 +117,27 @@ def test_curve25519_msm():
     assert ctx.msm(pts, sc) == O.msm(cv, pts, sc)
     assert ctx.msm([pts[0], O.pt_neg(cv, pts[0])], [5, 5]) is None
     assert ctx.msm([pts[0]] * 40, [3] * 40) == O.pt_mul(cv, 120, pts[0])
+
+
+def test_msm_host_chunked_overlap(ctx):
+    """bp_msm over host buffers splits large inputs into chunks whose H2D copies overlap the previous
+    chunk's kernels; the chunk sums are added on the host. Forced here with a tiny chunk size."""
+    cv = O.SECQ256K1
+    rnd = random.Random(4097)
+    n = 4097
+    pts = _points(cv, n, rnd)
+    sc = [rnd.randrange(cv.r) for _ in range(n)]
+    want = O.msm(cv, pts, sc)
+    for chunk in (1000, 512, 4096):
+        ctx.set_chunk(chunk)
+        try:
+            assert ctx.msm(pts, sc) == want
+        finally:
+            ctx.set_chunk(1 << 22)
+    # a chunk whose partial sum is the identity
+    ctx.set_chunk(100)
+    try:
+        z = [0] * 100 + sc[100:300]
+        assert ctx.msm(pts[:300], z) == O.msm(cv, pts[:300], z)
+    finally:
+        ctx.set_chunk(1 << 22)
