@@ -63,6 +63,9 @@ class Context:
         self._check(self.lib.bp_ctx_last_stage_ms(self.h, out))
         return {n: round(out[i], 4) for i, n in enumerate(self.STAGES)}
 
+    def set_ipa_nofold_threshold(self, n: int):
+        self._check(self.lib.bp_ipa_set_nofold_threshold(self.h, n))
+
     def set_chunk(self, points: int):
         self._check(self.lib.bp_msm_set_chunk(self.h, points))
 

@@ -90,6 +90,12 @@ int bp_msm_set_chunk(bp_ctx* ctx, size_t points) {
     return BP_OK;
 }
 
+int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n) {
+    if (!ctx) return BP_ERR_ARG;
+    ctx->ipa_nofold_n = n;
+    return BP_OK;
+}
+
 int bp_msm_set_window(bp_ctx* ctx, int c) {
     if (!ctx || c < 0 || c > 20 || c == 1 || c == 2) return BP_ERR_ARG;
     ctx->force_c = c;

@@ -44,7 +44,8 @@ struct bp_ctx {
     std::string err;
     uint64_t launches = 0;
     int force_c = 0;
-    size_t msm_chunk = (size_t)1 << 22;   // host-buffer MSMs above 1.5x this are chunked (copy/compute overlap)
+    size_t msm_chunk = (size_t)1 << 22;
+    size_t ipa_nofold_n = (size_t)1 << 14;   // IPA rounds with n <= this use MSMs over the stage generators instead of folding them   // host-buffer MSMs above 1.5x this are chunked (copy/compute overlap)
     int sm_count = 148;
     // MSM scratch
     bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;

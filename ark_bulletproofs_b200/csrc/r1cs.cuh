@@ -168,24 +168,52 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
     bool first = true;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    // stage of the last generator fold (no-fold rounds expand their scalars back to it)
+    size_t ns = 0;
+    NoFoldParams nf;
+    nf.nu = 0;
     while (n != 1) {
         auto t_a = now();
         size_t h = n / 2;
-        fe *sLG = s_all, *sLH = s_all + h, *sRG = s_all + 2 * h, *sRH = s_all + 3 * h;
+        const bool nofold = n <= ctx->ipa_nofold_n;
+        if (nofold && ns == 0) {
+            ns = n;                       // generators stay at this stage from now on
+            BP_CUDA_TRY(ctx, ctx->ipa_s.reserve((4 * ns + 8) * sizeof(fe)));
+            s_all = ctx->ipa_s.as<fe>();
+            nf.fG = fG;
+            nf.fH = fH;
+        }
         int blocks = (int)((h + 127) / 128);
         if (blocks > PREP_BLOCKS) blocks = PREP_BLOCKS;
-        ipa_prep_kernel<C><<<blocks, 128, 0, st>>>(d_a, d_b, h, first ? d_Gf : nullptr, first ? d_Hf : nullptr, fG, fH, sLG, sLH, sRG, sRH, parts);
-        BP_LAUNCH_CHECK(ctx);
+        MsmJob job;
+        if (!nofold) {
+            fe *sLG = s_all, *sLH = s_all + h, *sRG = s_all + 2 * h, *sRH = s_all + 3 * h;
+            ipa_prep_kernel<C><<<blocks, 128, 0, st>>>(d_a, d_b, h, first ? d_Gf : nullptr, first ? d_Hf : nullptr, fG, fH, sLG, sLH, sRG, sRH, parts);
+            BP_LAUNCH_CHECK(ctx);
+            // L = <a_L*gR, G_R> + <b_R*hL, H_L> + c_L*Q ; R = <a_R*gL, G_L> + <b_L*hR, H_R> + c_R*Q
+            job.add(curG + h, sLG, h, 0);
+            job.add(curH, sLH, h, 0);
+            job.add(d_Q, d_c, 1, 0);
+            job.add(curG, sRG, h, 1);
+            job.add(curH + h, sRH, h, 1);
+            job.add(d_Q, d_c + 1, 1, 1);
+        } else {
+            fe *sLG = s_all, *sLH = s_all + ns, *sRG = s_all + 2 * ns, *sRH = s_all + 3 * ns;
+            const bool stage0 = first;    // never folded: the factor vectors still apply per element
+            ipa_cross_kernel<C><<<blocks, 128, 0, st>>>(d_a, d_b, h, parts);
+            BP_LAUNCH_CHECK(ctx);
+            ipa_nofold_scalars_kernel<C><<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(d_a, d_b, ns, n, stage0 ? d_Gf : nullptr, stage0 ? d_Hf : nullptr, nf,
+                                                                                      sLG, sLH, sRG, sRH);
+            BP_LAUNCH_CHECK(ctx);
+            job.add(curG, sLG, ns, 0);
+            job.add(curH, sLH, ns, 0);
+            job.add(d_Q, d_c, 1, 0);
+            job.add(curG, sRG, ns, 1);
+            job.add(curH, sRH, ns, 1);
+            job.add(d_Q, d_c + 1, 1, 1);
+        }
         vec_reduce_partials_kernel<C, 2><<<1, 128, 0, st>>>(parts, blocks, d_c);
         BP_LAUNCH_CHECK(ctx);
-        // L = <a_L*gR, G_R> + <b_R*hL, H_L> + c_L*Q ; R = <a_R*gL, G_L> + <b_L*hR, H_R> + c_R*Q
-        MsmJob job;
-        job.add(curG + h, sLG, h, 0);
-        job.add(curH, sLH, h, 0);
-        job.add(d_Q, d_c, 1, 0);
-        job.add(curG, sRG, h, 1);
-        job.add(curH + h, sRH, h, 1);
-        job.add(d_Q, d_c + 1, 1, 1);
         uint8_t out[2][64];
         int ident[2];
         if (int rc = msm_run_job<C>(ctx, job, out, ident)) return rc;
@@ -204,23 +232,30 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
         ctx->stage_ms[ST_IPA_HOST] += ms(t_b, t_c);
         ipa_fold_scalars_kernel<C><<<(unsigned)((h + 255) / 256), 256, 0, st>>>(d_a, d_b, h, u, uinv);
         BP_LAUNCH_CHECK(ctx);
-        unsigned fgrid = (unsigned)((2 * h + 127) / 128);
-        if (first) {
-            // factors folded into the points (inner_product_proof.rs:143-155)
-            ipa_fold_points_joint_kernel<C><<<fgrid, 128, 0, st>>>(curG, d_Gf, uinv, u, wG, curH, d_Hf, u, uinv, wH, h);
-            BP_LAUNCH_CHECK(ctx);
+        if (nofold) {
+            if (nf.nu >= 32) return BP_ERR_LEN;
+            nf.u[nf.nu] = u;
+            nf.uinv[nf.nu] = uinv;
+            nf.nu++;
         } else {
-            // u^-1*G_L + u*G_R = u^-1*(G_L + u^2*G_R): the common factor moves into fG (resp. fH)
-            fe u2 = Fr::sqr(u), ui2 = Fr::sqr(uinv);
-            ipa_fold_points_uniform_kernel<C><<<fgrid, 128, 0, st>>>(curG, curG + h, wG, curH, curH + h, wH, h, D::bits(u2), D::bits(ui2));
-            BP_LAUNCH_CHECK(ctx);
-            fG = Fr::mul(fG, uinv);
-            fH = Fr::mul(fH, u);
+            unsigned fgrid = (unsigned)((2 * h + 127) / 128);
+            if (first) {
+                // factors folded into the points (inner_product_proof.rs:143-155)
+                ipa_fold_points_joint_kernel<C><<<fgrid, 128, 0, st>>>(curG, d_Gf, uinv, u, wG, curH, d_Hf, u, uinv, wH, h);
+                BP_LAUNCH_CHECK(ctx);
+            } else {
+                // u^-1*G_L + u*G_R = u^-1*(G_L + u^2*G_R): the common factor moves into fG (resp. fH)
+                fe u2 = Fr::sqr(u), ui2 = Fr::sqr(uinv);
+                ipa_fold_points_uniform_kernel<C><<<fgrid, 128, 0, st>>>(curG, curG + h, wG, curH, curH + h, wH, h, D::bits(u2), D::bits(ui2));
+                BP_LAUNCH_CHECK(ctx);
+                fG = Fr::mul(fG, uinv);
+                fH = Fr::mul(fH, u);
+            }
+            if (ctx->timing) { cudaStreamSynchronize(st); ctx->stage_ms[ST_IPA_FOLD] += ms(t_c, now()); }
+            curG = wG;
+            curH = wH;
+            first = false;
         }
-        if (ctx->timing) { cudaStreamSynchronize(st); ctx->stage_ms[ST_IPA_FOLD] += ms(t_c, now()); }
-        curG = wG;
-        curH = wH;
-        first = false;
         n = h;
     }
     fe ab[2];

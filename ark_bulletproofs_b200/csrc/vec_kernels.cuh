@@ -97,6 +97,69 @@ __global__ void __launch_bounds__(256) ipa_fold_scalars_kernel(fe* __restrict__ 
     st_fe(b + i, F::add(F::mul(bL, uinv), F::mul(u, bR)));
 }
 
+// ---- late IPA rounds without generator folding ---------------------------------------------------
+// Only L_j, R_j, a, b are observable (hard part 3), so once the vectors are short the
+// generators are no longer folded (a 256-step dependent scalar multiplication per round, latency
+// bound); instead round j's L and R are MSMs over the generators of the last folded stage s
+// (n_s points) with expanded scalars:  G^(j-1)_i = sum_tau cG(tau) * G^(s)_{i + n_{j-1}*tau},
+// cG(tau) = prod_m u_{j-1-m}^(+1 if bit m of tau else -1), and the mirror image for H.
+// Each stage point belongs to exactly one of L_j / R_j; the other MSM gets a zero scalar (skipped).
+struct NoFoldParams {
+    fe u[32], uinv[32];     // challenges of the unfolded rounds, oldest first (round s+1 at index 0)
+    int nu;                 // how many (= j-1-s)
+    fe fG, fH;              // uniform deferred factors of stage s (ignored when Gf/Hf are given)
+};
+
+template <class C>
+__global__ void __launch_bounds__(128) ipa_nofold_scalars_kernel(const fe* __restrict__ a, const fe* __restrict__ b, size_t ns, size_t ncur,
+                                                                 const fe* __restrict__ Gf, const fe* __restrict__ Hf,
+                                                                 const __grid_constant__ NoFoldParams p, fe* __restrict__ sLG,
+                                                                 fe* __restrict__ sLH, fe* __restrict__ sRG, fe* __restrict__ sRH) {
+    using F = Fp<typename C::Fr>;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ns) return;
+    const size_t h = ncur / 2;
+    size_t ip = t & (ncur - 1);          // index at the current level
+    size_t tau = t / ncur;
+    fe cG = Gf ? ld_fe_rw(Gf + t) : p.fG;
+    fe cH = Hf ? ld_fe_rw(Hf + t) : p.fH;
+    // bit m of tau belongs to round (j-1-m): index nu-1-m in the oldest-first arrays
+    for (int m = 0; m < p.nu; m++) {
+        bool bit = (tau >> m) & 1u;
+        cG = F::mul(cG, bit ? p.u[p.nu - 1 - m] : p.uinv[p.nu - 1 - m]);
+        cH = F::mul(cH, bit ? p.uinv[p.nu - 1 - m] : p.u[p.nu - 1 - m]);
+    }
+    fe z = F::zero();
+    if (ip >= h) {
+        // G_R half -> L (scalar a_L), H_R half -> R (scalar b_L)
+        st_fe(sLG + t, F::mul(ld_fe_rw(a + (ip - h)), cG));
+        st_fe(sRG + t, z);
+        st_fe(sRH + t, F::mul(ld_fe_rw(b + (ip - h)), cH));
+        st_fe(sLH + t, z);
+    } else {
+        // G_L half -> R (scalar a_R), H_L half -> L (scalar b_R)
+        st_fe(sRG + t, F::mul(ld_fe_rw(a + (h + ip)), cG));
+        st_fe(sLG + t, z);
+        st_fe(sLH + t, F::mul(ld_fe_rw(b + (h + ip)), cH));
+        st_fe(sRH + t, z);
+    }
+}
+
+// block partials of c_L = <a_L, b_R>, c_R = <a_R, b_L> only
+template <class C>
+__global__ void __launch_bounds__(128) ipa_cross_kernel(const fe* __restrict__ a, const fe* __restrict__ b, size_t h, fe* __restrict__ parts) {
+    using F = Fp<typename C::Fr>;
+    __shared__ fe sm[2 * 128];
+    fe acc[2] = {F::zero(), F::zero()};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < h; i += (size_t)gridDim.x * blockDim.x) {
+        fe aL = ld_fe_rw(a + i), aR = ld_fe_rw(a + h + i), bL = ld_fe_rw(b + i), bR = ld_fe_rw(b + h + i);
+        acc[0] = F::add(acc[0], F::mul(aL, bR));
+        acc[1] = F::add(acc[1], F::mul(aR, bL));
+    }
+    block_sum<F, 2, 128>(acc, sm);
+    if (threadIdx.x == 0) { st_fe(parts + 2 * blockIdx.x, acc[0]); st_fe(parts + 2 * blockIdx.x + 1, acc[1]); }
+}
+
 struct ScalarBits { uint32_t w[8]; };   // canonical (non-Montgomery) little-endian limbs
 
 // Generator fold with one scalar shared by every thread (uniform control flow):

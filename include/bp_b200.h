@@ -81,6 +81,9 @@ int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]);
 /* bp_msm over host buffers larger than 1.5x `points` is split into chunks of `points` whose H2D copies
  * overlap the previous chunk's kernels (default 2^22); exposed for tests and tuning. */
 int bp_msm_set_chunk(bp_ctx* ctx, size_t points);
+/* IPA rounds of length n <= this threshold do not fold the generators; their L/R are MSMs over the last
+ * folded stage with challenge-expanded scalars (same L, R, a, b). 0 = always fold. Default 2^14. */
+int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n);
 /* Force the Pippenger window width (0 = automatic); for parity tests and tuning. */
 int bp_msm_set_window(bp_ctx* ctx, int c);
 

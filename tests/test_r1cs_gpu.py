@@ -130,10 +130,14 @@ def test_generators_on_device(env):
 
 @pytest.mark.parametrize("n", [1, 2, 4, 8, 32, 64])
 @pytest.mark.parametrize("factors", ["ones_geometric", "random"])
-def test_ipa_create_matches_oracle(env, n, factors):
+@pytest.mark.parametrize("nofold", [0, 8, 1 << 14])
+def test_ipa_create_matches_oracle(env, n, factors, nofold):
+    """nofold = 0: every round folds the generators (joint first round, uniform-scalar later rounds);
+    8: folds down to 8 then switches to MSMs over the stage generators; 2^14: never folds."""
     from ark_bulletproofs_b200 import r1cs as R
     cv = O.SECQ256K1
     ctx, _ = env("secq256k1", 128)
+    ctx.set_ipa_nofold_threshold(nofold)
     bp = O.BulletproofGens(cv, 64, 1)
     rnd = random.Random(n * 3 + len(factors))
     Q = O.affine_rand(cv, O.ChaCha20Rng(hashlib.sha3_512(b"test point").digest()[:32]))   # inner_product_proof.rs:422-433
@@ -147,7 +151,10 @@ def test_ipa_create_matches_oracle(env, n, factors):
         Gf = [1] * n
         Hf = [pow(y_inv, i, cv.r) for i in range(n)]
     want = O.ipa_create(cv, O.Transcript(b"innerproducttest"), Q, Gf, Hf, bp.G(n), bp.H(n), a, b)
-    L, Rv, ao, bo = R.ipa_create(ctx, R.Transcript(b"innerproducttest"), Q, Gf, Hf, bp.G(n), bp.H(n), a, b)
+    try:
+        L, Rv, ao, bo = R.ipa_create(ctx, R.Transcript(b"innerproducttest"), Q, Gf, Hf, bp.G(n), bp.H(n), a, b)
+    finally:
+        ctx.set_ipa_nofold_threshold(1 << 14)
     assert (L, Rv, ao, bo) == (want.L_vec, want.R_vec, want.a, want.b)
     # and the proof verifies (make_ipp_*): P = <a,G> + <b*Hf,H> + <a,b>Q with Gf applied
     c = O.inner_product(cv, a, b)
@@ -302,3 +309,19 @@ def test_batch_verify_sharded(env):
     parts = run(bad)
     assert parts[0] is not None and parts[1] is None
     assert O.pt_add(cv, parts[0], parts[1]) is not None
+
+
+@pytest.mark.parametrize("nofold", [0, 16, 256])
+@pytest.mark.parametrize("name", ["chain1000", "shuffle42", "zorro_chain20", "c25519_chain20"])
+def test_golden_proofs_all_ipa_paths(env, name, nofold):
+    """The same golden proofs with the generator-folding IPA (threshold 0) and mixed fold / no-fold."""
+    from ark_bulletproofs_b200 import r1cs as R
+    g = GOLDEN[name]
+    curve, kind, params = g["curve"], g["kind"], g["params"]
+    ctx, gens = env(curve, max(g["gens_capacity"], 1))
+    ctx.set_ipa_nofold_threshold(nofold)
+    try:
+        proof, _ = gpu_prove_case(R, ctx, gens, kind, params, curve)
+    finally:
+        ctx.set_ipa_nofold_threshold(1 << 14)
+    assert proof.to_bytes().hex() == g["proof_hex"]
