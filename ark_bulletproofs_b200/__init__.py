@@ -66,6 +66,9 @@ class Context:
     def set_ipa_nofold_threshold(self, n: int):
         self._check(self.lib.bp_ipa_set_nofold_threshold(self.h, n))
 
+    def set_fp29(self, enable: bool):
+        self._check(self.lib.bp_msm_set_fp29(self.h, 1 if enable else 0))
+
     def set_chunk(self, points: int):
         self._check(self.lib.bp_msm_set_chunk(self.h, points))
 

@@ -96,6 +96,12 @@ int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n) {
     return BP_OK;
 }
 
+int bp_msm_set_fp29(bp_ctx* ctx, int enable) {
+    if (!ctx) return BP_ERR_ARG;
+    ctx->use_fp29 = enable != 0;
+    return BP_OK;
+}
+
 int bp_msm_set_window(bp_ctx* ctx, int c) {
     if (!ctx || c < 0 || c > 20 || c == 1 || c == 2) return BP_ERR_ARG;
     ctx->force_c = c;

@@ -13,52 +13,57 @@
 
 namespace bp {
 
-struct alignas(16) affine { fe x, y; };
-struct alignas(16) xyzz { fe x, y, zz, zzz; };
+template <class EL> struct affine_t { EL x, y; };
+template <class EL> struct xyzz_t { EL x, y, zz, zzz; };
+using affine = affine_t<fe>;   // 64 B in HBM (fe is 16-byte aligned)
+using xyzz = xyzz_t<fe>;       // 128 B in HBM
 
 template <class C, class F_ = Fp<typename C::Fq>>
 struct SW {
     using F = F_;
+    using el = typename F::el;
+    using aff = affine_t<el>;
+    using ext = xyzz_t<el>;
 
-    BP_HD static bool is_identity(const affine& p) { return F::is_zero(p.x) && F::is_zero(p.y); }
-    BP_HD static bool is_identity(const xyzz& p) { return F::is_zero(p.zz); }
-    BP_HD static xyzz identity() {
-        xyzz r;
+    BP_HD static bool is_identity(const aff& p) { return F::is_zero(p.x) && F::is_zero(p.y); }
+    BP_HD static bool is_identity(const ext& p) { return F::is_zero(p.zz); }
+    BP_HD static ext identity() {
+        ext r;
         r.x = F::zero(); r.y = F::zero(); r.zz = F::zero(); r.zzz = F::zero();
         return r;
     }
-    BP_HD static affine affine_identity() {
-        affine r;
+    BP_HD static aff affine_identity() {
+        aff r;
         r.x = F::zero(); r.y = F::zero();
         return r;
     }
-    BP_HD static xyzz from_affine(const affine& p) {
-        xyzz r;
+    BP_HD static ext from_affine(const aff& p) {
+        ext r;
         if (is_identity(p)) return identity();
         r.x = p.x; r.y = p.y; r.zz = F::one(); r.zzz = F::one();
         return r;
     }
-    BP_HD static affine neg(const affine& p) {
-        affine r;
+    BP_HD static aff neg(const aff& p) {
+        aff r;
         r.x = p.x; r.y = F::neg(p.y);
         return r;
     }
-    BP_HD static xyzz neg(const xyzz& p) {
-        xyzz r = p;
+    BP_HD static ext neg(const ext& p) {
+        ext r = p;
         r.y = F::neg(p.y);
         return r;
     }
-    BP_HD static fe mul_a(const fe& t) { return F::mul_small(t, C::A_SMALL); }
+    BP_HD static el mul_a(const el& t) { return F::mul_small(t, C::A_SMALL); }
 
     // 2*(x,y) -> XYZZ   [mdbl-2008-s-1]
-    BP_HD static xyzz dbl_affine(const affine& p) {
+    BP_HD static ext dbl_affine(const aff& p) {
         if (is_identity(p) || F::is_zero(p.y)) return identity();
-        xyzz r;
-        fe U = F::dbl(p.y);
-        fe V = F::sqr(U);
-        fe W = F::mul(U, V);
-        fe S = F::mul(p.x, V);
-        fe M = F::mul3(F::sqr(p.x));
+        ext r;
+        el U = F::dbl(p.y);
+        el V = F::sqr(U);
+        el W = F::mul(U, V);
+        el S = F::mul(p.x, V);
+        el M = F::mul3(F::sqr(p.x));
         if (C::A_SMALL != 0) M = F::add(M, F::from_u32(C::A_SMALL));
         r.x = F::sub(F::sqr(M), F::dbl(S));
         r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
@@ -68,14 +73,14 @@ struct SW {
     }
 
     // 2*P, XYZZ   [dbl-2008-s-1]
-    BP_HD static xyzz dbl(const xyzz& p) {
+    BP_HD static ext dbl(const ext& p) {
         if (is_identity(p) || F::is_zero(p.y)) return identity();
-        xyzz r;
-        fe U = F::dbl(p.y);
-        fe V = F::sqr(U);
-        fe W = F::mul(U, V);
-        fe S = F::mul(p.x, V);
-        fe M = F::mul3(F::sqr(p.x));
+        ext r;
+        el U = F::dbl(p.y);
+        el V = F::sqr(U);
+        el W = F::mul(U, V);
+        el S = F::mul(p.x, V);
+        el M = F::mul3(F::sqr(p.x));
         if (C::A_SMALL != 0) M = F::add(M, mul_a(F::sqr(p.zz)));
         r.x = F::sub(F::sqr(M), F::dbl(S));
         r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
@@ -85,23 +90,23 @@ struct SW {
     }
 
     // acc += (x2,y2)   [madd-2008-s], all special cases handled
-    BP_HD static void madd(xyzz& acc, const affine& q) {
+    BP_HD static void madd(ext& acc, const aff& q) {
         if (is_identity(q)) return;
         if (is_identity(acc)) { acc = from_affine(q); return; }
-        fe U2 = F::mul(q.x, acc.zz);
-        fe S2 = F::mul(q.y, acc.zzz);
-        fe P = F::sub(U2, acc.x);
-        fe R = F::sub(S2, acc.y);
+        el U2 = F::mul(q.x, acc.zz);
+        el S2 = F::mul(q.y, acc.zzz);
+        el P = F::sub(U2, acc.x);
+        el R = F::sub(S2, acc.y);
         if (F::is_zero(P)) {
             if (F::is_zero(R)) acc = dbl_affine(q);
             else acc = identity();
             return;
         }
-        fe PP = F::sqr(P);
-        fe PPP = F::mul(P, PP);
-        fe Q = F::mul(acc.x, PP);
-        fe X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
-        fe Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(acc.y, PPP));
+        el PP = F::sqr(P);
+        el PPP = F::mul(P, PP);
+        el Q = F::mul(acc.x, PP);
+        el X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+        el Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(acc.y, PPP));
         acc.x = X3;
         acc.y = Y3;
         acc.zz = F::mul(acc.zz, PP);
@@ -109,46 +114,46 @@ struct SW {
     }
 
     // acc += q, both XYZZ   [add-2008-s]
-    BP_HD static void add(xyzz& acc, const xyzz& q) {
+    BP_HD static void add(ext& acc, const ext& q) {
         if (is_identity(q)) return;
         if (is_identity(acc)) { acc = q; return; }
-        fe U1 = F::mul(acc.x, q.zz);
-        fe U2 = F::mul(q.x, acc.zz);
-        fe S1 = F::mul(acc.y, q.zzz);
-        fe S2 = F::mul(q.y, acc.zzz);
-        fe P = F::sub(U2, U1);
-        fe R = F::sub(S2, S1);
+        el U1 = F::mul(acc.x, q.zz);
+        el U2 = F::mul(q.x, acc.zz);
+        el S1 = F::mul(acc.y, q.zzz);
+        el S2 = F::mul(q.y, acc.zzz);
+        el P = F::sub(U2, U1);
+        el R = F::sub(S2, S1);
         if (F::is_zero(P)) {
             if (F::is_zero(R)) acc = dbl(acc);
             else acc = identity();
             return;
         }
-        fe PP = F::sqr(P);
-        fe PPP = F::mul(P, PP);
-        fe Q = F::mul(U1, PP);
-        fe X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
-        fe Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(S1, PPP));
+        el PP = F::sqr(P);
+        el PPP = F::mul(P, PP);
+        el Q = F::mul(U1, PP);
+        el X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+        el Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(S1, PPP));
         acc.x = X3;
         acc.y = Y3;
         acc.zz = F::mul(F::mul(acc.zz, q.zz), PP);
         acc.zzz = F::mul(F::mul(acc.zzz, q.zzz), PPP);
     }
 
-    // XYZZ -> affine with one field inversion (x = X/ZZ, y = Y/ZZZ)
-    BP_HD_NOINL static affine to_affine(const xyzz& p) {
+    // XYZZ -> aff with one field inversion (x = X/ZZ, y = Y/ZZZ)
+    BP_HD_NOINL static aff to_affine(const ext& p) {
         if (is_identity(p)) return affine_identity();
         // 1/ZZZ, then 1/ZZ = (1/ZZZ)^2 * ZZ^2 ... simpler: invert ZZ*ZZZ once
-        fe t = F::mul(p.zz, p.zzz);
-        fe ti = F::inv(t);
-        affine r;
+        el t = F::mul(p.zz, p.zzz);
+        el ti = F::inv(t);
+        aff r;
         r.x = F::mul(p.x, F::mul(ti, p.zzz));
         r.y = F::mul(p.y, F::mul(ti, p.zz));
         return r;
     }
 
     // k*P for a small non-negative k (double-and-add, MSB first); used by the bucket reduction
-    BP_HD_NOINL static xyzz mul_u32(const xyzz& p, uint32_t k) {
-        xyzz acc = identity();
+    BP_HD_NOINL static ext mul_u32(const ext& p, uint32_t k) {
+        ext acc = identity();
         int top = 31;
         while (top >= 0 && !((k >> top) & 1u)) top--;
         for (int bit = top; bit >= 0; bit--) {
@@ -159,8 +164,8 @@ struct SW {
     }
 
     // s*P for a canonical (non-Montgomery) 256-bit scalar given as 8 LE limbs
-    BP_HD_NOINL static xyzz mul_scalar(const affine& p, const uint32_t* s) {
-        xyzz acc = identity();
+    BP_HD_NOINL static ext mul_scalar(const aff& p, const uint32_t* s) {
+        ext acc = identity();
         for (int i = 7; i >= 0; i--) {
             for (int bit = 31; bit >= 0; bit--) {
                 acc = dbl(acc);
@@ -170,11 +175,10 @@ struct SW {
         return acc;
     }
 
-    BP_HD static bool on_curve(const affine& p) {
+    BP_HD static bool on_curve(const aff& p) {
         if (is_identity(p)) return true;
-        fe b;
-        for (int i = 0; i < 8; i++) b.v[i] = C::b(i);
-        fe rhs = F::add(F::mul(F::sqr(p.x), p.x), b);
+        el b = F::template curve_b<C>();
+        el rhs = F::add(F::mul(F::sqr(p.x), p.x), b);
         if (C::A_SMALL != 0) rhs = F::add(rhs, mul_a(p.x));
         return F::eq(F::sqr(p.y), rhs);
     }
@@ -185,84 +189,87 @@ struct SW {
 // XYZZ (fields x, y, zz, zzz = X, Y, Z, T). The unified addition law (add-2008-hwcd-3) is complete
 // for a = -1 (a square) and d a non-square, so there are no exceptional cases; "all zero" (Z = 0)
 // is accepted as an additional encoding of the identity so zero-initialised buckets work unchanged.
-// ABI: affine (x,y); the identity is (0,1) and, on input, also (0,0).
+// ABI: aff (x,y); the identity is (0,1) and, on input, also (0,0).
 template <class C, class F_ = Fp<typename C::Fq>>
 struct TE {
     using F = F_;
-    BP_HD static fe d2() { fe r; for (int i = 0; i < 8; i++) r.v[i] = C::d2(i); return r; }
-    BP_HD static fe dcoef() { fe r; for (int i = 0; i < 8; i++) r.v[i] = C::b(i); return r; }
-    BP_HD static bool is_identity(const affine& p) { return F::is_zero(p.x) && (F::is_zero(p.y) || F::eq(p.y, F::one())); }
-    BP_HD static bool is_identity(const xyzz& p) { return F::is_zero(p.zz) || (F::is_zero(p.x) && F::eq(p.y, p.zz)); }
-    BP_HD static xyzz identity() {
-        xyzz r;
+    using el = typename F::el;
+    using aff = affine_t<el>;
+    using ext = xyzz_t<el>;
+    BP_HD static el d2() { return F::template te_d2<C>(); }
+    BP_HD static el dcoef() { return F::template curve_b<C>(); }
+    BP_HD static bool is_identity(const aff& p) { return F::is_zero(p.x) && (F::is_zero(p.y) || F::eq(p.y, F::one())); }
+    BP_HD static bool is_identity(const ext& p) { return F::is_zero(p.zz) || (F::is_zero(p.x) && F::eq(p.y, p.zz)); }
+    BP_HD static ext identity() {
+        ext r;
         r.x = F::zero(); r.y = F::zero(); r.zz = F::zero(); r.zzz = F::zero();
         return r;
     }
-    BP_HD static affine affine_identity() {
-        affine r;
+    BP_HD static aff affine_identity() {
+        aff r;
         r.x = F::zero(); r.y = F::zero();
         return r;
     }
-    BP_HD static xyzz from_affine(const affine& p) {
+    BP_HD static ext from_affine(const aff& p) {
         if (is_identity(p)) return identity();
-        xyzz r;
+        ext r;
         r.x = p.x; r.y = p.y; r.zz = F::one(); r.zzz = F::mul(p.x, p.y);
         return r;
     }
-    BP_HD static affine neg(const affine& p) {
-        affine r;
+    BP_HD static aff neg(const aff& p) {
+        aff r;
         r.x = F::neg(p.x); r.y = p.y;
         return r;
     }
-    BP_HD static xyzz neg(const xyzz& p) {
-        xyzz r = p;
+    BP_HD static ext neg(const ext& p) {
+        ext r = p;
         r.x = F::neg(p.x); r.zzz = F::neg(p.zzz);
         return r;
     }
     // dbl-2008-hwcd with a = -1: 4M + 4S
-    BP_HD static xyzz dbl(const xyzz& p) {
+    BP_HD static ext dbl(const ext& p) {
         if (F::is_zero(p.zz)) return identity();
-        fe A = F::sqr(p.x), B = F::sqr(p.y), Cc = F::dbl(F::sqr(p.zz));
-        fe D = F::neg(A);
-        fe E = F::sub(F::sub(F::sqr(F::add(p.x, p.y)), A), B);
-        fe G = F::add(D, B), Fv = F::sub(G, Cc), H = F::sub(D, B);
-        xyzz r;
+        el A = F::sqr(p.x), B = F::sqr(p.y), Cc = F::dbl(F::sqr(p.zz));
+        el D = F::neg(A);
+        el E = F::sub(F::sub(F::sqr(F::add(p.x, p.y)), A), B);
+        el G = F::add(D, B), Fv = F::sub(G, Cc), H = F::sub(D, B);
+        ext r;
         r.x = F::mul(E, Fv); r.y = F::mul(G, H); r.zzz = F::mul(E, H); r.zz = F::mul(Fv, G);
         return r;
     }
-    BP_HD static xyzz dbl_affine(const affine& p) { return dbl(from_affine(p)); }
+    BP_HD static ext dbl_affine(const aff& p) { return dbl(from_affine(p)); }
     // acc += q (both extended): add-2008-hwcd-3, 8M + 1 (2d)
-    BP_HD static void add(xyzz& acc, const xyzz& q) {
+    BP_HD static void add(ext& acc, const ext& q) {
         if (F::is_zero(q.zz)) return;
         if (F::is_zero(acc.zz)) { acc = q; return; }
-        fe A = F::mul(F::sub(acc.y, acc.x), F::sub(q.y, q.x));
-        fe B = F::mul(F::add(acc.y, acc.x), F::add(q.y, q.x));
-        fe Cc = F::mul(F::mul(acc.zzz, d2()), q.zzz);
-        fe D = F::dbl(F::mul(acc.zz, q.zz));
-        fe E = F::sub(B, A), Fv = F::sub(D, Cc), G = F::add(D, Cc), H = F::add(B, A);
+        el A = F::mul(F::sub(acc.y, acc.x), F::sub(q.y, q.x));
+        el B = F::mul(F::add(acc.y, acc.x), F::add(q.y, q.x));
+        el Cc = F::mul(F::mul(acc.zzz, d2()), q.zzz);
+        el D = F::dbl(F::mul(acc.zz, q.zz));
+        el E = F::sub(B, A), Fv = F::sub(D, Cc), G = F::add(D, Cc), H = F::add(B, A);
         acc.x = F::mul(E, Fv); acc.y = F::mul(G, H); acc.zzz = F::mul(E, H); acc.zz = F::mul(Fv, G);
     }
-    // acc += affine q: 9M (T2 = x2*y2 computed on the fly)
-    BP_HD static void madd(xyzz& acc, const affine& q) {
+    // acc += aff q: 9M (T2 = x2*y2 computed on the fly)
+    BP_HD static void madd(ext& acc, const aff& q) {
         if (is_identity(q)) return;
         if (F::is_zero(acc.zz)) { acc = from_affine(q); return; }
-        fe A = F::mul(F::sub(acc.y, acc.x), F::sub(q.y, q.x));
-        fe B = F::mul(F::add(acc.y, acc.x), F::add(q.y, q.x));
-        fe Cc = F::mul(F::mul(acc.zzz, d2()), F::mul(q.x, q.y));
-        fe D = F::dbl(acc.zz);
-        fe E = F::sub(B, A), Fv = F::sub(D, Cc), G = F::add(D, Cc), H = F::add(B, A);
+        el A = F::mul(F::sub(acc.y, acc.x), F::sub(q.y, q.x));
+        el B = F::mul(F::add(acc.y, acc.x), F::add(q.y, q.x));
+        el Cc = F::mul(F::mul(acc.zzz, d2()), F::mul(q.x, q.y));
+        el D = F::dbl(acc.zz);
+        el E = F::sub(B, A), Fv = F::sub(D, Cc), G = F::add(D, Cc), H = F::add(B, A);
         acc.x = F::mul(E, Fv); acc.y = F::mul(G, H); acc.zzz = F::mul(E, H); acc.zz = F::mul(Fv, G);
     }
-    BP_HD_NOINL static affine to_affine(const xyzz& p) {
+    BP_HD_NOINL static aff to_affine(const ext& p) {
         if (is_identity(p)) return affine_identity();
-        fe zi = F::inv(p.zz);
-        affine r;
+        el zi = F::inv(p.zz);
+        aff r;
         r.x = F::mul(p.x, zi);
         r.y = F::mul(p.y, zi);
         return r;
     }
-    BP_HD_NOINL static xyzz mul_u32(const xyzz& p, uint32_t k) {
-        xyzz acc = identity();
+    BP_HD_NOINL static ext mul_u32(const ext& p, uint32_t k) {
+        ext acc = identity();
         int top = 31;
         while (top >= 0 && !((k >> top) & 1u)) top--;
         for (int bit = top; bit >= 0; bit--) {
@@ -271,8 +278,8 @@ struct TE {
         }
         return acc;
     }
-    BP_HD_NOINL static xyzz mul_scalar(const affine& p, const uint32_t* s) {
-        xyzz acc = identity();
+    BP_HD_NOINL static ext mul_scalar(const aff& p, const uint32_t* s) {
+        ext acc = identity();
         for (int i = 7; i >= 0; i--) {
             for (int bit = 31; bit >= 0; bit--) {
                 acc = dbl(acc);
@@ -281,11 +288,11 @@ struct TE {
         }
         return acc;
     }
-    BP_HD static bool on_curve(const affine& p) {
+    BP_HD static bool on_curve(const aff& p) {
         if (is_identity(p)) return true;
-        fe x2 = F::sqr(p.x), y2 = F::sqr(p.y);
-        fe lhs = F::sub(y2, x2);
-        fe rhs = F::add(F::one(), F::mul(dcoef(), F::mul(x2, y2)));
+        el x2 = F::sqr(p.x), y2 = F::sqr(p.y);
+        el lhs = F::sub(y2, x2);
+        el rhs = F::add(F::one(), F::mul(dcoef(), F::mul(x2, y2)));
         return F::eq(lhs, rhs);
     }
 };

@@ -98,6 +98,9 @@ inline void wmadc_to_cc(uint32_t& dlo, uint32_t& dhi, uint32_t a, uint32_t b, ui
 template <class M>
 struct Fp {
     using Mod = M;
+    using el = fe;
+    template <class C> BP_HD static fe te_d2() { fe r; for (int i = 0; i < 8; i++) r.v[i] = C::d2(i); return r; }
+    template <class C> BP_HD static fe curve_b() { fe r; for (int i = 0; i < 8; i++) r.v[i] = C::b(i); return r; }
     // r = t - m if t >= m, where t carries a possible 257th bit `top`
     BP_HD static void final_sub(fe& r, const uint32_t* t, uint32_t top) {
         uint32_t s[8];

@@ -13,6 +13,9 @@ namespace bp {
 template <class M>
 struct HostFp {
     using Mod = M;
+    using el = fe;
+    template <class C> static fe te_d2() { fe r; for (int i = 0; i < 8; i++) r.v[i] = C::d2(i); return r; }
+    template <class C> static fe curve_b() { fe r; for (int i = 0; i < 8; i++) r.v[i] = C::b(i); return r; }
     typedef unsigned __int128 u128;
     static inline uint64_t ml(int i) { return (uint64_t)M::m(2 * i) | ((uint64_t)M::m(2 * i + 1) << 32); }
     static inline void get(const fe& a, uint64_t* o) { memcpy(o, a.v, 32); }

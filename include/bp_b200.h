@@ -84,6 +84,9 @@ int bp_msm_set_chunk(bp_ctx* ctx, size_t points);
 /* IPA rounds of length n <= this threshold do not fold the generators; their L/R are MSMs over the last
  * folded stage with challenge-expanded scalars (same L, R, a, b). 0 = always fold. Default 2^14. */
 int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n);
+/* Bucket accumulation on 9 x 29-bit limbs (csrc/fp29.cuh; default on for secq256k1 and curve25519) or on the
+ * 8 x 32-bit limbs of csrc/fp.cuh; both give identical results. For A/B measurements and tests. */
+int bp_msm_set_fp29(bp_ctx* ctx, int enable);
 /* Force the Pippenger window width (0 = automatic); for parity tests and tuning. */
 int bp_msm_set_window(bp_ctx* ctx, int c);
 

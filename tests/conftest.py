@@ -12,3 +12,14 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The C-ABI library and the C oracle are build artefacts (git-ignored): build them once if a clean
+    checkout has not run __graft_entry__.build() yet. nvcc cross-compiles without a GPU."""
+    lib = os.path.join(ROOT, "ark_bulletproofs_b200", "libbp_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__ as g
+        g.build()
+    yield

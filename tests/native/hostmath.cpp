@@ -4,6 +4,7 @@
 #include <cstring>
 #include "../../ark_bulletproofs_b200/csrc/ec.cuh"
 #include "../../ark_bulletproofs_b200/csrc/host/fp_host.hpp"
+#include "../../ark_bulletproofs_b200/csrc/fp29.cuh"
 using namespace bp;
 
 template <class F> static int fp_op_t(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
@@ -68,6 +69,71 @@ extern "C" int hm_ec_op(int curve, int op, const uint32_t* p, const uint32_t* q,
         case 12: return ec_op_t<TE<Curve25519, HostFp<Fp25519>>>(op, p, q, s, out);
         case 10: return ec_op_t<SW<Secq256k1, HostFp<SecqFq>>>(op, p, q, s, out);
         case 11: return ec_op_t<SW<Zorro, HostFp<ZorroFq>>>(op, p, q, s, out);
+    }
+    return -1;
+}
+
+
+// ---- Fp29 (9 x 29-bit limbs, Montgomery domain 2^261); values cross as canonical 8 x 32-bit integers ----
+template <class M> static int fp29_op_t(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    using F = Fp29<M>;
+    fe x, y;
+    memcpy(x.v, a, 32);
+    memcpy(y.v, b, 32);
+    fl X = F::unpack(x), Y = F::unpack(y), R;
+    switch (op) {
+        case 0: R = F::mul(X, Y); break;
+        case 1: R = F::add(X, Y); break;
+        case 2: R = F::sub(X, Y); break;
+        case 3: R = F::sqr(X); break;
+        case 4: R = F::neg(X); break;
+        case 5: R = F::mul3(X); break;
+        // chains that exercise the loose bounds: ((x - y) - y + x) * (x + y + y) ; and ((x-y)^2 - 3x) * (y - x)
+        case 6: R = F::mul(F::add(F::sub(F::sub(X, Y), Y), X), F::add(F::add(X, Y), Y)); break;
+        case 7: R = F::mul(F::sub(F::sqr(F::sub(X, Y)), F::mul3(X)), F::sub(Y, X)); break;
+        case 8: { fe o = F::to_storage(X); memcpy(out, o.v, 32); return F::is_zero(X) ? 1 : 0; }
+        case 9: { bool e = F::eq(X, Y); fl d = F::sub(X, Y); fe o = F::pack_canonical(d); memcpy(out, o.v, 32); return e ? 1 : 0; }
+        default: return -1;
+    }
+    fe o = F::pack_canonical(R);
+    memcpy(out, o.v, 32);
+    return 0;
+}
+extern "C" int hm_fp29_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    switch (field) {
+        case 0: return fp29_op_t<SecqFq>(op, a, b, out);
+        case 1: return fp29_op_t<SecqFr>(op, a, b, out);
+        case 3: return fp29_op_t<Fp25519>(op, a, b, out);
+    }
+    return -1;
+}
+
+// group law over Fp29: points cross as canonical affine (x,y) in the 2^261 domain, (0,0) = identity
+template <class E> static int ec29_op_t(int op, const uint32_t* p, const uint32_t* q, const uint32_t* s, uint32_t* out) {
+    using F = typename E::F;
+    affine P, Q;
+    memcpy(&P, p, 64);
+    memcpy(&Q, q, 64);
+    typename E::aff Pl{F::unpack(P.x), F::unpack(P.y)}, Ql{F::unpack(Q.x), F::unpack(Q.y)};
+    typename E::ext r;
+    switch (op) {
+        case 0: r = E::from_affine(Pl); E::madd(r, Ql); break;
+        case 1: { typename E::ext a = E::dbl_affine(Pl); typename E::ext b = E::from_affine(Ql); b = E::dbl(b); r = a; E::add(r, b); break; }
+        case 2: r = E::dbl(E::dbl_affine(Pl)); break;
+        case 3: r = E::mul_scalar(Pl, s); break;
+        case 4: { r = E::dbl_affine(Pl); E::madd(r, Ql); break; }
+        case 5: { r = E::dbl_affine(Pl); typename E::ext b = E::dbl_affine(Ql); E::add(r, b); break; }
+        default: return -1;
+    }
+    // return the projective result as 4 canonical coordinates (128 B): the caller normalises
+    fe o[4] = {F::pack_canonical(r.x), F::pack_canonical(r.y), F::pack_canonical(r.zz), F::pack_canonical(r.zzz)};
+    memcpy(out, o, 128);
+    return E::is_identity(r) ? 1 : 0;
+}
+extern "C" int hm_ec29_op(int curve, int op, const uint32_t* p, const uint32_t* q, const uint32_t* s, uint32_t* out) {
+    switch (curve) {
+        case 0: return ec29_op_t<SW<Secq256k1, Fp29<SecqFq>>>(op, p, q, s, out);
+        case 2: return ec29_op_t<TE<Curve25519, Fp29<Fp25519>>>(op, p, q, s, out);
     }
     return -1;
 }

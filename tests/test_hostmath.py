@@ -99,3 +99,76 @@ def test_curve_ops(lib, cid, cv):
         assert _ec(lib, cid, cv, 3, P, None, s) == mul(s, P)
     for k in [0, 1, 5, 65535, 0xFFFFFFFF]:
         assert _ec(lib, cid, cv, 6, P, None, k) == mul(2 * k, P)
+
+
+R261 = 1 << 261
+
+
+@pytest.mark.parametrize("field", [0, 1, 3])
+def test_fp29_ops(lib, field):
+    """csrc/fp29.cuh: 9 x 29-bit unsaturated limbs, Montgomery domain 2^261, lazy ("tight") reduction."""
+    m = FIELDS[field]
+    rnd = random.Random(4321 + field)
+    rinv = pow(R261, -1, m)
+
+    def op(o, a, b=0):
+        out = (ctypes.c_uint32 * 8)()
+        rc = lib.hm_fp29_op(field, o, _b(a), _b(b), out)
+        assert rc >= 0
+        return int.from_bytes(bytes(out), "little"), rc
+    edge = [0, 1, 2, m - 1, m - 2, (1 << 255) % m, (1 << 232) - 1, (1 << 232), (m - 1) // 2, (1 << 145) - 1, m >> 1, (1 << 29) - 1]
+    vals = edge + [rnd.randrange(m) for _ in range(60)]
+    for a in vals:
+        for b in rnd.sample(vals, 6) + [m - 1, a, 0]:
+            assert op(0, a, b)[0] == a * b * rinv % m
+            assert op(1, a, b)[0] == (a + b) % m
+            assert op(2, a, b)[0] == (a - b) % m
+            assert op(6, a, b)[0] == ((a - b - b + a) * (a + b + b)) * rinv % m
+            assert op(7, a, b)[0] == (((a - b) ** 2 * rinv - 3 * a) * (b - a)) * rinv % m
+            d, e = op(9, a, b)
+            assert d == (a - b) % m and e == (1 if a == b else 0)
+        assert op(3, a)[0] == a * a * rinv % m
+        assert op(4, a)[0] == (-a) % m
+        assert op(5, a)[0] == 3 * a % m
+        st, z = op(8, a)
+        assert st == a * (1 << 256) * rinv % m and z == (1 if a == 0 else 0)
+
+
+@pytest.mark.parametrize("cid,cv", [(0, O.SECQ256K1), (2, O.CURVE25519)])
+def test_curve_ops_fp29(lib, cid, cv):
+    rnd = random.Random(199 + cid)
+    q = cv.q
+    rinv = pow(R261, -1, q)
+
+    def enc(P):
+        if P is None:
+            return (ctypes.c_uint32 * 16)()
+        return (ctypes.c_uint32 * 16).from_buffer_copy((P[0] * R261 % q).to_bytes(32, "little") + (P[1] * R261 % q).to_bytes(32, "little"))
+
+    def run(o, P, Q, s=0):
+        out = (ctypes.c_uint32 * 32)()
+        rc = lib.hm_ec29_op(cid, o, enc(P), enc(Q), _b(s), out)
+        assert rc >= 0
+        raw = bytes(out)
+        X, Y, ZZ, ZZZ = [int.from_bytes(raw[32 * i:32 * i + 32], "little") * rinv % q for i in range(4)]
+        if rc == 1:
+            return None
+        if cv.kind == "sw":
+            return (X * pow(ZZ, -1, q) % q, Y * pow(ZZZ, -1, q) % q)
+        x, y = X * pow(ZZ, -1, q) % q, Y * pow(ZZ, -1, q) % q      # extended: (X:Y:Z:T) in (x,y,zz,zzz)
+        return None if (x == 0 and y == 1) else (x, y)
+    G = cv.G
+    pts = [O.pt_mul(cv, rnd.randrange(1, cv.r), G) for _ in range(4)]
+    add, mul, neg = (lambda a, b: O.pt_add(cv, a, b)), (lambda k, a: O.pt_mul(cv, k, a)), (lambda a: O.pt_neg(cv, a))
+    cases = [(P, Q) for P in pts[:2] for Q in pts[2:]] + [(pts[0], pts[0]), (pts[0], neg(pts[0])), (pts[0], None), (None, pts[1]), (None, None)]
+    for P, Q in cases:
+        assert run(0, P, Q) == add(P, Q)
+        assert run(1, P, Q) == add(mul(2, P), mul(2, Q))
+        assert run(5, P, Q) == add(mul(2, P), mul(2, Q))
+        assert run(2, P, Q) == mul(4, P)
+        assert run(4, P, Q) == add(mul(2, P), Q)
+    P = pts[0]
+    assert run(4, P, mul(2, P)) == mul(4, P)
+    assert run(4, P, neg(mul(2, P))) is None
+    for s in [0, 1, 2, cv.r - 1, rnd.randrange(cv.r)]:
+        assert run(3, P, None, s) == mul(s, P)
