@@ -92,6 +92,7 @@ def load():
         "bp_prover_free": (None, [vp]),
         "bp_prover_cs": (vp, [vp]),
         "bp_prover_commit": (i32, [vp, vp, vp, vp, vp]),
+        "bp_prover_commit_batch": (i32, [vp, vp, vp, sz, vp, vp]),
         "bp_prover_prove": (i32, [vp, vp, pvp]),
         "bp_verifier_new": (i32, [vp, vp, pvp]),
         "bp_verifier_free": (None, [vp]),
@@ -107,6 +108,7 @@ def load():
         "bp_proof_get_field": (i32, [vp, i32, vp]),
         "bp_proof_set_field": (i32, [vp, i32, vp]),
         "bp_proof_rounds": (sz, [vp]),
+        "bp_ipa_verify": (i32, [vp, vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "bp_ipa_create": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]),
     }
     global EXPORTED_SYMBOLS

@@ -95,6 +95,10 @@ struct ApiImpl {
         memcpy(out_V, &V, 64);
         return rc;
     }
+    static int prover_commit_batch(void* p, const uint8_t* v, const uint8_t* blind, size_t m, uint8_t* out_V, Variable* vars) {
+        return static_cast<ProverT<C>*>(p)->commit_batch(reinterpret_cast<const fe*>(v), reinterpret_cast<const fe*>(blind), m,
+                                                        reinterpret_cast<affine*>(out_V), vars);
+    }
     static int prover_prove(void* p, Rng* rng, void** out_proof) {
         std::unique_ptr<ProofT<C>> pr(new ProofT<C>());
         int rc = static_cast<ProverT<C>*>(p)->prove(*rng, *pr);
@@ -205,12 +209,29 @@ struct ApiImpl {
         return BP_OK;
     }
 
+    static int ipa_verify_host(bp_ctx* ctx, Transcript* t, size_t n, const uint8_t* Lp, const uint8_t* Rp, const uint8_t* a, const uint8_t* b,
+                               const uint8_t* Gf, const uint8_t* Hf, const uint8_t* P, const uint8_t* Q, const uint8_t* G, const uint8_t* H) {
+        if (n == 0 || (n & (n - 1))) return BP_ERR_POW2;
+        size_t k = 0;
+        while (((size_t)1 << k) < n) k++;
+        DevBuf dG, dH, dGf, dHf;
+        struct Guard { DevBuf* b[4]; ~Guard() { for (auto* x : b) x->release(); } } guard{{&dG, &dH, &dGf, &dHf}};
+        BP_CUDA_TRY(ctx, dG.reserve(n * 64)); BP_CUDA_TRY(ctx, dH.reserve(n * 64));
+        BP_CUDA_TRY(ctx, dGf.reserve(n * 32)); BP_CUDA_TRY(ctx, dHf.reserve(n * 32));
+        using D = Dev<C>;
+        D::upload(ctx, dG.p, G, n * 64); D::upload(ctx, dH.p, H, n * 64); D::upload(ctx, dGf.p, Gf, n * 32);
+        if (int rc = D::upload(ctx, dHf.p, Hf, n * 32)) return rc;
+        std::vector<affine> L(k), R(k);
+        if (k) { memcpy(L.data(), Lp, k * 64); memcpy(R.data(), Rp, k * 64); }
+        return ipa_verify<C>(ctx, *t, n, L, R, ld(a), ld(b), dGf.as<fe>(), dHf.as<fe>(), ldp(P), ldp(Q), dG.as<affine>(), dH.as<affine>());
+    }
+
     static const CurveApi* table() {
         static const CurveApi api = {
             gens_generate_host, gens_create, gens_from_points, pedersen_commit, challenge_scalar, rng_scalar, scalar_to_bytes, scalar_from_bytes,
-            point_compress, point_uncompressed, point_decompress, prover_new, prover_free, prover_cs, prover_commit, prover_prove, verifier_new,
+            point_compress, point_uncompressed, point_decompress, prover_new, prover_free, prover_cs, prover_commit, prover_commit_batch, prover_prove, verifier_new,
             verifier_free, verifier_cs, verifier_commit, verifier_verify, batch_verify, batch_verify_partial, proof_free, proof_to_bytes, proof_from_bytes, proof_clone,
-            proof_field, proof_rounds, chain_circuit, ipa_create_host};
+            proof_field, proof_rounds, chain_circuit, ipa_create_host, ipa_verify_host};
         return &api;
     }
 };

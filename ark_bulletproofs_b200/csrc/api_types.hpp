@@ -28,6 +28,7 @@ struct CurveApi {
     void (*prover_free)(void*);
     ConstraintSystemBase* (*prover_cs)(void*);
     int (*prover_commit)(void*, const uint8_t* v, const uint8_t* blind, uint8_t* out_V, Variable* var);
+    int (*prover_commit_batch)(void*, const uint8_t* v, const uint8_t* blind, size_t m, uint8_t* out_V, Variable* vars);
     int (*prover_prove)(void*, Rng*, void** out_proof);
     void* (*verifier_new)(bp_ctx*, Transcript*);
     void (*verifier_free)(void*);
@@ -46,6 +47,8 @@ struct CurveApi {
     int (*chain_circuit)(ConstraintSystemBase*, const Variable* v0, size_t n, const uint8_t* ks, const uint8_t* x0);
     int (*ipa_create_host)(bp_ctx*, Transcript*, const uint8_t* Q, const uint8_t* Gf, const uint8_t* Hf, const uint8_t* G, const uint8_t* H,
                            const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out_L, uint8_t* out_R, uint8_t* out_a, uint8_t* out_b);
+    int (*ipa_verify_host)(bp_ctx*, Transcript*, size_t n, const uint8_t* L, const uint8_t* R, const uint8_t* a, const uint8_t* b, const uint8_t* Gf,
+                           const uint8_t* Hf, const uint8_t* P, const uint8_t* Q, const uint8_t* G, const uint8_t* H);
 };
 
 const CurveApi* curve_api_secq();

@@ -178,6 +178,7 @@ int bp_synth_points_device(bp_ctx* ctx, void* d_out_xy, size_t n, uint64_t start
     return bp::synth_points_dispatch(ctx, d_out_xy, n, start);
 }
 
+
 }  // extern "C"
 
 // =====================================================================================================
@@ -411,6 +412,16 @@ int bp_prover_commit(bp_prover* p, const uint8_t value[32], const uint8_t blindi
     put_var(out_var, v);
     return rc;
 }
+int bp_prover_commit_batch(bp_prover* p, const uint8_t* values, const uint8_t* blindings, size_t m, uint8_t* out_commitments, bp_var* out_vars) {
+    if (!p || (m && (!values || !blindings || !out_commitments || !out_vars))) return BP_ERR_ARG;
+    if (((uintptr_t)values | (uintptr_t)blindings | (uintptr_t)out_commitments) & 15) return BP_ERR_ARG;   // 16-byte aligned arrays
+    BP_CUDA_TRY(p->ctx, cudaSetDevice(p->ctx->device));
+    std::vector<bp::Variable> vars(m);
+    int rc = bp::curve_api(p->curve)->prover_commit_batch(p->impl, values, blindings, m, out_commitments, vars.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < m; i++) put_var(&out_vars[i], vars[i]);
+    return BP_OK;
+}
 int bp_prover_prove(bp_prover* p, bp_rng* rng, bp_proof** out) {
     if (!p || !rng || !out) return BP_ERR_ARG;
     BP_CUDA_TRY(p->ctx, cudaSetDevice(p->ctx->device));
@@ -511,6 +522,18 @@ int bp_ipa_create(bp_ctx* ctx, bp_transcript* transcript, const uint8_t Q[64], c
     if (!api) return BP_ERR_UNSUPPORTED;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return api->ipa_create_host(ctx, &transcript->t, Q, G_factors, H_factors, G_xy, H_xy, a, b, n, out_L, out_R, out_a, out_b);
+}
+
+
+int bp_ipa_verify(bp_ctx* ctx, bp_transcript* transcript, size_t n, const uint8_t* L_xy, const uint8_t* R_xy, const uint8_t a[32], const uint8_t b[32],
+                  const uint8_t* G_factors, const uint8_t* H_factors, const uint8_t P[64], const uint8_t Q[64], const uint8_t* G_xy,
+                  const uint8_t* H_xy) {
+    if (!ctx || !transcript || !a || !b || !G_factors || !H_factors || !P || !Q || !G_xy || !H_xy) return BP_ERR_ARG;
+    if (n > 1 && (!L_xy || !R_xy)) return BP_ERR_ARG;
+    auto api = bp::curve_api(ctx->curve);
+    if (!api) return BP_ERR_UNSUPPORTED;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return api->ipa_verify_host(ctx, &transcript->t, n, L_xy, R_xy, a, b, G_factors, H_factors, P, Q, G_xy, H_xy);
 }
 
 }  // extern "C"

@@ -266,6 +266,60 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
     return BP_OK;
 }
 
+// ---- InnerProductProof::verify (inner_product_proof.rs:321-382; test-only in the reference) ----------
+// Returns BP_OK iff  a*b*Q + <a*s*Gf, G> + <b*s^-1*Hf, H> - sum u_j^2 L_j - sum u_j^-2 R_j == P.
+template <class C>
+int ipa_verify(bp_ctx* ctx, Transcript& t, size_t n, const std::vector<affine>& L_vec, const std::vector<affine>& R_vec, const fe& a, const fe& b,
+               const fe* d_Gf, const fe* d_Hf, const affine& P, const affine& Q, const affine* d_G, const affine* d_H) {
+    using Fr = HostFp<typename C::Fr>;
+    using HC = HostCurve<C>;
+    using D = Dev<C>;
+    size_t lg_n = L_vec.size();
+    if (lg_n >= 32 || R_vec.size() != lg_n || n != ((size_t)1 << lg_n)) return BP_ERR_VERIFY;     // :256-264
+    t.append_message("dom-sep", (const uint8_t*)"ipp v1", 6);
+    t.append_u64("n", n);
+    VerifyInputs vin;
+    std::vector<fe> tail(1 + 2 * lg_n);
+    std::vector<affine> pts(1 + 2 * lg_n);
+    fe allinv = Fr::one();
+    for (size_t j = 0; j < lg_n; j++) {
+        if (TP<C>::validate_and_append_point(t, "L", L_vec[j])) return BP_ERR_VERIFY;
+        if (TP<C>::validate_and_append_point(t, "R", R_vec[j])) return BP_ERR_VERIFY;
+        fe u = TP<C>::challenge_scalar(t, "u");
+        fe ui = Fr::is_zero(u) ? u : Fr::inv(u);
+        if (!Fr::is_zero(ui)) allinv = Fr::mul(allinv, ui);
+        vin.usq[j] = Fr::sqr(u);
+        tail[1 + j] = Fr::neg(vin.usq[j]);                    // neg_u_sq
+        tail[1 + lg_n + j] = Fr::neg(Fr::sqr(ui));            // neg_u_inv_sq
+        pts[1 + j] = L_vec[j];
+        pts[1 + lg_n + j] = R_vec[j];
+    }
+    tail[0] = Fr::mul(a, b);
+    pts[0] = Q;
+    vin.wL = vin.wR = vin.wO = vin.yinvpow = nullptr;
+    vin.allinv = allinv; vin.a = a; vin.b = b; vin.x = Fr::zero(); vin.u = Fr::zero(); vin.lg_n = (int)lg_n;
+    BP_CUDA_TRY(ctx, ctx->v_g.reserve((n + 1) * sizeof(fe)));
+    BP_CUDA_TRY(ctx, ctx->v_h.reserve((n + 1) * sizeof(fe)));
+    BP_CUDA_TRY(ctx, ctx->v_pts.reserve((pts.size() + 1) * sizeof(affine)));
+    BP_CUDA_TRY(ctx, ctx->v_sc.reserve((tail.size() + 1) * sizeof(fe)));
+    ipa_verify_scalars_kernel<C><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(vin, n, d_Gf, d_Hf, ctx->v_g.as<fe>(), ctx->v_h.as<fe>());
+    BP_LAUNCH_CHECK(ctx);
+    D::upload(ctx, ctx->v_sc.p, tail.data(), tail.size() * sizeof(fe));
+    if (int rc = D::upload(ctx, ctx->v_pts.p, pts.data(), pts.size() * sizeof(affine))) return rc;
+    MsmJob job;
+    job.add(d_G, ctx->v_g.as<fe>(), n, 0);
+    job.add(d_H, ctx->v_h.as<fe>(), n, 0);
+    job.add(ctx->v_pts.as<affine>(), ctx->v_sc.as<fe>(), pts.size(), 0);
+    uint8_t o[1][64];
+    int id[1] = {0};
+    if (int rc = msm_run_job<C>(ctx, job, o, id)) return rc;
+    affine got;
+    memcpy(&got, o[0], 64);
+    const bool p_id = HC::E::is_identity(P);
+    if (id[0] || p_id) return (id[0] && p_id) ? BP_OK : BP_ERR_VERIFY;
+    return (HC::Fq::eq(got.x, P.x) && HC::Fq::eq(got.y, P.y)) ? BP_OK : BP_ERR_VERIFY;             // :377-381
+}
+
 // ---- constraint storage shared by prover and verifier -----------------------------------------------
 struct ConstraintStore {
     std::vector<uint8_t> kind;
@@ -450,6 +504,30 @@ struct ProverT : ConstraintSystemBase {
         V = HC::add(HC::mul(gens->B, val), HC::mul(gens->B_blinding, blind));                   // generators.rs:39-44
         TP<C>::append_point(*transcript, "V", V);
         var = {VAR_COMMITTED, i};
+        return BP_OK;
+    }
+    // m commitments at once: the scalar multiplications run on the GPU (pedersen_commit_kernel), the
+    // transcript appends stay in commit order on the host -- same V_i, same transcript as m commit() calls
+    int commit_batch(const fe* vals, const fe* blinds, size_t m, affine* V_out, Variable* vars) {
+        if (m == 0) return BP_OK;
+        DevBuf dv, db, dout;
+        struct Guard { DevBuf* b[3]; ~Guard() { for (auto* x : b) x->release(); } } guard{{&dv, &db, &dout}};
+        BP_CUDA_TRY(ctx, dv.reserve(m * sizeof(fe)));
+        BP_CUDA_TRY(ctx, db.reserve(m * sizeof(fe)));
+        BP_CUDA_TRY(ctx, dout.reserve(m * sizeof(affine)));
+        D::upload(ctx, dv.p, vals, m * sizeof(fe));
+        if (int rc = D::upload(ctx, db.p, blinds, m * sizeof(fe))) return rc;
+        affine BBb = HC::add(gens->B, gens->B_blinding);
+        pedersen_commit_kernel<C><<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(gens->B, gens->B_blinding, BBb, dv.as<fe>(), db.as<fe>(),
+                                                                                       dout.as<affine>(), m);
+        BP_LAUNCH_CHECK(ctx);
+        if (int rc = D::download(ctx, V_out, dout.p, m * sizeof(affine))) return rc;
+        for (size_t i = 0; i < m; i++) {
+            vars[i] = {VAR_COMMITTED, (uint64_t)v.size()};
+            v.push_back(vals[i]);
+            v_blinding.push_back(blinds[i]);
+            TP<C>::append_point(*transcript, "V", V_out[i]);
+        }
         return BP_OK;
     }
     int create_randomized_constraints() {                                                       // :418-441

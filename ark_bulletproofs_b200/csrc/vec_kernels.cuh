@@ -241,6 +241,31 @@ __global__ void __launch_bounds__(128) ipa_fold_points_joint_kernel(const affine
     st_fe(&out[i].y, r.y);
 }
 
+// ---- batched Pedersen commitments (generators.rs:39-44 called m times: prover.rs:327-341) ------------
+// out[i] = v[i]*B + r[i]*B_blinding. One thread per commitment, joint double-and-add over the shared
+// table {B, B_blinding, B + B_blinding} (all affine, so every addition is a mixed add).
+template <class C>
+__global__ void __launch_bounds__(128) pedersen_commit_kernel(const affine B, const affine Bb, const affine BBb, const fe* __restrict__ v,
+                                                              const fe* __restrict__ r, affine* __restrict__ out, size_t n) {
+    using E = GroupLaw<C>;
+    using Fr = Fp<typename C::Fr>;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe sv = Fr::from_mont(ld_fe(v + i)), sr = Fr::from_mont(ld_fe(r + i));
+    xyzz acc = E::identity();
+    for (int limb = 7; limb >= 0; limb--) {
+        uint32_t wv = sv.v[limb], wr = sr.v[limb];
+        for (int bit = 31; bit >= 0; bit--) {
+            acc = E::dbl(acc);
+            uint32_t sel = ((wv >> bit) & 1u) | (((wr >> bit) & 1u) << 1);
+            if (sel) E::madd(acc, sel == 1 ? B : sel == 2 ? Bb : BBb);
+        }
+    }
+    affine a = E::to_affine(acc);
+    st_fe(&out[i].x, a.x);
+    st_fe(&out[i].y, a.y);
+}
+
 // ---- R1CS prover vector kernels (prover.rs:674-756) ----------------------------------------------
 struct LrInputs {
     const fe *aL, *aR, *aO, *sL, *sR, *wL, *wR, *wO;   // length n
@@ -346,6 +371,20 @@ __global__ void __launch_bounds__(128) r1cs_verify_scalars_kernel(const __grid_c
     }
     block_sum<F, 1, 128>(acc, sm);
     if (threadIdx.x == 0) st_fe(delta_parts + blockIdx.x, acc[0]);
+}
+
+// InnerProductProof::verify scalars (inner_product_proof.rs:338-353):
+//   g[i] = (a * s_i) * G_factors[i] ,  h[i] = (b * s_{n-1-i}) * H_factors[i]
+template <class C>
+__global__ void __launch_bounds__(128) ipa_verify_scalars_kernel(const __grid_constant__ VerifyInputs in, size_t n, const fe* __restrict__ Gf,
+                                                                 const fe* __restrict__ Hf, fe* __restrict__ g, fe* __restrict__ h) {
+    using F = Fp<typename C::Fr>;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe si = s_value<F>(in, (uint32_t)i);
+    fe sinv = s_value<F>(in, (uint32_t)(n - 1 - i));
+    st_fe(g + i, F::mul(F::mul(in.a, si), ld_fe_rw(Gf + i)));
+    st_fe(h + i, F::mul(F::mul(in.b, sinv), ld_fe_rw(Hf + i)));
 }
 
 // out[i] = alpha * in[i]  (+ accumulate into acc[i] if acc != nullptr)      (verifier.rs:650-664)

@@ -287,6 +287,18 @@ class Prover(_CS):
         _chk(self.lib.bp_prover_commit(self.h, codec.enc_fe(v, self.r), codec.enc_fe(v_blinding, self.r), out, ctypes.byref(var)))
         return codec.dec_point(out.raw, self.curve), Variable(var.kind, var.index)
 
+    def commit_batch(self, vals, blindings):
+        """m commits in one call (GPU scalar multiplications); returns ([V], [Variable])."""
+        m = len(vals)
+        import numpy as np
+        vb = np.frombuffer(codec.enc_scalars(vals, self.curve), dtype=np.uint8).copy()
+        bb = np.frombuffer(codec.enc_scalars(blindings, self.curve), dtype=np.uint8).copy()
+        out = np.zeros(64 * max(m, 1), dtype=np.uint8)
+        vars_ = (BpVar * max(m, 1))()
+        _chk(self.lib.bp_prover_commit_batch(self.h, vb.ctypes.data, bb.ctypes.data, m, out.ctypes.data, vars_), "commit_batch")
+        raw = out.tobytes()
+        return ([codec.dec_point(raw[64 * i:64 * i + 64], self.curve) for i in range(m)], [Variable(vars_[i].kind, vars_[i].index) for i in range(m)])
+
     def prove(self, rng: ChaChaRng) -> Proof:
         ph = ctypes.c_void_p()
         self.ctx._check(self.lib.bp_prover_prove(self.h, rng.h, ctypes.byref(ph)))
@@ -355,6 +367,18 @@ def ipa_create(ctx, transcript: Transcript, Q, G_factors, H_factors, G, H, a, b)
     L = [codec.dec_point(oL.raw[64 * i:64 * i + 64], curve) for i in range(k)]
     R = [codec.dec_point(oR.raw[64 * i:64 * i + 64], curve) for i in range(k)]
     return L, R, codec.dec_fe(oa.raw, r), codec.dec_fe(ob.raw, r)
+
+
+def ipa_verify(ctx, transcript: Transcript, n, L, Rv, a, b, G_factors, H_factors, P, Q, G, H) -> bool:
+    """InnerProductProof::verify (inner_product_proof.rs:321-382): True iff the proof opens P."""
+    curve = ctx.curve
+    rc = ctx.lib.bp_ipa_verify(ctx.h, transcript.h, n, codec.enc_points(L, curve), codec.enc_points(Rv, curve), codec.enc_scalars([a], curve),
+                               codec.enc_scalars([b], curve), codec.enc_scalars(G_factors, curve), codec.enc_scalars(H_factors, curve),
+                               codec.enc_point(P, curve), codec.enc_point(Q, curve), codec.enc_points(G, curve), codec.enc_points(H, curve))
+    if rc == -7:
+        return False
+    ctx._check(rc)
+    return True
 
 
 # ---- gadgets of the reference's integration tests (tests/r1cs_secq256k1.rs), written against the

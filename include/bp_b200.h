@@ -182,6 +182,10 @@ int bp_prover_new(bp_ctx* ctx, const bp_gens* pc_gens, bp_transcript* transcript
 void bp_prover_free(bp_prover* p);
 bp_cs* bp_prover_cs(bp_prover* p);
 int bp_prover_commit(bp_prover* p, const uint8_t value[32], const uint8_t blinding[32], uint8_t out_commitment[64], bp_var* out_var);
+/* m successive Prover::commit calls in one go: the 2m scalar multiplications run as one GPU kernel, the
+ * transcript sees the same V_i in the same order (k-shuffle style circuits commit 2k inputs). Arrays are
+ * m x 32 / m x 64 bytes, 16-byte aligned. */
+int bp_prover_commit_batch(bp_prover* p, const uint8_t* values, const uint8_t* blindings, size_t m, uint8_t* out_commitments, bp_var* out_vars);
 /* Consumes the constraint system like `Prover::prove(self, prng, bp_gens)`; bp_gens are the ones
  * given to bp_prover_new. BP_ERR_GENS when gens_capacity < padded multipliers. */
 int bp_prover_prove(bp_prover* p, bp_rng* prng, bp_proof** out);
@@ -217,6 +221,11 @@ size_t bp_proof_rounds(const bp_proof* p);
 int bp_ipa_create(bp_ctx* ctx, bp_transcript* transcript, const uint8_t Q[64], const uint8_t* G_factors, const uint8_t* H_factors,
                   const uint8_t* G_xy, const uint8_t* H_xy, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out_L, uint8_t* out_R,
                   uint8_t out_a[32], uint8_t out_b[32]);
+/* ---- InnerProductProof::verify (src/inner_product_proof.rs:321-382, test-only in the reference): BP_OK iff the
+ * proof (L, R: log2(n) points; a, b) opens P with respect to G, H' = H*H_factors, Q. */
+int bp_ipa_verify(bp_ctx* ctx, bp_transcript* transcript, size_t n, const uint8_t* L_xy, const uint8_t* R_xy, const uint8_t a[32], const uint8_t b[32],
+                  const uint8_t* G_factors, const uint8_t* H_factors, const uint8_t P[64], const uint8_t Q[64], const uint8_t* G_xy,
+                  const uint8_t* H_xy);
 
 #ifdef __cplusplus
 }

@@ -160,6 +160,10 @@ def test_ipa_create_matches_oracle(env, n, factors, nofold):
     c = O.inner_product(cv, a, b)
     P = O.msm(cv, bp.G(n) + bp.H(n) + [Q], [x * g % cv.r for x, g in zip(a, Gf)] + [x * h % cv.r for x, h in zip(b, Hf)] + [c])
     O.ipa_verify(cv, O.InnerProductProof(L, Rv, ao, bo), n, O.Transcript(b"innerproducttest"), Gf, Hf, P, Q, bp.G(n), bp.H(n))
+    # InnerProductProof::verify on the GPU (row a5): accepts the proof, rejects a wrong P and a tampered a
+    assert R.ipa_verify(ctx, R.Transcript(b"innerproducttest"), n, L, Rv, ao, bo, Gf, Hf, P, Q, bp.G(n), bp.H(n))
+    assert not R.ipa_verify(ctx, R.Transcript(b"innerproducttest"), n, L, Rv, ao, bo, Gf, Hf, O.pt_add(cv, P, Q), Q, bp.G(n), bp.H(n))
+    assert not R.ipa_verify(ctx, R.Transcript(b"innerproducttest"), n, L, Rv, (ao + 1) % cv.r, bo, Gf, Hf, P, Q, bp.G(n), bp.H(n))
 
 
 @pytest.mark.parametrize("name", [c[0] for c in C.GOLDEN_CASES])
@@ -325,3 +329,37 @@ def test_golden_proofs_all_ipa_paths(env, name, nofold):
     finally:
         ctx.set_ipa_nofold_threshold(1 << 14)
     assert proof.to_bytes().hex() == g["proof_hex"]
+
+
+@pytest.mark.parametrize("curve", ["secq256k1", "curve25519"])
+def test_commit_batch_equals_commit(env, curve):
+    """bp_prover_commit_batch (GPU kernel) == m Prover::commit calls: same V_i, same transcript, same proof."""
+    from ark_bulletproofs_b200 import r1cs as R
+    cv = O.CURVES[curve]
+    ctx, gens = env(curve, 16)
+    inp, out = C.shuffle_values(5, 55)
+
+    def transcript():
+        t = R.Transcript(b"ShuffleProofTest")
+        t.append_message(b"dom-sep", b"ShuffleProof")
+        t.append_u64(b"k", 5)
+        return t
+    rng = R.ChaChaRng(bytes(range(32)))
+    p1 = R.Prover(ctx, gens, transcript())
+    blinds = [rng.scalar(curve) for _ in range(10)]
+    Vs, vars_ = p1.commit_batch(inp + out, blinds)
+    pc = O.PedersenGens(cv)
+    assert Vs == [pc.commit(v, b) for v, b in zip(inp + out, blinds)]
+    R.shuffle_gadget(p1, vars_[:5], vars_[5:])
+    proof1 = p1.prove(rng)
+    rng2 = R.ChaChaRng(bytes(range(32)))
+    p2 = R.Prover(ctx, gens, transcript())
+    cs = [p2.commit(v, rng2.scalar(curve)) for v in inp + out]
+    R.shuffle_gadget(p2, [v for _, v in cs[:5]], [v for _, v in cs[5:]])
+    assert proof1.to_bytes() == p2.prove(rng2).to_bytes()
+    # edge scalars
+    p3 = R.Prover(ctx, gens, transcript())
+    ev = [0, 1, cv.r - 1, 0]
+    eb = [0, cv.r - 1, 1, 5]
+    Vs, _ = p3.commit_batch(ev, eb)
+    assert Vs == [pc.commit(v, b) for v, b in zip(ev, eb)]
