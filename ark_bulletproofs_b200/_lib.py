@@ -67,6 +67,9 @@ def load():
         "bp_rng_words_used": (u64, [vp]),
         "bp_rng_scalar": (i32, [i32, vp, vp]),
         "bp_rng_scalars": (i32, [i32, vp, sz, vp]),
+        "bp_rng_next_u64": (u64, [vp]),
+        "bp_transcript_build_rng": (vp, [vp, vp, sz, vp, sz, vp]),
+        "bp_host_keccak_select": (i32, [i32]),
         "bp_cs_chain_circuit": (i32, [vp, vp, sz, vp, vp]),
         "bp_ctx_last_stage_ms": (i32, [vp, ctypes.POINTER(ctypes.c_double)]),
         "bp_scalar_to_bytes": (i32, [i32, vp, vp]),

@@ -69,6 +69,10 @@ struct ApiImpl {
         memcpy(out, s.v, 32);
         return BP_OK;
     }
+    static int rng_scalars(Rng* rng, size_t n, uint8_t* out) {
+        HC::scalar_rand_bulk(*rng, reinterpret_cast<fe*>(out), n);
+        return BP_OK;
+    }
     static int scalar_to_bytes(const uint8_t* mont, uint8_t* out) { HC::scalar_to_bytes(ld(mont), out); return BP_OK; }
     static int scalar_from_bytes(const uint8_t* in, uint8_t* mont) {
         fe s;
@@ -231,7 +235,7 @@ struct ApiImpl {
             gens_generate_host, gens_create, gens_from_points, pedersen_commit, challenge_scalar, rng_scalar, scalar_to_bytes, scalar_from_bytes,
             point_compress, point_uncompressed, point_decompress, prover_new, prover_free, prover_cs, prover_commit, prover_commit_batch, prover_prove, verifier_new,
             verifier_free, verifier_cs, verifier_commit, verifier_verify, batch_verify, batch_verify_partial, proof_free, proof_to_bytes, proof_from_bytes, proof_clone,
-            proof_field, proof_rounds, chain_circuit, ipa_create_host, ipa_verify_host};
+            proof_field, proof_rounds, chain_circuit, ipa_create_host, ipa_verify_host, rng_scalars};
         return &api;
     }
 };

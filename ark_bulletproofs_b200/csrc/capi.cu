@@ -267,9 +267,19 @@ uint64_t bp_rng_words_used(const bp_rng* r) { return r && r->chacha ? r->chacha-
 int bp_rng_scalars(int curve, bp_rng* r, size_t n, uint8_t* out) {
     const bp::CurveApi* api = bp::curve_api(curve);
     if (!api || !r || (n && !out)) return BP_ERR_ARG;
-    for (size_t i = 0; i < n; i++) api->rng_scalar(r->r.get(), out + 32 * i);
-    return BP_OK;
+    return api->rng_scalars(r->r.get(), n, out);
 }
+// merlin's TranscriptRngBuilder as the prover uses it (src/r1cs/prover.rs:483-494)
+bp_rng* bp_transcript_build_rng(const bp_transcript* t, const uint8_t* label, size_t llen, const uint8_t* witnesses, size_t nwit, bp_rng* external) {
+    if (!t || !external || (nwit && !witnesses)) return nullptr;
+    std::vector<std::vector<uint8_t>> wit;
+    for (size_t i = 0; i < nwit; i++) wit.emplace_back(witnesses + 32 * i, witnesses + 32 * i + 32);
+    bp_rng* r = new bp_rng();
+    r->r.reset(new bp::TranscriptRng(t->t.make_rng(lbl(label, llen).c_str(), wit, *external->r)));
+    return r;
+}
+uint64_t bp_rng_next_u64(bp_rng* r) { return r ? r->r->next_u64() : 0; }
+int bp_host_keccak_select(int which) { return bp::keccak_select(which); }
 int bp_rng_scalar(int curve, bp_rng* r, uint8_t out[32]) {
     const bp::CurveApi* api = bp::curve_api(curve);
     if (!api || !r) return BP_ERR_ARG;

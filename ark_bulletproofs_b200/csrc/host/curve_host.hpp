@@ -29,12 +29,33 @@ struct HostCurve {
         const uint64_t mask = shave == 64 ? 0 : (~0ull >> shave);
         while (true) {
             uint64_t l[4];
-            for (int i = 0; i < 4; i++) l[i] = rng.next_u64();
+            rng.draw_u64(l, 4);
             l[3] &= mask;
             if (!HostFp<M>::geq_m(l)) return HostFp<M>::put(l);
         }
     }
     static fe scalar_rand(Rng& rng) { return fp_rand<typename C::Fr>(rng); }
+    // n consecutive Fr::rand draws (prover.rs:510-513,599-602). The word stream is sequential, so drawing
+    // exactly the words still needed (4 per missing scalar) in bulk and parsing them in order consumes the
+    // same words as n single draws, rejections included.
+    static void scalar_rand_bulk(Rng& rng, fe* out, size_t n) {
+        using M = typename C::Fr;
+        const int shave = 256 - M::BITS;
+        const uint64_t mask = shave == 64 ? 0 : (~0ull >> shave);
+        std::vector<uint64_t> w;
+        size_t done = 0;
+        while (done < n) {
+            size_t want = n - done;
+            if (want > 4096) want = 4096;
+            w.resize(4 * want);
+            rng.draw_u64(w.data(), 4 * want);
+            for (size_t k = 0; k < want; k++) {
+                uint64_t* l = &w[4 * k];
+                l[3] &= mask;
+                if (!HostFp<M>::geq_m(l)) out[done++] = HostFp<M>::put(l);
+            }
+        }
+    }
 
     // ---- canonical little-endian bytes -----------------------------------------------------
     template <class F>

@@ -15,7 +15,7 @@ namespace bp {
 // ---- Keccak-f[1600] ---------------------------------------------------------------------
 static inline uint64_t rotl64(uint64_t v, int n) { return (v << n) | (v >> (64 - n)); }
 
-static inline void keccak_f1600(uint64_t* A) {
+static inline void keccak_f1600_scalar(uint64_t* A) {
     static const uint64_t RC[24] = {
         0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL, 0x000000000000808BULL,
         0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008AULL, 0x0000000000000088ULL,
@@ -53,6 +53,16 @@ static inline void keccak_f1600(uint64_t* A) {
     A[10] = a10; A[11] = a11; A[12] = a12; A[13] = a13; A[14] = a14; A[15] = a15; A[16] = a16; A[17] = a17; A[18] = a18; A[19] = a19;
     A[20] = a20; A[21] = a21; A[22] = a22; A[23] = a23; A[24] = a24;
 }
+
+// The permutation actually used. csrc/keccak_fast.cpp replaces both pointers at load time with AVX-512
+// versions when the CPU has them (bp::keccak_select switches for the tests); translation units that do not
+// link that file (tests/native) keep the scalar code.
+using keccak_fn = void (*)(uint64_t*);
+using rng_draw_fn = void (*)(uint64_t* state, uint64_t* out, size_t count);
+inline keccak_fn g_keccak = keccak_f1600_scalar;
+inline rng_draw_fn g_rng_draw = nullptr;
+static inline void keccak_f1600(uint64_t* A) { g_keccak(A); }
+int keccak_select(int which);
 
 // ---- SHA3-512 ---------------------------------------------------------------------------
 static inline void sha3_512(const uint8_t* data, size_t len, uint8_t out[64]) {
@@ -138,6 +148,8 @@ struct Rng {
     virtual uint32_t next_u32() = 0;
     virtual uint64_t next_u64() = 0;
     virtual void fill_bytes(uint8_t* out, size_t n) = 0;
+    // `count` consecutive next_u64 results (what ark-ff's BigInt::rand consumes); overridable for bulk draws
+    virtual void draw_u64(uint64_t* out, size_t count) { for (size_t i = 0; i < count; i++) out[i] = next_u64(); }
 };
 
 // ChaCha20Rng of rand_chacha 0.3: 64-bit block counter (words 12,13), stream id 0 (words 14,15)
@@ -202,7 +214,30 @@ struct TranscriptRng : Rng {
         strobe.prf(out, n, false);
     }
     uint32_t next_u32() override { uint32_t v; fill_bytes(reinterpret_cast<uint8_t*>(&v), 4); return v; }
-    uint64_t next_u64() override { uint64_t v; fill_bytes(reinterpret_cast<uint8_t*>(&v), 8); return v; }
+    uint64_t next_u64() override { uint64_t v; draw_u64(&v, 1); return v; }
+    // Steady state of consecutive next_u64 calls. After a prf squeeze of 8 bytes the STROBE state has
+    // pos = 8, pos_begin = 0 and state[0..8] = 0; the next fill_bytes(8) then absorbs, at fixed offsets,
+    //   meta_ad header [old_begin = 0, M|A = 0x12] at 8..9, the length LE32(8) at 10..13,
+    //   prf header [old_begin = 9, I|A|C = 7] at 14..15, and run_f XORs pos_begin = 15 at 16, 0x04 at 17, 0x80 at 167
+    // i.e. three 64-bit lane XORs, one permutation, and lane 0 is the output (then zeroed).
+    static constexpr uint64_t DRAW_LANE1 = 0x0709000000081200ULL, DRAW_LANE2 = 0x040FULL;
+    void draw_u64(uint64_t* out, size_t count) override {
+        while (count) {
+            if (strobe.pos == 8 && strobe.pos_begin == 0) {
+                uint64_t* A = reinterpret_cast<uint64_t*>(strobe.state);
+                if (g_rng_draw) { g_rng_draw(A, out, count); return; }
+                for (size_t i = 0; i < count; i++) {
+                    A[1] ^= DRAW_LANE1; A[2] ^= DRAW_LANE2; A[20] ^= 0x8000000000000000ULL;
+                    keccak_f1600(A);
+                    out[i] = A[0];
+                    A[0] = 0;
+                }
+                return;
+            }
+            fill_bytes(reinterpret_cast<uint8_t*>(out), 8);
+            out++; count--;
+        }
+    }
 };
 
 struct Transcript {

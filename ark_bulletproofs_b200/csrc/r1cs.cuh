@@ -579,8 +579,8 @@ struct ProverT : ConstraintSystemBase {
         fe bl1[3];
         for (int k = 0; k < 3; k++) bl1[k] = HC::scalar_rand(rng);                              // :506-508
         std::vector<fe> s_L(n1), s_R(n1);
-        for (size_t i = 0; i < n1; i++) s_L[i] = HC::scalar_rand(rng);                          // :510-513
-        for (size_t i = 0; i < n1; i++) s_R[i] = HC::scalar_rand(rng);
+        HC::scalar_rand_bulk(rng, s_L.data(), n1);                                              // :510-513
+        HC::scalar_rand_bulk(rng, s_R.data(), n1);
         tm.lap(ST_RNG);
         BP_CUDA_TRY(ctx, ctx->small.reserve(4096));
         // device vectors sized for phase 1; grown after the randomised phase
@@ -608,8 +608,8 @@ struct ProverT : ConstraintSystemBase {
         fe bl2[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
         if (n2 > 0) for (int k = 0; k < 3; k++) bl2[k] = HC::scalar_rand(rng);                   // :585-597
         s_L.resize(n); s_R.resize(n);
-        for (size_t i = n1; i < n; i++) s_L[i] = HC::scalar_rand(rng);                          // :599-602
-        for (size_t i = n1; i < n; i++) s_R[i] = HC::scalar_rand(rng);
+        HC::scalar_rand_bulk(rng, s_L.data() + n1, n - n1);                                     // :599-602
+        HC::scalar_rand_bulk(rng, s_R.data() + n1, n - n1);
         tm.lap(ST_RNG);
         if (n2 > 0) {
             // grow (contents of phase 1 are re-uploaded: the arena may move)

@@ -94,6 +94,14 @@ class Transcript:
         _chk(self.lib.bp_transcript_challenge_scalar(codec.CURVE_IDS[curve], self.h, label, len(label), out))
         return codec.dec_fe(out.raw, codec.MODULI[curve][1])
 
+    def build_rng(self, label: bytes, witnesses, external: "ChaChaRng") -> "ChaChaRng":
+        """merlin TranscriptRng keyed as Prover::prove does (prover.rs:483-494); witnesses = 32-byte strings."""
+        w = b"".join(witnesses)
+        h = self.lib.bp_transcript_build_rng(self.h, label, len(label), w, len(witnesses), external.h)
+        if not h:
+            raise ValueError("bp_transcript_build_rng failed")
+        return ChaChaRng(None, _h=h)
+
     def __del__(self):
         if getattr(self, "h", None):
             self.lib.bp_transcript_free(self.h)
@@ -101,9 +109,12 @@ class Transcript:
 
 
 class ChaChaRng:
-    def __init__(self, seed: bytes):
+    def __init__(self, seed: bytes, _h=None):
         self.lib = _lib.load()
-        self.h = self.lib.bp_rng_chacha20(seed)
+        self.h = _h if _h is not None else self.lib.bp_rng_chacha20(seed)
+
+    def next_u64(self) -> int:
+        return self.lib.bp_rng_next_u64(self.h)
 
     @property
     def words_used(self):

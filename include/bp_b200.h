@@ -138,6 +138,14 @@ uint64_t bp_rng_words_used(const bp_rng* r);
 /* `ScalarField::rand(rng)` (ark-ff UniformRand); out = Montgomery scalar */
 int bp_rng_scalar(int curve, bp_rng* r, uint8_t out[32]);
 int bp_rng_scalars(int curve, bp_rng* r, size_t n, uint8_t* out); /* n successive ScalarField::rand draws */
+uint64_t bp_rng_next_u64(bp_rng* r);
+/* merlin `transcript.build_rng().rekey_with_witness_bytes(label, w_i)...finalize(external)` exactly as
+ * Prover::prove builds its blinding RNG (src/r1cs/prover.rs:483-494); witnesses = nwit x 32 bytes. */
+bp_rng* bp_transcript_build_rng(const bp_transcript* t, const uint8_t* label, size_t llen, const uint8_t* witnesses, size_t nwit,
+                                bp_rng* external);
+/* Host Keccak-f[1600] implementation behind the transcript and TranscriptRng: 0 = portable scalar, 1 = AVX-512
+ * (default when the CPU has it), negative = query. Returns the active one, -1 if `which` is unsupported here. */
+int bp_host_keccak_select(int which);
 
 /* ---- ark-serialize canonical forms (src/transcript.rs:69-79, src/r1cs/proof.rs:74-91) */
 int bp_scalar_to_bytes(int curve, const uint8_t mont[32], uint8_t out[32]);

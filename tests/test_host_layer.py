@@ -131,3 +131,38 @@ def test_curve25519_serialisation():
     assert lib.bp_point_decompress(2, raw, ctypes.create_string_buffer(64)) == -8
     with pytest.raises(ValueError):
         O.de_point_compressed(c, raw)
+
+
+def _oracle_trng(curve, nwit):
+    t = O.Transcript(b"rngtest")
+    b = t.build_rng()
+    for i in range(nwit):
+        b.rekey_with_witness_bytes(b"v_blinding", bytes([i + 1]) * 32)
+    return b.finalize(O.ChaCha20Rng(bytes(range(32))))
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("curve", ["secq256k1", "curve25519"])
+def test_transcript_rng_matches_oracle(impl, curve):
+    """merlin TranscriptRng behind Prover::prove (prover.rs:483-513): single draws, the register-resident bulk
+    path and its rejection handling (curve25519's Fr rejects about half of the draws), scalar and AVX-512 Keccak."""
+    lib = _lib.load()
+    if lib.bp_host_keccak_select(impl) != impl:
+        pytest.skip("no AVX-512 on this host")
+    try:
+        c = O.CURVES[curve]
+        want = _oracle_trng(curve, 2)
+        got = R.Transcript(b"rngtest").build_rng(b"v_blinding", [bytes([1]) * 32, bytes([2]) * 32], R.ChaChaRng(bytes(range(32))))
+        for _ in range(3):
+            assert got.next_u64() == want.next_u64()
+        for _ in range(3):
+            assert got.scalar(curve) == O.scalar_rand(c, want)
+        raw = got.scalars_raw(curve, 37)
+        r = codec.MODULI[curve][1]
+        assert [codec.dec_fe(raw[32 * i:32 * i + 32], r) for i in range(37)] == [O.scalar_rand(c, want) for _ in range(37)]
+        assert got.next_u64() == want.next_u64()
+        # transcript challenges go through the same permutation
+        t1, t2 = R.Transcript(b"kat"), O.Transcript(b"kat")
+        assert t1.challenge_bytes(b"c", 300) == t2.challenge_bytes(b"c", 300)
+    finally:
+        lib.bp_host_keccak_select(1)

@@ -18,8 +18,13 @@ for lg in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "16,20,24").sp
     sc = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device="cuda", generator=g)
     sc.view(-1, 32)[:, 31] &= 0x7F
     torch.cuda.synchronize()
+    import time
     for _ in range(3):
         ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n)
+    wall = (time.perf_counter() - t0) / 5 * 1e3
     ph = ctx.last_phases()
-    print(lg, "c=%d W=%d" % (ph["c"], ph["windows"]), {k: round(v, 3) for k, v in ph["ms"].items()}, flush=True)
+    print(lg, "c=%d W=%d" % (ph["c"], ph["windows"]), {k: round(v, 3) for k, v in ph["ms"].items()}, "gpu_sum=%.3f wall=%.3f ms" % (sum(ph["ms"].values()), wall), flush=True)
     del pts, sc
