@@ -66,6 +66,30 @@ class Context:
     def set_ipa_nofold_threshold(self, n: int):
         self._check(self.lib.bp_ipa_set_nofold_threshold(self.h, n))
 
+    def set_collective(self, rank: int, world: int, allgather):
+        """Multi-GPU mode (bp_ctx_set_collective): `allgather(send: bytes) -> bytes` must return the concatenation
+        of every rank's `send` in rank order (ark_bulletproofs_b200.dist has torch.distributed and in-process
+        implementations). Call before creating generators."""
+        cb_t = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+        def tramp(_user, send, recv, nbytes):
+            try:
+                out = allgather(ctypes.string_at(send, nbytes))
+                if len(out) != nbytes * world:
+                    return 1
+                ctypes.memmove(recv, out, len(out))
+                return 0
+            except Exception:       # never unwind into C
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._coll_cb = cb_t(tramp)     # keep alive
+        self.rank, self.world = rank, world
+        self._check(self.lib.bp_ctx_set_collective(self.h, rank, world, ctypes.cast(self._coll_cb, ctypes.c_void_p), None))
+
+    def set_ipa_geometric(self, enable: bool):
+        self._check(self.lib.bp_ipa_set_geometric(self.h, 1 if enable else 0))
+
     def set_fp29(self, enable: bool):
         self._check(self.lib.bp_msm_set_fp29(self.h, 1 if enable else 0))
 

@@ -21,14 +21,26 @@ struct ApiImpl {
         g->capacity = cap;
         g->B = B;
         g->B_blinding = Bb;
-        BP_CUDA_TRY(ctx, g->G.reserve((cap + 1) * sizeof(affine)));
-        BP_CUDA_TRY(ctx, g->H.reserve((cap + 1) * sizeof(affine)));
+        g->rank = ctx->rank;
+        g->world = ctx->world;
+        std::vector<affine> lg, lh;
+        size_t lcap = cap;
+        if (ctx->world > 1) {
+            // keep this rank's cyclic shard only: generator i lives on rank i mod world
+            size_t lo;
+            g->slice(0, cap, lo, lcap);
+            lg.resize(lcap); lh.resize(lcap);
+            for (size_t j = 0; j < lcap; j++) { lg[j] = G[j * ctx->world + ctx->rank]; lh[j] = H[j * ctx->world + ctx->rank]; }
+            G = lg.data(); H = lh.data();
+        }
+        BP_CUDA_TRY(ctx, g->G.reserve((lcap + 1) * sizeof(affine)));
+        BP_CUDA_TRY(ctx, g->H.reserve((lcap + 1) * sizeof(affine)));
         BP_CUDA_TRY(ctx, g->pc.reserve(2 * sizeof(affine)));
         affine pc[2] = {B, Bb};
         BP_CUDA_TRY(ctx, cudaMemcpyAsync(g->pc.p, pc, sizeof(pc), cudaMemcpyHostToDevice, ctx->stream));
-        if (cap) {
-            BP_CUDA_TRY(ctx, cudaMemcpyAsync(g->G.p, G, cap * sizeof(affine), cudaMemcpyHostToDevice, ctx->stream));
-            BP_CUDA_TRY(ctx, cudaMemcpyAsync(g->H.p, H, cap * sizeof(affine), cudaMemcpyHostToDevice, ctx->stream));
+        if (lcap) {
+            BP_CUDA_TRY(ctx, cudaMemcpyAsync(g->G.p, G, lcap * sizeof(affine), cudaMemcpyHostToDevice, ctx->stream));
+            BP_CUDA_TRY(ctx, cudaMemcpyAsync(g->H.p, H, lcap * sizeof(affine), cudaMemcpyHostToDevice, ctx->stream));
         }
         BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         *out = g.release();
@@ -200,7 +212,22 @@ struct ApiImpl {
         BP_CUDA_TRY(ctx, dGf.reserve(n * 32)); BP_CUDA_TRY(ctx, dHf.reserve(n * 32));
         BP_CUDA_TRY(ctx, da.reserve(n * 32)); BP_CUDA_TRY(ctx, db.reserve(n * 32));
         using D = Dev<C>;
-        D::upload(ctx, dG.p, G, n * 64); D::upload(ctx, dH.p, H, n * 64); D::upload(ctx, dGf.p, Gf, n * 32);
+        std::vector<affine> lg, lh;
+        size_t nl = n;
+        if (ctx->world > 1) {
+            // multi-GPU context: the caller passes the full vectors on every rank; only this rank's cyclic shard
+            // of G and H (index = rank mod world) is kept on the device
+            if (n < (size_t)ctx->world || n % ctx->world) return BP_ERR_ARG;
+            nl = n / ctx->world;
+            lg.resize(nl); lh.resize(nl);
+            for (size_t j = 0; j < nl; j++) {
+                lg[j] = reinterpret_cast<const affine*>(G)[j * ctx->world + ctx->rank];
+                lh[j] = reinterpret_cast<const affine*>(H)[j * ctx->world + ctx->rank];
+            }
+            G = reinterpret_cast<const uint8_t*>(lg.data());
+            H = reinterpret_cast<const uint8_t*>(lh.data());
+        }
+        D::upload(ctx, dG.p, G, nl * 64); D::upload(ctx, dH.p, H, nl * 64); D::upload(ctx, dGf.p, Gf, n * 32);
         D::upload(ctx, dHf.p, Hf, n * 32); D::upload(ctx, da.p, a, n * 32);
         if (int rc = D::upload(ctx, db.p, b, n * 32)) return rc;
         std::vector<affine> L, R;

@@ -1,4 +1,8 @@
 // extern "C" surface of libbp_b200.so (declared in include/bp_b200.h).
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "ctx.cuh"
@@ -11,8 +15,18 @@ int synth_points_dispatch(bp_ctx* ctx, void* d_out, size_t n, uint64_t start);
 
 extern "C" {
 
+// BP_DEBUG_BACKTRACE=1: print a native backtrace on SIGFPE / SIGSEGV / SIGABRT (debugging aid for the ctypes harness)
+static void bp_debug_signal(int sig) {
+    void* frames[64];
+    int n = backtrace(frames, 64);
+    fprintf(stderr, "libbp_b200: signal %d, native backtrace:\n", sig);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 int bp_ctx_create(int curve, int device, bp_ctx** out) {
     if (!out) return BP_ERR_ARG;
+    if (getenv("BP_DEBUG_BACKTRACE")) { signal(SIGFPE, bp_debug_signal); signal(SIGSEGV, bp_debug_signal); signal(SIGABRT, bp_debug_signal); }
     *out = nullptr;
     if (curve < BP_CURVE_SECQ256K1 || curve > BP_CURVE_CURVE25519) return BP_ERR_ARG;
     int ndev = 0;
@@ -93,6 +107,21 @@ int bp_msm_set_chunk(bp_ctx* ctx, size_t points) {
 int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n) {
     if (!ctx) return BP_ERR_ARG;
     ctx->ipa_nofold_n = n;
+    return BP_OK;
+}
+
+int bp_ctx_set_collective(bp_ctx* ctx, int rank, int world, bp_allgather_fn fn, void* user) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world || (world & (world - 1)) || (world > 1 && !fn)) return BP_ERR_ARG;
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->coll = fn;
+    ctx->coll_user = user;
+    return BP_OK;
+}
+
+int bp_ipa_set_geometric(bp_ctx* ctx, int enable) {
+    if (!ctx) return BP_ERR_ARG;
+    ctx->ipa_geo = enable != 0;
     return BP_OK;
 }
 

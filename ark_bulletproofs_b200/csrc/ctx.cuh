@@ -47,7 +47,16 @@ struct bp_ctx {
     bool use_fp29 = false;                 // opt-in 29-bit-limb accumulate kernel (measured slower in round 1, see profiles/r1_mul29_experiment.txt)
     size_t msm_chunk = (size_t)1 << 22;
     size_t ipa_nofold_n = (size_t)1 << 14;   // IPA rounds with n <= this use MSMs over the stage generators instead of folding them   // host-buffer MSMs above 1.5x this are chunked (copy/compute overlap)
+    // Multi-GPU: one bp_ctx per process/GPU; generators are sharded cyclically by index
+    // (rank g holds i = g mod world), every MSM over them yields a partial point per rank, and the partials are
+    // exchanged through the host program's collective (NCCL / gloo all-gather) and added on every rank.
+    int rank = 0, world = 1;
+    bp_allgather_fn coll = nullptr;
+    void* coll_user = nullptr;
+    uint64_t coll_calls = 0, coll_bytes = 0;
+    bool ipa_geo = true;                     // use the uniform-scalar fold for geometric factor vectors (bp_ipa_set_geometric)
     int sm_count = 148;
+    size_t msm_warp_partials_below = (size_t)1 << 17;   // partial-slot lists shorter than this are reduced by warp-segmented scans
     // MSM scratch
     bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;
     bp::DevBuf stage_bases, stage_scalars;

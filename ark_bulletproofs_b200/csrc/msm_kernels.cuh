@@ -23,6 +23,7 @@
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cstring>
+#include <vector>
 #include "ctx.cuh"
 #include "fp29.cuh"
 
@@ -63,7 +64,7 @@ static inline MsmPlan make_plan(size_t n, int nmsm, int force_c, int sm_count) {
     p.key_bits = 1;
     while ((1ull << p.key_bits) <= nkeys) p.key_bits++;
     p.entries = n * (size_t)p.W;
-    size_t per = p.entries / ((size_t)sm_count * 256);
+    size_t per = p.entries / ((size_t)sm_count * 512);   // one resident wave (4 blocks x 128 threads per SM) before chunks grow
     p.L = (int)(per < 8 ? 8 : per > 64 ? 64 : per);
     p.T = (p.entries + p.L - 1) / p.L;
     uint32_t seg = p.nb / 1024;
@@ -88,8 +89,10 @@ struct MsmJob {
     uint32_t count[MSM_MAX_SEGS];
     uint32_t start[MSM_MAX_SEGS + 1];   // prefix sums of count
     uint32_t msm[MSM_MAX_SEGS];
-    void add(const affine* b, const fe* s, size_t n, int m) {
-        bases[nseg] = b; scalars[nseg] = s; count[nseg] = (uint32_t)n; msm[nseg] = (uint32_t)m;
+    uint32_t sstride[MSM_MAX_SEGS];     // scalar of term k of a segment = scalars[k * sstride] (cyclic generator shards read
+                                        // replicated scalar vectors with stride = world)
+    void add(const affine* b, const fe* s, size_t n, int m, uint32_t stride = 1) {
+        bases[nseg] = b; scalars[nseg] = s; count[nseg] = (uint32_t)n; msm[nseg] = (uint32_t)m; sstride[nseg] = stride;
         start[nseg] = nseg ? start[nseg - 1] + count[nseg - 1] : 0;
         nseg++;
         start[nseg] = start[nseg - 1] + (uint32_t)n;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const __grid_constant__
     for (int k = 1; k < MSM_MAX_SEGS; k++)
         if (k < job.nseg && i >= job.start[k]) sg = k;
     uint32_t local = (uint32_t)i - job.start[sg];
-    fe s = Fp<typename C::Fr>::from_mont(ld_fe(job.scalars[sg] + local));
+    fe s = Fp<typename C::Fr>::from_mont(ld_fe(job.scalars[sg] + (size_t)local * job.sstride[sg]));
     const uint32_t half = 1u << (c - 1);
     const uint32_t mask = (1u << c) - 1u;
     const uint32_t wbase = job.msm[sg] * (uint32_t)W;
@@ -345,6 +348,67 @@ __global__ void __launch_bounds__(128) msm_partials_level_kernel(const uint32_t*
     sink.flush(cur, acc, true);
 }
 
+// Warp-segmented level for short slot lists (small MSMs are latency-bound: the serial 16-slot chains of
+// msm_partials_level_kernel cost ~0.1 ms per level, and an IPA runs ~2 log n such MSMs back to back).
+// One slot per lane; a segmented Hillis-Steele scan over the sorted keys sums every run in 5 dependent
+// additions. Runs strictly inside the warp are complete (their key occurs nowhere else) and go to their
+// bucket; the run touching lane 0 and the run touching lane 31 go to the two output slots of the warp,
+// so a level shrinks the list 16x. With `final` set every run is complete and goes to its bucket.
+template <class C>
+__device__ __forceinline__ xyzz shfl_up_xyzz(const xyzz& v, int d) {
+    xyzz r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        r.x.v[k] = __shfl_up_sync(0xFFFFFFFFu, v.x.v[k], d);
+        r.y.v[k] = __shfl_up_sync(0xFFFFFFFFu, v.y.v[k], d);
+        r.zz.v[k] = __shfl_up_sync(0xFFFFFFFFu, v.zz.v[k], d);
+        r.zzz.v[k] = __shfl_up_sync(0xFFFFFFFFu, v.zzz.v[k], d);
+    }
+    return r;
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) msm_partials_warp_kernel(const uint32_t* __restrict__ in_keys, const xyzz* __restrict__ in_pts,
+                                                                size_t nslots, int final, xyzz* __restrict__ buckets,
+                                                                uint32_t* __restrict__ out_keys, xyzz* __restrict__ out_pts) {
+    using E = GroupLaw<C>;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t warp = p >> 5;
+    const int lane = (int)(threadIdx.x & 31u);
+    if ((warp << 5) >= nslots) return;                       // whole warp out of range
+    uint32_t key = p < nslots ? in_keys[p] : INVALID_KEY;
+    xyzz acc = E::identity();
+    if (key != INVALID_KEY) acc = ld_xyzz(in_pts + p);
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t ok = __shfl_up_sync(0xFFFFFFFFu, key, d);
+        xyzz o = shfl_up_xyzz<C>(acc, d);
+        if (lane >= d && ok == key && key != INVALID_KEY) E::add(acc, o);
+    }
+    const uint32_t knext = __shfl_down_sync(0xFFFFFFFFu, key, 1);
+    const uint32_t kfirst = __shfl_sync(0xFFFFFFFFu, key, 0);
+    const uint32_t klast = __shfl_sync(0xFFFFFFFFu, key, 31);
+    const bool run_end = lane == 31 || knext != key;
+    if (final) {
+        if (run_end && key != INVALID_KEY) st_xyzz(buckets + key, acc);
+        return;
+    }
+    if (lane == 0 && kfirst == klast) {                      // single run: keep the slot list dense
+        out_keys[2 * warp + 1] = kfirst;
+        st_xyzz(out_pts + 2 * warp + 1, E::identity());
+    }
+    if (!run_end) return;
+    if (key == kfirst) {
+        out_keys[2 * warp] = key;
+        if (key != INVALID_KEY) st_xyzz(out_pts + 2 * warp, acc);
+    } else if (key == klast) {
+        out_keys[2 * warp + 1] = key;
+        if (key != INVALID_KEY) st_xyzz(out_pts + 2 * warp + 1, acc);
+    } else {
+        st_xyzz(buckets + key, acc);
+    }
+}
+
 // last level: one thread per slot; the first slot of each key folds the following ones
 template <class C>
 __global__ void __launch_bounds__(128) msm_partials_final_kernel(const uint32_t* __restrict__ keys, const xyzz* __restrict__ pts,
@@ -510,7 +574,8 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
     xyzz* in_p = pp;
     uint32_t* out_k = pk + slots1;
     xyzz* out_p = pp + slots1;
-    while (nslots > 64) {
+    // long lists: serial 16-slot chunks (throughput); short lists: warp-segmented scans (latency)
+    while (nslots > ctx->msm_warp_partials_below) {
         size_t T2 = (nslots + PL - 1) / PL;
         msm_partials_level_kernel<C><<<(unsigned)((T2 + 127) / 128), 128, 0, st>>>(in_k, in_p, nslots, PL, T2, ctx->buckets.as<xyzz>(),
                                                                                    out_k, out_p);
@@ -519,7 +584,15 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
         uint32_t* tk = in_k; in_k = out_k; out_k = tk;
         xyzz* tp = in_p; in_p = out_p; out_p = tp;
     }
-    msm_partials_final_kernel<C><<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(in_k, in_p, nslots, ctx->buckets.as<xyzz>());
+    while (nslots > 32) {
+        size_t nw = (nslots + 31) / 32;
+        msm_partials_warp_kernel<C><<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(in_k, in_p, nslots, 0, ctx->buckets.as<xyzz>(), out_k, out_p);
+        BP_LAUNCH_CHECK(ctx);
+        nslots = 2 * nw;
+        uint32_t* tk = in_k; in_k = out_k; out_k = tk;
+        xyzz* tp = in_p; in_p = out_p; out_p = tp;
+    }
+    msm_partials_warp_kernel<C><<<1, 32, 0, st>>>(in_k, in_p, nslots, 1, ctx->buckets.as<xyzz>(), out_k, out_p);
     BP_LAUNCH_CHECK(ctx);
     mark(3);
     size_t rt = (size_t)NW * p.nseg;
@@ -545,6 +618,32 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
         int rc = host_combine(ctx->curve, (const xyzz*)ctx->h_result + (size_t)m * p.W, p.W, p.c, out_xy[m],
                               out_is_identity ? &out_is_identity[m] : nullptr);
         if (rc != BP_OK) return rc;
+    }
+    return BP_OK;
+}
+
+// Multi-GPU contexts (bp_ctx_set_collective): the job holds this rank's shard of each of the `nmsm` MSMs. The partial
+// points are all-gathered through the host program's collective (64 B per MSM and rank, identity = zeros) and added
+// on the host, so every rank returns the full sums. With world == 1 this is msm_run_job.
+int host_points_sum(int curve, const uint8_t* pts_xy, size_t n, uint8_t out_xy[64], int* out_is_identity);
+template <class C>
+int msm_run_job_sharded(bp_ctx* ctx, MsmJob& job, int nmsm, uint8_t (*out_xy)[64], int* out_is_identity) {
+    if (job.nmsm < nmsm) job.nmsm = nmsm;           // a rank may hold no term of some MSM
+    if (int rc = msm_run_job<C>(ctx, job, out_xy, out_is_identity)) return rc;
+    if (ctx->world <= 1) return BP_OK;
+    if (!ctx->coll) return BP_ERR_ARG;
+    const size_t bytes = (size_t)nmsm * 64;
+    std::vector<uint8_t> send(bytes), recv(bytes * ctx->world), pts((size_t)ctx->world * 64);
+    for (int m = 0; m < nmsm; m++) {
+        if (out_is_identity[m]) memset(&send[(size_t)m * 64], 0, 64);
+        else memcpy(&send[(size_t)m * 64], out_xy[m], 64);
+    }
+    if (ctx->coll(ctx->coll_user, send.data(), recv.data(), bytes)) { ctx->err = "collective all-gather failed"; return BP_ERR_CUDA; }
+    ctx->coll_calls++;
+    ctx->coll_bytes += bytes * ctx->world;
+    for (int m = 0; m < nmsm; m++) {
+        for (int r = 0; r < ctx->world; r++) memcpy(&pts[(size_t)r * 64], &recv[(size_t)r * bytes + (size_t)m * 64], 64);
+        if (int rc = host_points_sum(ctx->curve, pts.data(), ctx->world, out_xy[m], &out_is_identity[m])) return rc;
     }
     return BP_OK;
 }

@@ -138,16 +138,30 @@ struct Dev {
 // d_G, d_H: generators (read-only); d_Gf, d_Hf: factor vectors; d_a, d_b: overwritten.
 template <class C>
 int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, const fe* d_Hf, const affine* d_G, const affine* d_H,
-               fe* d_a, fe* d_b, size_t n, std::vector<affine>& L_vec, std::vector<affine>& R_vec, fe& a_out, fe& b_out) {
+               fe* d_a, fe* d_b, size_t n, std::vector<affine>& L_vec, std::vector<affine>& R_vec, fe& a_out, fe& b_out,
+               const fe* geo_rG = nullptr, const fe* geo_rH = nullptr) {
     using Fr = HostFp<typename C::Fr>;
     using D = Dev<C>;
     if (n == 0 || (n & (n - 1))) return BP_ERR_POW2;                     // assert at :66
+    // Geometric factor vectors (Gf[i+1] = rG*Gf[i], Hf[i+1] = rH*Hf[i]; the R1CS prover's are, prover.rs:781-789,
+    // whenever the circuit is one-phase without padding or all-phase-2): the two partners of every fold then
+    // differ by the *uniform* ratio r^h, so  cL*f[i]*P[i] + cR*f[h+i]*P[h+i] = cL*f[i]*(P[i] + (cR/cL)*r^h*P[h+i]):
+    // all rounds use the uniform-scalar fold, the generators stay unscaled, and the per-element factor
+    // f[i] (a prefix of the original vector) times the running common factor goes into the MSM scalars.
+    const bool geo = geo_rG && geo_rH;
     t.append_message("dom-sep", (const uint8_t*)"ipp v1", 6);            // transcript.rs:52-55
     t.append_u64("n", n);
     L_vec.clear();
     R_vec.clear();
     cudaStream_t st = ctx->stream;
-    size_t half = n / 2;
+    // Multi-GPU: d_G, d_H are this rank's cyclic shard (local j = global j*P + g), a, b and the
+    // factor vectors are replicated. Index i and its fold partner i + n/2 share a rank while n >= 2P, so the
+    // generator fold is local; each rank's L/R MSM runs over its shard (with its share of c_L, c_R on Q) and the
+    // partial points are all-gathered and summed. Once n < 2P (or below the no-fold threshold) the no-fold form
+    // is used, which needs no generator exchange at all.
+    const size_t P = (size_t)ctx->world, g = (size_t)ctx->rank;
+    if (P > 1 && (n < P || n % P)) return BP_ERR_ARG;
+    size_t half = n / 2 / P;
     BP_CUDA_TRY(ctx, ctx->ipa_G.reserve((half + 1) * sizeof(affine)));
     BP_CUDA_TRY(ctx, ctx->ipa_H.reserve((half + 1) * sizeof(affine)));
     BP_CUDA_TRY(ctx, ctx->ipa_s.reserve((4 * half + 8) * sizeof(fe)));
@@ -169,40 +183,44 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     // stage of the last generator fold (no-fold rounds expand their scalars back to it)
-    size_t ns = 0;
+    size_t ns = 0;                        // local length of that stage
     NoFoldParams nf;
     nf.nu = 0;
+    const ShardIdx sh{(uint32_t)P, (uint32_t)g};
     while (n != 1) {
         auto t_a = now();
         size_t h = n / 2;
-        const bool nofold = n <= ctx->ipa_nofold_n;
+        const size_t hl = h / P;          // local half length (0 once the partners live on different ranks)
+        const bool nofold = n <= ctx->ipa_nofold_n || hl == 0;
         if (nofold && ns == 0) {
-            ns = n;                       // generators stay at this stage from now on
+            ns = n / P;                   // generators stay at this stage from now on
             BP_CUDA_TRY(ctx, ctx->ipa_s.reserve((4 * ns + 8) * sizeof(fe)));
             s_all = ctx->ipa_s.as<fe>();
             nf.fG = fG;
             nf.fH = fH;
         }
-        int blocks = (int)((h + 127) / 128);
+        const size_t mine = (h + P - 1) / P;      // upper bound of this rank's indices below h
+        int blocks = (int)((mine + 127) / 128);
         if (blocks > PREP_BLOCKS) blocks = PREP_BLOCKS;
         MsmJob job;
         if (!nofold) {
-            fe *sLG = s_all, *sLH = s_all + h, *sRG = s_all + 2 * h, *sRH = s_all + 3 * h;
-            ipa_prep_kernel<C><<<blocks, 128, 0, st>>>(d_a, d_b, h, first ? d_Gf : nullptr, first ? d_Hf : nullptr, fG, fH, sLG, sLH, sRG, sRH, parts);
+            fe *sLG = s_all, *sLH = s_all + hl, *sRG = s_all + 2 * hl, *sRH = s_all + 3 * hl;
+            const bool perel = first || geo;
+            ipa_prep_kernel<C><<<blocks, 128, 0, st>>>(d_a, d_b, h, sh, perel ? d_Gf : nullptr, perel ? d_Hf : nullptr, fG, fH, sLG, sLH, sRG, sRH, parts);
             BP_LAUNCH_CHECK(ctx);
             // L = <a_L*gR, G_R> + <b_R*hL, H_L> + c_L*Q ; R = <a_R*gL, G_L> + <b_L*hR, H_R> + c_R*Q
-            job.add(curG + h, sLG, h, 0);
-            job.add(curH, sLH, h, 0);
+            job.add(curG + hl, sLG, hl, 0);
+            job.add(curH, sLH, hl, 0);
             job.add(d_Q, d_c, 1, 0);
-            job.add(curG, sRG, h, 1);
-            job.add(curH + h, sRH, h, 1);
+            job.add(curG, sRG, hl, 1);
+            job.add(curH + hl, sRH, hl, 1);
             job.add(d_Q, d_c + 1, 1, 1);
         } else {
             fe *sLG = s_all, *sLH = s_all + ns, *sRG = s_all + 2 * ns, *sRH = s_all + 3 * ns;
-            const bool stage0 = first;    // never folded: the factor vectors still apply per element
-            ipa_cross_kernel<C><<<blocks, 128, 0, st>>>(d_a, d_b, h, parts);
+            const bool stage0 = first || geo;    // never folded / geometric: the factor vectors still apply per element
+            ipa_cross_kernel<C><<<blocks, 128, 0, st>>>(d_a, d_b, h, sh, parts);
             BP_LAUNCH_CHECK(ctx);
-            ipa_nofold_scalars_kernel<C><<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(d_a, d_b, ns, n, stage0 ? d_Gf : nullptr, stage0 ? d_Hf : nullptr, nf,
+            ipa_nofold_scalars_kernel<C><<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(d_a, d_b, ns, n, sh, stage0 ? d_Gf : nullptr, stage0 ? d_Hf : nullptr, nf,
                                                                                       sLG, sLH, sRG, sRH);
             BP_LAUNCH_CHECK(ctx);
             job.add(curG, sLG, ns, 0);
@@ -216,7 +234,7 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
         BP_LAUNCH_CHECK(ctx);
         uint8_t out[2][64];
         int ident[2];
-        if (int rc = msm_run_job<C>(ctx, job, out, ident)) return rc;
+        if (int rc = msm_run_job_sharded<C>(ctx, job, 2, out, ident)) return rc;
         auto t_b = now();
         ctx->stage_ms[ST_IPA_MSM] += ms(t_a, t_b);
         affine Lp, Rp;
@@ -238,15 +256,25 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
             nf.uinv[nf.nu] = uinv;
             nf.nu++;
         } else {
-            unsigned fgrid = (unsigned)((2 * h + 127) / 128);
-            if (first) {
+            unsigned fgrid = (unsigned)((2 * hl + 127) / 128);
+            if (geo) {
+                size_t lg_h = 0;
+                while (((size_t)1 << lg_h) < h) lg_h++;
+                fe rGh = *geo_rG, rHh = *geo_rH;
+                for (size_t k = 0; k < lg_h; k++) { rGh = Fr::sqr(rGh); rHh = Fr::sqr(rHh); }
+                fe kG = Fr::mul(Fr::sqr(u), rGh), kH = Fr::mul(Fr::sqr(uinv), rHh);
+                ipa_fold_points_uniform_kernel<C><<<fgrid, 128, 0, st>>>(curG, curG + hl, wG, curH, curH + hl, wH, hl, D::bits(kG), D::bits(kH));
+                BP_LAUNCH_CHECK(ctx);
+                fG = Fr::mul(fG, uinv);
+                fH = Fr::mul(fH, u);
+            } else if (first) {
                 // factors folded into the points (inner_product_proof.rs:143-155)
-                ipa_fold_points_joint_kernel<C><<<fgrid, 128, 0, st>>>(curG, d_Gf, uinv, u, wG, curH, d_Hf, u, uinv, wH, h);
+                ipa_fold_points_joint_kernel<C><<<fgrid, 128, 0, st>>>(curG, d_Gf, uinv, u, wG, curH, d_Hf, u, uinv, wH, h, hl, sh);
                 BP_LAUNCH_CHECK(ctx);
             } else {
                 // u^-1*G_L + u*G_R = u^-1*(G_L + u^2*G_R): the common factor moves into fG (resp. fH)
                 fe u2 = Fr::sqr(u), ui2 = Fr::sqr(uinv);
-                ipa_fold_points_uniform_kernel<C><<<fgrid, 128, 0, st>>>(curG, curG + h, wG, curH, curH + h, wH, h, D::bits(u2), D::bits(ui2));
+                ipa_fold_points_uniform_kernel<C><<<fgrid, 128, 0, st>>>(curG, curG + hl, wG, curH, curH + hl, wH, hl, D::bits(u2), D::bits(ui2));
                 BP_LAUNCH_CHECK(ctx);
                 fG = Fr::mul(fG, uinv);
                 fH = Fr::mul(fH, u);
@@ -552,15 +580,19 @@ struct ProverT : ConstraintSystemBase {
         fe* d_bl = ctx->small.as<fe>() + 16;
         if (int rc = D::upload(ctx, d_bl, bl, 3 * sizeof(fe))) return rc;
         const affine* Bb = gens->pc.template as<affine>() + 1;
-        const affine* G = gens->G.template as<affine>() + off;
-        const affine* H = gens->H.template as<affine>() + off;
+        // sharded contexts: this rank's generators of [off, off+cnt) against the replicated scalar vectors; the
+        // blinding terms are added once (rank 0); the three partial points are all-gathered and summed
+        const bool lead = ctx->rank == 0;
         MsmJob job;
-        job.add(Bb, d_bl, 1, 0); job.add(G, d_aL, cnt, 0); job.add(H, d_aR, cnt, 0);   // A_I
-        job.add(Bb, d_bl + 1, 1, 1); job.add(G, d_aO, cnt, 1);                          // A_O
-        job.add(Bb, d_bl + 2, 1, 2); job.add(G, d_sL, cnt, 2); job.add(H, d_sR, cnt, 2);   // S
+        if (lead) job.add(Bb, d_bl, 1, 0);                                                             // A_I
+        gens->add_range(job, gens->G, d_aL, off, cnt, 0); gens->add_range(job, gens->H, d_aR, off, cnt, 0);
+        if (lead) job.add(Bb, d_bl + 1, 1, 1);                                                         // A_O
+        gens->add_range(job, gens->G, d_aO, off, cnt, 1);
+        if (lead) job.add(Bb, d_bl + 2, 1, 2);                                                         // S
+        gens->add_range(job, gens->G, d_sL, off, cnt, 2); gens->add_range(job, gens->H, d_sR, off, cnt, 2);
         uint8_t o[3][64];
         int id[3];
-        if (int rc = msm_run_job<C>(ctx, job, o, id)) return rc;
+        if (int rc = msm_run_job_sharded<C>(ctx, job, 3, o, id)) return rc;
         for (int k = 0; k < 3; k++) memcpy(&out[k], o[k], 64);
         return BP_OK;
     }
@@ -706,10 +738,12 @@ struct ProverT : ConstraintSystemBase {
         fe w = TP<C>::challenge_scalar(t, "w");                                                 // :777-779
         affine Q = HC::mul(gens->B, w);
         tm.lap(ST_VEC);
-        double ipa_sub[3] = {ctx->stage_ms[ST_IPA_MSM], ctx->stage_ms[ST_IPA_FOLD], ctx->stage_ms[ST_IPA_HOST]};
-        (void)ipa_sub;
+        // G_factors = [1]*n1 ++ [u]*(n2+pad), H_factors[i] = y^-i * G_factors[i] (:781-789): geometric iff one block
+        const bool geo = ctx->ipa_geo && (n1 == 0 || (n2 == 0 && pad == 0));
+        const fe geo_rG = Fr::one();
         int rc = ipa_create<C>(ctx, t, Q, ctx->p_Gf.as<fe>(), ctx->p_Hf.as<fe>(), gens->G.template as<affine>(), gens->H.template as<affine>(),
-                               ctx->p_l.as<fe>(), ctx->p_r.as<fe>(), padded_n, proof.L_vec, proof.R_vec, proof.a, proof.b);   // :791-800
+                               ctx->p_l.as<fe>(), ctx->p_r.as<fe>(), padded_n, proof.L_vec, proof.R_vec, proof.a, proof.b,
+                               geo ? &geo_rG : nullptr, geo ? &y_inv : nullptr);                                        // :791-800
         tm.lap(ST_IPA);
         // secrets: zero the device copies (mirrors prover.rs:74-94,805-812)
         DevBuf* sec[] = {&ctx->p_aL, &ctx->p_aR, &ctx->p_aO, &ctx->p_sL, &ctx->p_sR, &ctx->p_l, &ctx->p_r};
@@ -928,14 +962,16 @@ struct VerifierT : ConstraintSystemBase {
         D::upload(ctx, d_sc, head, 2 * sizeof(fe));
         D::upload(ctx, d_sc + 2, tail.data(), tail.size() * sizeof(fe));
         if (int rc = D::upload(ctx, ctx->v_pts.p, pts.data(), pts.size() * sizeof(affine))) return rc;
+        // sharded contexts: G/H terms on the rank that holds them, everything else once (rank 0)
+        const bool lead = ctx->rank == 0;
         MsmJob job;
-        job.add(gens.pc.template as<affine>(), d_sc, 2, 0);
-        job.add(gens.G.template as<affine>(), d_g, np, 0);
-        job.add(gens.H.template as<affine>(), d_h, np, 0);
-        job.add(ctx->v_pts.as<affine>(), d_sc + 2, pts.size(), 0);
+        if (lead) job.add(gens.pc.template as<affine>(), d_sc, 2, 0);
+        gens.add_range(job, gens.G, d_g, 0, np, 0);
+        gens.add_range(job, gens.H, d_h, 0, np, 0);
+        if (lead && !pts.empty()) job.add(ctx->v_pts.as<affine>(), d_sc + 2, pts.size(), 0);
         uint8_t o[1][64];
         int id[1] = {0};
-        if (int rc = msm_run_job<C>(ctx, job, o, id)) return rc;
+        if (int rc = msm_run_job_sharded<C>(ctx, job, 1, o, id)) return rc;
         memcpy(&sum, o[0], 64);
         is_identity = id[0];
         return BP_OK;

@@ -12,10 +12,24 @@ struct Variable { uint32_t kind; uint64_t idx; };
 // ---- device-resident generators (BulletproofGens share 0 + PedersenGens) ------------------------
 struct GensDev {
     bp_ctx* ctx = nullptr;
-    size_t capacity = 0;
+    size_t capacity = 0;      // global capacity (BulletproofGens::gens_capacity)
+    // cyclic shard of a multi-GPU context (bp_ctx_set_collective): G[j], H[j] hold generator j*world + rank
+    int rank = 0, world = 1;
     DevBuf G, H, pc;          // pc = [B, B_blinding]
     affine B, B_blinding;
     ~GensDev() { G.release(); H.release(); pc.release(); }
+    // generators [off, off+cnt) of the global numbering -> local entries [lo, hi); local j is global j*world + rank
+    void slice(size_t off, size_t cnt, size_t& lo, size_t& hi) const {
+        size_t end = off + cnt, r = (size_t)rank, w = (size_t)world;
+        lo = off > r ? (off - r + w - 1) / w : 0;
+        hi = end > r ? (end - r + w - 1) / w : 0;
+    }
+    // adds <scalars[0..cnt), generators[off..off+cnt)> to MSM m of the job; `scalars` is the replicated vector
+    template <class Job> void add_range(Job& job, const DevBuf& gen, const fe* scalars, size_t off, size_t cnt, int m) const {
+        size_t lo, hi;
+        slice(off, cnt, lo, hi);
+        if (hi > lo) job.add(gen.template as<affine>() + lo, scalars + (lo * world + rank - off), hi - lo, m, (uint32_t)world);
+    }
 };
 
 // ---- abstract interfaces for the C ABI ------------------------------------------------------------

@@ -61,24 +61,33 @@ __global__ void __launch_bounds__(128) vec_reduce_partials_kernel(const fe* __re
 
 // ---- IPA round preparation (inner_product_proof.rs:83-122 / 171-200) -----------------------------
 // With h = n/2:  sLG[i] = a[i]*gR_i, sLH[i] = b[h+i]*hL_i, sRG[i] = a[h+i]*gL_i, sRH[i] = b[i]*hR_i,
-// where (gL,gR,hL,hR) are Gf[i],Gf[h+i],Hf[i],Hf[h+i] in the first round and the uniform deferred
-// factors fG,fH afterwards; block partials of c_L = <a_L,b_R>, c_R = <a_R,b_L>.
+// where (gL,gR,hL,hR) = fG*Gf[i], fG*Gf[h+i], fH*Hf[i], fH*Hf[h+i] while per-element factors apply (first round;
+// every round when the factor vectors are geometric, see ipa_create) and the uniform deferred factors fG, fH
+// otherwise; block partials of c_L = <a_L,b_R>, c_R = <a_R,b_L>.
+// Multi-GPU shards: a rank owns the generators with global index i = j*P + g (j = local index);
+// the scalar vectors a, b, Gf, Hf are replicated and read at the global index, outputs are written at the local one.
+struct ShardIdx { uint32_t P, g; };
+
 template <class C>
-__global__ void __launch_bounds__(128) ipa_prep_kernel(const fe* __restrict__ a, const fe* __restrict__ b, size_t h,
+__global__ void __launch_bounds__(128) ipa_prep_kernel(const fe* __restrict__ a, const fe* __restrict__ b, size_t h, ShardIdx sh,
                                                        const fe* __restrict__ Gf, const fe* __restrict__ Hf, fe fG, fe fH,
                                                        fe* __restrict__ sLG, fe* __restrict__ sLH, fe* __restrict__ sRG,
                                                        fe* __restrict__ sRH, fe* __restrict__ parts) {
     using F = Fp<typename C::Fr>;
     __shared__ fe sm[2 * 128];
     fe acc[2] = {F::zero(), F::zero()};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < h; i += (size_t)gridDim.x * blockDim.x) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j * sh.P + sh.g < h; j += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = j * sh.P + sh.g;
         fe aL = ld_fe_rw(a + i), aR = ld_fe_rw(a + h + i), bL = ld_fe_rw(b + i), bR = ld_fe_rw(b + h + i);
         fe gL = fG, gR = fG, hL = fH, hR = fH;
-        if (Gf) { gL = ld_fe_rw(Gf + i); gR = ld_fe_rw(Gf + h + i); hL = ld_fe_rw(Hf + i); hR = ld_fe_rw(Hf + h + i); }
-        st_fe(sLG + i, F::mul(aL, gR));
-        st_fe(sLH + i, F::mul(bR, hL));
-        st_fe(sRG + i, F::mul(aR, gL));
-        st_fe(sRH + i, F::mul(bL, hR));
+        if (Gf) {
+            gL = F::mul(fG, ld_fe_rw(Gf + i)); gR = F::mul(fG, ld_fe_rw(Gf + h + i));
+            hL = F::mul(fH, ld_fe_rw(Hf + i)); hR = F::mul(fH, ld_fe_rw(Hf + h + i));
+        }
+        st_fe(sLG + j, F::mul(aL, gR));
+        st_fe(sLH + j, F::mul(bR, hL));
+        st_fe(sRG + j, F::mul(aR, gL));
+        st_fe(sRH + j, F::mul(bL, hR));
         acc[0] = F::add(acc[0], F::mul(aL, bR));
         acc[1] = F::add(acc[1], F::mul(aR, bL));
     }
@@ -107,22 +116,23 @@ __global__ void __launch_bounds__(256) ipa_fold_scalars_kernel(fe* __restrict__ 
 struct NoFoldParams {
     fe u[32], uinv[32];     // challenges of the unfolded rounds, oldest first (round s+1 at index 0)
     int nu;                 // how many (= j-1-s)
-    fe fG, fH;              // uniform deferred factors of stage s (ignored when Gf/Hf are given)
+    fe fG, fH;              // uniform deferred factors of stage s (times Gf[t], Hf[t] when those are given)
 };
 
 template <class C>
 __global__ void __launch_bounds__(128) ipa_nofold_scalars_kernel(const fe* __restrict__ a, const fe* __restrict__ b, size_t ns, size_t ncur,
-                                                                 const fe* __restrict__ Gf, const fe* __restrict__ Hf,
+                                                                 ShardIdx sh, const fe* __restrict__ Gf, const fe* __restrict__ Hf,
                                                                  const __grid_constant__ NoFoldParams p, fe* __restrict__ sLG,
                                                                  fe* __restrict__ sLH, fe* __restrict__ sRG, fe* __restrict__ sRH) {
     using F = Fp<typename C::Fr>;
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // local stage index (ns = local stage length)
     if (t >= ns) return;
     const size_t h = ncur / 2;
-    size_t ip = t & (ncur - 1);          // index at the current level
-    size_t tau = t / ncur;
-    fe cG = Gf ? ld_fe_rw(Gf + t) : p.fG;
-    fe cH = Hf ? ld_fe_rw(Hf + t) : p.fH;
+    const size_t gi = t * sh.P + sh.g;   // global stage index
+    size_t ip = gi & (ncur - 1);         // index at the current level (ncur = current global length)
+    size_t tau = gi / ncur;
+    fe cG = Gf ? F::mul(p.fG, ld_fe_rw(Gf + gi)) : p.fG;
+    fe cH = Hf ? F::mul(p.fH, ld_fe_rw(Hf + gi)) : p.fH;
     // bit m of tau belongs to round (j-1-m): index nu-1-m in the oldest-first arrays
     for (int m = 0; m < p.nu; m++) {
         bool bit = (tau >> m) & 1u;
@@ -147,11 +157,13 @@ __global__ void __launch_bounds__(128) ipa_nofold_scalars_kernel(const fe* __res
 
 // block partials of c_L = <a_L, b_R>, c_R = <a_R, b_L> only
 template <class C>
-__global__ void __launch_bounds__(128) ipa_cross_kernel(const fe* __restrict__ a, const fe* __restrict__ b, size_t h, fe* __restrict__ parts) {
+__global__ void __launch_bounds__(128) ipa_cross_kernel(const fe* __restrict__ a, const fe* __restrict__ b, size_t h, ShardIdx sh,
+                                                        fe* __restrict__ parts) {
     using F = Fp<typename C::Fr>;
     __shared__ fe sm[2 * 128];
     fe acc[2] = {F::zero(), F::zero()};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < h; i += (size_t)gridDim.x * blockDim.x) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j * sh.P + sh.g < h; j += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = j * sh.P + sh.g;
         fe aL = ld_fe_rw(a + i), aR = ld_fe_rw(a + h + i), bL = ld_fe_rw(b + i), bR = ld_fe_rw(b + h + i);
         acc[0] = F::add(acc[0], F::mul(aL, bR));
         acc[1] = F::add(acc[1], F::mul(aR, bL));
@@ -208,19 +220,21 @@ template <class C>
 __global__ void __launch_bounds__(128) ipa_fold_points_joint_kernel(const affine* __restrict__ P0, const fe* __restrict__ f0, fe cL0, fe cR0,
                                                                     affine* __restrict__ out0, const affine* __restrict__ P1,
                                                                     const fe* __restrict__ f1, fe cL1, fe cR1, affine* __restrict__ out1,
-                                                                    size_t h) {
+                                                                    size_t h, size_t hl, ShardIdx sh) {
     using E = GroupLaw<C>;
     using Fr = Fp<typename C::Fr>;
+    // h = global half length (factor vectors are replicated), hl = local half length (points are this rank's shard)
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * h) return;
-    const bool second = t >= h;
-    size_t i = second ? t - h : t;
+    if (t >= 2 * hl) return;
+    const bool second = t >= hl;
+    size_t i = second ? t - hl : t;
+    const size_t gi = i * sh.P + sh.g;
     const affine* P = second ? P1 : P0;
     const fe* f = second ? f1 : f0;
     affine* out = second ? out1 : out0;
-    fe sl = Fr::from_mont(Fr::mul(second ? cL1 : cL0, ld_fe_rw(f + i)));
-    fe sr = Fr::from_mont(Fr::mul(second ? cR1 : cR0, ld_fe_rw(f + h + i)));
-    affine pl = ld_affine(P + i), pr = ld_affine(P + h + i);
+    fe sl = Fr::from_mont(Fr::mul(second ? cL1 : cL0, ld_fe_rw(f + gi)));
+    fe sr = Fr::from_mont(Fr::mul(second ? cR1 : cR0, ld_fe_rw(f + h + gi)));
+    affine pl = ld_affine(P + i), pr = ld_affine(P + hl + i);
     xyzz both = E::from_affine(pl);
     E::madd(both, pr);
     xyzz xl = E::from_affine(pl), xr = E::from_affine(pr);

@@ -80,10 +80,27 @@ int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* window
 int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]);
 /* bp_msm over host buffers larger than 1.5x `points` is split into chunks of `points` whose H2D copies
  * overlap the previous chunk's kernels (default 2^22); exposed for tests and tuning. */
+/* ---- multi-GPU: one context per process and GPU --------------------------------------------
+ * `fn` must gather `bytes` bytes from every rank into recv[world * bytes] in rank order (an NCCL or gloo
+ * all-gather issued by the host program) and return 0. After this call:
+ *   - bp_gens_create keeps only the generators G_i, H_i with i = rank (mod world) on this GPU;
+ *   - every MSM over them inside prove / verify / InnerProductProof::create runs on the local shard and the
+ *     64-byte partial points are all-gathered and added on every rank (the reference's G::Group::msm call sites,
+ *     inner_product_proof.rs:104,124,187,202; prover.rs:516-559,607-648; verifier.rs:574);
+ *   - the IPA folds its shard of G and H locally (index i and its partner i + n/2 share a rank while n >= 2*world);
+ *   - scalars, transcript and TranscriptRng are replicated, so all ranks return the same proof bytes / verdict.
+ * world must be a power of two that divides every generator count used. */
+typedef int (*bp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes);
+int bp_ctx_set_collective(bp_ctx* ctx, int rank, int world, bp_allgather_fn fn, void* user);
 int bp_msm_set_chunk(bp_ctx* ctx, size_t points);
 /* IPA rounds of length n <= this threshold do not fold the generators; their L/R are MSMs over the last
  * folded stage with challenge-expanded scalars (same L, R, a, b). 0 = always fold. Default 2^14. */
 int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n);
+/* The R1CS prover's IPA factor vectors (src/r1cs/prover.rs:781-789) are geometric when the circuit is one-phase
+ * without padding, or entirely phase 2; every generator fold is then one scalar multiplication by a scalar shared
+ * by all threads (first round included) instead of the joint double-and-add of inner_product_proof.rs:143-155.
+ * Same L, R, a, b. Default on; 0 restores the general first round (tests run both). */
+int bp_ipa_set_geometric(bp_ctx* ctx, int enable);
 /* Bucket accumulation on 9 x 29-bit limbs (csrc/fp29.cuh; default on for secq256k1 and curve25519) or on the
  * 8 x 32-bit limbs of csrc/fp.cuh; both give identical results. For A/B measurements and tests. */
 int bp_msm_set_fp29(bp_ctx* ctx, int enable);

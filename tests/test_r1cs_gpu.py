@@ -315,20 +315,47 @@ def test_batch_verify_sharded(env):
     assert O.pt_add(cv, parts[0], parts[1]) is not None
 
 
+@pytest.mark.parametrize("geo", [1, 0])
 @pytest.mark.parametrize("nofold", [0, 16, 256])
-@pytest.mark.parametrize("name", ["chain1000", "shuffle42", "zorro_chain20", "c25519_chain20"])
-def test_golden_proofs_all_ipa_paths(env, name, nofold):
-    """The same golden proofs with the generator-folding IPA (threshold 0) and mixed fold / no-fold."""
+@pytest.mark.parametrize("name", ["chain1000", "shuffle42", "shuffle24", "v3_range8", "zorro_chain20", "zorro_shuffle3", "c25519_chain20",
+                                  "c25519_range8"])
+def test_golden_proofs_all_ipa_paths(env, name, nofold, geo):
+    """The same golden proofs with the generator-folding IPA (threshold 0) and mixed fold / no-fold, with and
+    without the uniform-scalar fold for geometric factor vectors (shuffles and the 8-bit range proof qualify)."""
     from ark_bulletproofs_b200 import r1cs as R
     g = GOLDEN[name]
     curve, kind, params = g["curve"], g["kind"], g["params"]
     ctx, gens = env(curve, max(g["gens_capacity"], 1))
     ctx.set_ipa_nofold_threshold(nofold)
+    ctx.set_ipa_geometric(bool(geo))
     try:
         proof, _ = gpu_prove_case(R, ctx, gens, kind, params, curve)
     finally:
         ctx.set_ipa_nofold_threshold(1 << 14)
+        ctx.set_ipa_geometric(True)
     assert proof.to_bytes().hex() == g["proof_hex"]
+
+
+@pytest.mark.parametrize("N,nofold", [(64, 0), (64, 8), (1 << 15, 1 << 14), (1 << 12, 1 << 10)])
+def test_pow2_chain_geometric_equals_general(env, N, nofold):
+    """One-phase circuit with a power-of-two multiplier count (no padding): the IPA factor vectors are
+    (1, y^-i), so every fold round takes the uniform-scalar path. The proof must be byte-identical to the one
+    from the general first round (itself pinned to the oracle by the golden cases), and verify."""
+    from ark_bulletproofs_b200 import r1cs as R
+    curve = "secq256k1"
+    ctx, gens = env(curve, N)
+    out = []
+    ctx.set_ipa_nofold_threshold(nofold)
+    try:
+        for geo in (True, False):
+            ctx.set_ipa_geometric(geo)
+            proof, coms = gpu_prove_case(R, ctx, gens, "chain", {"N": N}, curve)
+            out.append(proof.to_bytes())
+    finally:
+        ctx.set_ipa_nofold_threshold(1 << 14)
+        ctx.set_ipa_geometric(True)
+    assert out[0] == out[1]
+    gpu_verifier(R, ctx, "chain", {"N": N}, curve, coms).verify(R.Proof.from_bytes(curve, out[0]), gens)
 
 
 @pytest.mark.parametrize("curve", ["secq256k1", "curve25519"])
@@ -363,3 +390,70 @@ def test_commit_batch_equals_commit(env, curve):
     eb = [0, cv.r - 1, 1, 5]
     Vs, _ = p3.commit_batch(ev, eb)
     assert Vs == [pc.commit(v, b) for v, b in zip(ev, eb)]
+
+
+# ---- multi-GPU mode on one GPU: `world` contexts in threads, cyclic generator shards ---------------
+def _sharded(world, curve, fn):
+    """fn(R, ctx, rank) on `world` threads, each with its own sharded bp_ctx on cuda:0."""
+    from ark_bulletproofs_b200 import Context
+    from ark_bulletproofs_b200 import r1cs as R
+    from ark_bulletproofs_b200.dist import ThreadGroup
+
+    def work(rank, allgather):
+        ctx = Context(curve, 0)
+        ctx.set_collective(rank, world, allgather)
+        return fn(R, ctx, rank)
+    return ThreadGroup(world).run(work)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("n,nofold", [(64, 0), (64, 8), (8, 1 << 14), (4, 0)])
+def test_sharded_ipa_matches_oracle(world, n, nofold):
+    """InnerProductProof::create with G, H sharded cyclically over `world` contexts: the same L, R, a, b as the
+    oracle on every rank, through local folds (n >= 2*world), the no-fold tail and arbitrary factor vectors."""
+    curve = "secq256k1"
+    cv = O.SECQ256K1
+    rnd = random.Random(n * 31 + world)
+    bp = O.BulletproofGens(cv, n, 1)
+    Q = O.pt_mul(cv, 777, cv.G)
+    a = [rnd.randrange(cv.r) for _ in range(n)]
+    b = [rnd.randrange(cv.r) for _ in range(n)]
+    Gf = [rnd.randrange(1, cv.r) for _ in range(n)]
+    Hf = [rnd.randrange(1, cv.r) for _ in range(n)]
+    want = O.ipa_create(cv, O.Transcript(b"innerproducttest"), Q, Gf, Hf, bp.G(n), bp.H(n), a, b)
+
+    def run(R, ctx, rank):
+        ctx.set_ipa_nofold_threshold(nofold)
+        return R.ipa_create(ctx, R.Transcript(b"innerproducttest"), Q, Gf, Hf, bp.G(n), bp.H(n), a, b)
+    for got in _sharded(world, curve, run):
+        assert got == (want.L_vec, want.R_vec, want.a, want.b)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("name,nofold", [("chain100", 1 << 14), ("chain100", 0), ("shuffle42", 16), ("chain1000", 64), ("range63", 0),
+                                         ("zorro_chain20", 0), ("c25519_chain20", 8)])
+def test_sharded_prove_verify_golden(world, name, nofold):
+    """Prover and verifier with the generators sharded over `world` contexts: every rank emits the golden proof
+    bytes (commitment MSMs, IPA L/R and folds run on the shards, partial points all-gathered), every rank's
+    verifier accepts them and rejects a tampered copy."""
+    g = GOLDEN[name]
+    curve, kind, params = g["curve"], g["kind"], g["params"]
+
+    def run(R, ctx, rank):
+        gens = R.Gens(ctx, max(g["gens_capacity"], 1))
+        ctx.set_ipa_nofold_threshold(nofold)
+        proof, coms = gpu_prove_case(R, ctx, gens, kind, params, curve)
+        raw = proof.to_bytes()
+        gpu_verifier(R, ctx, kind, params, curve, coms).verify(R.Proof.from_bytes(curve, raw), gens)
+        bad = bytearray(raw)
+        bad[-32] ^= 1                                              # IPA scalar b (low byte: still canonical)
+        try:
+            gpu_verifier(R, ctx, kind, params, curve, coms).verify(R.Proof.from_bytes(curve, bytes(bad)), gens)
+            rejected = False
+        except Exception:
+            rejected = True
+        return raw.hex(), rejected, ctx.launches
+    for hexs, rejected, launches in _sharded(world, curve, run):
+        assert hexs == g["proof_hex"]
+        assert rejected
+        assert launches > 0
