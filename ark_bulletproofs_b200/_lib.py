@@ -73,6 +73,7 @@ def load():
         "bp_transcript_build_rng": (vp, [vp, vp, sz, vp, sz, vp]),
         "bp_host_keccak_select": (i32, [i32]),
         "bp_cs_chain_circuit": (i32, [vp, vp, sz, vp, vp]),
+        "bp_cs_shuffle_gadget": (i32, [vp, vp, vp, sz]),
         "bp_ctx_last_stage_ms": (i32, [vp, ctypes.POINTER(ctypes.c_double)]),
         "bp_scalar_to_bytes": (i32, [i32, vp, vp]),
         "bp_scalar_from_bytes": (i32, [i32, vp, vp]),
@@ -103,6 +104,7 @@ def load():
         "bp_verifier_free": (None, [vp]),
         "bp_verifier_cs": (vp, [vp]),
         "bp_verifier_commit": (i32, [vp, vp, vp]),
+        "bp_verifier_commit_batch": (i32, [vp, vp, sz, vp]),
         "bp_verifier_verify": (i32, [vp, vp, vp]),
         "bp_batch_verify": (i32, [vp, vp, vp, vp, sz, vp]),
         "bp_batch_verify_partial": (i32, [vp, vp, vp, vp, sz, vp, vp, pi32]),

@@ -201,6 +201,42 @@ struct ApiImpl {
         return BP_OK;
     }
 
+    // The reference's benchmark / test gadget (benches/r1cs_secq256k1.rs:35-75, tests/r1cs_secq256k1.rs:16-56): y is a
+    // permutation of x iff prod (x_i - z) == prod (y_i - z) for a random z; 2(k-1) phase-2 multipliers.
+    static int shuffle_gadget(ConstraintSystemBase* cs, const Variable* x, const Variable* y, size_t k) {
+        const fe one = Fr::one(), neg1 = Fr::neg(Fr::one());
+        if (k == 0) return BP_ERR_ARG;
+        if (k == 1) {
+            Variable v[2] = {y[0], x[0]};
+            fe c[2] = {one, neg1};
+            return cs->constrain(v, c, 2);
+        }
+        std::vector<Variable> xs(x, x + k), ys(y, y + k);
+        return cs->specify_randomized_constraints([xs, ys, k, one, neg1](ConstraintSystemBase& c) -> int {
+            fe z;
+            if (int rc = c.challenge_scalar("shuffle challenge", &z)) return rc;
+            const fe cz[2] = {one, Fr::neg(z)};
+            auto product = [&](const std::vector<Variable>& v, Variable& first) -> int {
+                Variable o[3];
+                Variable lv[2] = {v[k - 1], {VAR_ONE, 0}}, rv[2] = {v[k - 2], {VAR_ONE, 0}};
+                if (int rc = c.multiply(lv, cz, 2, rv, cz, 2, o)) return rc;
+                first = o[2];
+                for (size_t i = k - 2; i-- > 0;) {
+                    Variable l1[1] = {first}, r2[2] = {v[i], {VAR_ONE, 0}};
+                    if (int rc = c.multiply(l1, &one, 1, r2, cz, 2, o)) return rc;
+                    first = o[2];
+                }
+                return BP_OK;
+            };
+            Variable fx, fy;
+            if (int rc = product(xs, fx)) return rc;
+            if (int rc = product(ys, fy)) return rc;
+            Variable v[2] = {fx, fy};
+            fe cc[2] = {one, neg1};
+            return c.constrain(v, cc, 2);
+        });
+    }
+
     // ---- InnerProductProof::create over host buffers --------------------------------------------
     static int ipa_create_host(bp_ctx* ctx, Transcript* t, const uint8_t* Q, const uint8_t* Gf, const uint8_t* Hf, const uint8_t* G,
                                const uint8_t* H, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out_L, uint8_t* out_R,
@@ -262,7 +298,7 @@ struct ApiImpl {
             gens_generate_host, gens_create, gens_from_points, pedersen_commit, challenge_scalar, rng_scalar, scalar_to_bytes, scalar_from_bytes,
             point_compress, point_uncompressed, point_decompress, prover_new, prover_free, prover_cs, prover_commit, prover_commit_batch, prover_prove, verifier_new,
             verifier_free, verifier_cs, verifier_commit, verifier_verify, batch_verify, batch_verify_partial, proof_free, proof_to_bytes, proof_from_bytes, proof_clone,
-            proof_field, proof_rounds, chain_circuit, ipa_create_host, ipa_verify_host, rng_scalars};
+            proof_field, proof_rounds, chain_circuit, ipa_create_host, ipa_verify_host, rng_scalars, shuffle_gadget};
         return &api;
     }
 };

@@ -50,6 +50,7 @@ struct CurveApi {
     int (*ipa_verify_host)(bp_ctx*, Transcript*, size_t n, const uint8_t* L, const uint8_t* R, const uint8_t* a, const uint8_t* b, const uint8_t* Gf,
                            const uint8_t* Hf, const uint8_t* P, const uint8_t* Q, const uint8_t* G, const uint8_t* H);
     int (*rng_scalars)(Rng*, size_t n, uint8_t* out);
+    int (*shuffle_gadget)(ConstraintSystemBase*, const Variable* x, const Variable* y, size_t k);
 };
 
 const CurveApi* curve_api_secq();

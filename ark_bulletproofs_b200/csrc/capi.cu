@@ -432,6 +432,14 @@ int bp_cs_chain_circuit(bp_cs* cs, const bp_var* v0, size_t n, const uint8_t* ks
     return bp::curve_api(cs->curve)->chain_circuit(cs->cs, &v, n, ks, x0);
 }
 
+// k-shuffle gadget of the reference's benches and tests, built natively (benches/r1cs_secq256k1.rs:35-75).
+int bp_cs_shuffle_gadget(bp_cs* cs, const bp_var* x, const bp_var* y, size_t k) {
+    if (!cs || !x || !y || k == 0) return BP_ERR_ARG;
+    std::vector<bp::Variable> xs(k), ys(k);
+    for (size_t i = 0; i < k; i++) { xs[i] = {x[i].kind, x[i].index}; ys[i] = {y[i].kind, y[i].index}; }
+    return bp::curve_api(cs->curve)->shuffle_gadget(cs->cs, xs.data(), ys.data(), k);
+}
+
 // ---- prover ----
 int bp_prover_new(bp_ctx* ctx, const bp_gens* pc_gens, bp_transcript* transcript, bp_prover** out) {
     if (!ctx || !pc_gens || !transcript || !out) return BP_ERR_ARG;
@@ -489,6 +497,12 @@ int bp_verifier_commit(bp_verifier* v, const uint8_t commitment[64], bp_var* out
     int rc = bp::curve_api(v->curve)->verifier_commit(v->impl, commitment, &var);
     put_var(out_var, var);
     return rc;
+}
+int bp_verifier_commit_batch(bp_verifier* v, const uint8_t* commitments, size_t m, bp_var* out_vars) {
+    if (!v || (m && (!commitments || !out_vars))) return BP_ERR_ARG;
+    for (size_t i = 0; i < m; i++)
+        if (int rc = bp_verifier_commit(v, commitments + 64 * i, out_vars + i)) return rc;
+    return BP_OK;
 }
 int bp_verifier_verify(bp_verifier* v, const bp_proof* proof, const bp_gens* gens) {
     if (!v || !proof || !gens) return BP_ERR_ARG;

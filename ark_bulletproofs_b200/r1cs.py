@@ -225,6 +225,15 @@ class _CS:
         var = BpVar(v0[0], 0, v0[1])
         _chk(self.lib.bp_cs_chain_circuit(self.cs, ctypes.byref(var), n, ks_raw, x0_raw), "chain_circuit")
 
+    def shuffle_gadget_native(self, xs, ys):
+        """The reference's k-shuffle gadget built inside the library (bp_cs_shuffle_gadget); xs, ys: Variables."""
+        k = len(xs)
+        ax, ay = (BpVar * k)(), (BpVar * k)()
+        for i in range(k):
+            ax[i].kind, ax[i].index = xs[i][0], xs[i][1]
+            ay[i].kind, ay[i].index = ys[i][0], ys[i][1]
+        _chk(self.lib.bp_cs_shuffle_gadget(self.cs, ax, ay, k), "shuffle_gadget")
+
     def specify_randomized_constraints(self, fn):
         outer = self
 
@@ -310,6 +319,13 @@ class Prover(_CS):
         raw = out.tobytes()
         return ([codec.dec_point(raw[64 * i:64 * i + 64], self.curve) for i in range(m)], [Variable(vars_[i].kind, vars_[i].index) for i in range(m)])
 
+    def commit_batch_raw(self, vals_raw: bytes, blindings_raw: bytes, m: int):
+        """commit_batch over Montgomery byte strings; returns (m x 64 raw commitment bytes, [Variable])."""
+        out = ctypes.create_string_buffer(64 * max(m, 1))
+        vars_ = (BpVar * max(m, 1))()
+        _chk(self.lib.bp_prover_commit_batch(self.h, vals_raw, blindings_raw, m, out, vars_), "commit_batch")
+        return out.raw[:64 * m], [Variable(vars_[i].kind, vars_[i].index) for i in range(m)]
+
     def prove(self, rng: ChaChaRng) -> Proof:
         ph = ctypes.c_void_p()
         self.ctx._check(self.lib.bp_prover_prove(self.h, rng.h, ctypes.byref(ph)))
@@ -332,6 +348,11 @@ class Verifier(_CS):
         var = BpVar()
         _chk(self.lib.bp_verifier_commit(self.h, codec.enc_point(V, self.curve), ctypes.byref(var)))
         return Variable(var.kind, var.index)
+
+    def commit_batch_raw(self, commitments_raw: bytes, m: int):
+        vars_ = (BpVar * max(m, 1))()
+        _chk(self.lib.bp_verifier_commit_batch(self.h, commitments_raw, m, vars_), "verifier commit_batch")
+        return [Variable(vars_[i].kind, vars_[i].index) for i in range(m)]
 
     def verify(self, proof: Proof, gens: Gens):
         self.ctx._check(self.lib.bp_verifier_verify(self.h, proof.h, gens.h))

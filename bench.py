@@ -273,6 +273,20 @@ def main():
     assert res_e2e == ref, "host-buffer path disagrees with the device-resident path"
     e2e_val = world * n / (ms_e2e / args.steps * 1e-3) / 1e6
 
+    # secondary metric: R1CS prove / verify. With N > 1 the context switches to multi-GPU mode (cyclic generator
+    # shards, partial points all-gathered over NCCL) and every rank takes part in the same proof.
+    r1cs = None
+    if args.r1cs_lg_n > 0:
+        if world > 1:
+            from ark_bulletproofs_b200.dist import torch_allgather
+            ctx.set_collective(rank, world, torch_allgather(device=torch.device("cuda", local_rank)))
+        r1cs = r1cs_prove_verify(ctx, args.r1cs_lg_n)
+        if world > 1:
+            r1cs["sharding"] = "generators cyclic over %d GPUs; every MSM's 64 B partial points all-gathered (NCCL); scalars, transcript and TranscriptRng replicated" % world
+            t = torch.tensor([r1cs["prove_ms"], r1cs["verify_ms"]], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            r1cs["prove_ms"], r1cs["verify_ms"] = round(float(t[0]), 2), round(float(t[1]), 2)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -309,8 +323,8 @@ def main():
                          "peak_source": hbm_src, "launch_ms": round(phases["ms"]["sort"], 4)},
         "phases_ms": {k: round(v, 4) for k, v in phases["ms"].items()},
     }
-    if world == 1 and args.r1cs_lg_n > 0:
-        line["r1cs"] = r1cs_prove_verify(ctx, args.r1cs_lg_n)
+    if r1cs is not None:
+        line["r1cs"] = r1cs
     if world == 1 and not args.no_cpu_baseline:
         ncores = os.cpu_count() or 1
         lg = args.cpu_lg_n or (20 if ncores >= 16 else 18)

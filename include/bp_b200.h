@@ -201,6 +201,10 @@ int bp_cs_challenge_scalar(bp_cs* cs, const uint8_t* label, size_t llen, uint8_t
  * multipliers over the committed variable v0; ks = n Montgomery scalars; x0 = the prover's witness for
  * v0 (NULL on the verifier's side). Equivalent to n allocate_multiplier + 2n constrain calls. */
 int bp_cs_chain_circuit(bp_cs* cs, const bp_var* v0, size_t n, const uint8_t* ks, const uint8_t* x0);
+/* The reference's k-shuffle gadget (benches/r1cs_secq256k1.rs:35-75, tests/r1cs_secq256k1.rs:16-56) over k input
+ * and k output variables: registers the randomised (phase-2) constraints prod(x_i - z) == prod(y_i - z),
+ * 2(k-1) multipliers. Same constraint order as the Rust gadget, so proofs are byte-identical. */
+int bp_cs_shuffle_gadget(bp_cs* cs, const bp_var* x, const bp_var* y, size_t k);
 
 /* ---- Prover::new / commit / prove (src/r1cs/prover.rs:291,327,444) */
 int bp_prover_new(bp_ctx* ctx, const bp_gens* pc_gens, bp_transcript* transcript, bp_prover** out);
@@ -220,6 +224,8 @@ int bp_verifier_new(bp_ctx* ctx, bp_transcript* transcript, bp_verifier** out);
 void bp_verifier_free(bp_verifier* v);
 bp_cs* bp_verifier_cs(bp_verifier* v);
 int bp_verifier_commit(bp_verifier* v, const uint8_t commitment[64], bp_var* out_var);
+/* m successive Verifier::commit calls (src/r1cs/verifier.rs:279-291): commitments = m x 64 bytes */
+int bp_verifier_commit_batch(bp_verifier* v, const uint8_t* commitments, size_t m, bp_var* out_vars);
 int bp_verifier_verify(bp_verifier* v, const bp_proof* proof, const bp_gens* gens);
 int bp_batch_verify(bp_ctx* ctx, bp_rng* prng, bp_verifier* const* verifiers, const bp_proof* const* proofs, size_t n, const bp_gens* gens);
 

@@ -9,9 +9,9 @@ sys.path.insert(0, ROOT)
 from ark_bulletproofs_b200 import Context, codec  # noqa: E402
 from ark_bulletproofs_b200 import r1cs as R  # noqa: E402
 
-curve = "secq256k1"
 lgs = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [10, 12, 14, 16]
 timing = len(sys.argv) > 2 and sys.argv[2] == "timing"
+curve = sys.argv[3] if len(sys.argv) > 3 else "secq256k1"
 ctx = Context(curve, 0)
 ctx.set_timing(timing)
 r = codec.MODULI[curve][1]
@@ -43,11 +43,11 @@ for lg in lgs:
         v.verify(proof, gens)
         t_verify = time.perf_counter() - t0
         st_v = ctx.last_stage_ms()
-    row = {"lg_n": lg, "gens_s": round(t_gens, 2), "build_ms": round(t_build * 1e3, 1), "prove_ms": round(t_prove * 1e3, 2),
+    row = {"curve": curve, "lg_n": lg, "gens_s": round(t_gens, 2), "build_ms": round(t_build * 1e3, 1), "prove_ms": round(t_prove * 1e3, 2),
            "verify_ms": round(t_verify * 1e3, 2), "prove_stages": {k: v for k, v in st_p.items() if v}, "verify_stages": {k: v for k, v in st_v.items() if v},
            "proof_bytes": len(proof.to_bytes())}
     print(json.dumps(row), flush=True)
     res.append(row)
     del gens
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "prove_quick.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "prove_quick_%s.json" % curve), "w"), indent=1)
