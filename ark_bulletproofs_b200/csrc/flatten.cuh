@@ -2,7 +2,8 @@
 //
 // Replaces the serial sparse scatter of src/r1cs/prover.rs:354-397 / src/r1cs/verifier.rs:304-349:
 //   for constraint q, term (var, coeff):  w_{kind(var)}[index(var)] +-= z^(q+1) * coeff
-// as   contrib[t] = coeff_t * z^(q_t+1)            (one thread per constraint, powers from a 2^k table)
+// as   contrib[t] = coeff_t * z^(q_t+1)            (one thread per constraint, powers from a 2^k table; +-1 coefficients,
+//                                                   the bulk of real circuits, are not stored: 8 bytes per term cross PCIe)
 //      sort terms by (kind, index)                  (cub::DeviceRadixSort)
 //      sum runs of equal key                        (cub::DeviceReduce::ReduceByKey with the field add)
 //      scatter the per-variable sums into wL, wR, wO, wV, wc.
@@ -19,20 +20,22 @@ struct FeAddOp {
     __device__ __forceinline__ fe operator()(const fe& a, const fe& b) const { return Fp<typename C::Fr>::add(a, b); }
 };
 
-// key = kind << 29 | index   (index < 2^29; kind in 0..4)
+// The sort keys (kind << 29 | index, index < 2^29, kind in 0..4) are built on the host as the constraints are recorded
+// (ConstraintStore, r1cs.cuh) and uploaded as they are. cref: 0 = coefficient +1, 1 = -1, k + 2 = coeff_ex[k].
 template <class C>
-__global__ void __launch_bounds__(256) flatten_contrib_kernel(const uint8_t* __restrict__ kind, const uint64_t* __restrict__ idx,
-                                                              const fe* __restrict__ coeff, const uint64_t* __restrict__ start, size_t ncons,
-                                                              const __grid_constant__ PowTable zt, uint32_t* __restrict__ keys,
-                                                              uint32_t* __restrict__ perm, fe* __restrict__ contrib) {
+__global__ void __launch_bounds__(256) flatten_contrib_kernel(const uint32_t* __restrict__ cref, const fe* __restrict__ coeff_ex,
+                                                              const uint32_t* __restrict__ start, size_t ncons,
+                                                              const __grid_constant__ PowTable zt, uint32_t* __restrict__ perm,
+                                                              fe* __restrict__ contrib) {
     using F = Fp<typename C::Fr>;
     size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= ncons) return;
-    fe zp = pow_from_table<F>(zt, (uint32_t)q + 1u);           // exp_z for constraint q is z^(q+1)
-    for (uint64_t t = start[q]; t < start[q + 1]; t++) {
-        keys[t] = ((uint32_t)kind[t] << 29) | (uint32_t)idx[t];
-        perm[t] = (uint32_t)t;
-        st_fe(contrib + t, F::mul(zp, ld_fe(coeff + t)));
+    const fe zp = pow_from_table<F>(zt, (uint32_t)q + 1u);     // exp_z for constraint q is z^(q+1)
+    const fe zn = F::neg(zp);
+    for (uint32_t t = start[q]; t < start[q + 1]; t++) {
+        const uint32_t c = cref[t];
+        perm[t] = t;
+        st_fe(contrib + t, c == 0 ? zp : c == 1 ? zn : F::mul(zp, ld_fe(coeff_ex + (c - 2u))));
     }
 }
 

@@ -173,7 +173,103 @@ struct Fp {
     // a / m into the aligned array, odd-indexed into the offset array), then divides by
     // 2^32 by swapping roles: X' = Y + X[1] (carry handed to Y'), Y' = X >> 64.
     // Bounds: T < 2^33*m inside a round, so Y < 2m < 2^257 and X < 2^259: 9 limbs each.
+    // Same CIOS for moduli with a sparse high part, m = m_low + 2^A (+|-) 2^B with m_low < 2^(32*RED_LOW) -- all five
+    // moduli of this repository (secq256k1's base field is 2^256 - 2^129 + m_low, four limbs). q*m then needs only
+    // RED_LOW wide multiplies per round (the two-pass IMAD.WIDE.X is the bottleneck pipe); the
+    // rest, D = q*2^A (+|-) q*2^B >= 0, is built with shifts and one borrow chain and added on the single carry
+    // chain that X needs anyway to ripple the carry of its multiplies. All of D goes to X, so X grows to 10 limbs
+    // (X < 2^258 + 2^288); Y' = X >> 64 still fits 8 limbs before a_odd*b_k is added.
+    BP_HD static fe mul_sparse(const fe& a, const fe& b) {
+        constexpr int LC = M::RED_LOW, IA = M::RED_A / 32, SA = M::RED_A % 32;
+        constexpr int IB = M::RED_B >= 0 ? M::RED_B / 32 : 99, SB = M::RED_B >= 0 ? M::RED_B % 32 : 0;
+        static_assert(LC >= 2 && LC % 2 == 0 && LC <= 6, "RED_LOW");
+        static_assert(M::RED_BSIGN == 0 || (IB >= LC && IA >= IB + 2), "shifted terms must sit above the multiplies and not overlap");
+        static_assert(IA >= LC && IA <= 8, "RED_A");
+        uint32_t X[10], Y[10];
+#pragma unroll
+        for (int i = 0; i < 10; i++) { X[i] = 0; Y[i] = 0; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t bk = b.v[k];
+            uint32_t Xn[10], Yn[10];
+            Xn[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+            for (int j = 1; j < 9; j++) Xn[j] = Y[j];
+            Xn[9] = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) wmadc_to_cc(Yn[j], Yn[j + 1], a.v[j + 1], bk, X[j + 2], X[j + 3]);
+            Yn[8] = addc(0u, 0u);
+            wmad_cc(Xn[0], Xn[1], a.v[0], bk);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Xn[j], Xn[j + 1], a.v[j], bk);
+            Xn[8] = addc(Xn[8], 0u);
+            const uint32_t q = Xn[0] * M::INV32;
+            // D = q*2^A (+|-) q*2^B, limbs LC..9 (compile-time zero elsewhere)
+            uint32_t D[10];
+#pragma unroll
+            for (int j = 0; j < 10; j++) D[j] = 0;
+            const uint32_t qa_lo = q << SA, qa_hi = SA ? (q >> ((32 - SA) & 31)) : 0u;
+            if (M::RED_BSIGN < 0) {
+                const uint32_t qb_lo = q << SB, qb_hi = SB ? (q >> ((32 - SB) & 31)) : 0u;
+                D[IB] = sub_cc(0u, qb_lo);
+                D[IB + 1] = subc_cc(0u, qb_hi);
+                const uint32_t ext = subc(0u, 0u);            // 0, or 0xFFFFFFFF: sign extension of -q*2^B
+#pragma unroll
+                for (int j = IB + 2; j < IA; j++) D[j] = ext;
+                D[IA] = add_cc(qa_lo, ext);
+                if (IA + 1 < 10) D[IA + 1] = addc(qa_hi, ext);   // limbs above cancel to zero (D >= 0)
+            } else {
+                if (M::RED_BSIGN > 0) {
+                    D[IB] = q << SB;
+                    D[IB + 1] = SB ? (q >> ((32 - SB) & 31)) : 0u;
+                }
+                D[IA] = qa_lo;
+                if (IA + 1 < 10) D[IA + 1] = qa_hi;
+            }
+            // Y' += q * (odd limbs of m_low), carry rippled to the top
+            wmad_cc(Yn[0], Yn[1], q, M::m(1));
+#pragma unroll
+            for (int j = 2; j < LC; j += 2) wmadc_cc(Yn[j], Yn[j + 1], q, M::m(j + 1));
+#pragma unroll
+            for (int j = LC; j < 8; j++) Yn[j] = addc_cc(Yn[j], 0u);
+            Yn[8] = addc(Yn[8], 0u);
+            // X' += q * (even limbs of m_low) + D on one chain
+            wmad_cc(Xn[0], Xn[1], q, M::m(0));
+#pragma unroll
+            for (int j = 2; j < LC; j += 2) wmadc_cc(Xn[j], Xn[j + 1], q, M::m(j));
+#pragma unroll
+            for (int j = LC; j < 9; j++) Xn[j] = addc_cc(Xn[j], D[j]);
+            Xn[9] = addc(Xn[9], D[9]);
+#pragma unroll
+            for (int j = 0; j < 10; j++) { X[j] = Xn[j]; }
+#pragma unroll
+            for (int j = 0; j < 9; j++) { Y[j] = Yn[j]; }
+            Y[9] = 0;
+        }
+        uint32_t r[9];
+        r[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+        for (int j = 1; j < 8; j++) r[j] = addc_cc(Y[j], X[j + 1]);
+        r[8] = addc(Y[8], X[9]);
+        fe o;
+        final_sub(o, r, r[8]);
+        return o;
+    }
+
+    // Measured on B200 (round 1, gpurun_out/microbench_{sparse,generic}.json, msm_phases_sparse.log): mul_sparse has
+    // 96 instead of 128 two-pass IMAD.WIDE.X per product but ~145 instead of ~50 carry-chained IADD3.X, and is NOT
+    // faster -- Fp::mul 64.4 vs 66.8 G/s, mixed addition 5.3 vs 6.2 G/s, msm_accumulate 41.3 vs 36.0 ms at 2^24: the
+    // carry-chained adds do not overlap with the carry-chained multiplies the way plain ALU work does. It stays as a
+    // tested alternative (BP_SPARSE_MONT selects it; tests/test_hostmath.py checks it against the oracle on all five
+    // moduli); the default is the generic CIOS.
     BP_HD static fe mul(const fe& a, const fe& b) {
+#if defined(BP_SPARSE_MONT)
+        if (M::RED_SPARSE) return mul_sparse(a, b);
+#endif
+        return mul_generic(a, b);
+    }
+
+    BP_HD static fe mul_generic(const fe& a, const fe& b) {
         uint32_t X[10], Y[10];
 #pragma unroll
         for (int i = 0; i < 10; i++) { X[i] = 0; Y[i] = 0; }

@@ -349,43 +349,31 @@ int ipa_verify(bp_ctx* ctx, Transcript& t, size_t n, const std::vector<affine>& 
 }
 
 // ---- constraint storage shared by prover and verifier -----------------------------------------------
+// Terms are kept in the compact form the device flatten consumes, because the whole store crosses PCIe on every
+// prove / verify (4n terms for the chain circuit): a 32-bit sort key (kind << 29 | index) and a 32-bit coefficient
+// reference -- 0 = +1, 1 = -1 (the bulk of real circuits), k + 2 = coeff_ex[k] -- instead of 41 bytes per term.
 struct ConstraintStore {
-    std::vector<uint8_t> kind;
-    std::vector<uint64_t> idx;
-    std::vector<fe> coeff;
-    std::vector<size_t> start;   // constraint q covers terms [start[q], start[q+1])
+    std::vector<uint32_t> key;        // kind << 29 | index
+    std::vector<uint32_t> cref;
+    std::vector<fe> coeff_ex;
+    std::vector<uint32_t> start;      // constraint q covers terms [start[q], start[q+1])
+    fe one, minus_one;
+    bool overflow = false;            // an index >= 2^29 or more than 2^32 - 3 terms: reported by flatten_device
     ConstraintStore() { start.push_back(0); }
+    void push_term(const Variable& v, const fe& c) {
+        if (v.idx >= (1ull << 29) || key.size() >= 0xFFFFFFF0ull) overflow = true;
+        key.push_back(((uint32_t)v.kind << 29) | (uint32_t)(v.idx & 0x1FFFFFFFu));
+        if (memcmp(c.v, one.v, 32) == 0) cref.push_back(0u);
+        else if (memcmp(c.v, minus_one.v, 32) == 0) cref.push_back(1u);
+        else { cref.push_back((uint32_t)coeff_ex.size() + 2u); coeff_ex.push_back(c); }
+    }
     void push(const Variable* v, const fe* c, size_t n, const Variable* extra_v = nullptr, const fe* extra_c = nullptr) {
-        for (size_t i = 0; i < n; i++) { kind.push_back((uint8_t)v[i].kind); idx.push_back(v[i].idx); coeff.push_back(c[i]); }
-        if (extra_v) { kind.push_back((uint8_t)extra_v->kind); idx.push_back(extra_v->idx); coeff.push_back(*extra_c); }
-        start.push_back(kind.size());
+        for (size_t i = 0; i < n; i++) push_term(v[i], c[i]);
+        if (extra_v) push_term(*extra_v, *extra_c);
+        start.push_back((uint32_t)key.size());
     }
     size_t count() const { return start.size() - 1; }
 };
-
-// flattened_constraints (prover.rs:354-397 / verifier.rs:304-349): host sparse scatter
-template <class C>
-static void flatten(const ConstraintStore& cs, const fe& z, size_t n, size_t m, std::vector<fe>& wL, std::vector<fe>& wR,
-                    std::vector<fe>& wO, std::vector<fe>& wV, fe* wc) {
-    using Fr = HostFp<typename C::Fr>;
-    wL.assign(n, Fr::zero()); wR.assign(n, Fr::zero()); wO.assign(n, Fr::zero()); wV.assign(m, Fr::zero());
-    if (wc) *wc = Fr::zero();
-    fe exp_z = z;
-    for (size_t q = 0; q < cs.count(); q++) {
-        for (size_t k = cs.start[q]; k < cs.start[q + 1]; k++) {
-            fe term = Fr::mul(exp_z, cs.coeff[k]);
-            size_t i = cs.idx[k];
-            switch (cs.kind[k]) {
-                case VAR_MUL_LEFT: wL[i] = Fr::add(wL[i], term); break;
-                case VAR_MUL_RIGHT: wR[i] = Fr::add(wR[i], term); break;
-                case VAR_MUL_OUT: wO[i] = Fr::add(wO[i], term); break;
-                case VAR_COMMITTED: wV[i] = Fr::sub(wV[i], term); break;
-                case VAR_ONE: if (wc) *wc = Fr::sub(*wc, term); break;
-            }
-        }
-        exp_z = Fr::mul(exp_z, z);
-    }
-}
 
 // Device flatten: d_wL/d_wR/d_wO (n each, device) are filled; wV (m) and wc come back to the host.
 template <class C>
@@ -394,18 +382,17 @@ int flatten_device(bp_ctx* ctx, const ConstraintStore& cs, const fe& z, size_t n
     using Fr = HostFp<typename C::Fr>;
     using D = Dev<C>;
     cudaStream_t st = ctx->stream;
-    size_t T = cs.kind.size(), Q = cs.count();
-    if (n >= (1u << 29) || m >= (1u << 29) || T >= (1ull << 32)) return BP_ERR_LEN;
+    size_t T = cs.key.size(), Q = cs.count(), E = cs.coeff_ex.size();
+    if (n >= (1u << 29) || m >= (1u << 29) || cs.overflow) return BP_ERR_LEN;
     wV.assign(m, Fr::zero());
     if (wc) *wc = Fr::zero();
     BP_CUDA_TRY(ctx, cudaMemsetAsync(d_wL, 0, n * sizeof(fe), st));
     BP_CUDA_TRY(ctx, cudaMemsetAsync(d_wR, 0, n * sizeof(fe), st));
     BP_CUDA_TRY(ctx, cudaMemsetAsync(d_wO, 0, n * sizeof(fe), st));
     if (T == 0) return BP_OK;
-    BP_CUDA_TRY(ctx, ctx->f_kind.reserve(T));
-    BP_CUDA_TRY(ctx, ctx->f_idx.reserve(T * 8));
-    BP_CUDA_TRY(ctx, ctx->f_coeff.reserve(T * sizeof(fe)));
-    BP_CUDA_TRY(ctx, ctx->f_start.reserve((Q + 1) * 8));
+    BP_CUDA_TRY(ctx, ctx->f_idx.reserve(T * 4));
+    BP_CUDA_TRY(ctx, ctx->f_coeff.reserve((E + 1) * sizeof(fe)));
+    BP_CUDA_TRY(ctx, ctx->f_start.reserve((Q + 1) * 4));
     BP_CUDA_TRY(ctx, ctx->f_keys.reserve(T * 4));
     BP_CUDA_TRY(ctx, ctx->f_keys2.reserve(T * 4));
     BP_CUDA_TRY(ctx, ctx->f_perm.reserve(T * 4));
@@ -415,14 +402,13 @@ int flatten_device(bp_ctx* ctx, const ConstraintStore& cs, const fe& z, size_t n
     BP_CUDA_TRY(ctx, ctx->f_ukeys.reserve(T * 4));
     BP_CUDA_TRY(ctx, ctx->f_sums.reserve(T * sizeof(fe)));
     BP_CUDA_TRY(ctx, ctx->f_wv.reserve((m + 2) * sizeof(fe) + 16));
-    D::upload(ctx, ctx->f_kind.p, cs.kind.data(), T);
-    D::upload(ctx, ctx->f_idx.p, cs.idx.data(), T * 8);
-    D::upload(ctx, ctx->f_coeff.p, cs.coeff.data(), T * sizeof(fe));
-    static_assert(sizeof(size_t) == 8, "64-bit host");
-    if (int rc = D::upload(ctx, ctx->f_start.p, cs.start.data(), (Q + 1) * 8)) return rc;
+    D::upload(ctx, ctx->f_keys.p, cs.key.data(), T * 4);
+    D::upload(ctx, ctx->f_idx.p, cs.cref.data(), T * 4);
+    D::upload(ctx, ctx->f_coeff.p, cs.coeff_ex.data(), E * sizeof(fe));
+    if (int rc = D::upload(ctx, ctx->f_start.p, cs.start.data(), (Q + 1) * 4)) return rc;
     uint32_t *keys = ctx->f_keys.as<uint32_t>(), *keys2 = ctx->f_keys2.as<uint32_t>(), *perm = ctx->f_perm.as<uint32_t>(), *perm2 = ctx->f_perm2.as<uint32_t>();
-    flatten_contrib_kernel<C><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(ctx->f_kind.as<uint8_t>(), ctx->f_idx.as<uint64_t>(), ctx->f_coeff.as<fe>(),
-                                                                          ctx->f_start.as<uint64_t>(), Q, D::pow_table(z), keys, perm, ctx->f_contrib.as<fe>());
+    flatten_contrib_kernel<C><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(ctx->f_idx.as<uint32_t>(), ctx->f_coeff.as<fe>(), ctx->f_start.as<uint32_t>(), Q,
+                                                                          D::pow_table(z), perm, ctx->f_contrib.as<fe>());
     BP_LAUNCH_CHECK(ctx);
     size_t tmp1 = 0, tmp2 = 0;
     BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp1, keys, keys2, perm, perm2, T, 0, 32, st));
@@ -466,6 +452,8 @@ struct ProverT : ConstraintSystemBase {
 
     ProverT(bp_ctx* c, const GensDev* g, Transcript* t) : ctx(c), gens(g), transcript(t) {     // prover.rs:291-308
         t->append_message("dom-sep", (const uint8_t*)"r1cs v1", 7);
+        cs.one = Fr::one();
+        cs.minus_one = Fr::neg(Fr::one());
     }
     fe eval(const Variable* vars, const fe* coeffs, size_t n) const {                          // prover.rs:399-414
         fe tot = Fr::zero();
@@ -769,7 +757,11 @@ struct VerifierT : ConstraintSystemBase {
     bool has_pending = false, randomizing = false;
     size_t pending = 0;
 
-    VerifierT(bp_ctx* c, Transcript* t) : ctx(c), transcript(t) { t->append_message("dom-sep", (const uint8_t*)"r1cs v1", 7); }   // :252-263
+    VerifierT(bp_ctx* c, Transcript* t) : ctx(c), transcript(t) {                               // :252-263
+        t->append_message("dom-sep", (const uint8_t*)"r1cs v1", 7);
+        cs.one = Fr::one();
+        cs.minus_one = Fr::neg(Fr::one());
+    }
     int multiply(const Variable* lv, const fe* lc, size_t ln, const Variable* rv, const fe* rc, size_t rn, Variable out[3]) override {   // :74-98
         uint64_t i = num_vars++;
         out[0] = {VAR_MUL_LEFT, i}; out[1] = {VAR_MUL_RIGHT, i}; out[2] = {VAR_MUL_OUT, i};

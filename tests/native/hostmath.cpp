@@ -7,6 +7,10 @@
 #include "../../ark_bulletproofs_b200/csrc/fp29.cuh"
 using namespace bp;
 
+// Fp<M>::mul_sparse where it exists (the device templates), the ordinary product for the host reference class
+template <class F> static auto fp_mul_sparse(const fe& x, const fe& y) -> decltype(F::mul_sparse(x, y)) { return F::mul_sparse(x, y); }
+template <class F, class... A> static fe fp_mul_sparse(const fe& x, const fe& y, A...) { return F::mul(x, y); }
+
 template <class F> static int fp_op_t(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     fe x, y, r;
     memcpy(x.v, a, 32);
@@ -20,6 +24,7 @@ template <class F> static int fp_op_t(int op, const uint32_t* a, const uint32_t*
         case 5: r = F::to_mont(x); break;
         case 6: r = F::neg(x); break;
         case 7: r = F::sqr(x); break;
+        case 8: r = fp_mul_sparse<F>(x, y); break;   // alternative reduction for sparse moduli (fp.cuh)
         default: return -1;
     }
     memcpy(out, r.v, 32);

@@ -42,6 +42,7 @@ def test_field_ops(lib, field):
     for a in vals:
         for b in rnd.sample(vals, 8) + [m - 1, a]:
             assert _fp(lib, field, 0, a, b) == a * b * rinv % m
+            assert _fp(lib, field, 8, a, b) == a * b * rinv % m      # sparse-modulus reduction variant
             assert _fp(lib, field, 1, a, b) == (a + b) % m
             assert _fp(lib, field, 2, a, b) == (a - b) % m
         assert _fp(lib, field, 4, a) == a * rinv % m
