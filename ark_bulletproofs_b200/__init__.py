@@ -87,6 +87,9 @@ class Context:
         self.rank, self.world = rank, world
         self._check(self.lib.bp_ctx_set_collective(self.h, rank, world, ctypes.cast(self._coll_cb, ctypes.c_void_p), None))
 
+    def set_device_gens(self, enable: bool):
+        self._check(self.lib.bp_gens_set_device_generation(self.h, 1 if enable else 0))
+
     def set_ipa_geometric(self, enable: bool):
         self._check(self.lib.bp_ipa_set_geometric(self.h, 1 if enable else 0))
 

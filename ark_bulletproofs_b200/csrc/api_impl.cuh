@@ -3,6 +3,7 @@
 #pragma once
 #include "api_types.hpp"
 #include "r1cs.cuh"
+#include "gens_kernels.cuh"
 
 namespace bp {
 
@@ -55,9 +56,38 @@ struct ApiImpl {
         return BP_OK;
     }
     static int gens_create(bp_ctx* ctx, size_t cap, GensDev** out) {
-        std::vector<affine> G(cap), H(cap);
         affine b, bb;
         GensHost<C>::pedersen_default(b, bb);
+        // secq256k1: every Affine::rand attempt reads 9 keystream words, so the chains are generated on the device
+        // (gens_kernels.cuh); other curves, tiny capacities and the 2^-128 irregular stream use the host generator
+        constexpr bool fixed_stride = C::KIND == 0 && C::Fq::m(7) == 0xFFFFFFFFu && C::Fq::m(6) == 0xFFFFFFFFu && C::Fq::m(5) == 0xFFFFFFFFu;
+        if constexpr (fixed_stride) {
+            if (ctx->gens_on_device && cap >= 256) {
+                std::unique_ptr<GensDev> g(new GensDev());
+                g->ctx = ctx; g->capacity = cap; g->B = b; g->B_blinding = bb; g->rank = ctx->rank; g->world = ctx->world;
+                size_t lo, lcap;
+                g->slice(0, cap, lo, lcap);
+                BP_CUDA_TRY(ctx, g->G.reserve((lcap + 1) * sizeof(affine)));
+                BP_CUDA_TRY(ctx, g->H.reserve((lcap + 1) * sizeof(affine)));
+                BP_CUDA_TRY(ctx, g->pc.reserve(2 * sizeof(affine)));
+                affine pc[2] = {b, bb};
+                BP_CUDA_TRY(ctx, cudaMemcpyAsync(g->pc.p, pc, sizeof(pc), cudaMemcpyHostToDevice, ctx->stream));
+                const auto& ts = HC::ts_params();
+                SqrtParams sp;
+                memcpy(sp.t, ts.t, 32); memcpy(sp.t1h, ts.t1h, 32); sp.z = ts.z; sp.s = ts.s;
+                uint8_t label[5] = {'G', 0, 0, 0, 0}, seed[32];                                   // generators.rs:196-221, party 0
+                GensHost<C>::chain_seed(label, 5, seed);
+                int rc = gens_chain_device<C>(ctx, seed, sp, cap, ctx->rank, ctx->world, g->G.template as<affine>());
+                if (rc == BP_OK) {
+                    label[0] = 'H';
+                    GensHost<C>::chain_seed(label, 5, seed);
+                    rc = gens_chain_device<C>(ctx, seed, sp, cap, ctx->rank, ctx->world, g->H.template as<affine>());
+                }
+                if (rc == BP_OK) { *out = g.release(); return BP_OK; }
+                if (rc != BP_ERR_UNSUPPORTED) return rc;
+            }
+        }
+        std::vector<affine> G(cap), H(cap);
         GensHost<C>::bulletproof_gens(cap, G.data(), H.data());
         return gens_upload(ctx, b, bb, G.data(), H.data(), cap, out);
     }

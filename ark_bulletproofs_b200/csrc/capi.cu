@@ -119,6 +119,12 @@ int bp_ctx_set_collective(bp_ctx* ctx, int rank, int world, bp_allgather_fn fn, 
     return BP_OK;
 }
 
+int bp_gens_set_device_generation(bp_ctx* ctx, int enable) {
+    if (!ctx) return BP_ERR_ARG;
+    ctx->gens_on_device = enable != 0;
+    return BP_OK;
+}
+
 int bp_ipa_set_geometric(bp_ctx* ctx, int enable) {
     if (!ctx) return BP_ERR_ARG;
     ctx->ipa_geo = enable != 0;
@@ -356,7 +362,8 @@ int bp_gens_export(const bp_gens* g, int which, size_t offset, size_t count, uin
     if (!g || !out_xy) return BP_ERR_ARG;
     bp_ctx* ctx = g->g->ctx;
     const bp::DevBuf& b = which == 0 ? g->g->G : which == 1 ? g->g->H : g->g->pc;
-    size_t lim = which == 2 ? 2 : g->g->capacity;
+    size_t lim = 2;
+    if (which != 2) { size_t lo; g->g->slice(0, g->g->capacity, lo, lim); }   // sharded contexts export their own shard
     if (offset + count > lim) return BP_ERR_LEN;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     BP_CUDA_TRY(ctx, cudaMemcpyAsync(out_xy, b.as<uint8_t>() + offset * 64, count * 64, cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,0 +1,174 @@
+// BulletproofGens generation on the device.
+//
+// Replaces the serial loop of GeneratorsChain (src/generators.rs:71-121: `G::rand(&mut ChaChaRng)` until `capacity`
+// points exist) for curves whose `Affine::rand` attempt consumes a fixed number of ChaCha20 words. On secq256k1 the
+// base field is within 2^129 of 2^256, so the x draw (4 x next_u64) is never rejected and attempt j reads exactly
+// words [9j, 9j+9) of the keystream: 8 words of x (raw limbs = the Montgomery representation, ark-ff Fp::rand) and
+// one word whose top bit is `greatest` (ark-ec get_point_from_x_unchecked). The keystream is seekable, so every
+// attempt is independent: one thread per attempt computes its ChaCha block(s), y = sqrt(x^3 + a*x + b) by
+// Tonelli-Shanks (2-adicity 6 for secq256k1's base field), and picks the root `greatest` asks for; the accepted
+// points are compacted in stream order (cub::DeviceSelect) and the first `capacity` kept. A raw x >= q (probability
+// 2^-128) would shift the stream: it raises a flag and the caller falls back to the host path.
+// The host implementation (host/gens_host.hpp) stays for the other curves (zorro's x draw rejects with p ~ 1/2,
+// curve25519 clears the cofactor) and is what the device result is tested against.
+#pragma once
+#include <cub/device/device_select.cuh>
+#include "ctx.cuh"
+
+namespace bp {
+
+struct ChaChaKey { uint32_t k[8]; };
+struct SqrtParams {
+    uint32_t t[8];      // q - 1 = 2^s * t
+    uint32_t t1h[8];    // (t + 1) / 2
+    fe z;               // z^t for a quadratic non-residue z
+    int s;
+};
+
+__device__ __forceinline__ uint32_t gk_rotl(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
+// rand_chacha 0.3 ChaCha20Rng block: 64-bit counter in words 12-13, stream id 0 (same as host/merlin.hpp)
+__device__ inline void chacha20_block_dev(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+    uint32_t s[16] = {0x61707865u, 0x3320646Eu, 0x79622D32u, 0x6B206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                      (uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = s[i];
+#define BP_GQR(a, b, c, d)                                                                                        \
+    w[a] += w[b]; w[d] = gk_rotl(w[d] ^ w[a], 16); w[c] += w[d]; w[b] = gk_rotl(w[b] ^ w[c], 12);                 \
+    w[a] += w[b]; w[d] = gk_rotl(w[d] ^ w[a], 8);  w[c] += w[d]; w[b] = gk_rotl(w[b] ^ w[c], 7);
+#pragma unroll 1
+    for (int i = 0; i < 10; i++) {
+        BP_GQR(0, 4, 8, 12) BP_GQR(1, 5, 9, 13) BP_GQR(2, 6, 10, 14) BP_GQR(3, 7, 11, 15)
+        BP_GQR(0, 5, 10, 15) BP_GQR(1, 6, 11, 12) BP_GQR(2, 7, 8, 13) BP_GQR(3, 4, 9, 14)
+    }
+#undef BP_GQR
+#pragma unroll
+    for (int i = 0; i < 16; i++) out[i] = w[i] + s[i];
+}
+
+// Tonelli-Shanks without the Euler pre-check: a non-residue shows up as "no i < m with t^(2^i) = 1"
+template <class F>
+__device__ bool fq_sqrt_dev(const fe& a, const SqrtParams& sp, fe& out) {
+    if (F::is_zero(a)) { out = a; return true; }
+    const fe one = F::one();
+    int m = sp.s;
+    fe c = sp.z, t = F::pow(a, sp.t), r = F::pow(a, sp.t1h);
+    while (!F::eq(t, one)) {
+        int i = 0;
+        fe t2 = t;
+        while (!F::eq(t2, one)) {
+            t2 = F::sqr(t2);
+            if (++i == m) return false;
+        }
+        fe b = c;
+        for (int k = 0; k < m - i - 1; k++) b = F::sqr(b);
+        m = i;
+        c = F::sqr(b);
+        t = F::mul(t, c);
+        r = F::mul(r, b);
+    }
+    out = r;
+    return true;
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) gens_attempt_kernel(const __grid_constant__ ChaChaKey key, uint64_t attempt0, size_t count,
+                                                           const __grid_constant__ SqrtParams sp, affine* __restrict__ pts,
+                                                           uint8_t* __restrict__ ok, int* __restrict__ irregular) {
+    using F = Fp<typename C::Fq>;
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const uint64_t w0 = (attempt0 + j) * 9u;
+    const uint64_t blk = w0 / 16u;
+    const int off = (int)(w0 % 16u);
+    uint32_t buf[32];
+    chacha20_block_dev(key.k, blk, buf);
+    if (off + 9 > 16) chacha20_block_dev(key.k, blk + 1, buf + 16);
+    fe x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) x.v[k] = buf[off + k];        // 4 x next_u64 = 8 little-endian words; raw = Montgomery repr
+    const bool greatest = (buf[off + 8] >> 31) & 1u;           // bool::rand = top bit of next_u32
+    // x >= q cannot be shaved (256-bit modulus): Fp::rand would redraw and shift the stream
+    bool geq = true;
+    for (int k = 7; k >= 0; k--) {
+        uint32_t mk = C::Fq::m(k);
+        if (x.v[k] != mk) { geq = x.v[k] > mk; break; }
+    }
+    if (geq) { atomicExch(irregular, 1); ok[j] = 0; return; }
+    fe rhs = F::add(F::mul(F::sqr(x), x), F::template curve_b<C>());
+    if (C::A_SMALL != 0) rhs = F::add(rhs, F::mul_small(x, C::A_SMALL));
+    fe y;
+    if (!fq_sqrt_dev<F>(rhs, sp, y)) { ok[j] = 0; return; }
+    // ark: pick the larger / smaller root as canonical integers
+    fe ny = F::neg(y);
+    fe yc = F::from_mont(y), nc = F::from_mont(ny);
+    bool y_larger = false;
+    for (int k = 7; k >= 0; k--)
+        if (yc.v[k] != nc.v[k]) { y_larger = yc.v[k] > nc.v[k]; break; }
+    affine p;
+    p.x = x;
+    p.y = (greatest == y_larger) ? y : ny;
+    st_fe(&pts[j].x, p.x);
+    st_fe(&pts[j].y, p.y);
+    ok[j] = 1;
+}
+
+// out[j] = in[j * stride + offset]  (this rank's cyclic shard of the chain)
+static __global__ void __launch_bounds__(256) gens_stride_kernel(const affine* __restrict__ in, size_t n_out, size_t stride, size_t offset,
+                                                                 affine* __restrict__ out) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    affine p = ld_affine(in + j * stride + offset);
+    st_fe(&out[j].x, p.x);
+    st_fe(&out[j].y, p.y);
+}
+
+// First `count` points of the chain seeded by `seed`, shard (rank, world) of them into d_out. Returns BP_ERR_UNSUPPORTED when the
+// stream turned out irregular (caller falls back to the host generator).
+template <class C>
+int gens_chain_device(bp_ctx* ctx, const uint8_t seed[32], const SqrtParams& sp, size_t count, int rank, int world, affine* d_out) {
+    cudaStream_t st = ctx->stream;
+    ChaChaKey key;
+    memcpy(key.k, seed, 32);
+    DevBuf full, att, okb, sel, misc, tmp;
+    struct Guard { DevBuf* b[6]; ~Guard() { for (auto* x : b) x->release(); } } guard{{&full, &att, &okb, &sel, &misc, &tmp}};
+    BP_CUDA_TRY(ctx, full.reserve((count + 1) * sizeof(affine)));
+    BP_CUDA_TRY(ctx, misc.reserve(64));
+    int* d_irregular = misc.as<int>();
+    int* d_nsel = misc.as<int>() + 4;
+    BP_CUDA_TRY(ctx, cudaMemsetAsync(misc.p, 0, 64, st));
+    size_t produced = 0;
+    uint64_t attempt0 = 0;
+    while (produced < count) {
+        size_t want = (count - produced) * 2 + 1024;
+        if (want > ((size_t)1 << 30)) return BP_ERR_LEN;
+        BP_CUDA_TRY(ctx, att.reserve(want * sizeof(affine)));
+        BP_CUDA_TRY(ctx, sel.reserve(want * sizeof(affine)));
+        BP_CUDA_TRY(ctx, okb.reserve(want));
+        gens_attempt_kernel<C><<<(unsigned)((want + 127) / 128), 128, 0, st>>>(key, attempt0, want, sp, att.as<affine>(), okb.as<uint8_t>(), d_irregular);
+        BP_LAUNCH_CHECK(ctx);
+        size_t tb = 0;
+        BP_CUDA_TRY(ctx, cub::DeviceSelect::Flagged(nullptr, tb, att.as<affine>(), okb.as<uint8_t>(), sel.as<affine>(), d_nsel, (int)want, st));
+        BP_CUDA_TRY(ctx, tmp.reserve(tb));
+        BP_CUDA_TRY(ctx, cub::DeviceSelect::Flagged(tmp.p, tb, att.as<affine>(), okb.as<uint8_t>(), sel.as<affine>(), d_nsel, (int)want, st));
+        int h[8];
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(h, misc.p, 32, cudaMemcpyDeviceToHost, st));
+        BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (h[0]) return BP_ERR_UNSUPPORTED;
+        size_t got = (size_t)h[4];
+        size_t take = got < count - produced ? got : count - produced;
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(full.as<affine>() + produced, sel.p, take * sizeof(affine), cudaMemcpyDeviceToDevice, st));
+        produced += take;
+        attempt0 += want;
+    }
+    size_t r = (size_t)rank, w = (size_t)world;
+    size_t n_out = count > r ? (count - r + w - 1) / w : 0;
+    if (n_out) {
+        gens_stride_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(full.as<affine>(), n_out, w, r, d_out);
+        BP_LAUNCH_CHECK(ctx);
+    }
+    BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return BP_OK;
+}
+
+}  // namespace bp

@@ -117,8 +117,8 @@ struct HostCurve {
     }
 
     // Tonelli-Shanks; returns false for non-residues
-    static bool fq_sqrt(const fe& a, fe& out) {
-        struct TS { int s; uint32_t t[8]; uint32_t t1h[8]; fe z; uint32_t half[8]; };
+    struct TS { int s; uint32_t t[8]; uint32_t t1h[8]; fe z; uint32_t half[8]; };
+    static const TS& ts_params() {
         static const TS ts = [] {
             TS r;
             uint32_t e[8];
@@ -147,6 +147,10 @@ struct HostCurve {
             }
             return r;
         }();
+        return ts;
+    }
+    static bool fq_sqrt(const fe& a, fe& out) {
+        const TS& ts = ts_params();
         if (Fq::is_zero(a)) { out = a; return true; }
         fe one = Fq::one();
         if (!Fq::eq(Fq::pow(a, ts.half), one)) return false;

@@ -101,6 +101,11 @@ int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n);
  * by all threads (first round included) instead of the joint double-and-add of inner_product_proof.rs:143-155.
  * Same L, R, a, b. Default on; 0 restores the general first round (tests run both). */
 int bp_ipa_set_geometric(bp_ctx* ctx, int enable);
+/* BulletproofGens::new (src/generators.rs:174-221): on secq256k1 every `G::rand` attempt of the GeneratorsChain reads
+ * exactly 9 ChaCha20 words, so bp_gens_create evaluates the attempts on the GPU (seekable keystream, Tonelli-Shanks,
+ * stream-order compaction) for capacities >= 256. Same points as the host generator (bp_gens_generate_host), which
+ * remains the path for zorro / curve25519. Default on; 0 forces the host generator. */
+int bp_gens_set_device_generation(bp_ctx* ctx, int enable);
 /* Bucket accumulation on 9 x 29-bit limbs (csrc/fp29.cuh; default on for secq256k1 and curve25519) or on the
  * 8 x 32-bit limbs of csrc/fp.cuh; both give identical results. For A/B measurements and tests. */
 int bp_msm_set_fp29(bp_ctx* ctx, int enable);

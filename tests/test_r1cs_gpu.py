@@ -487,3 +487,34 @@ def test_native_shuffle_gadget_golden(env, name):
     vv = v.commit_batch_raw(coms_raw, 2 * k)
     v.shuffle_gadget_native(vv[:k], vv[k:])
     v.verify(proof, gens)
+
+
+@pytest.mark.parametrize("cap", [256, 1000, 5000])
+def test_device_generators_match_host(cap):
+    """BulletproofGens chains generated on the GPU (gens_kernels.cuh: seekable ChaCha, Tonelli-Shanks, stream-order
+    compaction) are the points of the host generator, which tests/test_host_layer.py pins to the oracle."""
+    from ark_bulletproofs_b200 import Context
+    from ark_bulletproofs_b200 import r1cs as R
+    curve = "secq256k1"
+    ctx = Context(curve, 0)
+    g = R.Gens(ctx, cap)                       # device path (default)
+    _, _, G, H = R.generate_gens_host(curve, cap)
+    assert g.export(0, 0, cap) == G
+    assert g.export(1, 0, cap) == H
+    ctx.set_device_gens(False)
+    g2 = R.Gens(ctx, cap)                      # host path, uploaded
+    assert g2.export(0, 0, cap) == G and g2.export(1, 0, cap) == H
+
+
+def test_device_generators_sharded():
+    """Sharded contexts keep generator i on rank i mod world, whichever side generated the chain."""
+    from ark_bulletproofs_b200 import r1cs as R
+    curve, cap, world = "secq256k1", 600, 4
+    _, _, G, H = R.generate_gens_host(curve, cap)
+
+    def run(R_, ctx, rank):
+        g = R_.Gens(ctx, cap)
+        n_loc = len(range(rank, cap, world))
+        return g.export(0, 0, n_loc), g.export(1, 0, n_loc)
+    for rank, (gl, hl) in enumerate(_sharded(world, curve, run)):
+        assert gl == G[rank::world] and hl == H[rank::world]
