@@ -154,6 +154,48 @@ def r1cs_prove_verify(ctx, lg_n):
     return best
 
 
+def kshuffle_prove_verify(ctx, k):
+    """The reference's own criterion bench (benches/r1cs_secq256k1.rs:156-250): k-shuffle proof creation (2k Pedersen
+    commitments + gadget + prove) and verification (2k commits + gadget + verify), through the C ABI."""
+    import random
+    from ark_bulletproofs_b200 import codec
+    from ark_bulletproofs_b200 import r1cs as R
+    cap = 1
+    while cap < 2 * (k - 1):
+        cap <<= 1
+    gens = R.Gens(ctx, cap)
+    rnd = random.Random(k)
+    inp = [rnd.randrange(1 << 64) for _ in range(k)]
+    out = list(inp)
+    rnd.shuffle(out)
+    vals_raw = codec.enc_scalars(inp + out, CURVE)
+
+    def transcript():
+        t = R.Transcript(b"ShuffleProofTest")
+        t.append_message(b"dom-sep", b"ShuffleProof")
+        t.append_u64(b"k", k)
+        return t
+    bp_, bv = None, None
+    for _ in range(3):
+        rng = R.ChaChaRng(bytes(range(32)))
+        blinds_raw = rng.scalars_raw(CURVE, 2 * k)
+        t0 = time.perf_counter()
+        p = R.Prover(ctx, gens, transcript())
+        coms_raw, vars_ = p.commit_batch_raw(vals_raw, blinds_raw, 2 * k)
+        p.shuffle_gadget_native(vars_[:k], vars_[k:])
+        proof = p.prove(rng)
+        tp = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        v = R.Verifier(ctx, transcript())
+        vv = v.commit_batch_raw(coms_raw, 2 * k)
+        v.shuffle_gadget_native(vv[:k], vv[k:])
+        v.verify(proof, gens)
+        tv = (time.perf_counter() - t0) * 1e3
+        bp_ = tp if bp_ is None or tp < bp_ else bp_
+        bv = tv if bv is None or tv < bv else bv
+    return {"k": k, "multipliers": 2 * (k - 1), "prove_ms": round(bp_, 2), "verify_ms": round(bv, 2), "proof_bytes": len(proof.to_bytes())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,7 +205,8 @@ def main():
     ap.add_argument("--lg-n", type=int, default=24, help="log2 of the MSM size per GPU")
     ap.add_argument("--cpu-lg-n", type=int, default=0, help="log2 of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--r1cs-lg-n", type=int, default=16, help="log2 multipliers of the secondary R1CS prove/verify measurement (0 = skip)")
+    ap.add_argument("--r1cs-lg-n", default="16,20", help="log2 multipliers of the secondary R1CS prove/verify measurements, comma separated (0 = skip)")
+    ap.add_argument("--shuffle-k", type=int, default=1024, help="k of the reference's own k-shuffle bench, reported next to r1cs (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -276,16 +319,26 @@ def main():
     # secondary metric: R1CS prove / verify. With N > 1 the context switches to multi-GPU mode (cyclic generator
     # shards, partial points all-gathered over NCCL) and every rank takes part in the same proof.
     r1cs = None
-    if args.r1cs_lg_n > 0:
+    lgs = [int(x) for x in str(args.r1cs_lg_n).split(",") if int(x) > 0]
+    if lgs:
         if world > 1:
             from ark_bulletproofs_b200.dist import torch_allgather
             ctx.set_collective(rank, world, torch_allgather(device=torch.device("cuda", local_rank)))
-        r1cs = r1cs_prove_verify(ctx, args.r1cs_lg_n)
+        runs = []
+        for lg in lgs:
+            one = r1cs_prove_verify(ctx, lg)
+            if world > 1:
+                t = torch.tensor([one["prove_ms"], one["verify_ms"]], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                one["prove_ms"], one["verify_ms"] = round(float(t[0]), 2), round(float(t[1]), 2)
+            runs.append(one)
+        r1cs = dict(runs[0])                     # the 2^16 circuit of BASELINE's config 2 stays at the top level
+        r1cs["sizes"] = {"2^%d" % lg: {"prove_ms": o["prove_ms"], "verify_ms": o["verify_ms"], "proof_bytes": o["proof_bytes"],
+                                        "rng_ms": o["prove_stages_ms"].get("rng"), "ipa_ms": o["prove_stages_ms"].get("ipa")} for lg, o in zip(lgs, runs)}
         if world > 1:
             r1cs["sharding"] = "generators cyclic over %d GPUs; every MSM's 64 B partial points all-gathered (NCCL); scalars, transcript and TranscriptRng replicated" % world
-            t = torch.tensor([r1cs["prove_ms"], r1cs["verify_ms"]], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            r1cs["prove_ms"], r1cs["verify_ms"] = round(float(t[0]), 2), round(float(t[1]), 2)
+        elif args.shuffle_k > 1:
+            r1cs["reference_bench_kshuffle"] = kshuffle_prove_verify(ctx, args.shuffle_k)
 
     if rank != 0:
         if world > 1:
