@@ -90,6 +90,9 @@ class Context:
     def set_device_gens(self, enable: bool):
         self._check(self.lib.bp_gens_set_device_generation(self.h, 1 if enable else 0))
 
+    def set_ipa_glv(self, enable: bool):
+        self._check(self.lib.bp_ipa_set_glv(self.h, 1 if enable else 0))
+
     def set_ipa_geometric(self, enable: bool):
         self._check(self.lib.bp_ipa_set_geometric(self.h, 1 if enable else 0))
 

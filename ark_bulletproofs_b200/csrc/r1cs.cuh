@@ -20,6 +20,7 @@
 #include "r1cs_types.hpp"
 #include "msm_kernels.cuh"
 #include "flatten.cuh"
+#include "host/glv_host.hpp"
 #include "vec_kernels.cuh"
 
 namespace bp {
@@ -187,6 +188,25 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
     NoFoldParams nf;
     nf.nu = 0;
     const ShardIdx sh{(uint32_t)P, (uint32_t)g};
+    // out = L + kappa*R for both generator vectors; GLV (129-step chain) where the curve has the endomorphism
+    auto fold_uniform = [&](const affine* GL, const affine* GR, affine* Gout, const affine* HL, const affine* HR, affine* Hout, size_t cnt,
+                            const fe& kG, const fe& kH) -> int {
+        unsigned grid = (unsigned)((2 * cnt + 127) / 128);
+        if constexpr (C::HAS_GLV) {
+            GlvSplit sG, sH;
+            if (ctx->ipa_glv && GlvHost<C>::split(kG, sG) && GlvHost<C>::split(kH, sH)) {
+                GlvBits bG, bH;
+                memcpy(bG.k1, sG.k1, 20); memcpy(bG.k2, sG.k2, 20); bG.neg1 = sG.neg1; bG.neg2 = sG.neg2; bG.top = sG.top;
+                memcpy(bH.k1, sH.k1, 20); memcpy(bH.k2, sH.k2, 20); bH.neg1 = sH.neg1; bH.neg2 = sH.neg2; bH.top = sH.top;
+                ipa_fold_points_glv_kernel<C><<<grid, 128, 0, st>>>(GL, GR, Gout, HL, HR, Hout, cnt, bG, bH);
+                BP_LAUNCH_CHECK(ctx);
+                return BP_OK;
+            }
+        }
+        ipa_fold_points_uniform_kernel<C><<<grid, 128, 0, st>>>(GL, GR, Gout, HL, HR, Hout, cnt, D::bits(kG), D::bits(kH));
+        BP_LAUNCH_CHECK(ctx);
+        return BP_OK;
+    };
     while (n != 1) {
         auto t_a = now();
         size_t h = n / 2;
@@ -263,8 +283,7 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
                 fe rGh = *geo_rG, rHh = *geo_rH;
                 for (size_t k = 0; k < lg_h; k++) { rGh = Fr::sqr(rGh); rHh = Fr::sqr(rHh); }
                 fe kG = Fr::mul(Fr::sqr(u), rGh), kH = Fr::mul(Fr::sqr(uinv), rHh);
-                ipa_fold_points_uniform_kernel<C><<<fgrid, 128, 0, st>>>(curG, curG + hl, wG, curH, curH + hl, wH, hl, D::bits(kG), D::bits(kH));
-                BP_LAUNCH_CHECK(ctx);
+                if (int rc = fold_uniform(curG, curG + hl, wG, curH, curH + hl, wH, hl, kG, kH)) return rc;
                 fG = Fr::mul(fG, uinv);
                 fH = Fr::mul(fH, u);
             } else if (first) {
@@ -274,8 +293,7 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
             } else {
                 // u^-1*G_L + u*G_R = u^-1*(G_L + u^2*G_R): the common factor moves into fG (resp. fH)
                 fe u2 = Fr::sqr(u), ui2 = Fr::sqr(uinv);
-                ipa_fold_points_uniform_kernel<C><<<fgrid, 128, 0, st>>>(curG, curG + hl, wG, curH, curH + hl, wH, hl, D::bits(u2), D::bits(ui2));
-                BP_LAUNCH_CHECK(ctx);
+                if (int rc = fold_uniform(curG, curG + hl, wG, curH, curH + hl, wH, hl, u2, ui2)) return rc;
                 fG = Fr::mul(fG, uinv);
                 fH = Fr::mul(fH, u);
             }

@@ -212,6 +212,55 @@ __global__ void __launch_bounds__(128) ipa_fold_points_uniform_kernel(const affi
     st_fe(&out[i].y, r.y);
 }
 
+// The same fold on curves with the GLV endomorphism phi(x, y) = (beta*x, y) = lambda*(x, y) (secq256k1): the host splits
+// kappa = k1 + k2*lambda with |k1|, |k2| < 2^130 (host/glv_host.hpp), so out[i] = L[i] + k1*R[i] + k2*phi(R[i]) is a joint
+// double-and-add of ~129 steps over the table {+-R, +-phi(R), their sum} instead of 256 steps. The split is uniform
+// over the launch, so control flow stays uniform.
+struct GlvBits { uint32_t k1[5], k2[5]; int neg1, neg2, top; };
+
+template <class C>
+__global__ void __launch_bounds__(128) ipa_fold_points_glv_kernel(const affine* __restrict__ L0, const affine* __restrict__ R0,
+                                                                  affine* __restrict__ out0, const affine* __restrict__ L1,
+                                                                  const affine* __restrict__ R1, affine* __restrict__ out1,
+                                                                  size_t count, const __grid_constant__ GlvBits g0,
+                                                                  const __grid_constant__ GlvBits g1) {
+    using E = GroupLaw<C>;
+    using F = Fp<typename C::Fq>;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * count) return;
+    const bool second = t >= count;
+    size_t i = second ? t - count : t;
+    const affine* L = second ? L1 : L0;
+    const affine* R = second ? R1 : R0;
+    affine* out = second ? out1 : out0;
+    const GlvBits& g = second ? g1 : g0;
+    affine p1 = ld_affine(R + i);
+    affine p2;
+    fe beta;
+#pragma unroll
+    for (int k = 0; k < 8; k++) beta.v[k] = C::glv_beta(k);
+    p2.x = F::mul(p1.x, beta);
+    p2.y = p1.y;
+    if (E::is_identity(p1)) p2 = p1;
+    if (g.neg1) p1 = E::neg(p1);
+    if (g.neg2) p2 = E::neg(p2);
+    xyzz both = E::from_affine(p1);
+    E::madd(both, p2);
+    xyzz acc = E::identity();
+    for (int bit = g.top; bit >= 0; bit--) {
+        acc = E::dbl(acc);
+        const uint32_t sel = ((g.k1[bit >> 5] >> (bit & 31)) & 1u) | (((g.k2[bit >> 5] >> (bit & 31)) & 1u) << 1);
+        if (sel == 1) E::madd(acc, p1);
+        else if (sel == 2) E::madd(acc, p2);
+        else if (sel == 3) E::add(acc, both);
+    }
+    affine pl = ld_affine(L + i);
+    E::madd(acc, pl);
+    affine r = E::to_affine(acc);
+    st_fe(&out[i].x, r.x);
+    st_fe(&out[i].y, r.y);
+}
+
 // First-round fold with per-element factors (inner_product_proof.rs:143-155):
 //   out[i] = (cL*f[i]) * P[i] + (cR*f[h+i]) * P[h+i]      (joint double-and-add)
 // Threads [0,h) handle (P0,f0,cL0,cR0) = (G, G_factors, u^-1, u); threads [h,2h) handle H with

@@ -101,6 +101,10 @@ int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n);
  * by all threads (first round included) instead of the joint double-and-add of inner_product_proof.rs:143-155.
  * Same L, R, a, b. Default on; 0 restores the general first round (tests run both). */
 int bp_ipa_set_geometric(bp_ctx* ctx, int enable);
+/* secq256k1 has the endomorphism (x, y) -> (beta*x, y) = lambda*(x, y): the uniform fold scalar of each IPA round is
+ * split as k1 + k2*lambda with 129-bit halves, halving the double-and-add chain of the generator fold
+ * (inner_product_proof.rs:216-225). Same folded generators, hence the same L, R. Default on; 0 = plain 256-step fold. */
+int bp_ipa_set_glv(bp_ctx* ctx, int enable);
 /* BulletproofGens::new (src/generators.rs:174-221): on secq256k1 every `G::rand` attempt of the GeneratorsChain reads
  * exactly 9 ChaCha20 words, so bp_gens_create evaluates the attempts on the GPU (seekable keystream, Tonelli-Shanks,
  * stream-order compaction) for capacities >= 256. Same points as the host generator (bp_gens_generate_host), which

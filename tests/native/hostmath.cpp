@@ -5,6 +5,7 @@
 #include "../../ark_bulletproofs_b200/csrc/ec.cuh"
 #include "../../ark_bulletproofs_b200/csrc/host/fp_host.hpp"
 #include "../../ark_bulletproofs_b200/csrc/fp29.cuh"
+#include "../../ark_bulletproofs_b200/csrc/host/glv_host.hpp"
 using namespace bp;
 
 // Fp<M>::mul_sparse where it exists (the device templates), the ordinary product for the host reference class
@@ -141,4 +142,16 @@ extern "C" int hm_ec29_op(int curve, int op, const uint32_t* p, const uint32_t* 
         case 2: return ec29_op_t<TE<Curve25519, Fp29<Fp25519>>>(op, p, q, s, out);
     }
     return -1;
+}
+
+// GLV split of a Montgomery scalar of secq256k1 (host/glv_host.hpp): out = k1[5] | k2[5] | neg1 | neg2 | top
+extern "C" int hm_glv_split(const uint32_t* kappa_mont, uint32_t* out) {
+    fe k;
+    memcpy(k.v, kappa_mont, 32);
+    GlvSplit s;
+    if (!GlvHost<Secq256k1>::split(k, s)) return 0;
+    memcpy(out, s.k1, 20);
+    memcpy(out + 5, s.k2, 20);
+    out[10] = (uint32_t)s.neg1; out[11] = (uint32_t)s.neg2; out[12] = (uint32_t)s.top;
+    return 1;
 }

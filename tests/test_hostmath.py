@@ -173,3 +173,28 @@ def test_curve_ops_fp29(lib, cid, cv):
     assert run(4, P, neg(mul(2, P))) is None
     for s in [0, 1, 2, cv.r - 1, rnd.randrange(cv.r)]:
         assert run(3, P, None, s) == mul(s, P)
+
+
+def test_glv_split(lib):
+    """secq256k1 GLV decomposition used by the IPA generator fold: k = k1 + k2*lambda (mod r) with both halves below
+    2^130 -- for random scalars and the edge values; lambda is the cube root of unity matching beta (x -> beta*x)."""
+    r = FIELDS[1]
+    lam = 0x7ae96a2b657c07106e64479eac3434e99cf0497512f58995c1396c28719501ee
+    beta = 0x5363ad4cc05c30e0a5261c028812645a122e22ea20816678df02967c1b23bd72
+    q = FIELDS[0]
+    assert pow(lam, 3, r) == 1 and lam != 1 and pow(beta, 3, q) == 1 and beta != 1
+    # phi(G) = lambda*G on the curve (checked with the oracle's arithmetic)
+    import bp_oracle as O
+    cv = O.SECQ256K1
+    assert O.pt_mul(cv, lam, cv.G) == (beta * cv.G[0] % q, cv.G[1])
+    rnd = random.Random(77)
+    vals = [0, 1, 2, r - 1, r - 2, lam, r - lam, (1 << 128), (1 << 255) % r] + [rnd.randrange(r) for _ in range(300)]
+    for k in vals:
+        out = (ctypes.c_uint32 * 13)()
+        assert lib.hm_glv_split(_b(k * R % r), out) == 1
+        k1 = sum(out[i] << (32 * i) for i in range(5)) * (-1 if out[10] else 1)
+        k2 = sum(out[5 + i] << (32 * i) for i in range(5)) * (-1 if out[11] else 1)
+        assert (k1 + k2 * lam - k) % r == 0
+        assert abs(k1) < 1 << 130 and abs(k2) < 1 << 130
+        top = max(abs(k1).bit_length(), abs(k2).bit_length()) - 1
+        assert ctypes.c_int32(out[12]).value == top

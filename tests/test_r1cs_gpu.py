@@ -518,3 +518,21 @@ def test_device_generators_sharded():
         return g.export(0, 0, n_loc), g.export(1, 0, n_loc)
     for rank, (gl, hl) in enumerate(_sharded(world, curve, run)):
         assert gl == G[rank::world] and hl == H[rank::world]
+
+
+@pytest.mark.parametrize("name", ["chain1000", "shuffle42"])
+def test_golden_proofs_without_glv(env, name):
+    """The generator fold defaults to the GLV split on secq256k1 (every other test); the plain 256-step fold must
+    give the same golden bytes."""
+    from ark_bulletproofs_b200 import r1cs as R
+    g = GOLDEN[name]
+    curve, kind, params = g["curve"], g["kind"], g["params"]
+    ctx, gens = env(curve, max(g["gens_capacity"], 1))
+    ctx.set_ipa_nofold_threshold(0)
+    ctx.set_ipa_glv(False)
+    try:
+        proof, _ = gpu_prove_case(R, ctx, gens, kind, params, curve)
+    finally:
+        ctx.set_ipa_nofold_threshold(1 << 14)
+        ctx.set_ipa_glv(True)
+    assert proof.to_bytes().hex() == g["proof_hex"]
