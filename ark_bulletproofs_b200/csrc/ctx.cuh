@@ -46,7 +46,7 @@ struct bp_ctx {
     int force_c = 0;
     bool use_fp29 = false;                 // opt-in 29-bit-limb accumulate kernel (measured slower in round 1, see profiles/r1_mul29_experiment.txt)
     size_t msm_chunk = (size_t)1 << 22;
-    size_t ipa_nofold_n = (size_t)1 << 14;   // IPA rounds with n <= this use MSMs over the stage generators instead of folding them   // host-buffer MSMs above 1.5x this are chunked (copy/compute overlap)
+    size_t ipa_nofold_n = (size_t)1 << 13;   // IPA rounds with n <= this use MSMs over the stage generators instead of folding them   // host-buffer MSMs above 1.5x this are chunked (copy/compute overlap)
     // Multi-GPU: one bp_ctx per process/GPU; generators are sharded cyclically by index
     // (rank g holds i = g mod world), every MSM over them yields a partial point per rank, and the partials are
     // exchanged through the host program's collective (NCCL / gloo all-gather) and added on every rank.

@@ -129,7 +129,7 @@ def r1cs_prove_verify(ctx, lg_n):
     wit = R.ChaChaRng(bytes([3] * 32))
     x0_raw = wit.scalars_raw(CURVE, 1)
     ks_raw = wit.scalars_raw(CURVE, N)
-    best = None
+    best, best_v = None, None
     for _ in range(3):
         rng = R.ChaChaRng(bytes(range(32)))
         p = R.Prover(ctx, gens, R.Transcript(b"ChainCircuit"))
@@ -146,11 +146,14 @@ def r1cs_prove_verify(ctx, lg_n):
         v.verify(proof, gens)
         t_verify = (time.perf_counter() - t0) * 1e3
         st_v = ctx.last_stage_ms()
+        if best_v is None or t_verify < best_v[0]:
+            best_v = (t_verify, {k: v_ for k, v_ in st_v.items() if v_})
         if best is None or t_prove < best["prove_ms"]:
             best = {"circuit": "one-phase public-multiplier chain, 2^%d multipliers, m=1" % lg_n, "prove_ms": round(t_prove, 2),
                     "verify_ms": round(t_verify, 2), "proof_bytes": len(proof.to_bytes()),
                     "prove_stages_ms": {k: v_ for k, v_ in st_p.items() if v_}, "verify_stages_ms": {k: v_ for k, v_ in st_v.items() if v_},
-                    "note": "prove includes the serial TranscriptRng (8n Keccak-f on one host core, stage 'rng') that any byte-identical prover pays"}
+                    "note": "best of 3 each; prove includes the serial TranscriptRng (8n Keccak-f on one host core, stage 'rng') that any byte-identical prover pays"}
+    best["verify_ms"], best["verify_stages_ms"] = round(best_v[0], 2), best_v[1]
     return best
 
 

@@ -154,7 +154,7 @@ def test_ipa_create_matches_oracle(env, n, factors, nofold):
     try:
         L, Rv, ao, bo = R.ipa_create(ctx, R.Transcript(b"innerproducttest"), Q, Gf, Hf, bp.G(n), bp.H(n), a, b)
     finally:
-        ctx.set_ipa_nofold_threshold(1 << 14)
+        ctx.set_ipa_nofold_threshold(1 << 13)      # library default
     assert (L, Rv, ao, bo) == (want.L_vec, want.R_vec, want.a, want.b)
     # and the proof verifies (make_ipp_*): P = <a,G> + <b*Hf,H> + <a,b>Q with Gf applied
     c = O.inner_product(cv, a, b)
@@ -331,7 +331,7 @@ def test_golden_proofs_all_ipa_paths(env, name, nofold, geo):
     try:
         proof, _ = gpu_prove_case(R, ctx, gens, kind, params, curve)
     finally:
-        ctx.set_ipa_nofold_threshold(1 << 14)
+        ctx.set_ipa_nofold_threshold(1 << 13)      # library default
         ctx.set_ipa_geometric(True)
     assert proof.to_bytes().hex() == g["proof_hex"]
 
@@ -352,7 +352,7 @@ def test_pow2_chain_geometric_equals_general(env, N, nofold):
             proof, coms = gpu_prove_case(R, ctx, gens, "chain", {"N": N}, curve)
             out.append(proof.to_bytes())
     finally:
-        ctx.set_ipa_nofold_threshold(1 << 14)
+        ctx.set_ipa_nofold_threshold(1 << 13)      # library default
         ctx.set_ipa_geometric(True)
     assert out[0] == out[1]
     gpu_verifier(R, ctx, "chain", {"N": N}, curve, coms).verify(R.Proof.from_bytes(curve, out[0]), gens)
@@ -533,6 +533,6 @@ def test_golden_proofs_without_glv(env, name):
     try:
         proof, _ = gpu_prove_case(R, ctx, gens, kind, params, curve)
     finally:
-        ctx.set_ipa_nofold_threshold(1 << 14)
+        ctx.set_ipa_nofold_threshold(1 << 13)      # library default
         ctx.set_ipa_glv(True)
     assert proof.to_bytes().hex() == g["proof_hex"]
