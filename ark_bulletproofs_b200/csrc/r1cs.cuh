@@ -15,6 +15,7 @@
 #include <chrono>
 #include <functional>
 #include <memory>
+#include <thread>
 #include <vector>
 #include "host/gens_host.hpp"
 #include "r1cs_types.hpp"
@@ -581,25 +582,35 @@ struct ProverT : ConstraintSystemBase {
     }
 
     // three vector commitments over generators [off, off+cnt) in one batched MSM (prover.rs:516-559 / 604-649)
+    // `which`: bit 0 = A_I and A_O (out[0], out[1]), bit 1 = S (out[2]); 3 = all three in one batch. Large one-phase
+    // circuits commit A_I/A_O while the host is still drawing s_L, s_R (see prove()).
     int commit_phase(size_t off, size_t cnt, const fe bl[3], const fe* d_aL, const fe* d_aR, const fe* d_aO, const fe* d_sL, const fe* d_sR,
-                     affine out[3]) {
+                     affine out[3], int which = 3) {
         fe* d_bl = ctx->small.as<fe>() + 16;
         if (int rc = D::upload(ctx, d_bl, bl, 3 * sizeof(fe))) return rc;
         const affine* Bb = gens->pc.template as<affine>() + 1;
         // sharded contexts: this rank's generators of [off, off+cnt) against the replicated scalar vectors; the
-        // blinding terms are added once (rank 0); the three partial points are all-gathered and summed
+        // blinding terms are added once (rank 0); the partial points are all-gathered and summed
         const bool lead = ctx->rank == 0;
         MsmJob job;
-        if (lead) job.add(Bb, d_bl, 1, 0);                                                             // A_I
-        gens->add_range(job, gens->G, d_aL, off, cnt, 0); gens->add_range(job, gens->H, d_aR, off, cnt, 0);
-        if (lead) job.add(Bb, d_bl + 1, 1, 1);                                                         // A_O
-        gens->add_range(job, gens->G, d_aO, off, cnt, 1);
-        if (lead) job.add(Bb, d_bl + 2, 1, 2);                                                         // S
-        gens->add_range(job, gens->G, d_sL, off, cnt, 2); gens->add_range(job, gens->H, d_sR, off, cnt, 2);
+        int nm = 0, slot[3] = {-1, -1, -1};
+        if (which & 1) {
+            slot[0] = nm++; slot[1] = nm++;
+            if (lead) job.add(Bb, d_bl, 1, slot[0]);                                                   // A_I
+            gens->add_range(job, gens->G, d_aL, off, cnt, slot[0]); gens->add_range(job, gens->H, d_aR, off, cnt, slot[0]);
+            if (lead) job.add(Bb, d_bl + 1, 1, slot[1]);                                               // A_O
+            gens->add_range(job, gens->G, d_aO, off, cnt, slot[1]);
+        }
+        if (which & 2) {
+            slot[2] = nm++;
+            if (lead) job.add(Bb, d_bl + 2, 1, slot[2]);                                               // S
+            gens->add_range(job, gens->G, d_sL, off, cnt, slot[2]); gens->add_range(job, gens->H, d_sR, off, cnt, slot[2]);
+        }
         uint8_t o[3][64];
         int id[3];
-        if (int rc = msm_run_job_sharded<C>(ctx, job, 3, o, id)) return rc;
-        for (int k = 0; k < 3; k++) memcpy(&out[k], o[k], 64);
+        if (int rc = msm_run_job_sharded<C>(ctx, job, nm, o, id)) return rc;
+        for (int k = 0; k < 3; k++)
+            if (slot[k] >= 0) memcpy(&out[k], o[slot[k]], 64);
         return BP_OK;
     }
 
@@ -617,9 +628,19 @@ struct ProverT : ConstraintSystemBase {
         fe bl1[3];
         for (int k = 0; k < 3; k++) bl1[k] = HC::scalar_rand(rng);                              // :506-508
         std::vector<fe> s_L(n1), s_R(n1);
-        HC::scalar_rand_bulk(rng, s_L.data(), n1);                                              // :510-513
-        HC::scalar_rand_bulk(rng, s_R.data(), n1);
-        tm.lap(ST_RNG);
+        // The 8*n1 dependent Keccak permutations behind s_L, s_R are the longest stage of a large proof and need only
+        // the host: for large one-phase parts they run on a second host thread while this one uploads a_L, a_R, a_O and
+        // commits A_I, A_O (which do not depend on them); S follows when the draws are done. Same draws, same order.
+        const bool overlap = n1 >= 2048;
+        std::thread drawer;
+        auto draw = [&] {
+            HC::scalar_rand_bulk(rng, s_L.data(), n1);                                          // :510-513
+            HC::scalar_rand_bulk(rng, s_R.data(), n1);
+        };
+        if (overlap) drawer = std::thread(draw);
+        else draw();
+        struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{drawer};   // also on the error paths
+        if (!overlap) tm.lap(ST_RNG);
         BP_CUDA_TRY(ctx, ctx->small.reserve(4096));
         // device vectors sized for phase 1; grown after the randomised phase
         auto need = [&](size_t n_) -> int {
@@ -630,11 +651,17 @@ struct ProverT : ConstraintSystemBase {
         if (int rc = need(n1)) return rc;
         fe *d_aL = ctx->p_aL.as<fe>(), *d_aR = ctx->p_aR.as<fe>(), *d_aO = ctx->p_aO.as<fe>(), *d_sL = ctx->p_sL.as<fe>(), *d_sR = ctx->p_sR.as<fe>();
         D::upload(ctx, d_aL, a_L.data(), n1 * sizeof(fe)); D::upload(ctx, d_aR, a_R.data(), n1 * sizeof(fe));
-        D::upload(ctx, d_aO, a_O.data(), n1 * sizeof(fe)); D::upload(ctx, d_sL, s_L.data(), n1 * sizeof(fe));
+        if (int rc = D::upload(ctx, d_aO, a_O.data(), n1 * sizeof(fe))) return rc;
+        affine c1[3];
+        if (overlap) {
+            if (int rc = commit_phase(0, n1, bl1, d_aL, d_aR, d_aO, d_sL, d_sR, c1, 1)) return rc;   // A_I, A_O under the draws
+            drawer.join();
+            tm.lap(ST_RNG);
+        }
+        D::upload(ctx, d_sL, s_L.data(), n1 * sizeof(fe));
         if (int rc = D::upload(ctx, d_sR, s_R.data(), n1 * sizeof(fe))) return rc;
         tm.lap(ST_UPLOAD);
-        affine c1[3];
-        if (int rc = commit_phase(0, n1, bl1, d_aL, d_aR, d_aO, d_sL, d_sR, c1)) return rc;
+        if (int rc = commit_phase(0, n1, bl1, d_aL, d_aR, d_aO, d_sL, d_sR, c1, overlap ? 2 : 3)) return rc;
         tm.lap(ST_COMMIT);
         proof.A_I1 = c1[0]; proof.A_O1 = c1[1]; proof.S1 = c1[2];
         TP<C>::append_point(t, "A_I1", proof.A_I1);                                             // :561-564
