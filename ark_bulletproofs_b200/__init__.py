@@ -56,7 +56,7 @@ class Context:
         names = ["digits", "sort", "accumulate", "partials", "reduce"]
         return {"ms": {n: ph[i] for i, n in enumerate(names)}, "c": c.value, "windows": w.value, "entries": e.value}
 
-    STAGES = ["rng", "commit", "flatten", "vec", "t_commit", "ipa", "ipa_msm", "ipa_fold", "ipa_host", "verify_scalars", "verify_msm", "upload"]
+    STAGES = ["rng", "commit", "flatten", "vec", "t_commit", "ipa", "ipa_msm", "ipa_fold", "ipa_host", "verify_scalars", "verify_msm", "upload", "tail"]
 
     def last_stage_ms(self):
         out = (ctypes.c_double * 16)()

@@ -12,6 +12,7 @@
 // proofs are byte-identical to the CPU oracle; all O(n) arithmetic runs in the kernels of
 // msm_kernels.cuh / vec_kernels.cuh on the context's stream.
 #pragma once
+#include <string.h>
 #include <chrono>
 #include <functional>
 #include <memory>
@@ -101,7 +102,7 @@ struct StageTimer {
     }
 };
 enum { ST_RNG = 0, ST_COMMIT = 1, ST_FLATTEN = 2, ST_VEC = 3, ST_TCOMMIT = 4, ST_IPA = 5, ST_IPA_MSM = 6, ST_IPA_FOLD = 7, ST_IPA_HOST = 8,
-       ST_VSCALARS = 9, ST_VMSM = 10, ST_UPLOAD = 11 };
+       ST_VSCALARS = 9, ST_VMSM = 10, ST_UPLOAD = 11, ST_TAIL = 12 };
 
 // ---- device helpers -----------------------------------------------------------------------------
 template <class C>
@@ -781,8 +782,9 @@ struct ProverT : ConstraintSystemBase {
         // secrets: zero the device copies (mirrors prover.rs:74-94,805-812)
         DevBuf* sec[] = {&ctx->p_aL, &ctx->p_aR, &ctx->p_aO, &ctx->p_sL, &ctx->p_sR, &ctx->p_l, &ctx->p_r};
         for (auto* b : sec) if (b->p) cudaMemsetAsync(b->p, 0, b->cap, st);
-        for (auto& s : s_L) s = Fr::zero();
-        for (auto& s : s_R) s = Fr::zero();
+        if (!s_L.empty()) explicit_bzero(s_L.data(), s_L.size() * sizeof(fe));   // one bulk clear the compiler may not elide
+        if (!s_R.empty()) explicit_bzero(s_R.data(), s_R.size() * sizeof(fe));
+        tm.lap(ST_TAIL);
         return rc;
     }
 };

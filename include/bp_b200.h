@@ -76,7 +76,7 @@ int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* window
 /* Host wall-clock split (ms) of the last bp_prover_prove / bp_verifier_verify on this context:
  * 0 rng (TranscriptRng draws), 1 vector commitments, 2 flatten constraints, 3 l/r/t vector kernels,
  * 4 T commitments, 5 IPA total, 6 IPA MSMs, 7 IPA folds (only with timing enabled), 8 IPA host
- * (transcript, challenge inverse), 9 verification scalars, 10 mega-MSM, 11 uploads. */
+ * (transcript, challenge inverse), 9 verification scalars, 10 mega-MSM, 11 uploads, 12 clearing of the secrets. */
 int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]);
 /* bp_msm over host buffers larger than 1.5x `points` is split into chunks of `points` whose H2D copies
  * overlap the previous chunk's kernels (default 2^22); exposed for tests and tuning. */
