@@ -90,6 +90,9 @@ class Context:
     def set_device_gens(self, enable: bool):
         self._check(self.lib.bp_gens_set_device_generation(self.h, 1 if enable else 0))
 
+    def set_pedersen_table(self, enable: bool):
+        self._check(self.lib.bp_pedersen_set_table(self.h, 1 if enable else 0))
+
     def set_ipa_glv(self, enable: bool):
         self._check(self.lib.bp_ipa_set_glv(self.h, 1 if enable else 0))
 

@@ -51,6 +51,7 @@ def load():
         "bp_ipa_set_nofold_threshold": (i32, [vp, sz]),
         "bp_ipa_set_geometric": (i32, [vp, i32]),
         "bp_ipa_set_glv": (i32, [vp, i32]),
+        "bp_pedersen_set_table": (i32, [vp, i32]),
         "bp_gens_set_device_generation": (i32, [vp, i32]),
         "bp_ctx_set_collective": (i32, [vp, i32, i32, vp, vp]),
         "bp_ctx_set_timing": (i32, [vp, i32]),

@@ -125,6 +125,12 @@ int bp_gens_set_device_generation(bp_ctx* ctx, int enable) {
     return BP_OK;
 }
 
+int bp_pedersen_set_table(bp_ctx* ctx, int enable) {
+    if (!ctx) return BP_ERR_ARG;
+    ctx->pedersen_table = enable != 0;
+    return BP_OK;
+}
+
 int bp_ipa_set_glv(bp_ctx* ctx, int enable) {
     if (!ctx) return BP_ERR_ARG;
     ctx->ipa_glv = enable != 0;

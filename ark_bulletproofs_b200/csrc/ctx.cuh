@@ -55,6 +55,7 @@ struct bp_ctx {
     void* coll_user = nullptr;
     uint64_t coll_calls = 0, coll_bytes = 0;
     bool gens_on_device = true;              // BulletproofGens chains on the GPU where the stream is seekable (bp_gens_set_device_generation)
+    bool pedersen_table = true;              // batched Pedersen commitments through the fixed-base table (bp_pedersen_set_table)
     bool ipa_glv = true;                     // GLV split of the uniform fold scalar where the curve has the endomorphism (bp_ipa_set_glv)
     bool ipa_geo = true;                     // use the uniform-scalar fold for geometric factor vectors (bp_ipa_set_geometric)
     int sm_count = 148;

@@ -70,6 +70,9 @@ static inline MsmPlan make_plan(size_t n, int nmsm, int force_c, int sm_count) {
     p.T = (p.entries + p.L - 1) / p.L;
     uint32_t seg = p.nb / 1024;
     p.seg = seg < 4 ? 4 : seg > 32 ? 32 : seg;
+    // the largest windows still fill the machine with 64-bucket segments, and the per-segment lo*run multiplication
+    // (~28 additions) is amortised over twice as many buckets
+    if ((uint64_t)nmsm * p.W * p.nb / 64 >= (uint64_t)sm_count * 512) p.seg = 64;
     if (p.seg > p.nb) p.seg = p.nb;
     p.nseg = (p.nb + p.seg - 1) / p.seg;
     return p;

@@ -553,9 +553,28 @@ struct ProverT : ConstraintSystemBase {
         BP_CUDA_TRY(ctx, dout.reserve(m * sizeof(affine)));
         D::upload(ctx, dv.p, vals, m * sizeof(fe));
         if (int rc = D::upload(ctx, db.p, blinds, m * sizeof(fe))) return rc;
-        affine BBb = HC::add(gens->B, gens->B_blinding);
-        pedersen_commit_kernel<C><<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(gens->B, gens->B_blinding, BBb, dv.as<fe>(), db.as<fe>(),
-                                                                                       dout.as<affine>(), m);
+        if (ctx->pedersen_table) {
+            if (!gens->has_pc_table) {
+                DevBuf win;
+                BP_CUDA_TRY(ctx, win.reserve(64 * sizeof(affine)));
+                cudaError_t e = gens->pc_table.reserve((size_t)2 * 32 * 256 * sizeof(affine));
+                if (e != cudaSuccess) { win.release(); ctx->err = "pc_table"; return BP_ERR_CUDA; }
+                pedersen_window_kernel<C><<<1, 64, 0, ctx->stream>>>(gens->B, gens->B_blinding, win.as<affine>());
+                ctx->launches++;
+                pedersen_table_kernel<C><<<(2 * 32 * 256) / 128, 128, 0, ctx->stream>>>(win.as<affine>(), gens->pc_table.template as<affine>());
+                ctx->launches++;
+                e = cudaStreamSynchronize(ctx->stream);
+                win.release();
+                if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return BP_ERR_CUDA; }
+                gens->has_pc_table = true;
+            }
+            pedersen_commit_table_kernel<C><<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(gens->pc_table.template as<affine>(), dv.as<fe>(),
+                                                                                                 db.as<fe>(), dout.as<affine>(), m);
+        } else {
+            affine BBb = HC::add(gens->B, gens->B_blinding);
+            pedersen_commit_kernel<C><<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(gens->B, gens->B_blinding, BBb, dv.as<fe>(), db.as<fe>(),
+                                                                                           dout.as<affine>(), m);
+        }
         BP_LAUNCH_CHECK(ctx);
         if (int rc = D::download(ctx, V_out, dout.p, m * sizeof(affine))) return rc;
         for (size_t i = 0; i < m; i++) {

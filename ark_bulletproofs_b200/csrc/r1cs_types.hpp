@@ -16,8 +16,10 @@ struct GensDev {
     // cyclic shard of a multi-GPU context (bp_ctx_set_collective): G[j], H[j] hold generator j*world + rank
     int rank = 0, world = 1;
     DevBuf G, H, pc;          // pc = [B, B_blinding]
+    mutable DevBuf pc_table;  // fixed-base table of B and B_blinding (vec_kernels.cuh), built on the first batched commit
+    mutable bool has_pc_table = false;
     affine B, B_blinding;
-    ~GensDev() { G.release(); H.release(); pc.release(); }
+    ~GensDev() { G.release(); H.release(); pc.release(); pc_table.release(); }
     // generators [off, off+cnt) of the global numbering -> local entries [lo, hi); local j is global j*world + rank
     void slice(size_t off, size_t cnt, size_t& lo, size_t& hi) const {
         size_t end = off + cnt, r = (size_t)rank, w = (size_t)world;

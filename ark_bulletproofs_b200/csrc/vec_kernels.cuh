@@ -329,6 +329,55 @@ __global__ void __launch_bounds__(128) pedersen_commit_kernel(const affine B, co
     st_fe(&out[i].y, a.y);
 }
 
+// Fixed-base form of the same commitments ("fixed-base -> precomputed tables"): B and B_blinding
+// never change, so a table T[b][j][d] = d * 2^(8j) * P_b (2 bases x 32 byte-windows x 256 digits, 1 MB, built once per
+// generator set) turns a commitment into at most 64 mixed additions and no doubling -- the 256-step chain above is
+// pure latency (2.5 ms per launch however few commitments there are), this is ~0.3 ms.
+// pedersen_window_kernel: W[b][j] = 2^(8j) * P_b (one thread per (b, j)); pedersen_table_kernel: the 256 multiples.
+template <class C>
+__global__ void __launch_bounds__(64) pedersen_window_kernel(const affine B, const affine Bb, affine* __restrict__ win) {
+    using E = GroupLaw<C>;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 64) return;
+    const int b = t >> 5, j = t & 31;
+    xyzz acc = E::from_affine(b ? Bb : B);
+    for (int k = 0; k < 8 * j; k++) acc = E::dbl(acc);
+    affine a = E::to_affine(acc);
+    st_fe(&win[t].x, a.x);
+    st_fe(&win[t].y, a.y);
+}
+template <class C>
+__global__ void __launch_bounds__(128) pedersen_table_kernel(const affine* __restrict__ win, affine* __restrict__ table) {
+    using E = GroupLaw<C>;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;       // (b*32 + j)*256 + d
+    if (t >= 2 * 32 * 256) return;
+    const uint32_t d = (uint32_t)t & 255u;
+    affine w = ld_affine(win + (t >> 8));
+    xyzz acc = E::mul_u32(E::from_affine(w), d);          // d = 0 -> identity -> (0, 0)
+    affine a = E::to_affine(acc);
+    st_fe(&table[t].x, a.x);
+    st_fe(&table[t].y, a.y);
+}
+template <class C>
+__global__ void __launch_bounds__(128) pedersen_commit_table_kernel(const affine* __restrict__ table, const fe* __restrict__ v,
+                                                                    const fe* __restrict__ r, affine* __restrict__ out, size_t n) {
+    using E = GroupLaw<C>;
+    using Fr = Fp<typename C::Fr>;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe sv = Fr::from_mont(ld_fe(v + i)), sr = Fr::from_mont(ld_fe(r + i));
+    xyzz acc = E::identity();
+#pragma unroll 1
+    for (int j = 0; j < 32; j++) {
+        const uint32_t dv = (sv.v[j >> 2] >> (8 * (j & 3))) & 255u, dr = (sr.v[j >> 2] >> (8 * (j & 3))) & 255u;
+        if (dv) { affine p = ld_affine(table + ((size_t)j << 8) + dv); E::madd(acc, p); }
+        if (dr) { affine p = ld_affine(table + ((size_t)(32 + j) << 8) + dr); E::madd(acc, p); }
+    }
+    affine a = E::to_affine(acc);
+    st_fe(&out[i].x, a.x);
+    st_fe(&out[i].y, a.y);
+}
+
 // ---- R1CS prover vector kernels (prover.rs:674-756) ----------------------------------------------
 struct LrInputs {
     const fe *aL, *aR, *aO, *sL, *sR, *wL, *wR, *wO;   // length n

@@ -105,6 +105,10 @@ int bp_ipa_set_geometric(bp_ctx* ctx, int enable);
  * split as k1 + k2*lambda with 129-bit halves, halving the double-and-add chain of the generator fold
  * (inner_product_proof.rs:216-225). Same folded generators, hence the same L, R. Default on; 0 = plain 256-step fold. */
 int bp_ipa_set_glv(bp_ctx* ctx, int enable);
+/* bp_prover_commit_batch (m x PedersenGens::commit, src/generators.rs:39-44) uses a fixed-base table of B and B_blinding
+ * (2 x 32 byte-windows x 256 multiples, built on first use per generator set): at most 64 mixed additions per
+ * commitment instead of a 256-step double-and-add. Default on; 0 = the double-and-add kernel (tests compare both). */
+int bp_pedersen_set_table(bp_ctx* ctx, int enable);
 /* BulletproofGens::new (src/generators.rs:174-221): on secq256k1 every `G::rand` attempt of the GeneratorsChain reads
  * exactly 9 ChaCha20 words, so bp_gens_create evaluates the attempts on the GPU (seekable keystream, Tonelli-Shanks,
  * stream-order compaction) for capacities >= 256. Same points as the host generator (bp_gens_generate_host), which

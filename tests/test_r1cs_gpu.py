@@ -390,6 +390,22 @@ def test_commit_batch_equals_commit(env, curve):
     eb = [0, cv.r - 1, 1, 5]
     Vs, _ = p3.commit_batch(ev, eb)
     assert Vs == [pc.commit(v, b) for v, b in zip(ev, eb)]
+    # the fixed-base table (default) and the double-and-add kernel agree, also on random and byte-boundary scalars
+    rnd = random.Random(9)
+    vals = [rnd.randrange(cv.r) for _ in range(20)] + [255, 256, (1 << 64) - 1, 1 << 248, cv.r - 2]
+    bls = [rnd.randrange(cv.r) for _ in range(24)] + [0]
+    want = [pc.commit(v, b) for v, b in zip(vals[:6], bls[:6])]
+    for table in (True, False):
+        ctx.set_pedersen_table(table)
+        try:
+            got, _ = R.Prover(ctx, gens, transcript()).commit_batch(vals, bls)
+        finally:
+            ctx.set_pedersen_table(True)
+        assert got[:6] == want
+        if table:
+            ref = got
+        else:
+            assert got == ref
 
 
 # ---- multi-GPU mode on one GPU: `world` contexts in threads, cyclic generator shards ---------------
@@ -406,8 +422,8 @@ def _sharded(world, curve, fn):
     return ThreadGroup(world).run(work)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("n,nofold", [(64, 0), (64, 8), (8, 1 << 14), (4, 0)])
+@pytest.mark.parametrize("world,n,nofold", [(2, 64, 0), (2, 64, 8), (2, 8, 1 << 14), (2, 4, 0), (4, 64, 0), (4, 64, 8), (4, 8, 1 << 14), (4, 4, 0),
+                                            (8, 64, 0), (8, 16, 4), (8, 8, 0)])
 def test_sharded_ipa_matches_oracle(world, n, nofold):
     """InnerProductProof::create with G, H sharded cyclically over `world` contexts: the same L, R, a, b as the
     oracle on every rank, through local folds (n >= 2*world), the no-fold tail and arbitrary factor vectors."""
