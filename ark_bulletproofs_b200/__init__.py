@@ -105,6 +105,9 @@ class Context:
     def set_chunk(self, points: int):
         self._check(self.lib.bp_msm_set_chunk(self.h, points))
 
+    def set_tiny(self, max_terms: int):
+        self._check(self.lib.bp_msm_set_tiny(self.h, max_terms))
+
     def set_window(self, c: int):
         self._check(self.lib.bp_msm_set_window(self.h, c))
 

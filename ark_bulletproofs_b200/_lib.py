@@ -46,6 +46,7 @@ def load():
         "bp_msm": (i32, [vp, vp, vp, sz, vp, pi32]),
         "bp_msm_device": (i32, [vp, vp, vp, sz, vp, pi32]),
         "bp_msm_set_window": (i32, [vp, i32]),
+        "bp_msm_set_tiny": (i32, [vp, i32]),
         "bp_msm_set_chunk": (i32, [vp, sz]),
         "bp_msm_set_fp29": (i32, [vp, i32]),
         "bp_ipa_set_nofold_threshold": (i32, [vp, sz]),

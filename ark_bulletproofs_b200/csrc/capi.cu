@@ -149,6 +149,12 @@ int bp_msm_set_fp29(bp_ctx* ctx, int enable) {
     return BP_OK;
 }
 
+int bp_msm_set_tiny(bp_ctx* ctx, int max_terms) {
+    if (!ctx || max_terms < 0 || max_terms > 4096) return BP_ERR_ARG;
+    ctx->msm_tiny_max = max_terms;
+    return BP_OK;
+}
+
 int bp_msm_set_window(bp_ctx* ctx, int c) {
     if (!ctx || c < 0 || c > 20 || c == 1 || c == 2) return BP_ERR_ARG;
     ctx->force_c = c;

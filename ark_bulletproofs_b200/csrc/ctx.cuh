@@ -59,6 +59,7 @@ struct bp_ctx {
     bool ipa_glv = true;                     // GLV split of the uniform fold scalar where the curve has the endomorphism (bp_ipa_set_glv)
     bool ipa_geo = true;                     // use the uniform-scalar fold for geometric factor vectors (bp_ipa_set_geometric)
     int sm_count = 148;
+    int msm_tiny_max = 768;                  // MSMs of a batch with at most this many terms each take the single-launch path (0 = never; bp_msm_set_tiny)
     size_t msm_warp_partials_below = (size_t)1 << 17;   // partial-slot lists shorter than this are reduced by warp-segmented scans
     // MSM scratch
     bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;

@@ -481,6 +481,58 @@ __global__ void __launch_bounds__(128) msm_window_sum_kernel(const xyzz* __restr
     if (threadIdx.x == 0) st_xyzz(win_out + w, sh[0]);
 }
 
+// ---- tiny MSMs ---------------------------------------------------------------------------------
+// Below ~256 terms per MSM the bucket pipeline is nothing but launch and dependency latency (0.45-0.55 ms for any size,
+// and a small proof runs a dozen of them: every IPA round, the T commitments, the blinding-only phase-1 commitments).
+// One launch instead: block (w, m) handles the 4-bit window w of MSM m -- every thread multiplies its (up to three)
+// bases by their digits (<= 15: at most 4 doublings + 4 additions) and the block tree-sums the products in shared
+// memory (8 levels).
+// The 64 window sums per MSM go through the same host Horner as the bucket path (c = 4).
+static constexpr int MSM_TINY_C = 4, MSM_TINY_W = 64, MSM_TINY_THREADS = 256;
+
+template <class C>
+__global__ void __launch_bounds__(MSM_TINY_THREADS) msm_tiny_kernel(const __grid_constant__ MsmJob job, xyzz* __restrict__ win_out) {
+    using E = GroupLaw<C>;
+    __shared__ xyzz sh[MSM_TINY_THREADS];
+    const int w = blockIdx.x, m = blockIdx.y;
+    // terms threadIdx.x, threadIdx.x + 256, ... of MSM m: walk the segments that belong to m
+    int total = 0;
+    for (int sg = 0; sg < job.nseg; sg++)
+        if ((int)job.msm[sg] == m) total += (int)job.count[sg];
+    xyzz acc = E::identity();
+#pragma unroll 1
+    for (int term = (int)threadIdx.x; term < total; term += MSM_TINY_THREADS) {
+        int left = term;
+#pragma unroll 1
+        for (int sg = 0; sg < job.nseg; sg++) {
+            if ((int)job.msm[sg] != m) continue;
+            if (left < (int)job.count[sg]) {
+                fe s = Fp<typename C::Fr>::from_mont(ld_fe(job.scalars[sg] + (size_t)left * job.sstride[sg]));
+                const uint32_t d = (s.v[w >> 3] >> (4 * (w & 7))) & 15u;
+                if (d) {
+                    affine p = ld_affine(job.bases[sg] + left);
+                    xyzz q = E::mul_u32(E::from_affine(p), d);
+                    E::add(acc, q);
+                }
+                break;
+            }
+            left -= (int)job.count[sg];
+        }
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int stride = MSM_TINY_THREADS / 2; stride > 0; stride >>= 1) {
+        if ((int)threadIdx.x < stride) {
+            xyzz a = sh[threadIdx.x];
+            xyzz b = sh[threadIdx.x + stride];
+            E::add(a, b);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_xyzz(win_out + (size_t)m * MSM_TINY_W + w, sh[0]);
+}
+
 // synthetic workload: out[i] = (start + i + 1) * G
 template <class C>
 __global__ void __launch_bounds__(128) synth_points_kernel(affine* __restrict__ out, size_t n, uint64_t start) {
@@ -516,6 +568,35 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
     for (int k = 0; k < job.nseg; k++)
         if (job.count[k] > MSM_IDX_MASK) return BP_ERR_LEN;
     if (n >= (1ull << 31)) return BP_ERR_LEN;
+    // tiny batches: one launch (msm_tiny_kernel)
+    if (ctx->force_c == 0 && ctx->msm_tiny_max > 0) {
+        uint32_t per[MSM_MAX_BATCH] = {0}, worst = 0;
+        for (int k = 0; k < job.nseg; k++) per[job.msm[k]] += job.count[k];
+        for (int m = 0; m < job.nmsm; m++) worst = per[m] > worst ? per[m] : worst;
+        if (worst <= (uint32_t)ctx->msm_tiny_max) {
+            const int NWt = job.nmsm * MSM_TINY_W;
+            BP_CUDA_TRY(ctx, ctx->win_out.reserve((size_t)NWt * sizeof(xyzz)));
+            if ((size_t)NWt * sizeof(xyzz) > BP_HOST_RESULT_BYTES) return BP_ERR_LEN;
+            ctx->last_c = MSM_TINY_C; ctx->last_W = MSM_TINY_W; ctx->last_entries = n * MSM_TINY_W;
+            msm_tiny_kernel<C><<<dim3(MSM_TINY_W, job.nmsm), MSM_TINY_THREADS, 0, st>>>(job, ctx->win_out.as<xyzz>());
+            BP_LAUNCH_CHECK(ctx);
+            BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_result, ctx->win_out.p, (size_t)NWt * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
+            BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            if (ctx->timing) for (int i = 0; i < 5; i++) ctx->phase_ms[i] = 0;
+            int rcs[MSM_MAX_BATCH] = {0};
+            auto combine = [&](int m) {
+                rcs[m] = host_combine(ctx->curve, (const xyzz*)ctx->h_result + (size_t)m * MSM_TINY_W, MSM_TINY_W, MSM_TINY_C, out_xy[m],
+                                      out_is_identity ? &out_is_identity[m] : nullptr);
+            };
+            std::thread extra[MSM_MAX_BATCH];
+            for (int m = 1; m < job.nmsm; m++) extra[m] = std::thread(combine, m);
+            combine(0);
+            for (int m = 1; m < job.nmsm; m++) extra[m].join();
+            for (int m = 0; m < job.nmsm; m++)
+                if (rcs[m] != BP_OK) return rcs[m];
+            return BP_OK;
+        }
+    }
     MsmPlan p = make_plan(n, job.nmsm, ctx->force_c, ctx->sm_count);
     const int NW = job.nmsm * p.W;   // windows over the whole batch
     BP_CUDA_TRY(ctx, ctx->keys_a.reserve(p.entries * 4));

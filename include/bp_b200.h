@@ -119,6 +119,10 @@ int bp_gens_set_device_generation(bp_ctx* ctx, int enable);
 int bp_msm_set_fp29(bp_ctx* ctx, int enable);
 /* Force the Pippenger window width (0 = automatic); for parity tests and tuning. */
 int bp_msm_set_window(bp_ctx* ctx, int c);
+/* MSMs with at most `max_terms` (default 768) terms each run as one kernel launch (4-bit windows, digit
+ * multiples tree-summed per window) instead of the bucket pipeline, which at that size is pure latency; 0 disables
+ * (a forced window also selects the bucket pipeline). Same results. */
+int bp_msm_set_tiny(bp_ctx* ctx, int max_terms);
 
 /* Sum of n affine points (host). Used to combine per-GPU partial MSM results after the
  * all-gather of SURVEY.md 8(e). */

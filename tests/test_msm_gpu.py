@@ -11,9 +11,18 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
-def ctx():
+def _ctx():
     from ark_bulletproofs_b200 import Context
     return Context("secq256k1", 0)
+
+
+@pytest.fixture(params=["tiny", "buckets"])
+def ctx(_ctx, request):
+    """Every case runs through both small-MSM paths: the single-launch kernel for <= 768 terms per MSM (default) and
+    the bucket pipeline that larger inputs always take (bp_msm_set_tiny(0))."""
+    _ctx.set_tiny(768 if request.param == "tiny" else 0)
+    yield _ctx
+    _ctx.set_tiny(768)
 
 
 def _points(cv, n, rnd):
@@ -90,21 +99,23 @@ def test_points_sum(ctx):
     assert ctx.points_sum(pts) == want
 
 
-def test_zorro_msm():
+@pytest.mark.parametrize("n", [300, 100])
+def test_zorro_msm(n):
     from ark_bulletproofs_b200 import Context
     cv = O.ZORRO
     ctx = Context("zorro", 0)
     rnd = random.Random(77)
-    n = 300
     pts = _points(cv, n, rnd)
     sc = [rnd.randrange(cv.r) for _ in range(n)]
     assert ctx.msm(pts, sc) == O.msm(cv, pts, sc)
 
 
-def test_curve25519_msm():
+@pytest.mark.parametrize("tiny", [768, 0])
+def test_curve25519_msm(tiny):
     from ark_bulletproofs_b200 import Context
     cv = O.CURVE25519
     ctx = Context("curve25519", 0)
+    ctx.set_tiny(tiny)
     rnd = random.Random(78)
     n = 200
     pts = _points(cv, n, rnd)

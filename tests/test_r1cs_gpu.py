@@ -552,3 +552,20 @@ def test_golden_proofs_without_glv(env, name):
         ctx.set_ipa_nofold_threshold(1 << 13)      # library default
         ctx.set_ipa_glv(True)
     assert proof.to_bytes().hex() == g["proof_hex"]
+
+
+@pytest.mark.parametrize("name", ["v1_example", "shuffle7", "chain100", "zorro_shuffle3", "c25519_range8"])
+def test_golden_proofs_without_tiny_msm(env, name):
+    """Small proofs run their MSMs through the single-launch kernel by default; the bucket pipeline must give the same
+    golden bytes (it is the only path for anything larger)."""
+    from ark_bulletproofs_b200 import r1cs as R
+    g = GOLDEN[name]
+    curve, kind, params = g["curve"], g["kind"], g["params"]
+    ctx, gens = env(curve, max(g["gens_capacity"], 1))
+    ctx.set_tiny(0)
+    try:
+        proof, coms = gpu_prove_case(R, ctx, gens, kind, params, curve)
+        gpu_verifier(R, ctx, kind, params, curve, coms).verify(proof, gens)
+    finally:
+        ctx.set_tiny(768)
+    assert proof.to_bytes().hex() == g["proof_hex"]
