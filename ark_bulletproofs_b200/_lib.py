@@ -115,6 +115,7 @@ def load():
         "bp_proof_free": (None, [vp]),
         "bp_proof_to_bytes": (i32, [vp, vp, sz, psz]),
         "bp_proof_from_bytes": (i32, [i32, vp, sz, pvp]),
+        "bp_proofs_from_bytes_batch": (i32, [vp, vp, vp, sz, vp, vp]),
         "bp_proof_clone": (vp, [vp]),
         "bp_proof_get_field": (i32, [vp, i32, vp]),
         "bp_proof_set_field": (i32, [vp, i32, vp]),

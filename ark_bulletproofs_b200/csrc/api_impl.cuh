@@ -190,6 +190,49 @@ struct ApiImpl {
         if (rc == BP_OK) *out = pr.release();
         return rc;
     }
+    // Many proofs at once (batch-verification ingest): the structure and the scalars are parsed on the host, all
+    // compressed points of all proofs are decompressed and validated in one GPU launch (gens_kernels.cuh). status[i] is
+    // BP_OK or BP_ERR_FORMAT exactly as from_bytes would decide; out[i] is NULL for rejected proofs.
+    static int proofs_from_bytes_batch(bp_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, size_t n, void** out, int* status) {
+        std::vector<std::unique_ptr<ProofT<C>>> prs(n);
+        if constexpr (C::KIND != 0) {
+            for (size_t i = 0; i < n; i++) {       // twisted Edwards: subgroup check per point; host path
+                prs[i].reset(new ProofT<C>());
+                status[i] = ProofT<C>::from_bytes(bufs[i], lens[i], *prs[i]);
+                out[i] = status[i] == BP_OK ? prs[i].release() : nullptr;
+            }
+            return BP_OK;
+        } else {
+            std::vector<std::pair<const uint8_t*, affine*>> defer;
+            std::vector<size_t> first(n + 1, 0);
+            for (size_t i = 0; i < n; i++) {
+                prs[i].reset(new ProofT<C>());
+                first[i] = defer.size();
+                status[i] = ProofT<C>::from_bytes(bufs[i], lens[i], *prs[i], &defer);
+                if (status[i] != BP_OK) defer.resize(first[i]);
+            }
+            first[n] = defer.size();
+            const size_t np = defer.size();
+            std::vector<uint8_t> comp(np * 33), ok(np);
+            std::vector<affine> pts(np);
+            for (size_t k = 0; k < np; k++) memcpy(&comp[k * 33], defer[k].first, 33);
+            const auto& ts = HC::ts_params();
+            SqrtParams sp;
+            memcpy(sp.t, ts.t, 32); memcpy(sp.t1h, ts.t1h, 32); sp.z = ts.z; sp.s = ts.s;
+            if (int rc = points_decompress_device<C>(ctx, comp.data(), np, sp, pts.data(), ok.data())) return rc;
+            for (size_t i = 0; i < n; i++) {
+                if (status[i] == BP_OK) {
+                    size_t lo = first[i], hi = first[i + 1];
+                    for (size_t k = lo; k < hi; k++) {
+                        if (!ok[k]) { status[i] = BP_ERR_FORMAT; break; }
+                        *defer[k].second = pts[k];
+                    }
+                }
+                out[i] = status[i] == BP_OK ? prs[i].release() : nullptr;
+            }
+            return BP_OK;
+        }
+    }
     static void* proof_clone(const void* p) { return new ProofT<C>(*static_cast<const ProofT<C>*>(p)); }
     // field access for tamper tests: which = 0 t_x, 1 t_x_blinding, 2 e_blinding, 3 a, 4 b (scalars);
     // 10.. = points A_I1,A_O1,S1,A_I2,A_O2,S2,T_1,T_3,T_4,T_5,T_6 ; 100+j = L_j ; 200+j = R_j
@@ -328,7 +371,7 @@ struct ApiImpl {
             gens_generate_host, gens_create, gens_from_points, pedersen_commit, challenge_scalar, rng_scalar, scalar_to_bytes, scalar_from_bytes,
             point_compress, point_uncompressed, point_decompress, prover_new, prover_free, prover_cs, prover_commit, prover_commit_batch, prover_prove, verifier_new,
             verifier_free, verifier_cs, verifier_commit, verifier_verify, batch_verify, batch_verify_partial, proof_free, proof_to_bytes, proof_from_bytes, proof_clone,
-            proof_field, proof_rounds, chain_circuit, ipa_create_host, ipa_verify_host, rng_scalars, shuffle_gadget};
+            proof_field, proof_rounds, chain_circuit, ipa_create_host, ipa_verify_host, rng_scalars, shuffle_gadget, proofs_from_bytes_batch};
         return &api;
     }
 };

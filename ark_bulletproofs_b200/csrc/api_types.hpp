@@ -51,6 +51,7 @@ struct CurveApi {
                            const uint8_t* Hf, const uint8_t* P, const uint8_t* Q, const uint8_t* G, const uint8_t* H);
     int (*rng_scalars)(Rng*, size_t n, uint8_t* out);
     int (*shuffle_gadget)(ConstraintSystemBase*, const Variable* x, const Variable* y, size_t k);
+    int (*proofs_from_bytes_batch)(bp_ctx*, const uint8_t* const* bufs, const size_t* lens, size_t n, void** out, int* status);
 };
 
 const CurveApi* curve_api_secq();

@@ -583,6 +583,17 @@ int bp_proof_from_bytes(int curve, const uint8_t* data, size_t len, bp_proof** o
     *out = new bp_proof{curve, pr};
     return BP_OK;
 }
+int bp_proofs_from_bytes_batch(bp_ctx* ctx, const uint8_t* const* data, const size_t* lens, size_t n, bp_proof** out, int* status) {
+    if (!ctx || (n && (!data || !lens || !out || !status))) return BP_ERR_ARG;
+    auto a = bp::curve_api(ctx->curve);
+    if (!a) return BP_ERR_UNSUPPORTED;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<void*> impl(n, nullptr);
+    int rc = a->proofs_from_bytes_batch(ctx, data, lens, n, impl.data(), status);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; i++) out[i] = impl[i] ? new bp_proof{ctx->curve, impl[i]} : nullptr;
+    return BP_OK;
+}
 bp_proof* bp_proof_clone(const bp_proof* p) { return p ? new bp_proof{p->curve, bp::curve_api(p->curve)->proof_clone(p->impl)} : nullptr; }
 int bp_proof_get_field(const bp_proof* p, int which, uint8_t* buf) { return p && buf ? bp::curve_api(p->curve)->proof_field(p->impl, which, buf, 0) : BP_ERR_ARG; }
 int bp_proof_set_field(bp_proof* p, int which, const uint8_t* buf) {

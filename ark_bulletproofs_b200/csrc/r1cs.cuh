@@ -49,10 +49,19 @@ struct ProofT : ProofBase {
         sc(a); sc(b);
         return out;
     }
-    static int from_bytes(const uint8_t* d, size_t len, ProofT& pr) {     // proof.rs:83-91 (FormatError)
+    // `defer`: instead of decompressing each point on the host, record (compressed bytes, destination) pairs for one
+    // batched GPU decompression over many proofs (api_impl.cuh: proofs_from_bytes_batch)
+    static int from_bytes(const uint8_t* d, size_t len, ProofT& pr, std::vector<std::pair<const uint8_t*, affine*>>* defer = nullptr) {     // proof.rs:83-91 (FormatError)
         size_t off = 0;
         constexpr size_t PC = HC::POINT_COMPRESSED;
-        auto pt = [&](affine& p) { if (off + PC > len) return false; bool ok = HC::point_from_compressed(d + off, p); off += PC; return ok; };
+        auto pt = [&](affine& p) {
+            if (off + PC > len) return false;
+            bool ok = true;
+            if (defer) defer->emplace_back(d + off, &p);
+            else ok = HC::point_from_compressed(d + off, p);
+            off += PC;
+            return ok;
+        };
         auto sc = [&](fe& s) { if (off + 32 > len) return false; bool ok = HC::scalar_from_bytes(d + off, s); off += 32; return ok; };
         affine* pts[11] = {&pr.A_I1, &pr.A_O1, &pr.S1, &pr.A_I2, &pr.A_O2, &pr.S2, &pr.T_1, &pr.T_3, &pr.T_4, &pr.T_5, &pr.T_6};
         for (auto p : pts) if (!pt(*p)) return BP_ERR_FORMAT;

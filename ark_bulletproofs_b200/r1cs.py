@@ -266,6 +266,19 @@ class Proof:
         _chk(lib.bp_proof_from_bytes(codec.CURVE_IDS[curve], data, len(data), ctypes.byref(h)), "from_bytes")
         return Proof(lib, h, curve)
 
+    @staticmethod
+    def from_bytes_batch(ctx, blobs):
+        """Many proofs at once with GPU point decompression (bp_proofs_from_bytes_batch): a list with a Proof, or
+        None where from_bytes would raise a format error."""
+        n = len(blobs)
+        bufs = [ctypes.create_string_buffer(b, len(b)) for b in blobs]
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[ctypes.addressof(b) for b in bufs])
+        lens = (ctypes.c_size_t * max(n, 1))(*[len(b) for b in blobs])
+        out = (ctypes.c_void_p * max(n, 1))()
+        status = (ctypes.c_int * max(n, 1))()
+        ctx._check(ctx.lib.bp_proofs_from_bytes_batch(ctx.h, ptrs, lens, n, out, status))
+        return [Proof(ctx.lib, ctypes.c_void_p(out[i]), ctx.curve) if status[i] == 0 else None for i in range(n)]
+
     def clone(self):
         return Proof(self.lib, ctypes.c_void_p(self.lib.bp_proof_clone(self.h)), self.curve)
 

@@ -257,6 +257,11 @@ int bp_batch_verify_partial(bp_ctx* ctx, const uint8_t* alphas, bp_verifier* con
 void bp_proof_free(bp_proof* p);
 int bp_proof_to_bytes(const bp_proof* p, uint8_t* out, size_t cap, size_t* len);
 int bp_proof_from_bytes(int curve, const uint8_t* data, size_t len, bp_proof** out);
+/* n x R1CSProof::from_bytes (src/r1cs/proof.rs:83-91) for batch verification: structure and scalars are parsed on the
+ * host, the 11 + 2k compressed points of every proof are decompressed and validated in one GPU launch (secq256k1,
+ * zorro; curve25519 uses the host path). status[i] = BP_OK or BP_ERR_FORMAT exactly as bp_proof_from_bytes decides;
+ * out[i] = NULL for rejected proofs. */
+int bp_proofs_from_bytes_batch(bp_ctx* ctx, const uint8_t* const* data, const size_t* lens, size_t n, bp_proof** out, int* status);
 bp_proof* bp_proof_clone(const bp_proof* p);
 /* Field access (tamper tests). which: 0 t_x, 1 t_x_blinding, 2 e_blinding, 3 ipp.a, 4 ipp.b (32 B, Montgomery);
  * 10..20 = A_I1,A_O1,S1,A_I2,A_O2,S2,T_1,T_3,T_4,T_5,T_6; 100+j = L_j; 200+j = R_j (64 B affine). */

@@ -569,3 +569,45 @@ def test_golden_proofs_without_tiny_msm(env, name):
     finally:
         ctx.set_tiny(768)
     assert proof.to_bytes().hex() == g["proof_hex"]
+
+
+@pytest.mark.parametrize("curve", ["secq256k1", "zorro", "curve25519"])
+def test_proofs_from_bytes_batch(curve):
+    """Batch ingest with GPU point decompression: the same proofs (re-serialised byte for byte) and the same
+    accept / reject decisions as bp_proof_from_bytes -- golden proofs plus copies with a non-residue x, a flipped sign
+    bit (still a valid encoding: accepted, different point), bad flag bits, a non-canonical x, a truncated blob, a
+    non-canonical scalar."""
+    from ark_bulletproofs_b200 import Context
+    from ark_bulletproofs_b200 import r1cs as R
+    ctx = Context(curve, 0)
+    names = [n for n, g in GOLDEN.items() if g["curve"] == curve]
+    blobs = [bytes.fromhex(GOLDEN[n]["proof_hex"]) for n in names]
+    pc = 32 if curve == "curve25519" else 33
+    base = blobs[0]
+    bad = []
+    for delta in range(1, 40):                         # some x + delta is not on the curve
+        b = bytearray(base)
+        b[0] = (b[0] + delta) & 0xFF
+        bad.append(bytes(b))
+    sign = bytearray(base); sign[pc - 1] ^= 0x80; bad.append(bytes(sign))
+    if pc == 33:
+        fl = bytearray(base); fl[32] |= 0x01; bad.append(bytes(fl))            # unused flag bit
+        inf = bytearray(base); inf[32] = 0xC0; bad.append(bytes(inf))           # infinity + sign
+        big = bytearray(base); big[0:32] = b"\xff" * 32; bad.append(bytes(big))  # x >= q
+    bad.append(base[:-5])
+    sc = bytearray(base); sc[-32:] = b"\xff" * 32; bad.append(bytes(sc))        # scalar >= r
+    allb = blobs + bad
+    got = R.Proof.from_bytes_batch(ctx, allb)
+    n_rej = 0
+    for blob, pr in zip(allb, got):
+        try:
+            want = R.Proof.from_bytes(curve, blob)
+        except Exception:
+            want = None
+        assert (pr is None) == (want is None)
+        if pr is not None:
+            assert pr.to_bytes() == want.to_bytes() == blob
+        else:
+            n_rej += 1
+    assert n_rej >= 3 and all(p is not None for p in got[:len(blobs)])
+    assert R.Proof.from_bytes_batch(ctx, []) == []
