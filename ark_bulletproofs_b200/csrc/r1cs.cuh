@@ -151,14 +151,15 @@ struct Dev {
 template <class C>
 int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, const fe* d_Hf, const affine* d_G, const affine* d_H,
                fe* d_a, fe* d_b, size_t n, std::vector<affine>& L_vec, std::vector<affine>& R_vec, fe& a_out, fe& b_out,
-               const fe* geo_rG = nullptr, const fe* geo_rH = nullptr) {
+               const fe* geo_rG = nullptr, const fe* geo_rH = nullptr, size_t geo_n1 = 0, const fe* geo_jump = nullptr) {
     using Fr = HostFp<typename C::Fr>;
     using D = Dev<C>;
     if (n == 0 || (n & (n - 1))) return BP_ERR_POW2;                     // assert at :66
-    // Geometric factor vectors (Gf[i+1] = rG*Gf[i], Hf[i+1] = rH*Hf[i]; the R1CS prover's are, prover.rs:781-789,
-    // whenever the circuit is one-phase without padding or all-phase-2): the two partners of every fold then
-    // differ by the *uniform* ratio r^h, so  cL*f[i]*P[i] + cR*f[h+i]*P[h+i] = cL*f[i]*(P[i] + (cR/cL)*r^h*P[h+i]):
-    // all rounds use the uniform-scalar fold, the generators stay unscaled, and the per-element factor
+    // Piecewise-geometric factor vectors: Gf[i+1] = rG*Gf[i], Hf[i+1] = rH*Hf[i], except for one jump by `geo_jump` at
+    // index geo_n1. The R1CS prover's always are (prover.rs:781-789: G_f = [1]*n1 ++ [u]*(n2+pad), H_f[i] = y^-i*G_f[i]).
+    // The two partners of a fold then differ by r^h, or by r^h*jump when the boundary lies between them, so
+    //   cL*f[i]*P[i] + cR*f[h+i]*P[h+i] = cL*f[i]*(P[i] + (cR/cL)*r^h*[jump]*P[h+i]):
+    // all rounds use the (two-)uniform-scalar fold, the generators stay unscaled, and the per-element factor
     // f[i] (a prefix of the original vector) times the running common factor goes into the MSM scalars.
     const bool geo = geo_rG && geo_rH;
     t.append_message("dom-sep", (const uint8_t*)"ipp v1", 6);            // transcript.rs:52-55
@@ -200,21 +201,29 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
     nf.nu = 0;
     const ShardIdx sh{(uint32_t)P, (uint32_t)g};
     // out = L + kappa*R for both generator vectors; GLV (129-step chain) where the curve has the endomorphism
+    // Elements with global index in [cross_lo, cross_hi) use the second pair of scalars (kGx, kHx): the partner of such an
+    // element lies across the block boundary of a piecewise-geometric factor vector (see below).
     auto fold_uniform = [&](const affine* GL, const affine* GR, affine* Gout, const affine* HL, const affine* HR, affine* Hout, size_t cnt,
-                            const fe& kG, const fe& kH) -> int {
+                            const fe& kG, const fe& kH, const fe& kGx, const fe& kHx, size_t cross_lo, size_t cross_hi) -> int {
         unsigned grid = (unsigned)((2 * cnt + 127) / 128);
         if constexpr (C::HAS_GLV) {
-            GlvSplit sG, sH;
-            if (ctx->ipa_glv && GlvHost<C>::split(kG, sG) && GlvHost<C>::split(kH, sH)) {
-                GlvBits bG, bH;
-                memcpy(bG.k1, sG.k1, 20); memcpy(bG.k2, sG.k2, 20); bG.neg1 = sG.neg1; bG.neg2 = sG.neg2; bG.top = sG.top;
-                memcpy(bH.k1, sH.k1, 20); memcpy(bH.k2, sH.k2, 20); bH.neg1 = sH.neg1; bH.neg2 = sH.neg2; bH.top = sH.top;
-                ipa_fold_points_glv_kernel<C><<<grid, 128, 0, st>>>(GL, GR, Gout, HL, HR, Hout, cnt, bG, bH);
+            GlvSplit sp[4];
+            const fe* ks[4] = {&kG, &kH, &kGx, &kHx};
+            bool ok = ctx->ipa_glv;
+            for (int q = 0; q < 4 && ok; q++) ok = GlvHost<C>::split(*ks[q], sp[q]);
+            if (ok) {
+                GlvBits b[4];
+                for (int q = 0; q < 4; q++) {
+                    memcpy(b[q].k1, sp[q].k1, 20); memcpy(b[q].k2, sp[q].k2, 20);
+                    b[q].neg1 = sp[q].neg1; b[q].neg2 = sp[q].neg2; b[q].top = sp[q].top;
+                }
+                ipa_fold_points_glv_kernel<C><<<grid, 128, 0, st>>>(GL, GR, Gout, HL, HR, Hout, cnt, b[0], b[1], b[2], b[3], cross_lo, cross_hi, sh);
                 BP_LAUNCH_CHECK(ctx);
                 return BP_OK;
             }
         }
-        ipa_fold_points_uniform_kernel<C><<<grid, 128, 0, st>>>(GL, GR, Gout, HL, HR, Hout, cnt, D::bits(kG), D::bits(kH));
+        ipa_fold_points_uniform_kernel<C><<<grid, 128, 0, st>>>(GL, GR, Gout, HL, HR, Hout, cnt, D::bits(kG), D::bits(kH), D::bits(kGx), D::bits(kHx),
+                                                                 cross_lo, cross_hi, sh);
         BP_LAUNCH_CHECK(ctx);
         return BP_OK;
     };
@@ -294,7 +303,17 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
                 fe rGh = *geo_rG, rHh = *geo_rH;
                 for (size_t k = 0; k < lg_h; k++) { rGh = Fr::sqr(rGh); rHh = Fr::sqr(rHh); }
                 fe kG = Fr::mul(Fr::sqr(u), rGh), kH = Fr::mul(Fr::sqr(uinv), rHh);
-                if (int rc = fold_uniform(curG, curG + hl, wG, curH, curH + hl, wH, hl, kG, kH)) return rc;
+                // block boundary: f[i] jumps by `geo_jump` at index geo_n1, so partners (i, i+h) with i < n1 <= i+h differ by
+                // r^h * jump instead of r^h
+                fe kGx = kG, kHx = kH;
+                size_t cross_lo = 0, cross_hi = 0;
+                if (geo_jump && geo_n1 > 0 && geo_n1 < n) {
+                    kGx = Fr::mul(kG, *geo_jump);
+                    kHx = Fr::mul(kH, *geo_jump);
+                    cross_lo = geo_n1 > h ? geo_n1 - h : 0;
+                    cross_hi = geo_n1 < h ? geo_n1 : h;
+                }
+                if (int rc = fold_uniform(curG, curG + hl, wG, curH, curH + hl, wH, hl, kG, kH, kGx, kHx, cross_lo, cross_hi)) return rc;
                 fG = Fr::mul(fG, uinv);
                 fH = Fr::mul(fH, u);
             } else if (first) {
@@ -304,7 +323,7 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
             } else {
                 // u^-1*G_L + u*G_R = u^-1*(G_L + u^2*G_R): the common factor moves into fG (resp. fH)
                 fe u2 = Fr::sqr(u), ui2 = Fr::sqr(uinv);
-                if (int rc = fold_uniform(curG, curG + hl, wG, curH, curH + hl, wH, hl, u2, ui2)) return rc;
+                if (int rc = fold_uniform(curG, curG + hl, wG, curH, curH + hl, wH, hl, u2, ui2, u2, ui2, 0, 0)) return rc;
                 fG = Fr::mul(fG, uinv);
                 fH = Fr::mul(fH, u);
             }
@@ -800,12 +819,12 @@ struct ProverT : ConstraintSystemBase {
         fe w = TP<C>::challenge_scalar(t, "w");                                                 // :777-779
         affine Q = HC::mul(gens->B, w);
         tm.lap(ST_VEC);
-        // G_factors = [1]*n1 ++ [u]*(n2+pad), H_factors[i] = y^-i * G_factors[i] (:781-789): geometric iff one block
-        const bool geo = ctx->ipa_geo && (n1 == 0 || (n2 == 0 && pad == 0));
+        // G_factors = [1]*n1 ++ [u]*(n2+pad), H_factors[i] = y^-i * G_factors[i] (:781-789): geometric with one jump (by u, at n1)
+        const bool geo = ctx->ipa_geo;
         const fe geo_rG = Fr::one();
         int rc = ipa_create<C>(ctx, t, Q, ctx->p_Gf.as<fe>(), ctx->p_Hf.as<fe>(), gens->G.template as<affine>(), gens->H.template as<affine>(),
                                ctx->p_l.as<fe>(), ctx->p_r.as<fe>(), padded_n, proof.L_vec, proof.R_vec, proof.a, proof.b,
-                               geo ? &geo_rG : nullptr, geo ? &y_inv : nullptr);                                        // :791-800
+                               geo ? &geo_rG : nullptr, geo ? &y_inv : nullptr, n1, &u);                                // :791-800
         tm.lap(ST_IPA);
         // secrets: zero the device copies (mirrors prover.rs:74-94,805-812)
         DevBuf* sec[] = {&ctx->p_aL, &ctx->p_aR, &ctx->p_aO, &ctx->p_sL, &ctx->p_sR, &ctx->p_l, &ctx->p_r};

@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(128) ipa_fold_points_uniform_kernel(const affi
                                                                       affine* __restrict__ out0, const affine* __restrict__ L1,
                                                                       const affine* __restrict__ R1, affine* __restrict__ out1,
                                                                       size_t count, const __grid_constant__ ScalarBits k0,
-                                                                      const __grid_constant__ ScalarBits k1) {
+                                                                      const __grid_constant__ ScalarBits k1, const __grid_constant__ ScalarBits k0x,
+                                                                      const __grid_constant__ ScalarBits k1x, size_t cross_lo, size_t cross_hi, ShardIdx sh) {
     using E = GroupLaw<C>;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * count) return;
@@ -195,7 +196,10 @@ __global__ void __launch_bounds__(128) ipa_fold_points_uniform_kernel(const affi
     const affine* L = second ? L1 : L0;
     const affine* R = second ? R1 : R0;
     affine* out = second ? out1 : out0;
-    const ScalarBits& k = second ? k1 : k0;
+    // piecewise-geometric factor vectors: elements whose partner lies across the block boundary use the second scalar
+    const size_t gi = i * sh.P + sh.g;
+    const bool cross = gi >= cross_lo && gi < cross_hi;
+    const ScalarBits& k = second ? (cross ? k1x : k1) : (cross ? k0x : k0);
     affine pr = ld_affine(R + i);
     xyzz acc = E::identity();
     for (int limb = 7; limb >= 0; limb--) {
@@ -223,7 +227,8 @@ __global__ void __launch_bounds__(128) ipa_fold_points_glv_kernel(const affine* 
                                                                   affine* __restrict__ out0, const affine* __restrict__ L1,
                                                                   const affine* __restrict__ R1, affine* __restrict__ out1,
                                                                   size_t count, const __grid_constant__ GlvBits g0,
-                                                                  const __grid_constant__ GlvBits g1) {
+                                                                  const __grid_constant__ GlvBits g1, const __grid_constant__ GlvBits g0x,
+                                                                  const __grid_constant__ GlvBits g1x, size_t cross_lo, size_t cross_hi, ShardIdx sh) {
     using E = GroupLaw<C>;
     using F = Fp<typename C::Fq>;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,7 +238,9 @@ __global__ void __launch_bounds__(128) ipa_fold_points_glv_kernel(const affine* 
     const affine* L = second ? L1 : L0;
     const affine* R = second ? R1 : R0;
     affine* out = second ? out1 : out0;
-    const GlvBits& g = second ? g1 : g0;
+    const size_t gi = i * sh.P + sh.g;
+    const bool cross = gi >= cross_lo && gi < cross_hi;     // see ipa_fold_points_uniform_kernel
+    const GlvBits& g = second ? (cross ? g1x : g1) : (cross ? g0x : g0);
     affine p1 = ld_affine(R + i);
     affine p2;
     fe beta;

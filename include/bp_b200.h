@@ -96,10 +96,11 @@ int bp_msm_set_chunk(bp_ctx* ctx, size_t points);
 /* IPA rounds of length n <= this threshold do not fold the generators; their L/R are MSMs over the last
  * folded stage with challenge-expanded scalars (same L, R, a, b). 0 = always fold. Default 2^13 (measured optimum with the GLV fold). */
 int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n);
-/* The R1CS prover's IPA factor vectors (src/r1cs/prover.rs:781-789) are geometric when the circuit is one-phase
- * without padding, or entirely phase 2; every generator fold is then one scalar multiplication by a scalar shared
- * by all threads (first round included) instead of the joint double-and-add of inner_product_proof.rs:143-155.
- * Same L, R, a, b. Default on; 0 restores the general first round (tests run both). */
+/* The R1CS prover's IPA factor vectors (src/r1cs/prover.rs:781-789) are geometric with one jump: G_f = [1]*n1 ++
+ * [u]*(n2+pad), H_f[i] = y^-i * G_f[i]. Partners i and i + n/2 of a fold therefore differ by one of two scalars shared
+ * by all threads, and every generator fold (first round included) is one scalar multiplication per output instead of the
+ * joint double-and-add of inner_product_proof.rs:143-155. Same L, R, a, b. Default on; 0 restores the general first
+ * round, which bp_ipa_create always uses for its arbitrary factor vectors (tests run both). */
 int bp_ipa_set_geometric(bp_ctx* ctx, int enable);
 /* secq256k1 has the endomorphism (x, y) -> (beta*x, y) = lambda*(x, y): the uniform fold scalar of each IPA round is
  * split as k1 + k2*lambda with 129-bit halves, halving the double-and-add chain of the generator fold

@@ -9,7 +9,8 @@ sys.path.insert(0, ROOT)
 from ark_bulletproofs_b200 import Context, codec  # noqa: E402
 from ark_bulletproofs_b200 import r1cs as R  # noqa: E402
 
-lgs = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [10, 12, 14, 16]
+# sizes: log2 of the multiplier count, or a literal count prefixed with n (e.g. n50000: a padded circuit)
+lgs = [x for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else ["10", "12", "14", "16"]
 timing = len(sys.argv) > 2 and sys.argv[2] == "timing"
 curve = sys.argv[3] if len(sys.argv) > 3 else "secq256k1"
 ctx = Context(curve, 0)
@@ -19,9 +20,12 @@ if os.environ.get("BP_NOFOLD"):
 r = codec.MODULI[curve][1]
 res = []
 for lg in lgs:
-    N = 1 << lg
+    N = int(lg[1:]) if lg.startswith("n") else 1 << int(lg)
+    cap = 1
+    while cap < N:
+        cap <<= 1
     t0 = time.perf_counter()
-    gens = R.Gens(ctx, N)
+    gens = R.Gens(ctx, cap)
     t_gens = time.perf_counter() - t0
     wit = R.ChaChaRng(bytes([3] * 32))
     x0_raw = wit.scalars_raw(curve, 1)
@@ -45,7 +49,7 @@ for lg in lgs:
         v.verify(proof, gens)
         t_verify = time.perf_counter() - t0
         st_v = ctx.last_stage_ms()
-    row = {"curve": curve, "lg_n": lg, "gens_s": round(t_gens, 2), "build_ms": round(t_build * 1e3, 1), "prove_ms": round(t_prove * 1e3, 2),
+    row = {"curve": curve, "lg_n": lg if lg.startswith("n") else int(lg), "gens_s": round(t_gens, 2), "build_ms": round(t_build * 1e3, 1), "prove_ms": round(t_prove * 1e3, 2),
            "verify_ms": round(t_verify * 1e3, 2), "prove_stages": {k: v for k, v in st_p.items() if v}, "verify_stages": {k: v for k, v in st_v.items() if v},
            "proof_bytes": len(proof.to_bytes())}
     print(json.dumps(row), flush=True)
