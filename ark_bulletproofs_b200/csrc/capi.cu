@@ -183,15 +183,30 @@ int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t 
         }
         return bp::msm_dispatch(ctx, ctx->stage_bases.p, ctx->stage_scalars.p, n, out_xy, out_is_identity);
     }
-    size_t nchunks = (n + CHUNK - 1) / CHUNK;
+    // Chunk schedule: the first copy cannot be hidden, and large chunks run the MSM more efficiently (wider windows,
+    // one bucket reduction), so the chunks start at CHUNK/2 and double: [a, a, 2a, 4a, ...]. For 2^24 points and the
+    // default CHUNK = 2^22: 2M, 2M, 4M, 8M -- measured 66.1 -> see DESIGN.md section 5 (4 equal chunks before).
+    std::vector<size_t> lo_of, cnt_of;
+    {
+        size_t a = CHUNK / 2 ? CHUNK / 2 : 1, rem = n, lo = 0;
+        while (rem > 0) {
+            size_t take = a < rem ? a : rem;
+            if (rem - take < a / 2) take = rem;
+            lo_of.push_back(lo); cnt_of.push_back(take);
+            lo += take; rem -= take;
+            if (lo_of.size() >= 2 && a < ((size_t)1 << 24)) a *= 2;   // staging buffers stay below 2 x 1.6 GB
+        }
+    }
+    size_t nchunks = lo_of.size(), maxc = 0;
+    for (size_t c : cnt_of) maxc = c > maxc ? c : maxc;
     bp::DevBuf* sb[2] = {&ctx->stage_bases, &ctx->stage2_bases};
     bp::DevBuf* ss[2] = {&ctx->stage_scalars, &ctx->stage2_scalars};
     for (int i = 0; i < 2; i++) {
-        BP_CUDA_TRY(ctx, sb[i]->reserve(CHUNK * 64));
-        BP_CUDA_TRY(ctx, ss[i]->reserve(CHUNK * 32));
+        BP_CUDA_TRY(ctx, sb[i]->reserve(maxc * 64));
+        BP_CUDA_TRY(ctx, ss[i]->reserve(maxc * 32));
     }
     auto issue_copy = [&](size_t k) -> int {
-        size_t lo = k * CHUNK, cnt = (lo + CHUNK <= n) ? CHUNK : n - lo;
+        size_t lo = lo_of[k], cnt = cnt_of[k];
         int s = (int)(k & 1);
         BP_CUDA_TRY(ctx, cudaMemcpyAsync(sb[s]->p, bases_xy + lo * 64, cnt * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
         BP_CUDA_TRY(ctx, cudaMemcpyAsync(ss[s]->p, scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -204,10 +219,9 @@ int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t 
         if (k + 1 < nchunks)
             if (int rc = issue_copy(k + 1)) return rc;       // buffer (k+1)&1 is free: the MSM of chunk k-1 has completed
         int s = (int)(k & 1);
-        size_t lo = k * CHUNK, cnt = (lo + CHUNK <= n) ? CHUNK : n - lo;
         BP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[s], 0));
         int ident = 0;
-        int rc = bp::msm_dispatch(ctx, sb[s]->p, ss[s]->p, cnt, &partials[k * 64], &ident);
+        int rc = bp::msm_dispatch(ctx, sb[s]->p, ss[s]->p, cnt_of[k], &partials[k * 64], &ident);
         if (rc) return rc;
         if (ident) memset(&partials[k * 64], 0, 64);
     }
