@@ -443,10 +443,13 @@ __global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz* __restrict_
     uint32_t hi = lo + seg < nb ? lo + seg : nb;
     const xyzz* B = buckets + (size_t)w * nb;
     xyzz run = E::identity(), acc = E::identity();
+    xyzz v = ld_xyzz(B + hi - 1);
     for (uint32_t b = hi; b-- > lo;) {
-        xyzz v = ld_xyzz(B + b);
+        xyzz nxt = v;
+        if (b > lo) nxt = ld_xyzz(B + b - 1);     // the next bucket is in flight during the two additions
         E::add(run, v);
         E::add(acc, run);
+        v = nxt;
     }
     // acc = sum (b - lo + 1) B_b ; weights are b + 1  ->  add lo * run
     if (lo != 0 && !E::is_identity(run)) {
