@@ -65,11 +65,11 @@ struct bp_ctx {
     bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;
     bp::DevBuf stage_bases, stage_scalars;
     // IPA / prover / verifier work buffers (r1cs.cuh)
-    bp::DevBuf ipa_G, ipa_H, ipa_s, ipa_parts, small;
+    bp::DevBuf ipa_G, ipa_H, ipa_s, ipa_parts, small, c_v, c_b, c_out;
     bp::DevBuf p_aL, p_aR, p_aO, p_sL, p_sR, p_wL, p_wR, p_wO, p_ypow, p_yinv, p_l, p_r, p_Gf, p_Hf, v_pts, v_sc, v_g, v_h, v_accg, v_acch, f_kind, f_idx, f_coeff, f_start, f_keys, f_keys2, f_perm, f_perm2, f_contrib, f_sorted, f_ukeys, f_sums, f_tmp, f_wv;
     template <class F> void for_each_buf(F f) {
         bp::DevBuf* all[] = {&keys_a, &keys_b, &vals_a, &vals_b, &cub_tmp, &buckets, &part_keys, &part_pts, &seg_out, &win_out, &result,
-                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &pts29, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
+                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &pts29, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &c_v, &c_b, &c_out, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
                              &p_wL, &p_wR, &p_wO, &p_ypow, &p_yinv, &p_l, &p_r, &p_Gf, &p_Hf, &v_pts, &v_sc, &v_g, &v_h, &v_accg, &v_acch, &f_kind, &f_idx, &f_coeff, &f_start, &f_keys, &f_keys2, &f_perm, &f_perm2, &f_contrib, &f_sorted,
                              &f_ukeys, &f_sums, &f_tmp, &f_wv};
         for (auto* b : all) f(b);

@@ -574,8 +574,9 @@ struct ProverT : ConstraintSystemBase {
     // transcript appends stay in commit order on the host -- same V_i, same transcript as m commit() calls
     int commit_batch(const fe* vals, const fe* blinds, size_t m, affine* V_out, Variable* vars) {
         if (m == 0) return BP_OK;
-        DevBuf dv, db, dout;
-        struct Guard { DevBuf* b[3]; ~Guard() { for (auto* x : b) x->release(); } } guard{{&dv, &db, &dout}};
+        // context-owned grow-only buffers: a cudaMalloc/cudaFree pair per call synchronises the device and was measured at
+        // up to ~100 ms in a process that holds many GB of other allocations (bench.py after the 2^24 MSM)
+        DevBuf &dv = ctx->c_v, &db = ctx->c_b, &dout = ctx->c_out;
         BP_CUDA_TRY(ctx, dv.reserve(m * sizeof(fe)));
         BP_CUDA_TRY(ctx, db.reserve(m * sizeof(fe)));
         BP_CUDA_TRY(ctx, dout.reserve(m * sizeof(affine)));

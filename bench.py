@@ -179,7 +179,8 @@ def kshuffle_prove_verify(ctx, k):
         t.append_u64(b"k", k)
         return t
     bp_, bv = None, None
-    for _ in range(3):
+    reps = []
+    for _ in range(5):
         rng = R.ChaChaRng(bytes(range(32)))
         blinds_raw = rng.scalars_raw(CURVE, 2 * k)
         t0 = time.perf_counter()
@@ -188,6 +189,7 @@ def kshuffle_prove_verify(ctx, k):
         p.shuffle_gadget_native(vars_[:k], vars_[k:])
         proof = p.prove(rng)
         tp = (time.perf_counter() - t0) * 1e3
+        reps.append(round(tp, 2))
         if bp_ is None or tp < bp_:
             st_best = {a: b for a, b in ctx.last_stage_ms().items() if b}
         t0 = time.perf_counter()
@@ -199,7 +201,7 @@ def kshuffle_prove_verify(ctx, k):
         bp_ = tp if bp_ is None or tp < bp_ else bp_
         bv = tv if bv is None or tv < bv else bv
     return {"k": k, "multipliers": 2 * (k - 1), "prove_ms": round(bp_, 2), "verify_ms": round(bv, 2), "proof_bytes": len(proof.to_bytes()),
-            "prove_stages_ms": st_best, "note": "prove_ms includes the 2k Pedersen commitments and the gadget, like the reference's bench"}
+            "prove_stages_ms": st_best, "prove_reps_ms": reps, "note": "prove_ms includes the 2k Pedersen commitments and the gadget, like the reference's bench"}
 
 
 def main():
