@@ -6,6 +6,10 @@
 #include <cstring>
 #include <vector>
 #include "ctx.cuh"
+#include <new>
+
+// No C++ exception unwinds across the C ABI: every multi-statement entry point is a function-try-block.
+#define BP_ABI_CATCH catch (const std::bad_alloc&) { return BP_ERR_INTERNAL; } catch (...) { return BP_ERR_INTERNAL; }
 
 namespace bp {
 int msm_dispatch(bp_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, uint8_t out_xy[64], int* out_is_identity);
@@ -24,7 +28,7 @@ static void bp_debug_signal(int sig) {
     _exit(128 + sig);
 }
 
-int bp_ctx_create(int curve, int device, bp_ctx** out) {
+int bp_ctx_create(int curve, int device, bp_ctx** out) try {
     if (!out) return BP_ERR_ARG;
     if (getenv("BP_DEBUG_BACKTRACE")) { signal(SIGFPE, bp_debug_signal); signal(SIGSEGV, bp_debug_signal); signal(SIGABRT, bp_debug_signal); }
     *out = nullptr;
@@ -48,7 +52,7 @@ int bp_ctx_create(int curve, int device, bp_ctx** out) {
     }
     *out = ctx;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
 void bp_ctx_destroy(bp_ctx* ctx) {
     if (!ctx) return;
@@ -67,107 +71,107 @@ const char* bp_last_error(const bp_ctx* ctx) { return ctx ? ctx->err.c_str() : "
 void* bp_ctx_stream(bp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t bp_ctx_launch_count(const bp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int bp_ctx_sync(bp_ctx* ctx) {
+int bp_ctx_sync(bp_ctx* ctx) try {
     if (!ctx) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_ctx_set_timing(bp_ctx* ctx, int enable) {
+int bp_ctx_set_timing(bp_ctx* ctx, int enable) try {
     if (!ctx) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (enable && !ctx->ev[0])
         for (int i = 0; i < 8; i++) BP_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i]));
     ctx->timing = enable != 0;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* windows, uint64_t* entries) {
+int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* windows, uint64_t* entries) try {
     if (!ctx || !phase_ms) return BP_ERR_ARG;
     for (int i = 0; i < 8; i++) phase_ms[i] = ctx->phase_ms[i];
     if (c) *c = ctx->last_c;
     if (windows) *windows = ctx->last_W;
     if (entries) *entries = ctx->last_entries;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]) {
+int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]) try {
     if (!ctx || !out) return BP_ERR_ARG;
     for (int i = 0; i < 16; i++) out[i] = ctx->stage_ms[i];
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_msm_set_chunk(bp_ctx* ctx, size_t points) {
+int bp_msm_set_chunk(bp_ctx* ctx, size_t points) try {
     if (!ctx || points == 0) return BP_ERR_ARG;
     ctx->msm_chunk = points;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n) {
+int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n) try {
     if (!ctx) return BP_ERR_ARG;
     ctx->ipa_nofold_n = n;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_ctx_set_collective(bp_ctx* ctx, int rank, int world, bp_allgather_fn fn, void* user) {
+int bp_ctx_set_collective(bp_ctx* ctx, int rank, int world, bp_allgather_fn fn, void* user) try {
     if (!ctx || world < 1 || rank < 0 || rank >= world || (world & (world - 1)) || (world > 1 && !fn)) return BP_ERR_ARG;
     ctx->rank = rank;
     ctx->world = world;
     ctx->coll = fn;
     ctx->coll_user = user;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_gens_set_device_generation(bp_ctx* ctx, int enable) {
+int bp_gens_set_device_generation(bp_ctx* ctx, int enable) try {
     if (!ctx) return BP_ERR_ARG;
     ctx->gens_on_device = enable != 0;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_pedersen_set_table(bp_ctx* ctx, int enable) {
+int bp_pedersen_set_table(bp_ctx* ctx, int enable) try {
     if (!ctx) return BP_ERR_ARG;
     ctx->pedersen_table = enable != 0;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_ipa_set_glv(bp_ctx* ctx, int enable) {
+int bp_ipa_set_glv(bp_ctx* ctx, int enable) try {
     if (!ctx) return BP_ERR_ARG;
     ctx->ipa_glv = enable != 0;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_ipa_set_geometric(bp_ctx* ctx, int enable) {
+int bp_ipa_set_geometric(bp_ctx* ctx, int enable) try {
     if (!ctx) return BP_ERR_ARG;
     ctx->ipa_geo = enable != 0;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_msm_set_fp29(bp_ctx* ctx, int enable) {
+int bp_msm_set_fp29(bp_ctx* ctx, int enable) try {
     if (!ctx) return BP_ERR_ARG;
     ctx->use_fp29 = enable != 0;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_msm_set_tiny(bp_ctx* ctx, int max_terms) {
+int bp_msm_set_tiny(bp_ctx* ctx, int max_terms) try {
     if (!ctx || max_terms < 0 || max_terms > 4096) return BP_ERR_ARG;
     ctx->msm_tiny_max = max_terms;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_msm_set_window(bp_ctx* ctx, int c) {
+int bp_msm_set_window(bp_ctx* ctx, int c) try {
     if (!ctx || c < 0 || c > 20 || c == 1 || c == 2) return BP_ERR_ARG;
     ctx->force_c = c;
     return BP_OK;
-}
+} BP_ABI_CATCH
 
-int bp_msm_device(bp_ctx* ctx, const void* d_bases_xy, const void* d_scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) {
+int bp_msm_device(bp_ctx* ctx, const void* d_bases_xy, const void* d_scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) try {
     if (!ctx || !out_xy || (n && (!d_bases_xy || !d_scalars))) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return bp::msm_dispatch(ctx, d_bases_xy, d_scalars, n, out_xy, out_is_identity);
-}
+} BP_ABI_CATCH
 
-int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) {
+int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) try {
     if (!ctx || !out_xy || (n && (!bases_xy || !scalars))) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     // Large host-resident inputs are processed in chunks: the H2D copy of chunk k+1 (copy stream) overlaps
@@ -226,24 +230,24 @@ int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t 
         if (ident) memset(&partials[k * 64], 0, 64);
     }
     return bp::host_points_sum(ctx->curve, partials.data(), nchunks, out_xy, out_is_identity);
-}
+} BP_ABI_CATCH
 
-int bp_points_sum(bp_ctx* ctx, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity) {
+int bp_points_sum(bp_ctx* ctx, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity) try {
     if (!ctx || !out_xy || (n && !points_xy)) return BP_ERR_ARG;
     // a handful of points (one per GPU): serial adds + one inversion, done on the host (host_tail.cpp)
     return bp::host_points_sum(ctx->curve, points_xy, n, out_xy, out_is_identity);
-}
+} BP_ABI_CATCH
 
-int bp_points_sum_curve(int curve, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity) {
+int bp_points_sum_curve(int curve, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity) try {
     if (!out_xy || (n && !points_xy)) return BP_ERR_ARG;
     return bp::host_points_sum(curve, points_xy, n, out_xy, out_is_identity);
-}
+} BP_ABI_CATCH
 
-int bp_synth_points_device(bp_ctx* ctx, void* d_out_xy, size_t n, uint64_t start) {
+int bp_synth_points_device(bp_ctx* ctx, void* d_out_xy, size_t n, uint64_t start) try {
     if (!ctx || (n && !d_out_xy)) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return bp::synth_points_dispatch(ctx, d_out_xy, n, start);
-}
+} BP_ABI_CATCH
 
 
 }  // extern "C"
@@ -309,11 +313,11 @@ void bp_transcript_append_u64(bp_transcript* t, const uint8_t* label, size_t lle
 void bp_transcript_challenge_bytes(bp_transcript* t, const uint8_t* label, size_t llen, uint8_t* out, size_t n) {
     t->t.challenge_bytes_l(label, llen, out, n);
 }
-int bp_transcript_challenge_scalar(int curve, bp_transcript* t, const uint8_t* label, size_t llen, uint8_t out[32]) {
+int bp_transcript_challenge_scalar(int curve, bp_transcript* t, const uint8_t* label, size_t llen, uint8_t out[32]) try {
     const bp::CurveApi* api = bp::curve_api(curve);
     if (!api || !t) return BP_ERR_ARG;
     return api->challenge_scalar(&t->t, lbl(label, llen).c_str(), out);
-}
+} BP_ABI_CATCH
 
 // ---- RNG (rand_core::RngCore) ----
 bp_rng* bp_rng_chacha20(const uint8_t seed[32]) {
@@ -331,11 +335,11 @@ bp_rng* bp_rng_from_callbacks(void* user, uint64_t (*next_u64)(void*), uint32_t 
 }
 void bp_rng_free(bp_rng* r) { delete r; }
 uint64_t bp_rng_words_used(const bp_rng* r) { return r && r->chacha ? r->chacha->words_used : 0; }
-int bp_rng_scalars(int curve, bp_rng* r, size_t n, uint8_t* out) {
+int bp_rng_scalars(int curve, bp_rng* r, size_t n, uint8_t* out) try {
     const bp::CurveApi* api = bp::curve_api(curve);
     if (!api || !r || (n && !out)) return BP_ERR_ARG;
     return api->rng_scalars(r->r.get(), n, out);
-}
+} BP_ABI_CATCH
 // merlin's TranscriptRngBuilder as the prover uses it (src/r1cs/prover.rs:483-494)
 bp_rng* bp_transcript_build_rng(const bp_transcript* t, const uint8_t* label, size_t llen, const uint8_t* witnesses, size_t nwit, bp_rng* external) {
     if (!t || !external || (nwit && !witnesses)) return nullptr;
@@ -347,11 +351,11 @@ bp_rng* bp_transcript_build_rng(const bp_transcript* t, const uint8_t* label, si
 }
 uint64_t bp_rng_next_u64(bp_rng* r) { return r ? r->r->next_u64() : 0; }
 int bp_host_keccak_select(int which) { return bp::keccak_select(which); }
-int bp_rng_scalar(int curve, bp_rng* r, uint8_t out[32]) {
+int bp_rng_scalar(int curve, bp_rng* r, uint8_t out[32]) try {
     const bp::CurveApi* api = bp::curve_api(curve);
     if (!api || !r) return BP_ERR_ARG;
     return api->rng_scalar(r->r.get(), out);
-}
+} BP_ABI_CATCH
 
 // ---- serialisation helpers (ark-serialize) ----
 int bp_scalar_to_bytes(int curve, const uint8_t mont[32], uint8_t out[32]) { auto a = bp::curve_api(curve); return a ? a->scalar_to_bytes(mont, out) : BP_ERR_ARG; }
@@ -361,11 +365,11 @@ int bp_point_serialize_uncompressed(int curve, const uint8_t xy[64], uint8_t out
 int bp_point_decompress(int curve, const uint8_t in[33], uint8_t xy[64]) { auto a = bp::curve_api(curve); return a ? a->point_decompress(in, xy) : BP_ERR_ARG; }
 
 // ---- generators ----
-int bp_gens_generate_host(int curve, size_t capacity, uint8_t* G_xy, uint8_t* H_xy, uint8_t B[64], uint8_t B_blinding[64]) {
+int bp_gens_generate_host(int curve, size_t capacity, uint8_t* G_xy, uint8_t* H_xy, uint8_t B[64], uint8_t B_blinding[64]) try {
     auto a = bp::curve_api(curve);
     return a ? a->gens_generate_host(capacity, G_xy, H_xy, B, B_blinding) : BP_ERR_ARG;
-}
-int bp_gens_create(bp_ctx* ctx, size_t capacity, bp_gens** out) {
+} BP_ABI_CATCH
+int bp_gens_create(bp_ctx* ctx, size_t capacity, bp_gens** out) try {
     if (!ctx || !out) return BP_ERR_ARG;
     auto a = bp::curve_api(ctx->curve);
     if (!a) return BP_ERR_UNSUPPORTED;
@@ -375,9 +379,9 @@ int bp_gens_create(bp_ctx* ctx, size_t capacity, bp_gens** out) {
     if (rc) return rc;
     *out = new bp_gens{ctx->curve, g};
     return BP_OK;
-}
+} BP_ABI_CATCH
 int bp_gens_from_points(bp_ctx* ctx, const uint8_t B[64], const uint8_t B_blinding[64], const uint8_t* G_xy, const uint8_t* H_xy, size_t capacity,
-                        bp_gens** out) {
+                        bp_gens** out) try {
     if (!ctx || !out || !B || !B_blinding || (capacity && (!G_xy || !H_xy))) return BP_ERR_ARG;
     auto a = bp::curve_api(ctx->curve);
     if (!a) return BP_ERR_UNSUPPORTED;
@@ -387,10 +391,10 @@ int bp_gens_from_points(bp_ctx* ctx, const uint8_t B[64], const uint8_t B_blindi
     if (rc) return rc;
     *out = new bp_gens{ctx->curve, g};
     return BP_OK;
-}
+} BP_ABI_CATCH
 void bp_gens_free(bp_gens* g) { if (g) { delete g->g; delete g; } }
 size_t bp_gens_capacity(const bp_gens* g) { return g ? g->g->capacity : 0; }
-int bp_gens_export(const bp_gens* g, int which, size_t offset, size_t count, uint8_t* out_xy) {
+int bp_gens_export(const bp_gens* g, int which, size_t offset, size_t count, uint8_t* out_xy) try {
     if (!g || !out_xy) return BP_ERR_ARG;
     bp_ctx* ctx = g->g->ctx;
     const bp::DevBuf& b = which == 0 ? g->g->G : which == 1 ? g->g->H : g->g->pc;
@@ -401,14 +405,14 @@ int bp_gens_export(const bp_gens* g, int which, size_t offset, size_t count, uin
     BP_CUDA_TRY(ctx, cudaMemcpyAsync(out_xy, b.as<uint8_t>() + offset * 64, count * 64, cudaMemcpyDeviceToHost, ctx->stream));
     BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return BP_OK;
-}
-int bp_pedersen_commit(const bp_gens* g, const uint8_t value[32], const uint8_t blinding[32], uint8_t out_xy[64]) {
+} BP_ABI_CATCH
+int bp_pedersen_commit(const bp_gens* g, const uint8_t value[32], const uint8_t blinding[32], uint8_t out_xy[64]) try {
     if (!g) return BP_ERR_ARG;
     return bp::curve_api(g->curve)->pedersen_commit(g->g, value, blinding, out_xy);
-}
+} BP_ABI_CATCH
 
 // ---- constraint system (trait ConstraintSystem / RandomizableConstraintSystem) ----
-int bp_cs_multiply(bp_cs* cs, const bp_term* left, size_t nl, const bp_term* right, size_t nr, bp_var out[3]) {
+int bp_cs_multiply(bp_cs* cs, const bp_term* left, size_t nl, const bp_term* right, size_t nr, bp_var out[3]) try {
     if (!cs || !out) return BP_ERR_ARG;
     std::vector<bp::Variable> lv, rv;
     std::vector<bp::fe> lc, rc;
@@ -418,8 +422,8 @@ int bp_cs_multiply(bp_cs* cs, const bp_term* left, size_t nl, const bp_term* rig
     int r = cs->cs->multiply(lv.data(), lc.data(), nl, rv.data(), rc.data(), nr, o);
     for (int i = 0; i < 3; i++) put_var(&out[i], o[i]);
     return r;
-}
-int bp_cs_allocate(bp_cs* cs, const uint8_t* assignment, bp_var* out) {
+} BP_ABI_CATCH
+int bp_cs_allocate(bp_cs* cs, const uint8_t* assignment, bp_var* out) try {
     if (!cs || !out) return BP_ERR_ARG;
     bp::fe a;
     if (assignment) memcpy(a.v, assignment, 32);
@@ -427,8 +431,8 @@ int bp_cs_allocate(bp_cs* cs, const uint8_t* assignment, bp_var* out) {
     int r = cs->cs->allocate(assignment ? &a : nullptr, &o);
     put_var(out, o);
     return r;
-}
-int bp_cs_allocate_multiplier(bp_cs* cs, const uint8_t* left, const uint8_t* right, bp_var out[3]) {
+} BP_ABI_CATCH
+int bp_cs_allocate_multiplier(bp_cs* cs, const uint8_t* left, const uint8_t* right, bp_var out[3]) try {
     if (!cs || !out) return BP_ERR_ARG;
     bp::fe l, r;
     if (left) memcpy(l.v, left, 32);
@@ -437,50 +441,50 @@ int bp_cs_allocate_multiplier(bp_cs* cs, const uint8_t* left, const uint8_t* rig
     int rc = cs->cs->allocate_multiplier(left ? &l : nullptr, right ? &r : nullptr, o);
     for (int i = 0; i < 3; i++) put_var(&out[i], o[i]);
     return rc;
-}
-int bp_cs_constrain(bp_cs* cs, const bp_term* terms, size_t n) {
+} BP_ABI_CATCH
+int bp_cs_constrain(bp_cs* cs, const bp_term* terms, size_t n) try {
     if (!cs) return BP_ERR_ARG;
     std::vector<bp::Variable> v;
     std::vector<bp::fe> c;
     split_terms(terms, n, v, c);
     return cs->cs->constrain(v.data(), c.data(), n);
-}
+} BP_ABI_CATCH
 size_t bp_cs_multipliers_len(const bp_cs* cs) { return cs ? cs->cs->multipliers_len() : 0; }
-int bp_cs_specify_randomized_constraints(bp_cs* cs, bp_randomized_cb cb, void* user) {
+int bp_cs_specify_randomized_constraints(bp_cs* cs, bp_randomized_cb cb, void* user) try {
     if (!cs || !cb) return BP_ERR_ARG;
     int curve = cs->curve;
     return cs->cs->specify_randomized_constraints([cb, user, curve](bp::ConstraintSystemBase& inner) {
         bp_cs h{curve, &inner};
         return cb(&h, user);
     });
-}
-int bp_cs_challenge_scalar(bp_cs* cs, const uint8_t* label, size_t llen, uint8_t out[32]) {
+} BP_ABI_CATCH
+int bp_cs_challenge_scalar(bp_cs* cs, const uint8_t* label, size_t llen, uint8_t out[32]) try {
     if (!cs || !out) return BP_ERR_ARG;
     bp::fe s;
     int rc = cs->cs->challenge_scalar(lbl(label, llen).c_str(), &s);
     if (rc == BP_OK) memcpy(out, s.v, 32);
     return rc;
-}
+} BP_ABI_CATCH
 
 // Synthetic measurement circuit of SURVEY.md 8(d) config 2(i): the one-phase public-multiplier chain.
 //   (L_i,R_i,O_i) = allocate_multiplier((x_i,k_i)); constrain(R_i - k_i); constrain(L_0 - V) / constrain(L_i - O_{i-1}).
 // x0 == NULL builds the verifier's side. ks: n Montgomery scalars.
-int bp_cs_chain_circuit(bp_cs* cs, const bp_var* v0, size_t n, const uint8_t* ks, const uint8_t* x0) {
+int bp_cs_chain_circuit(bp_cs* cs, const bp_var* v0, size_t n, const uint8_t* ks, const uint8_t* x0) try {
     if (!cs || !v0 || (n && !ks)) return BP_ERR_ARG;
     bp::Variable v{v0->kind, v0->index};
     return bp::curve_api(cs->curve)->chain_circuit(cs->cs, &v, n, ks, x0);
-}
+} BP_ABI_CATCH
 
 // k-shuffle gadget of the reference's benches and tests, built natively (benches/r1cs_secq256k1.rs:35-75).
-int bp_cs_shuffle_gadget(bp_cs* cs, const bp_var* x, const bp_var* y, size_t k) {
+int bp_cs_shuffle_gadget(bp_cs* cs, const bp_var* x, const bp_var* y, size_t k) try {
     if (!cs || !x || !y || k == 0) return BP_ERR_ARG;
     std::vector<bp::Variable> xs(k), ys(k);
     for (size_t i = 0; i < k; i++) { xs[i] = {x[i].kind, x[i].index}; ys[i] = {y[i].kind, y[i].index}; }
     return bp::curve_api(cs->curve)->shuffle_gadget(cs->cs, xs.data(), ys.data(), k);
-}
+} BP_ABI_CATCH
 
 // ---- prover ----
-int bp_prover_new(bp_ctx* ctx, const bp_gens* pc_gens, bp_transcript* transcript, bp_prover** out) {
+int bp_prover_new(bp_ctx* ctx, const bp_gens* pc_gens, bp_transcript* transcript, bp_prover** out) try {
     if (!ctx || !pc_gens || !transcript || !out) return BP_ERR_ARG;
     auto a = bp::curve_api(ctx->curve);
     if (!a || pc_gens->curve != ctx->curve) return BP_ERR_UNSUPPORTED;
@@ -488,17 +492,17 @@ int bp_prover_new(bp_ctx* ctx, const bp_gens* pc_gens, bp_transcript* transcript
     p->cs.cs = a->prover_cs(p->impl);
     *out = p;
     return BP_OK;
-}
+} BP_ABI_CATCH
 void bp_prover_free(bp_prover* p) { if (p) { bp::curve_api(p->curve)->prover_free(p->impl); delete p; } }
 bp_cs* bp_prover_cs(bp_prover* p) { return p ? &p->cs : nullptr; }
-int bp_prover_commit(bp_prover* p, const uint8_t value[32], const uint8_t blinding[32], uint8_t out_commitment[64], bp_var* out_var) {
+int bp_prover_commit(bp_prover* p, const uint8_t value[32], const uint8_t blinding[32], uint8_t out_commitment[64], bp_var* out_var) try {
     if (!p || !value || !blinding || !out_commitment || !out_var) return BP_ERR_ARG;
     bp::Variable v{0, 0};
     int rc = bp::curve_api(p->curve)->prover_commit(p->impl, value, blinding, out_commitment, &v);
     put_var(out_var, v);
     return rc;
-}
-int bp_prover_commit_batch(bp_prover* p, const uint8_t* values, const uint8_t* blindings, size_t m, uint8_t* out_commitments, bp_var* out_vars) {
+} BP_ABI_CATCH
+int bp_prover_commit_batch(bp_prover* p, const uint8_t* values, const uint8_t* blindings, size_t m, uint8_t* out_commitments, bp_var* out_vars) try {
     if (!p || (m && (!values || !blindings || !out_commitments || !out_vars))) return BP_ERR_ARG;
     if (((uintptr_t)values | (uintptr_t)blindings | (uintptr_t)out_commitments) & 15) return BP_ERR_ARG;   // 16-byte aligned arrays
     BP_CUDA_TRY(p->ctx, cudaSetDevice(p->ctx->device));
@@ -507,8 +511,8 @@ int bp_prover_commit_batch(bp_prover* p, const uint8_t* values, const uint8_t* b
     if (rc) return rc;
     for (size_t i = 0; i < m; i++) put_var(&out_vars[i], vars[i]);
     return BP_OK;
-}
-int bp_prover_prove(bp_prover* p, bp_rng* rng, bp_proof** out) {
+} BP_ABI_CATCH
+int bp_prover_prove(bp_prover* p, bp_rng* rng, bp_proof** out) try {
     if (!p || !rng || !out) return BP_ERR_ARG;
     BP_CUDA_TRY(p->ctx, cudaSetDevice(p->ctx->device));
     void* pr = nullptr;
@@ -516,10 +520,10 @@ int bp_prover_prove(bp_prover* p, bp_rng* rng, bp_proof** out) {
     if (rc) return rc;
     *out = new bp_proof{p->curve, pr};
     return BP_OK;
-}
+} BP_ABI_CATCH
 
 // ---- verifier ----
-int bp_verifier_new(bp_ctx* ctx, bp_transcript* transcript, bp_verifier** out) {
+int bp_verifier_new(bp_ctx* ctx, bp_transcript* transcript, bp_verifier** out) try {
     if (!ctx || !transcript || !out) return BP_ERR_ARG;
     auto a = bp::curve_api(ctx->curve);
     if (!a) return BP_ERR_UNSUPPORTED;
@@ -527,29 +531,29 @@ int bp_verifier_new(bp_ctx* ctx, bp_transcript* transcript, bp_verifier** out) {
     v->cs.cs = a->verifier_cs(v->impl);
     *out = v;
     return BP_OK;
-}
+} BP_ABI_CATCH
 void bp_verifier_free(bp_verifier* v) { if (v) { bp::curve_api(v->curve)->verifier_free(v->impl); delete v; } }
 bp_cs* bp_verifier_cs(bp_verifier* v) { return v ? &v->cs : nullptr; }
-int bp_verifier_commit(bp_verifier* v, const uint8_t commitment[64], bp_var* out_var) {
+int bp_verifier_commit(bp_verifier* v, const uint8_t commitment[64], bp_var* out_var) try {
     if (!v || !commitment || !out_var) return BP_ERR_ARG;
     bp::Variable var{0, 0};
     int rc = bp::curve_api(v->curve)->verifier_commit(v->impl, commitment, &var);
     put_var(out_var, var);
     return rc;
-}
-int bp_verifier_commit_batch(bp_verifier* v, const uint8_t* commitments, size_t m, bp_var* out_vars) {
+} BP_ABI_CATCH
+int bp_verifier_commit_batch(bp_verifier* v, const uint8_t* commitments, size_t m, bp_var* out_vars) try {
     if (!v || (m && (!commitments || !out_vars))) return BP_ERR_ARG;
     for (size_t i = 0; i < m; i++)
         if (int rc = bp_verifier_commit(v, commitments + 64 * i, out_vars + i)) return rc;
     return BP_OK;
-}
-int bp_verifier_verify(bp_verifier* v, const bp_proof* proof, const bp_gens* gens) {
+} BP_ABI_CATCH
+int bp_verifier_verify(bp_verifier* v, const bp_proof* proof, const bp_gens* gens) try {
     if (!v || !proof || !gens) return BP_ERR_ARG;
     if (proof->curve != v->curve || gens->curve != v->curve) return BP_ERR_ARG;
     BP_CUDA_TRY(v->ctx, cudaSetDevice(v->ctx->device));
     return bp::curve_api(v->curve)->verifier_verify(v->impl, proof->impl, gens->g);
-}
-int bp_batch_verify(bp_ctx* ctx, bp_rng* rng, bp_verifier* const* verifiers, const bp_proof* const* proofs, size_t n, const bp_gens* gens) {
+} BP_ABI_CATCH
+int bp_batch_verify(bp_ctx* ctx, bp_rng* rng, bp_verifier* const* verifiers, const bp_proof* const* proofs, size_t n, const bp_gens* gens) try {
     if (!ctx || !rng || !gens || (n && (!verifiers || !proofs))) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     std::vector<void*> vs(n);
@@ -560,10 +564,10 @@ int bp_batch_verify(bp_ctx* ctx, bp_rng* rng, bp_verifier* const* verifiers, con
         ps[i] = proofs[i]->impl;
     }
     return bp::curve_api(ctx->curve)->batch_verify(ctx, rng->r.get(), vs.data(), ps.data(), n, gens->g);
-}
+} BP_ABI_CATCH
 
 int bp_batch_verify_partial(bp_ctx* ctx, const uint8_t* alphas, bp_verifier* const* verifiers, const bp_proof* const* proofs, size_t n,
-                            const bp_gens* gens, uint8_t out_xy[64], int* out_is_identity) {
+                            const bp_gens* gens, uint8_t out_xy[64], int* out_is_identity) try {
     if (!ctx || !gens || !out_xy || !out_is_identity || (n && (!verifiers || !proofs || !alphas))) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     std::vector<void*> vs(n);
@@ -574,11 +578,11 @@ int bp_batch_verify_partial(bp_ctx* ctx, const uint8_t* alphas, bp_verifier* con
         ps[i] = proofs[i]->impl;
     }
     return bp::curve_api(ctx->curve)->batch_verify_partial(ctx, alphas, vs.data(), ps.data(), n, gens->g, out_xy, out_is_identity);
-}
+} BP_ABI_CATCH
 
 // ---- proofs ----
 void bp_proof_free(bp_proof* p) { if (p) { bp::curve_api(p->curve)->proof_free(p->impl); delete p; } }
-int bp_proof_to_bytes(const bp_proof* p, uint8_t* out, size_t cap, size_t* len) {
+int bp_proof_to_bytes(const bp_proof* p, uint8_t* out, size_t cap, size_t* len) try {
     if (!p || !len) return BP_ERR_ARG;
     std::vector<uint8_t> b;
     bp::curve_api(p->curve)->proof_to_bytes(p->impl, b);
@@ -587,8 +591,8 @@ int bp_proof_to_bytes(const bp_proof* p, uint8_t* out, size_t cap, size_t* len) 
     if (cap < b.size()) return BP_ERR_LEN;
     memcpy(out, b.data(), b.size());
     return BP_OK;
-}
-int bp_proof_from_bytes(int curve, const uint8_t* data, size_t len, bp_proof** out) {
+} BP_ABI_CATCH
+int bp_proof_from_bytes(int curve, const uint8_t* data, size_t len, bp_proof** out) try {
     auto a = bp::curve_api(curve);
     if (!a || !data || !out) return BP_ERR_ARG;
     void* pr = nullptr;
@@ -596,8 +600,8 @@ int bp_proof_from_bytes(int curve, const uint8_t* data, size_t len, bp_proof** o
     if (rc) return rc;
     *out = new bp_proof{curve, pr};
     return BP_OK;
-}
-int bp_proofs_from_bytes_batch(bp_ctx* ctx, const uint8_t* const* data, const size_t* lens, size_t n, bp_proof** out, int* status) {
+} BP_ABI_CATCH
+int bp_proofs_from_bytes_batch(bp_ctx* ctx, const uint8_t* const* data, const size_t* lens, size_t n, bp_proof** out, int* status) try {
     if (!ctx || (n && (!data || !lens || !out || !status))) return BP_ERR_ARG;
     auto a = bp::curve_api(ctx->curve);
     if (!a) return BP_ERR_UNSUPPORTED;
@@ -607,36 +611,36 @@ int bp_proofs_from_bytes_batch(bp_ctx* ctx, const uint8_t* const* data, const si
     if (rc) return rc;
     for (size_t i = 0; i < n; i++) out[i] = impl[i] ? new bp_proof{ctx->curve, impl[i]} : nullptr;
     return BP_OK;
-}
+} BP_ABI_CATCH
 bp_proof* bp_proof_clone(const bp_proof* p) { return p ? new bp_proof{p->curve, bp::curve_api(p->curve)->proof_clone(p->impl)} : nullptr; }
 int bp_proof_get_field(const bp_proof* p, int which, uint8_t* buf) { return p && buf ? bp::curve_api(p->curve)->proof_field(p->impl, which, buf, 0) : BP_ERR_ARG; }
-int bp_proof_set_field(bp_proof* p, int which, const uint8_t* buf) {
+int bp_proof_set_field(bp_proof* p, int which, const uint8_t* buf) try {
     return p && buf ? bp::curve_api(p->curve)->proof_field(p->impl, which, const_cast<uint8_t*>(buf), 1) : BP_ERR_ARG;
-}
+} BP_ABI_CATCH
 size_t bp_proof_rounds(const bp_proof* p) { return p ? bp::curve_api(p->curve)->proof_rounds(p->impl) : 0; }
 
 // ---- InnerProductProof::create ----
 int bp_ipa_create(bp_ctx* ctx, bp_transcript* transcript, const uint8_t Q[64], const uint8_t* G_factors, const uint8_t* H_factors,
                   const uint8_t* G_xy, const uint8_t* H_xy, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out_L, uint8_t* out_R,
-                  uint8_t out_a[32], uint8_t out_b[32]) {
+                  uint8_t out_a[32], uint8_t out_b[32]) try {
     if (!ctx || !transcript || !Q || !G_factors || !H_factors || !G_xy || !H_xy || !a || !b || !out_a || !out_b) return BP_ERR_ARG;
     if (n > 1 && (!out_L || !out_R)) return BP_ERR_ARG;
     auto api = bp::curve_api(ctx->curve);
     if (!api) return BP_ERR_UNSUPPORTED;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return api->ipa_create_host(ctx, &transcript->t, Q, G_factors, H_factors, G_xy, H_xy, a, b, n, out_L, out_R, out_a, out_b);
-}
+} BP_ABI_CATCH
 
 
 int bp_ipa_verify(bp_ctx* ctx, bp_transcript* transcript, size_t n, const uint8_t* L_xy, const uint8_t* R_xy, const uint8_t a[32], const uint8_t b[32],
                   const uint8_t* G_factors, const uint8_t* H_factors, const uint8_t P[64], const uint8_t Q[64], const uint8_t* G_xy,
-                  const uint8_t* H_xy) {
+                  const uint8_t* H_xy) try {
     if (!ctx || !transcript || !a || !b || !G_factors || !H_factors || !P || !Q || !G_xy || !H_xy) return BP_ERR_ARG;
     if (n > 1 && (!L_xy || !R_xy)) return BP_ERR_ARG;
     auto api = bp::curve_api(ctx->curve);
     if (!api) return BP_ERR_UNSUPPORTED;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return api->ipa_verify_host(ctx, &transcript->t, n, L_xy, R_xy, a, b, G_factors, H_factors, P, Q, G_xy, H_xy);
-}
+} BP_ABI_CATCH
 
 }  // extern "C"

@@ -43,7 +43,8 @@ enum bp_status {
     BP_ERR_VERIFY = -7,   /* R1CSError::VerificationError (src/r1cs/verifier.rs:595-597) */
     BP_ERR_FORMAT = -8,   /* R1CSError::FormatError (src/r1cs/proof.rs:83-91) */
     BP_ERR_MISSING = -9,  /* R1CSError::MissingAssignment (src/r1cs/prover.rs:139,170) */
-    BP_ERR_UNSUPPORTED = -10
+    BP_ERR_UNSUPPORTED = -10,
+    BP_ERR_INTERNAL = -11 /* a C++ exception (e.g. host allocation failure) was caught at the boundary: nothing unwinds across the ABI */
 };
 
 /* ---- context ------------------------------------------------------------------------ */
