@@ -117,6 +117,51 @@ def cpu_reference_run(lg_sample, steps, warmup, threads=None):
     return n / dt / 1e6, dt * 1e3, threads
 
 
+def cpu_r1cs_baseline(lg_n, threads=None):
+    """The reference's CPU schedule for one proof of 2^lg_n multipliers, assembled from bounded samples of its two hot
+    operations timed on this box's host cores with the C restatement (oracle/c/bp_ref.c): the per-element generator fold
+    of inner_product_proof.rs:216-225 (one 2-point msm + into_affine per output, 2(N-1) outputs for G and H together) and
+    ark's Pippenger for the commitments (5N points) and the L/R cross terms (4N points over all rounds); verification is
+    one MSM of 2N + 13 + 2 lg N points, timed directly. The serial TranscriptRng and the O(N) scalar loops are left
+    out, so the prove figure is a lower bound. Returned for all host threads (the analogue of feature `parallel`) and
+    for one thread (the crate's default features)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
+    import c_oracle
+    from ark_bulletproofs_b200 import codec
+    import bp_oracle as O
+    N = 1 << lg_n
+    threads = threads or c_oracle.num_threads()
+    g = codec.enc_point(O.SECQ256K1.G, CURVE)
+    rng = np.random.default_rng(7)
+
+    def scalars(k):
+        sc = rng.integers(0, 256, size=k * 32, dtype=np.uint8)
+        sc.reshape(k, 32)[:, 31] &= 0x7F
+        return sc.tobytes()
+    out = {}
+    for label, th in (("all_cores", threads), ("one_thread", 1)):
+        h = 2048 if th > 1 else 256
+        pts = c_oracle.synth_points(0, g, 2 * h, 0)
+        t0 = time.perf_counter()
+        c_oracle.fold_points(0, pts, h, scalars(1), scalars(1), th)
+        t_fold = (time.perf_counter() - t0) / h                      # seconds per folded output
+        n_s = 1 << (16 if th > 1 else 15)
+        ptb, scb = bytes(c_oracle.synth_points(0, g, n_s, 0)), scalars(n_s)
+        t0 = time.perf_counter()
+        c_oracle.msm_bytes(0, ptb, scb, n_s, th)
+        t_pt = (time.perf_counter() - t0) / n_s                      # seconds per MSM point at this size
+        prove = t_fold * 2 * (N - 1) + t_pt * 9 * N
+        verify = t_pt * (2 * N + 13 + 2 * lg_n)
+        out[label] = {"threads": th, "prove_ms_lower_bound": round(prove * 1e3, 1), "verify_ms": round(verify * 1e3, 1),
+                      "fold_us_per_output": round(t_fold * 1e6, 1), "msm_us_per_point": round(t_pt * 1e6, 3)}
+    out["kind"] = "port"
+    out["sample"] = ("oracle/c/bp_ref.c on this box: 2048 (256) folded outputs and one 2^16 (2^15)-point MSM with all cores (one thread), "
+                     "scaled to the reference's operation counts for 2^%d multipliers; TranscriptRng and scalar loops excluded" % lg_n)
+    return out
+
+
 def r1cs_prove_verify(ctx, lg_n):
     """Secondary metric of BASELINE.json: secq256k1 R1CS prove / verify ms on the synthetic one-phase
     chain circuit with 2^lg_n multipliers, through the C ABI; the proof is
@@ -347,6 +392,8 @@ def main():
             r1cs["sharding"] = "generators cyclic over %d GPUs; every MSM's 64 B partial points all-gathered (NCCL); scalars, transcript and TranscriptRng replicated" % world
         elif args.shuffle_k > 1:
             r1cs["reference_bench_kshuffle"] = kshuffle_prove_verify(ctx, args.shuffle_k)
+        if world == 1 and not args.no_cpu_baseline:
+            r1cs["cpu_baseline"] = cpu_r1cs_baseline(lgs[0])
 
     if rank != 0:
         if world > 1:
