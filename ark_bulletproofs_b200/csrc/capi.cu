@@ -15,6 +15,8 @@ namespace bp {
 int msm_dispatch(bp_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, uint8_t out_xy[64], int* out_is_identity);
 int host_points_sum(int curve, const uint8_t* pts_xy, size_t n, uint8_t out_xy[64], int* out_is_identity);
 int synth_points_dispatch(bp_ctx* ctx, void* d_out, size_t n, uint64_t start);
+int msm_streamed_dispatch(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scalars, size_t n, const std::vector<size_t>& lo_of,
+                          const std::vector<size_t>& cnt_of, uint8_t out_xy[64], int* out_is_identity);
 }  // namespace bp
 
 extern "C" {
@@ -174,9 +176,9 @@ int bp_msm_device(bp_ctx* ctx, const void* d_bases_xy, const void* d_scalars, si
 int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) try {
     if (!ctx || !out_xy || (n && (!bases_xy || !scalars))) return BP_ERR_ARG;
     BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    // Large host-resident inputs are processed in chunks: the H2D copy of chunk k+1 (copy stream) overlaps
-    // the MSM of chunk k (compute stream); the per-chunk partial points are added on the host. An MSM is a
-    // sum of independent terms, so chunking does not change the value.
+    // Large host-resident inputs are streamed in chunks: the H2D copy of chunk k+1 (copy stream) overlaps the kernels
+    // of chunk k (compute stream), and every chunk adds into the one bucket array of the whole MSM
+    // (bp::msm_run_streamed, msm_kernels.cuh). An MSM is a sum of independent terms, so chunking does not change the value.
     const size_t CHUNK = ctx->msm_chunk;
     if (n <= CHUNK + CHUNK / 2) {
         if (n) {
@@ -187,49 +189,23 @@ int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t 
         }
         return bp::msm_dispatch(ctx, ctx->stage_bases.p, ctx->stage_scalars.p, n, out_xy, out_is_identity);
     }
-    // Chunk schedule: the first copy cannot be hidden, and large chunks run the MSM more efficiently (wider windows,
-    // one bucket reduction), so the chunks start at CHUNK/2 and double: [a, a, 2a, 4a, ...]. For 2^24 points and the
-    // default CHUNK = 2^22: 2M, 2M, 4M, 8M -- measured 66.1 -> see DESIGN.md section 5 (4 equal chunks before).
+    // Chunk schedule: the first copy cannot be hidden, so the first chunk is CHUNK/4 points; all later chunks are CHUNK/2.
+    // The kernels are slower than the copies (2.5 vs ~1.7 ms per 2^20 points) and the copy of chunk k+1 starts when
+    // chunk k-1 releases its staging buffer, so with equal chunks the GPU never waits for PCIe after the first one
+    // (a doubling schedule does: its last chunk is half of the input and cannot start before the whole copy has ended).
+    // 2^24 points with the default CHUNK = 2^22: 1M + 7 x 2M + 1M.
     std::vector<size_t> lo_of, cnt_of;
     {
-        size_t a = CHUNK / 2 ? CHUNK / 2 : 1, rem = n, lo = 0;
+        const size_t full = CHUNK / 2 ? CHUNK / 2 : 1;
+        size_t rem = n, lo = 0;
         while (rem > 0) {
-            size_t take = a < rem ? a : rem;
-            if (rem - take < a / 2) take = rem;
+            size_t take = lo == 0 ? (full / 2 ? full / 2 : 1) : full;
+            if (take > rem || rem - take < full / 4) take = rem;
             lo_of.push_back(lo); cnt_of.push_back(take);
             lo += take; rem -= take;
-            if (lo_of.size() >= 2 && a < ((size_t)1 << 24)) a *= 2;   // staging buffers stay below 2 x 1.6 GB
         }
     }
-    size_t nchunks = lo_of.size(), maxc = 0;
-    for (size_t c : cnt_of) maxc = c > maxc ? c : maxc;
-    bp::DevBuf* sb[2] = {&ctx->stage_bases, &ctx->stage2_bases};
-    bp::DevBuf* ss[2] = {&ctx->stage_scalars, &ctx->stage2_scalars};
-    for (int i = 0; i < 2; i++) {
-        BP_CUDA_TRY(ctx, sb[i]->reserve(maxc * 64));
-        BP_CUDA_TRY(ctx, ss[i]->reserve(maxc * 32));
-    }
-    auto issue_copy = [&](size_t k) -> int {
-        size_t lo = lo_of[k], cnt = cnt_of[k];
-        int s = (int)(k & 1);
-        BP_CUDA_TRY(ctx, cudaMemcpyAsync(sb[s]->p, bases_xy + lo * 64, cnt * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
-        BP_CUDA_TRY(ctx, cudaMemcpyAsync(ss[s]->p, scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-        BP_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[s], ctx->copy_stream));
-        return BP_OK;
-    };
-    std::vector<uint8_t> partials(nchunks * 64);
-    if (int rc = issue_copy(0)) return rc;
-    for (size_t k = 0; k < nchunks; k++) {
-        if (k + 1 < nchunks)
-            if (int rc = issue_copy(k + 1)) return rc;       // buffer (k+1)&1 is free: the MSM of chunk k-1 has completed
-        int s = (int)(k & 1);
-        BP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[s], 0));
-        int ident = 0;
-        int rc = bp::msm_dispatch(ctx, sb[s]->p, ss[s]->p, cnt_of[k], &partials[k * 64], &ident);
-        if (rc) return rc;
-        if (ident) memset(&partials[k * 64], 0, 64);
-    }
-    return bp::host_points_sum(ctx->curve, partials.data(), nchunks, out_xy, out_is_identity);
+    return bp::msm_streamed_dispatch(ctx, bases_xy, scalars, n, lo_of, cnt_of, out_xy, out_is_identity);
 } BP_ABI_CATCH
 
 int bp_points_sum(bp_ctx* ctx, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity) try {

@@ -148,7 +148,11 @@ __device__ __forceinline__ affine gather_point(const MsmJob& job, uint32_t v) {
 // Run bookkeeping shared by all levels: the first run of a chunk goes to slot 0, the last run
 // (if it is not also the first) to slot 1, runs strictly inside the chunk own their bucket.
 // A single-run chunk fills slot 1 with (key, identity) so the slot list stays dense and sorted.
-template <class C>
+// MODE 0: buckets are written once per MSM (plain stores). MODE 1 / 2 serve the streamed MSM (msm_run_streamed), whose
+// chunks all add into one bucket array: at level 1 (MODE 1) a run that owns its bucket *starts* from the bucket's current
+// value, so the store below already carries it; a run that turns out to be cut by the chunk edge moves that value into
+// its slot and leaves the identity behind. At the slot levels (MODE 2) complete sums are added to the bucket.
+template <class C, int MODE = 0>
 struct RunSink {
     using E = GroupLaw<C>;
     xyzz* buckets;
@@ -167,6 +171,11 @@ struct RunSink {
         } else if (is_last) {
             out_keys[2 * t + 1] = key;
             st_xyzz(out_pts + 2 * t + 1, acc);
+            if (MODE == 1) st_xyzz(buckets + key, E::identity());
+        } else if (MODE == 2) {
+            xyzz b = ld_xyzz(buckets + key);
+            E::add(b, acc);
+            st_xyzz(buckets + key, b);
         } else {
             st_xyzz(buckets + key, acc);
         }
@@ -182,7 +191,7 @@ struct RunSink {
 // Software pipeline (ncu: 12.5 % long-scoreboard stalls before it): while point i is being added, the
 // gather of point i+1 is in flight and (key, val) of entry i+2 are being loaded; the sign is applied
 // when a point is consumed, not when it is loaded, so nothing waits on a load it has just issued.
-template <class C>
+template <class C, bool ACC = false>
 __global__ void __launch_bounds__(128, BP_ACC_MIN_BLOCKS) msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                              size_t M, int L, size_t T, const __grid_constant__ MsmJob job,
                                                              xyzz* __restrict__ buckets, uint32_t* __restrict__ out_keys,
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(128, BP_ACC_MIN_BLOCKS) msm_accumulate_kernel(
     if (t >= T) return;
     size_t s = t * (size_t)L;
     size_t e = s + L < M ? s + L : M;
-    RunSink<C> sink{buckets, out_keys, out_pts, t};
+    RunSink<C, ACC ? 1 : 0> sink{buckets, out_keys, out_pts, t};
     uint32_t cur = __ldg(keys + s);
     if (cur == INVALID_KEY) { sink.empty(); return; }
     uint32_t vcur = __ldg(vals + s);
@@ -215,7 +224,8 @@ __global__ void __launch_bounds__(128, BP_ACC_MIN_BLOCKS) msm_accumulate_kernel(
             sink.flush(cur, acc, !have_next);
             if (!have_next) break;
             cur = k1;
-            acc = E::identity();
+            if (ACC) acc = ld_xyzz(buckets + cur);     // sums of the earlier chunks (streamed MSM)
+            else acc = E::identity();
         }
         p = pnext;
         vcur = v1;
@@ -324,7 +334,7 @@ __global__ void __launch_bounds__(128, 3) msm_accumulate29_kernel(const uint32_t
 }
 
 // level >= 2: dense sorted (key, XYZZ partial) slots -> run sums
-template <class C>
+template <class C, bool ACC = false>
 __global__ void __launch_bounds__(128) msm_partials_level_kernel(const uint32_t* __restrict__ in_keys, const xyzz* __restrict__ in_pts,
                                                                  size_t nslots, int L, size_t T, xyzz* __restrict__ buckets,
                                                                  uint32_t* __restrict__ out_keys, xyzz* __restrict__ out_pts) {
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(128) msm_partials_level_kernel(const uint32_t*
     if (t >= T) return;
     size_t s = t * (size_t)L;
     size_t e = s + L < nslots ? s + L : nslots;
-    RunSink<C> sink{buckets, out_keys, out_pts, t};
+    RunSink<C, ACC ? 2 : 0> sink{buckets, out_keys, out_pts, t};
     uint32_t cur = in_keys[s];
     if (cur == INVALID_KEY) { sink.empty(); return; }
     xyzz acc = ld_xyzz(in_pts + s);
@@ -371,7 +381,7 @@ __device__ __forceinline__ xyzz shfl_up_xyzz(const xyzz& v, int d) {
     return r;
 }
 
-template <class C>
+template <class C, bool ACC = false>
 __global__ void __launch_bounds__(128) msm_partials_warp_kernel(const uint32_t* __restrict__ in_keys, const xyzz* __restrict__ in_pts,
                                                                 size_t nslots, int final, xyzz* __restrict__ buckets,
                                                                 uint32_t* __restrict__ out_keys, xyzz* __restrict__ out_pts) {
@@ -394,7 +404,10 @@ __global__ void __launch_bounds__(128) msm_partials_warp_kernel(const uint32_t* 
     const uint32_t klast = __shfl_sync(0xFFFFFFFFu, key, 31);
     const bool run_end = lane == 31 || knext != key;
     if (final) {
-        if (run_end && key != INVALID_KEY) st_xyzz(buckets + key, acc);
+        if (run_end && key != INVALID_KEY) {
+            if (ACC) { xyzz b = ld_xyzz(buckets + key); E::add(b, acc); st_xyzz(buckets + key, b); }
+            else st_xyzz(buckets + key, acc);
+        }
         return;
     }
     if (lane == 0 && kfirst == klast) {                      // single run: keep the slot list dense
@@ -408,6 +421,10 @@ __global__ void __launch_bounds__(128) msm_partials_warp_kernel(const uint32_t* 
     } else if (key == klast) {
         out_keys[2 * warp + 1] = key;
         if (key != INVALID_KEY) st_xyzz(out_pts + 2 * warp + 1, acc);
+    } else if (ACC) {
+        xyzz b = ld_xyzz(buckets + key);
+        E::add(b, acc);
+        st_xyzz(buckets + key, b);
     } else {
         st_xyzz(buckets + key, acc);
     }
@@ -559,6 +576,42 @@ __global__ void __launch_bounds__(128) synth_points_kernel(affine* __restrict__ 
 // ---- host driver -----------------------------------------------------------------------------
 int host_combine(int curve, const void* win, int W, int c, uint8_t out_xy[64], int* out_is_identity);
 
+// Hierarchical reduction of the level-1 slot list (2 slots per accumulate thread, at the start of part_keys / part_pts;
+// the levels ping-pong between that region and the one behind it). Long lists: serial 16-slot chunks (throughput);
+// short lists: warp-segmented scans (latency).
+static constexpr int MSM_PL = 16;
+template <class C, bool ACC>
+int msm_fold_slots(bp_ctx* ctx, size_t slots1, cudaStream_t st) {
+    const int PL = MSM_PL;
+    uint32_t* pk = ctx->part_keys.as<uint32_t>();
+    xyzz* pp = ctx->part_pts.as<xyzz>();
+    size_t nslots = slots1;
+    uint32_t* in_k = pk;
+    xyzz* in_p = pp;
+    uint32_t* out_k = pk + slots1;
+    xyzz* out_p = pp + slots1;
+    while (nslots > ctx->msm_warp_partials_below) {
+        size_t T2 = (nslots + PL - 1) / PL;
+        msm_partials_level_kernel<C, ACC><<<(unsigned)((T2 + 127) / 128), 128, 0, st>>>(in_k, in_p, nslots, PL, T2, ctx->buckets.as<xyzz>(),
+                                                                                        out_k, out_p);
+        BP_LAUNCH_CHECK(ctx);
+        nslots = 2 * T2;
+        uint32_t* tk = in_k; in_k = out_k; out_k = tk;
+        xyzz* tp = in_p; in_p = out_p; out_p = tp;
+    }
+    while (nslots > 32) {
+        size_t nw = (nslots + 31) / 32;
+        msm_partials_warp_kernel<C, ACC><<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(in_k, in_p, nslots, 0, ctx->buckets.as<xyzz>(), out_k, out_p);
+        BP_LAUNCH_CHECK(ctx);
+        nslots = 2 * nw;
+        uint32_t* tk = in_k; in_k = out_k; out_k = tk;
+        xyzz* tp = in_p; in_p = out_p; out_p = tp;
+    }
+    msm_partials_warp_kernel<C, ACC><<<1, 32, 0, st>>>(in_k, in_p, nslots, 1, ctx->buckets.as<xyzz>(), out_k, out_p);
+    BP_LAUNCH_CHECK(ctx);
+    return BP_OK;
+}
+
 // Runs the batch; out_xy / out_is_identity have job.nmsm entries.
 template <class C>
 int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_is_identity) {
@@ -609,7 +662,7 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
     size_t nbuckets = (size_t)NW * p.nb;
     BP_CUDA_TRY(ctx, ctx->buckets.reserve(nbuckets * sizeof(xyzz)));
     // partial slot lists: level 1 has 2T slots, every further level shrinks by PL/2
-    const int PL = 16;
+    const int PL = MSM_PL;
     size_t slots1 = 2 * p.T;
     size_t slots2 = 2 * ((slots1 + PL - 1) / PL);
     BP_CUDA_TRY(ctx, ctx->part_keys.reserve((slots1 + slots2 + 64) * 4));
@@ -656,32 +709,7 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
         BP_LAUNCH_CHECK(ctx);
     }
     mark(2);
-    // hierarchical reduction of the boundary partials (ping-pong inside the two regions)
-    size_t nslots = slots1;
-    uint32_t* in_k = pk;
-    xyzz* in_p = pp;
-    uint32_t* out_k = pk + slots1;
-    xyzz* out_p = pp + slots1;
-    // long lists: serial 16-slot chunks (throughput); short lists: warp-segmented scans (latency)
-    while (nslots > ctx->msm_warp_partials_below) {
-        size_t T2 = (nslots + PL - 1) / PL;
-        msm_partials_level_kernel<C><<<(unsigned)((T2 + 127) / 128), 128, 0, st>>>(in_k, in_p, nslots, PL, T2, ctx->buckets.as<xyzz>(),
-                                                                                   out_k, out_p);
-        BP_LAUNCH_CHECK(ctx);
-        nslots = 2 * T2;
-        uint32_t* tk = in_k; in_k = out_k; out_k = tk;
-        xyzz* tp = in_p; in_p = out_p; out_p = tp;
-    }
-    while (nslots > 32) {
-        size_t nw = (nslots + 31) / 32;
-        msm_partials_warp_kernel<C><<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(in_k, in_p, nslots, 0, ctx->buckets.as<xyzz>(), out_k, out_p);
-        BP_LAUNCH_CHECK(ctx);
-        nslots = 2 * nw;
-        uint32_t* tk = in_k; in_k = out_k; out_k = tk;
-        xyzz* tp = in_p; in_p = out_p; out_p = tp;
-    }
-    msm_partials_warp_kernel<C><<<1, 32, 0, st>>>(in_k, in_p, nslots, 1, ctx->buckets.as<xyzz>(), out_k, out_p);
-    BP_LAUNCH_CHECK(ctx);
+    if (int rc = msm_fold_slots<C, false>(ctx, slots1, st)) return rc;
     mark(3);
     size_t rt = (size_t)NW * p.nseg;
     msm_reduce_kernel<C><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, NW,
@@ -756,6 +784,140 @@ int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, u
     memcpy(out_xy, out[0], 64);
     if (out_is_identity) *out_is_identity = ident[0];
     return BP_OK;
+}
+
+// Host-resident MSM streamed through the GPU (bp_msm above ~6 M points): the input is cut into chunks, the H2D copy of
+// chunk k+1 (copy stream, second staging buffer) overlaps the kernels of chunk k, and **all chunks add into one bucket
+// array** with the window width of the whole MSM, so the total work is that of the one-shot MSM (one bucket reduction,
+// W * n bucket additions) -- independent per-chunk MSMs, the first implementation, use narrower windows and a reduction
+// each: +29 % modmul at 2^24 points in 2M/2M/4M/8M chunks, which was exactly the gap between `e2e` and `value`.
+// digits -> sort -> accumulate<ACC> -> slot levels<ACC> per chunk; reduce, window sums and the host Horner once.
+template <class C>
+int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scalars, size_t n, const std::vector<size_t>& lo_of,
+                     const std::vector<size_t>& cnt_of, uint8_t out_xy[64], int* out_is_identity) {
+    cudaStream_t st = ctx->stream;
+    if (n > MSM_IDX_MASK) return BP_ERR_LEN;
+    const size_t nchunks = lo_of.size();
+    size_t maxc = 0;
+    for (size_t c : cnt_of) maxc = c > maxc ? c : maxc;
+    MsmPlan p = make_plan(n, 1, ctx->force_c, ctx->sm_count);        // windows of the whole MSM
+    const size_t max_entries = (maxc * (size_t)p.W + 63) & ~(size_t)63;   // 256-byte aligned halves of the double buffers
+    DevBuf* sb[2] = {&ctx->stage_bases, &ctx->stage2_bases};
+    DevBuf* ss[2] = {&ctx->stage_scalars, &ctx->stage2_scalars};
+    for (int i = 0; i < 2; i++) {
+        BP_CUDA_TRY(ctx, sb[i]->reserve(maxc * 64));
+        BP_CUDA_TRY(ctx, ss[i]->reserve(maxc * 32));
+    }
+    BP_CUDA_TRY(ctx, ctx->keys_a.reserve(max_entries * 4));
+    BP_CUDA_TRY(ctx, ctx->keys_b.reserve(2 * max_entries * 4));     // sorted pairs: one buffer per chunk parity
+    BP_CUDA_TRY(ctx, ctx->vals_a.reserve(max_entries * 4));
+    BP_CUDA_TRY(ctx, ctx->vals_b.reserve(2 * max_entries * 4));
+    const size_t nbuckets = (size_t)p.W * p.nb;
+    BP_CUDA_TRY(ctx, ctx->buckets.reserve(nbuckets * sizeof(xyzz)));
+    {
+        size_t worst1 = 0;
+        for (size_t c : cnt_of) {
+            MsmPlan q = make_plan(c, 1, p.c, ctx->sm_count);
+            worst1 = 2 * q.T > worst1 ? 2 * q.T : worst1;
+        }
+        size_t slots2 = 2 * ((worst1 + MSM_PL - 1) / MSM_PL);
+        BP_CUDA_TRY(ctx, ctx->part_keys.reserve((worst1 + slots2 + 64) * 4));
+        BP_CUDA_TRY(ctx, ctx->part_pts.reserve((worst1 + slots2 + 64) * sizeof(xyzz)));
+    }
+    BP_CUDA_TRY(ctx, ctx->seg_out.reserve((size_t)p.W * p.nseg * sizeof(xyzz)));
+    BP_CUDA_TRY(ctx, ctx->win_out.reserve((size_t)p.W * sizeof(xyzz)));
+    if ((size_t)p.W * sizeof(xyzz) > BP_HOST_RESULT_BYTES) return BP_ERR_LEN;
+    size_t tmp_bytes = 0;
+    BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->keys_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(),
+                                                     ctx->vals_a.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), max_entries, 0,
+                                                     p.key_bits, st));
+    BP_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
+    ctx->last_c = p.c; ctx->last_W = p.W; ctx->last_entries = n * (size_t)p.W;
+    if (ctx->timing) for (int i = 0; i < 5; i++) ctx->phase_ms[i] = 0;
+
+    auto issue_copy = [&](size_t k) -> int {
+        size_t lo = lo_of[k], cnt = cnt_of[k];
+        int s = (int)(k & 1);
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(sb[s]->p, h_bases + lo * 64, cnt * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(ss[s]->p, h_scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BP_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[s], ctx->copy_stream));
+        return BP_OK;
+    };
+    // Three streams besides the copy stream, all queued up front (the host never blocks):
+    //   prep : digits + radix sort of chunk k (HBM-bound) -- runs next to the accumulate kernel of chunk k-1
+    //          (IMAD-bound, DRAM ~10 % busy) and fills that kernel's tail; sorted pairs are double-buffered
+    //   main : accumulate of chunk k, after its pairs are sorted and the slots of chunk k-1 are folded
+    //   fold : the slot levels of chunk k -- a handful of latency-bound launches -- next to the prep of chunk k+1
+    // prep and fold have the higher priority, so their blocks take the SM slots the long accumulate blocks free.
+    // Staging buffer k&1 and sorted-pair buffer k&1 are free again once the accumulate kernel of chunk k has run.
+    struct Scoped {
+        cudaEvent_t used[2] = {nullptr, nullptr}, sorted[2] = {nullptr, nullptr};
+        cudaEvent_t acc_done = nullptr, fold_done = nullptr;
+        cudaStream_t fold = nullptr, prep = nullptr;
+        ~Scoped() {
+            for (auto x : used) if (x) cudaEventDestroy(x);
+            for (auto x : sorted) if (x) cudaEventDestroy(x);
+            if (acc_done) cudaEventDestroy(acc_done);
+            if (fold_done) cudaEventDestroy(fold_done);
+            if (fold) cudaStreamDestroy(fold);
+            if (prep) cudaStreamDestroy(prep);
+        }
+    } sc;
+    for (auto& x : sc.used) BP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+    for (auto& x : sc.sorted) BP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+    BP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sc.acc_done, cudaEventDisableTiming));
+    BP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sc.fold_done, cudaEventDisableTiming));
+    int prio_lo = 0, prio_hi = 0;
+    BP_CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    BP_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&sc.fold, cudaStreamNonBlocking, prio_hi));
+    BP_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&sc.prep, cudaStreamNonBlocking, prio_hi));
+    if (int rc = issue_copy(0)) return rc;
+    BP_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, nbuckets * sizeof(xyzz), st));
+    for (size_t k = 0; k < nchunks; k++) {
+        if (k + 1 < nchunks) {
+            if (k >= 1) BP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, sc.used[(k + 1) & 1], 0));   // chunk k-1 is done with it
+            if (int rc = issue_copy(k + 1)) return rc;
+        }
+        const int s = (int)(k & 1);
+        const size_t cnt = cnt_of[k];
+        uint32_t* skeys = ctx->keys_b.as<uint32_t>() + (size_t)s * max_entries;
+        uint32_t* svals = ctx->vals_b.as<uint32_t>() + (size_t)s * max_entries;
+        MsmJob job;
+        job.add((const affine*)sb[s]->p, (const fe*)ss[s]->p, cnt, 0);
+        MsmPlan q = make_plan(cnt, 1, p.c, ctx->sm_count);   // same c, W, nb, key_bits; L and T of this chunk
+        // prep
+        BP_CUDA_TRY(ctx, cudaStreamWaitEvent(sc.prep, ctx->copy_ev[s], 0));
+        if (k >= 2) BP_CUDA_TRY(ctx, cudaStreamWaitEvent(sc.prep, sc.used[s], 0));   // chunk k-2 has consumed its sorted pairs
+        msm_digits_kernel<C><<<(unsigned)((cnt + 255) / 256), 256, 0, sc.prep>>>(job, cnt, q.c, q.W, ctx->keys_a.as<uint32_t>(),
+                                                                                ctx->vals_a.as<uint32_t>());
+        BP_LAUNCH_CHECK(ctx);
+        BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->keys_a.as<uint32_t>(), skeys,
+                                                         ctx->vals_a.as<uint32_t>(), svals, q.entries, 0, q.key_bits, sc.prep));
+        BP_CUDA_TRY(ctx, cudaEventRecord(sc.sorted[s], sc.prep));
+        // main
+        BP_CUDA_TRY(ctx, cudaStreamWaitEvent(st, sc.sorted[s], 0));
+        if (k >= 1) BP_CUDA_TRY(ctx, cudaStreamWaitEvent(st, sc.fold_done, 0));      // slots of chunk k-1 folded into the buckets
+        msm_accumulate_kernel<C, true><<<(unsigned)((q.T + 127) / 128), 128, 0, st>>>(skeys, svals, q.entries, q.L, q.T, job,
+                                                                                      ctx->buckets.as<xyzz>(), ctx->part_keys.as<uint32_t>(),
+                                                                                      ctx->part_pts.as<xyzz>());
+        BP_LAUNCH_CHECK(ctx);
+        BP_CUDA_TRY(ctx, cudaEventRecord(sc.used[s], st));
+        BP_CUDA_TRY(ctx, cudaEventRecord(sc.acc_done, st));
+        // fold
+        BP_CUDA_TRY(ctx, cudaStreamWaitEvent(sc.fold, sc.acc_done, 0));
+        if (int rc = msm_fold_slots<C, true>(ctx, 2 * q.T, sc.fold)) return rc;
+        BP_CUDA_TRY(ctx, cudaEventRecord(sc.fold_done, sc.fold));
+    }
+    BP_CUDA_TRY(ctx, cudaStreamWaitEvent(st, sc.fold_done, 0));
+    size_t rt = (size_t)p.W * p.nseg;
+    msm_reduce_kernel<C><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, p.W,
+                                                                       ctx->seg_out.as<xyzz>());
+    BP_LAUNCH_CHECK(ctx);
+    msm_window_sum_kernel<C><<<p.W, 128, 0, st>>>(ctx->seg_out.as<xyzz>(), p.nseg, ctx->win_out.as<xyzz>());
+    BP_LAUNCH_CHECK(ctx);
+    BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_result, ctx->win_out.p, (size_t)p.W * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
+    BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return host_combine(ctx->curve, (const xyzz*)ctx->h_result, p.W, p.c, out_xy, out_is_identity);
 }
 
 template <class C>

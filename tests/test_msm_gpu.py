@@ -131,8 +131,8 @@ def test_curve25519_msm(tiny):
 
 
 def test_msm_host_chunked_overlap(ctx):
-    """bp_msm over host buffers splits large inputs into chunks whose H2D copies overlap the previous
-    chunk's kernels; the chunk sums are added on the host. Forced here with a tiny chunk size."""
+    """bp_msm over host buffers streams large inputs in chunks whose H2D copies overlap the previous chunk's kernels;
+    all chunks add into one bucket array (msm_run_streamed). Forced here with a tiny chunk size."""
     cv = O.SECQ256K1
     rnd = random.Random(4097)
     n = 4097
@@ -152,6 +152,49 @@ def test_msm_host_chunked_overlap(ctx):
         assert ctx.msm(pts[:300], z) == O.msm(cv, pts[:300], z)
     finally:
         ctx.set_chunk(1 << 22)
+
+
+def test_msm_streamed_edge_cases(_ctx):
+    """The streamed MSM keeps bucket sums across chunks (interior runs start from the bucket, runs cut by a thread's
+    chunk edge move the bucket into their slot, slot sums are added to the bucket): SURVEY 8(d)'s adversarial scalar
+    sets -- all-equal scalars (every thread a single run), half zeros, p-1, one repeated point (P + P inside a
+    bucket), P and -P (bucket sums passing through the identity) -- against the oracle and the one-shot path."""
+    cv = O.SECQ256K1
+    rnd = random.Random(77)
+    n = 1500
+    pts = _points(cv, n, rnd)
+    same = rnd.randrange(cv.r)
+    cases = [
+        (pts, [same] * n),
+        (pts, [0 if i % 2 else rnd.randrange(cv.r) for i in range(n)]),
+        (pts, [cv.r - 1] * n),
+        ([pts[3]] * n, [rnd.randrange(1 << 20) for _ in range(n)]),
+        ([pts[i // 2] if i % 2 == 0 else O.pt_neg(cv, pts[i // 2]) for i in range(n)], [same] * n),
+        (pts, [rnd.randrange(cv.r) for _ in range(n)]),
+    ]
+    for bases, sc in cases:
+        want = O.msm(cv, bases, sc)
+        assert _ctx.msm(bases, sc) == want
+        for chunk in (64, 700, 1024):
+            _ctx.set_chunk(chunk)
+            try:
+                assert _ctx.msm(bases, sc) == want
+            finally:
+                _ctx.set_chunk(1 << 22)
+
+
+@pytest.mark.parametrize("curve", ["zorro", "curve25519"])
+def test_msm_streamed_other_curves(curve):
+    from ark_bulletproofs_b200 import Context
+    cv = O.CURVES[curve]
+    c = Context(curve, 0)
+    rnd = random.Random(78)
+    n = 600
+    pts = _points(cv, n, rnd)
+    sc = [rnd.randrange(cv.r) for _ in range(n)]
+    want = O.msm(cv, pts, sc)
+    c.set_chunk(128)
+    assert c.msm(pts, sc) == want
 
 
 @pytest.mark.parametrize("curve", ["secq256k1", "curve25519"])
