@@ -197,9 +197,11 @@ int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t 
     std::vector<size_t> lo_of, cnt_of;
     {
         const size_t full = CHUNK / 2 ? CHUNK / 2 : 1;
+        size_t first = full / 2 ? full / 2 : 1;
+        if (const char* e = getenv("BP_MSM_FIRST_CHUNK")) { size_t v = strtoull(e, nullptr, 10); if (v) first = v < full ? v : full; }
         size_t rem = n, lo = 0;
         while (rem > 0) {
-            size_t take = lo == 0 ? (full / 2 ? full / 2 : 1) : full;
+            size_t take = lo == 0 ? first : full;
             if (take > rem || rem - take < full / 4) take = rem;
             lo_of.push_back(lo); cnt_of.push_back(take);
             lo += take; rem -= take;
