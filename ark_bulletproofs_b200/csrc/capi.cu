@@ -189,22 +189,22 @@ int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t 
         }
         return bp::msm_dispatch(ctx, ctx->stage_bases.p, ctx->stage_scalars.p, n, out_xy, out_is_identity);
     }
-    // Chunk schedule: the first copy cannot be hidden, so the first chunk is CHUNK/4 points; all later chunks are CHUNK/2.
-    // The kernels are slower than the copies (2.5 vs ~1.7 ms per 2^20 points) and the copy of chunk k+1 starts when
-    // chunk k-1 releases its staging buffer, so with equal chunks the GPU never waits for PCIe after the first one
-    // (a doubling schedule does: its last chunk is half of the input and cannot start before the whole copy has ended).
-    // 2^24 points with the default CHUNK = 2^22: 1M + 7 x 2M + 1M.
+    // Chunk schedule: the copy stream runs back to back (55 GB/s: 1.7 ms per 2^20 points), the kernels follow at ~2.4 ms
+    // per 2^20 points plus ~0.5 ms of slot levels per chunk. The first copy cannot be hidden, so the first chunk is small
+    // (CHUNK/4); large chunks are cheaper per point (longer runs per bucket, fewer slot levels), and chunk k+1 has arrived
+    // when chunk k is done as long as it is at most ~1.4x as large -- so the chunks grow by 1.5x, up to 2 CHUNK.
+    // 2^24 points with the default CHUNK = 2^22: 1M, 1.5M, 2.25M, 3.4M, 5.1M, 2.8M.
     std::vector<size_t> lo_of, cnt_of;
     {
-        const size_t full = CHUNK / 2 ? CHUNK / 2 : 1;
-        size_t first = full / 2 ? full / 2 : 1;
-        if (const char* e = getenv("BP_MSM_FIRST_CHUNK")) { size_t v = strtoull(e, nullptr, 10); if (v) first = v < full ? v : full; }
-        size_t rem = n, lo = 0;
+        size_t a = CHUNK / 4 ? CHUNK / 4 : 1, rem = n, lo = 0;
+        if (const char* e = getenv("BP_MSM_FIRST_CHUNK")) { size_t v = strtoull(e, nullptr, 10); if (v) a = v; }
         while (rem > 0) {
-            size_t take = lo == 0 ? first : full;
-            if (take > rem || rem - take < full / 4) take = rem;
+            size_t take = a < rem ? a : rem;
+            if (rem - take < a / 2) take = rem;
             lo_of.push_back(lo); cnt_of.push_back(take);
             lo += take; rem -= take;
+            a += a / 2 ? a / 2 : 1;
+            if (a > 2 * CHUNK) a = 2 * CHUNK;
         }
     }
     return bp::msm_streamed_dispatch(ctx, bases_xy, scalars, n, lo_of, cnt_of, out_xy, out_is_identity);

@@ -786,8 +786,8 @@ int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, u
     return BP_OK;
 }
 
-// Host-resident MSM streamed through the GPU (bp_msm above ~6 M points): the input is cut into chunks, the H2D copy of
-// chunk k+1 (copy stream, second staging buffer) overlaps the kernels of chunk k, and **all chunks add into one bucket
+// Host-resident MSM streamed through the GPU (bp_msm above ~6 M points): the input is cut into chunks, the H2D copies run
+// back to back on the copy stream while the kernels of the chunks already there run, and **all chunks add into one bucket
 // array** with the window width of the whole MSM, so the total work is that of the one-shot MSM (one bucket reduction,
 // W * n bucket additions) -- independent per-chunk MSMs, the first implementation, use narrower windows and a reduction
 // each: +29 % modmul at 2^24 points in 2M/2M/4M/8M chunks, which was exactly the gap between `e2e` and `value`.
@@ -802,12 +802,10 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
     for (size_t c : cnt_of) maxc = c > maxc ? c : maxc;
     MsmPlan p = make_plan(n, 1, ctx->force_c, ctx->sm_count);        // windows of the whole MSM
     const size_t max_entries = (maxc * (size_t)p.W + 63) & ~(size_t)63;   // 256-byte aligned halves of the double buffers
-    DevBuf* sb[2] = {&ctx->stage_bases, &ctx->stage2_bases};
-    DevBuf* ss[2] = {&ctx->stage_scalars, &ctx->stage2_scalars};
-    for (int i = 0; i < 2; i++) {
-        BP_CUDA_TRY(ctx, sb[i]->reserve(maxc * 64));
-        BP_CUDA_TRY(ctx, ss[i]->reserve(maxc * 32));
-    }
+    // the whole input is staged (96 B per point: 1.6 GB at 2^24, 26 GB at the 2^28 limit of the pair format -- HBM has
+    // 180 GB), so the copy stream runs back to back from the first byte to the last and never waits for a kernel
+    BP_CUDA_TRY(ctx, ctx->stage_bases.reserve(n * 64));
+    BP_CUDA_TRY(ctx, ctx->stage_scalars.reserve(n * 32));
     BP_CUDA_TRY(ctx, ctx->keys_a.reserve(max_entries * 4));
     BP_CUDA_TRY(ctx, ctx->keys_b.reserve(2 * max_entries * 4));     // sorted pairs: one buffer per chunk parity
     BP_CUDA_TRY(ctx, ctx->vals_a.reserve(max_entries * 4));
@@ -835,26 +833,20 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
     ctx->last_c = p.c; ctx->last_W = p.W; ctx->last_entries = n * (size_t)p.W;
     if (ctx->timing) for (int i = 0; i < 5; i++) ctx->phase_ms[i] = 0;
 
-    auto issue_copy = [&](size_t k) -> int {
-        size_t lo = lo_of[k], cnt = cnt_of[k];
-        int s = (int)(k & 1);
-        BP_CUDA_TRY(ctx, cudaMemcpyAsync(sb[s]->p, h_bases + lo * 64, cnt * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
-        BP_CUDA_TRY(ctx, cudaMemcpyAsync(ss[s]->p, h_scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-        BP_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[s], ctx->copy_stream));
-        return BP_OK;
-    };
     // Three streams besides the copy stream, all queued up front (the host never blocks):
     //   prep : digits + radix sort of chunk k (HBM-bound) -- runs next to the accumulate kernel of chunk k-1
     //          (IMAD-bound, DRAM ~10 % busy) and fills that kernel's tail; sorted pairs are double-buffered
     //   main : accumulate of chunk k, after its pairs are sorted and the slots of chunk k-1 are folded
     //   fold : the slot levels of chunk k -- a handful of latency-bound launches -- next to the prep of chunk k+1
     // prep and fold have the higher priority, so their blocks take the SM slots the long accumulate blocks free.
-    // Staging buffer k&1 and sorted-pair buffer k&1 are free again once the accumulate kernel of chunk k has run.
+    // Sorted-pair buffer k&1 is free again once the accumulate kernel of chunk k has run.
     struct Scoped {
         cudaEvent_t used[2] = {nullptr, nullptr}, sorted[2] = {nullptr, nullptr};
         cudaEvent_t acc_done = nullptr, fold_done = nullptr;
         cudaStream_t fold = nullptr, prep = nullptr;
+        std::vector<cudaEvent_t> copied;
         ~Scoped() {
+            for (auto x : copied) if (x) cudaEventDestroy(x);
             for (auto x : used) if (x) cudaEventDestroy(x);
             for (auto x : sorted) if (x) cudaEventDestroy(x);
             if (acc_done) cudaEventDestroy(acc_done);
@@ -871,22 +863,25 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
     BP_CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     BP_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&sc.fold, cudaStreamNonBlocking, prio_hi));
     BP_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&sc.prep, cudaStreamNonBlocking, prio_hi));
-    if (int rc = issue_copy(0)) return rc;
+    sc.copied.assign(nchunks, nullptr);
+    for (size_t k = 0; k < nchunks; k++) {
+        BP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sc.copied[k], cudaEventDisableTiming));
+        const size_t lo = lo_of[k], cnt = cnt_of[k];
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->stage_bases.p + lo * 64, h_bases + lo * 64, cnt * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->stage_scalars.p + lo * 32, h_scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BP_CUDA_TRY(ctx, cudaEventRecord(sc.copied[k], ctx->copy_stream));
+    }
     BP_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, nbuckets * sizeof(xyzz), st));
     for (size_t k = 0; k < nchunks; k++) {
-        if (k + 1 < nchunks) {
-            if (k >= 1) BP_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, sc.used[(k + 1) & 1], 0));   // chunk k-1 is done with it
-            if (int rc = issue_copy(k + 1)) return rc;
-        }
         const int s = (int)(k & 1);
-        const size_t cnt = cnt_of[k];
+        const size_t lo = lo_of[k], cnt = cnt_of[k];
         uint32_t* skeys = ctx->keys_b.as<uint32_t>() + (size_t)s * max_entries;
         uint32_t* svals = ctx->vals_b.as<uint32_t>() + (size_t)s * max_entries;
         MsmJob job;
-        job.add((const affine*)sb[s]->p, (const fe*)ss[s]->p, cnt, 0);
+        job.add(ctx->stage_bases.as<affine>() + lo, ctx->stage_scalars.as<fe>() + lo, cnt, 0);
         MsmPlan q = make_plan(cnt, 1, p.c, ctx->sm_count);   // same c, W, nb, key_bits; L and T of this chunk
         // prep
-        BP_CUDA_TRY(ctx, cudaStreamWaitEvent(sc.prep, ctx->copy_ev[s], 0));
+        BP_CUDA_TRY(ctx, cudaStreamWaitEvent(sc.prep, sc.copied[k], 0));
         if (k >= 2) BP_CUDA_TRY(ctx, cudaStreamWaitEvent(sc.prep, sc.used[s], 0));   // chunk k-2 has consumed its sorted pairs
         msm_digits_kernel<C><<<(unsigned)((cnt + 255) / 256), 256, 0, sc.prep>>>(job, cnt, q.c, q.W, ctx->keys_a.as<uint32_t>(),
                                                                                 ctx->vals_a.as<uint32_t>());
