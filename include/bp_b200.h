@@ -79,8 +79,6 @@ int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* window
  * 4 T commitments, 5 IPA total, 6 IPA MSMs, 7 IPA folds (only with timing enabled), 8 IPA host
  * (transcript, challenge inverse), 9 verification scalars, 10 mega-MSM, 11 uploads, 12 clearing of the secrets. */
 int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]);
-/* bp_msm over host buffers larger than 1.5x `points` is split into chunks of `points` whose H2D copies
- * overlap the previous chunk's kernels (default 2^22); exposed for tests and tuning. */
 /* ---- multi-GPU: one context per process and GPU --------------------------------------------
  * `fn` must gather `bytes` bytes from every rank into recv[world * bytes] in rank order (an NCCL or gloo
  * all-gather issued by the host program) and return 0. After this call:
@@ -93,6 +91,9 @@ int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]);
  * world must be a power of two that divides every generator count used. */
 typedef int (*bp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes);
 int bp_ctx_set_collective(bp_ctx* ctx, int rank, int world, bp_allgather_fn fn, void* user);
+/* bp_msm over host buffers of more than 1.5x `points` points (default 2^22) is streamed: the input is copied chunk by
+ * chunk (first chunk points/4, each next one 1.5x larger, at most 2x points) while the kernels of the chunks already
+ * on the device run, all chunks adding into one bucket array. Exposed for tests and tuning. */
 int bp_msm_set_chunk(bp_ctx* ctx, size_t points);
 /* IPA rounds of length n <= this threshold do not fold the generators; their L/R are MSMs over the last
  * folded stage with challenge-expanded scalars (same L, R, a, b). 0 = always fold. Default 2^13 (measured optimum with the GLV fold). */
