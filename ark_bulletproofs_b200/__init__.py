@@ -99,9 +99,6 @@ class Context:
     def set_ipa_geometric(self, enable: bool):
         self._check(self.lib.bp_ipa_set_geometric(self.h, 1 if enable else 0))
 
-    def set_fp29(self, enable: bool):
-        self._check(self.lib.bp_msm_set_fp29(self.h, 1 if enable else 0))
-
     def set_chunk(self, points: int):
         self._check(self.lib.bp_msm_set_chunk(self.h, points))
 

@@ -48,7 +48,6 @@ def load():
         "bp_msm_set_window": (i32, [vp, i32]),
         "bp_msm_set_tiny": (i32, [vp, i32]),
         "bp_msm_set_chunk": (i32, [vp, sz]),
-        "bp_msm_set_fp29": (i32, [vp, i32]),
         "bp_ipa_set_nofold_threshold": (i32, [vp, sz]),
         "bp_ipa_set_geometric": (i32, [vp, i32]),
         "bp_ipa_set_glv": (i32, [vp, i32]),

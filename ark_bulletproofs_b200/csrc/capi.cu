@@ -149,12 +149,6 @@ int bp_ipa_set_geometric(bp_ctx* ctx, int enable) try {
     return BP_OK;
 } BP_ABI_CATCH
 
-int bp_msm_set_fp29(bp_ctx* ctx, int enable) try {
-    if (!ctx) return BP_ERR_ARG;
-    ctx->use_fp29 = enable != 0;
-    return BP_OK;
-} BP_ABI_CATCH
-
 int bp_msm_set_tiny(bp_ctx* ctx, int max_terms) try {
     if (!ctx || max_terms < 0 || max_terms > 4096) return BP_ERR_ARG;
     ctx->msm_tiny_max = max_terms;

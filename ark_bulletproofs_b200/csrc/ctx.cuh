@@ -40,11 +40,10 @@ struct bp_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // H2D of the next MSM chunk while the current one computes
     cudaEvent_t copy_ev[2] = {nullptr, nullptr};
-    bp::DevBuf stage2_bases, stage2_scalars, pts29;
+    bp::DevBuf stage2_bases, stage2_scalars;
     std::string err;
     uint64_t launches = 0;
     int force_c = 0;
-    bool use_fp29 = false;                 // opt-in 29-bit-limb accumulate kernel (measured slower in round 1, see profiles/r1_mul29_experiment.txt)
     size_t msm_chunk = (size_t)1 << 22;
     size_t ipa_nofold_n = (size_t)1 << 13;   // IPA rounds with n <= this use MSMs over the stage generators instead of folding them   // host-buffer MSMs above 1.5x this are chunked (copy/compute overlap)
     // Multi-GPU: one bp_ctx per process/GPU; generators are sharded cyclically by index
@@ -69,7 +68,7 @@ struct bp_ctx {
     bp::DevBuf p_aL, p_aR, p_aO, p_sL, p_sR, p_wL, p_wR, p_wO, p_ypow, p_yinv, p_l, p_r, p_Gf, p_Hf, v_pts, v_sc, v_g, v_h, v_accg, v_acch, f_kind, f_idx, f_coeff, f_start, f_keys, f_keys2, f_perm, f_perm2, f_contrib, f_sorted, f_ukeys, f_sums, f_tmp, f_wv;
     template <class F> void for_each_buf(F f) {
         bp::DevBuf* all[] = {&keys_a, &keys_b, &vals_a, &vals_b, &cub_tmp, &buckets, &part_keys, &part_pts, &seg_out, &win_out, &result,
-                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &pts29, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &c_v, &c_b, &c_out, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
+                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &c_v, &c_b, &c_out, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
                              &p_wL, &p_wR, &p_wO, &p_ypow, &p_yinv, &p_l, &p_r, &p_Gf, &p_Hf, &v_pts, &v_sc, &v_g, &v_h, &v_accg, &v_acch, &f_kind, &f_idx, &f_coeff, &f_start, &f_keys, &f_keys2, &f_perm, &f_perm2, &f_contrib, &f_sorted,
                              &f_ukeys, &f_sums, &f_tmp, &f_wv};
         for (auto* b : all) f(b);

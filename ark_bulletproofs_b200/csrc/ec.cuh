@@ -65,7 +65,7 @@ struct SW {
         el S = F::mul(p.x, V);
         el M = F::mul3(F::sqr(p.x));
         if (C::A_SMALL != 0) M = F::add(M, F::from_u32(C::A_SMALL));
-        r.x = F::sub(F::sqr(M), F::dbl(S));
+        r.x = F::sub(F::sqr(M), F::dbl_l(S));
         r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
         r.zz = V;
         r.zzz = W;
@@ -82,7 +82,7 @@ struct SW {
         el S = F::mul(p.x, V);
         el M = F::mul3(F::sqr(p.x));
         if (C::A_SMALL != 0) M = F::add(M, mul_a(F::sqr(p.zz)));
-        r.x = F::sub(F::sqr(M), F::dbl(S));
+        r.x = F::sub(F::sqr(M), F::dbl_l(S));
         r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
         r.zz = F::mul(V, p.zz);
         r.zzz = F::mul(W, p.zzz);
@@ -105,7 +105,7 @@ struct SW {
         el PP = F::sqr(P);
         el PPP = F::mul(P, PP);
         el Q = F::mul(acc.x, PP);
-        el X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+        el X3 = F::sub(F::sub_l(F::sqr(R), PPP), F::dbl_l(Q));
         el Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(acc.y, PPP));
         acc.x = X3;
         acc.y = Y3;
@@ -131,7 +131,7 @@ struct SW {
         el PP = F::sqr(P);
         el PPP = F::mul(P, PP);
         el Q = F::mul(U1, PP);
-        el X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+        el X3 = F::sub(F::sub_l(F::sqr(R), PPP), F::dbl_l(Q));
         el Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(S1, PPP));
         acc.x = X3;
         acc.y = Y3;
@@ -229,10 +229,11 @@ struct TE {
     // dbl-2008-hwcd with a = -1: 4M + 4S
     BP_HD static ext dbl(const ext& p) {
         if (F::is_zero(p.zz)) return identity();
-        el A = F::sqr(p.x), B = F::sqr(p.y), Cc = F::dbl(F::sqr(p.zz));
+        el A = F::sqr(p.x), B = F::sqr(p.y), Cc = F::dbl_l(F::sqr(p.zz));
         el D = F::neg(A);
-        el E = F::sub(F::sub(F::sqr(F::add(p.x, p.y)), A), B);
-        el G = F::add(D, B), Fv = F::sub(G, Cc), H = F::sub(D, B);
+        el E = F::sub(F::sub_l(F::sqr(F::add(p.x, p.y)), A), B);
+        el Gl = F::add_l(D, B);
+        el G = F::norm(Gl), Fv = F::sub(Gl, Cc), H = F::sub(D, B);
         ext r;
         r.x = F::mul(E, Fv); r.y = F::mul(G, H); r.zzz = F::mul(E, H); r.zz = F::mul(Fv, G);
         return r;
@@ -245,7 +246,7 @@ struct TE {
         el A = F::mul(F::sub(acc.y, acc.x), F::sub(q.y, q.x));
         el B = F::mul(F::add(acc.y, acc.x), F::add(q.y, q.x));
         el Cc = F::mul(F::mul(acc.zzz, d2()), q.zzz);
-        el D = F::dbl(F::mul(acc.zz, q.zz));
+        el D = F::dbl_l(F::mul(acc.zz, q.zz));
         el E = F::sub(B, A), Fv = F::sub(D, Cc), G = F::add(D, Cc), H = F::add(B, A);
         acc.x = F::mul(E, Fv); acc.y = F::mul(G, H); acc.zzz = F::mul(E, H); acc.zz = F::mul(Fv, G);
     }
@@ -256,7 +257,7 @@ struct TE {
         el A = F::mul(F::sub(acc.y, acc.x), F::sub(q.y, q.x));
         el B = F::mul(F::add(acc.y, acc.x), F::add(q.y, q.x));
         el Cc = F::mul(F::mul(acc.zzz, d2()), F::mul(q.x, q.y));
-        el D = F::dbl(acc.zz);
+        el D = F::dbl_l(acc.zz);
         el E = F::sub(B, A), Fv = F::sub(D, Cc), G = F::add(D, Cc), H = F::add(B, A);
         acc.x = F::mul(E, Fv); acc.y = F::mul(G, H); acc.zzz = F::mul(E, H); acc.zz = F::mul(Fv, G);
     }

@@ -157,6 +157,11 @@ struct Fp {
     }
     BP_HD static fe neg(const fe& a) { return is_zero(a) ? a : sub(zero(), a); }
     BP_HD static fe dbl(const fe& a) { return add(a, a); }
+    // lazy variants of the unsaturated field layer (fp29.cuh); every value is fully reduced here
+    BP_HD static fe add_l(const fe& a, const fe& b) { return add(a, b); }
+    BP_HD static fe sub_l(const fe& a, const fe& b) { return sub(a, b); }
+    BP_HD static fe dbl_l(const fe& a) { return add(a, a); }
+    BP_HD static fe norm(const fe& a) { return a; }
     BP_HD static fe mul3(const fe& a) { return add(dbl(a), a); }
     BP_HD static fe mul_small(const fe& a, int k) {   // k in {0..8}, by additions
         fe r = zero();

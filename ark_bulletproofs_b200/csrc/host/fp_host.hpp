@@ -76,6 +76,10 @@ struct HostFp {
     static inline bool eq(const fe& a, const fe& b) { return memcmp(a.v, b.v, 32) == 0; }
     static inline fe neg(const fe& a) { return is_zero(a) ? a : sub(zero(), a); }
     static inline fe dbl(const fe& a) { return add(a, a); }
+    static inline fe add_l(const fe& a, const fe& b) { return add(a, b); }
+    static inline fe sub_l(const fe& a, const fe& b) { return sub(a, b); }
+    static inline fe dbl_l(const fe& a) { return add(a, a); }
+    static inline fe norm(const fe& a) { return a; }
     static inline fe mul3(const fe& a) { return add(dbl(a), a); }
     static inline fe mul_small(const fe& a, int k) {
         fe r = zero(), p = a;

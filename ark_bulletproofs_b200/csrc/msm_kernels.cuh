@@ -26,7 +26,6 @@
 #include <thread>
 #include <vector>
 #include "ctx.cuh"
-#include "fp29.cuh"
 
 namespace bp {
 
@@ -226,104 +225,6 @@ __global__ void __launch_bounds__(128, BP_ACC_MIN_BLOCKS) msm_accumulate_kernel(
             cur = k1;
             if (ACC) acc = ld_xyzz(buckets + cur);     // sums of the earlier chunks (streamed MSM)
             else acc = E::identity();
-        }
-        p = pnext;
-        vcur = v1;
-        k1 = k2;
-        v1 = v2;
-        i++;
-    }
-}
-
-// ---- level 1 on 29-bit limbs (moduli 2^E - c: secq256k1, curve25519) ------------------------------------
-// bases -> Montgomery domain 2^261 (x * 2^5), written contiguously in job order so the gather indices stay valid
-template <class C>
-__global__ void __launch_bounds__(256) msm_to29_kernel(const __grid_constant__ MsmJob job, size_t n, affine* __restrict__ out) {
-    using F = Fp<typename C::Fq>;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int sg = 0;
-#pragma unroll
-    for (int k = 1; k < MSM_MAX_SEGS; k++)
-        if (k < job.nseg && i >= job.start[k]) sg = k;
-    affine p = ld_affine(job.bases[sg] + (i - job.start[sg]));
-    fe k32 = F::from_u32(32u);
-    st_fe(&out[i].x, F::mul(p.x, k32));
-    st_fe(&out[i].y, F::mul(p.y, k32));
-}
-
-template <class C>
-struct RunSink29 {
-    using F = Fp29<typename C::Fq>;
-    using E = GroupLaw<C, F>;
-    xyzz* buckets;
-    uint32_t* out_keys;
-    xyzz* out_pts;
-    size_t t;
-    int nruns = 0;
-    __device__ __forceinline__ static xyzz to_storage(const typename E::ext& a) {
-        xyzz r;
-        r.x = F::to_storage(a.x); r.y = F::to_storage(a.y); r.zz = F::to_storage(a.zz); r.zzz = F::to_storage(a.zzz);
-        return r;
-    }
-    __device__ __forceinline__ void flush(uint32_t key, const typename E::ext& acc, bool is_last) {
-        xyzz v = to_storage(acc);
-        if (nruns == 0) {
-            out_keys[2 * t] = key;
-            st_xyzz(out_pts + 2 * t, v);
-            if (is_last) {
-                out_keys[2 * t + 1] = key;
-                st_xyzz(out_pts + 2 * t + 1, GroupLaw<C>::identity());
-            }
-        } else if (is_last) {
-            out_keys[2 * t + 1] = key;
-            st_xyzz(out_pts + 2 * t + 1, v);
-        } else {
-            st_xyzz(buckets + key, v);
-        }
-        nruns++;
-    }
-    __device__ __forceinline__ void empty() {
-        out_keys[2 * t] = INVALID_KEY;
-        out_keys[2 * t + 1] = INVALID_KEY;
-    }
-};
-
-// Same software pipeline as msm_accumulate_kernel; `pts29` holds the bases in the 2^261 domain (msm_to29_kernel).
-template <class C>
-__global__ void __launch_bounds__(128, 3) msm_accumulate29_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                                  size_t M, int L, size_t T, const __grid_constant__ MsmJob job,
-                                                                  const affine* __restrict__ pts29, xyzz* __restrict__ buckets,
-                                                                  uint32_t* __restrict__ out_keys, xyzz* __restrict__ out_pts) {
-    using F = Fp29<typename C::Fq>;
-    using E = GroupLaw<C, F>;
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    size_t s = t * (size_t)L;
-    size_t e = s + L < M ? s + L : M;
-    RunSink29<C> sink{buckets, out_keys, out_pts, t};
-    uint32_t cur = __ldg(keys + s);
-    if (cur == INVALID_KEY) { sink.empty(); return; }
-    uint32_t vcur = __ldg(vals + s);
-    uint32_t k1 = INVALID_KEY, v1 = 0;
-    if (s + 1 < e) { k1 = __ldg(keys + s + 1); v1 = __ldg(vals + s + 1); }
-    affine p = ld_affine(pts29 + job.start[(vcur >> 28) & 7u] + (vcur & MSM_IDX_MASK));
-    typename E::ext acc = E::identity();
-    size_t i = s;
-    while (true) {
-        const bool have_next = k1 != INVALID_KEY;
-        affine pnext;
-        if (have_next) pnext = ld_affine(pts29 + job.start[(v1 >> 28) & 7u] + (v1 & MSM_IDX_MASK));
-        uint32_t k2 = INVALID_KEY, v2 = 0;
-        if (i + 2 < e) { k2 = __ldg(keys + i + 2); v2 = __ldg(vals + i + 2); }
-        typename E::aff q{F::unpack(p.x), F::unpack(p.y)};
-        if (vcur >> 31) q = E::neg(q);
-        E::madd(acc, q);
-        if (k1 != cur) {
-            sink.flush(cur, acc, !have_next);
-            if (!have_next) break;
-            cur = k1;
-            acc = E::identity();
         }
         p = pnext;
         vcur = v1;
@@ -690,24 +591,9 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
     BP_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, nbuckets * sizeof(xyzz), st));
     uint32_t* pk = ctx->part_keys.as<uint32_t>();
     xyzz* pp = ctx->part_pts.as<xyzz>();
-    if constexpr (C::Fq::RED_NEG29) {
-        if (ctx->use_fp29) {
-            BP_CUDA_TRY(ctx, ctx->pts29.reserve(n * sizeof(affine)));
-            msm_to29_kernel<C><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(job, n, ctx->pts29.as<affine>());
-            BP_LAUNCH_CHECK(ctx);
-            msm_accumulate29_kernel<C><<<(unsigned)((p.T + 127) / 128), 128, 0, st>>>(ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, p.L,
-                                                                                      p.T, job, ctx->pts29.as<affine>(), ctx->buckets.as<xyzz>(), pk, pp);
-            BP_LAUNCH_CHECK(ctx);
-        } else {
-            msm_accumulate_kernel<C><<<(unsigned)((p.T + 127) / 128), 128, 0, st>>>(ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, p.L,
-                                                                                    p.T, job, ctx->buckets.as<xyzz>(), pk, pp);
-            BP_LAUNCH_CHECK(ctx);
-        }
-    } else {
-        msm_accumulate_kernel<C><<<(unsigned)((p.T + 127) / 128), 128, 0, st>>>(ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, p.L,
-                                                                                p.T, job, ctx->buckets.as<xyzz>(), pk, pp);
-        BP_LAUNCH_CHECK(ctx);
-    }
+    msm_accumulate_kernel<C><<<(unsigned)((p.T + 127) / 128), 128, 0, st>>>(ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, p.L,
+                                                                            p.T, job, ctx->buckets.as<xyzz>(), pk, pp);
+    BP_LAUNCH_CHECK(ctx);
     mark(2);
     if (int rc = msm_fold_slots<C, false>(ctx, slots1, st)) return rc;
     mark(3);

@@ -117,9 +117,6 @@ int bp_pedersen_set_table(bp_ctx* ctx, int enable);
  * stream-order compaction) for capacities >= 256. Same points as the host generator (bp_gens_generate_host), which
  * remains the path for zorro / curve25519. Default on; 0 forces the host generator. */
 int bp_gens_set_device_generation(bp_ctx* ctx, int enable);
-/* Bucket accumulation on 9 x 29-bit limbs (csrc/fp29.cuh; default on for secq256k1 and curve25519) or on the
- * 8 x 32-bit limbs of csrc/fp.cuh; both give identical results. For A/B measurements and tests. */
-int bp_msm_set_fp29(bp_ctx* ctx, int enable);
 /* Force the Pippenger window width (0 = automatic); for parity tests and tuning. */
 int bp_msm_set_window(bp_ctx* ctx, int c);
 /* MSMs with at most `max_terms` (default 768) terms each run as one kernel launch (4-bit windows, digit

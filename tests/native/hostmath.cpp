@@ -2,9 +2,10 @@
 // The carry primitives are emulated on the host (see fp.cuh), so the exact same
 // algorithms that run in the kernels are checked here against the Python oracle.
 #include <cstring>
+#define BP_FP29_CHECK 1
 #include "../../ark_bulletproofs_b200/csrc/ec.cuh"
 #include "../../ark_bulletproofs_b200/csrc/host/fp_host.hpp"
-#include "../../ark_bulletproofs_b200/csrc/fp29.cuh"
+#include "../../ark_bulletproofs_b200/csrc/experimental/fp29.cuh"
 #include "../../ark_bulletproofs_b200/csrc/host/glv_host.hpp"
 using namespace bp;
 
@@ -80,7 +81,8 @@ extern "C" int hm_ec_op(int curve, int op, const uint32_t* p, const uint32_t* q,
 }
 
 
-// ---- Fp29 (9 x 29-bit limbs, Montgomery domain 2^261); values cross as canonical 8 x 32-bit integers ----
+// ---- Fp29 (balanced 9 x 29-bit limbs, Montgomery domain 2^261); values cross as canonical 8 x 32-bit integers ----
+extern "C" long hm_fp29_violations() { return fp29_violations(); }
 template <class M> static int fp29_op_t(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     using F = Fp29<M>;
     fe x, y;
@@ -95,10 +97,29 @@ template <class M> static int fp29_op_t(int op, const uint32_t* a, const uint32_
         case 4: R = F::neg(X); break;
         case 5: R = F::mul3(X); break;
         // chains that exercise the loose bounds: ((x - y) - y + x) * (x + y + y) ; and ((x-y)^2 - 3x) * (y - x)
-        case 6: R = F::mul(F::add(F::sub(F::sub(X, Y), Y), X), F::add(F::add(X, Y), Y)); break;
+        case 6: R = F::mul(F::add(F::sub(F::sub_l(X, Y), Y), X), F::add(F::add_l(X, Y), Y)); break;
         case 7: R = F::mul(F::sub(F::sqr(F::sub(X, Y)), F::mul3(X)), F::sub(Y, X)); break;
         case 8: { fe o = F::to_storage(X); memcpy(out, o.v, 32); return F::is_zero(X) ? 1 : 0; }
-        case 9: { bool e = F::eq(X, Y); fl d = F::sub(X, Y); fe o = F::pack_canonical(d); memcpy(out, o.v, 32); return e ? 1 : 0; }
+        case 9: { bool e = F::eq(X, Y); fl d = F::sub_l(X, Y); fe o = F::pack_canonical(d); memcpy(out, o.v, 32); return e ? 1 : 0; }
+        case 10: R = F::from_storage(x); break;                              // x * 2^5 as an integer (domain 2^256 -> 2^261)
+        case 11: {                                                           // the MSM's pre-converted base format
+            fe u = Fp<M>::add(x, F::bias_d());                               // caller passes the canonical integer U - D... see test
+            R = F::load_biased(F::to_biased(u));
+            break;
+        }
+        case 12: R = F::inv(X); break;
+        case 13: R = F::mul_small(X, (int)(y.v[0] & 7)); break;
+        // is_zero on multiples of m reached through arithmetic: (x - y) + (y - x), x*3 - x - x - x, and k*m literally
+        case 14: { fl d = F::add_l(F::sub_l(X, Y), F::sub_l(Y, X)); return F::is_zero(d) ? 1 : 0; }
+        case 15: {
+            fl d = X;
+            const int k = (int)(y.v[0] % 9) - 4;
+            for (int i = 0; i < 9; i++) d.v[i] += k * M::mb(i);
+            int z = F::is_zero(F::sub_l(d, X)) ? 1 : 0;                       // k*m, un-normalized
+            fe o = F::pack_canonical(d);
+            memcpy(out, o.v, 32);
+            return z;
+        }
         default: return -1;
     }
     fe o = F::pack_canonical(R);
@@ -109,7 +130,9 @@ extern "C" int hm_fp29_op(int field, int op, const uint32_t* a, const uint32_t* 
     switch (field) {
         case 0: return fp29_op_t<SecqFq>(op, a, b, out);
         case 1: return fp29_op_t<SecqFr>(op, a, b, out);
+        case 2: return fp29_op_t<ZorroFq>(op, a, b, out);
         case 3: return fp29_op_t<Fp25519>(op, a, b, out);
+        case 4: return fp29_op_t<Fr25519>(op, a, b, out);
     }
     return -1;
 }
@@ -129,6 +152,15 @@ template <class E> static int ec29_op_t(int op, const uint32_t* p, const uint32_
         case 3: r = E::mul_scalar(Pl, s); break;
         case 4: { r = E::dbl_affine(Pl); E::madd(r, Ql); break; }
         case 5: { r = E::dbl_affine(Pl); typename E::ext b = E::dbl_affine(Ql); E::add(r, b); break; }
+        case 6: {                                                           // long chain: ((P + Q) + Q) ... 64 mixed additions, then doublings
+            r = E::from_affine(Pl);
+            for (int i = 0; i < 64; i++) E::madd(r, (i & 1) ? Pl : Ql);
+            for (int i = 0; i < 8; i++) r = E::dbl(r);
+            typename E::ext t = r;
+            for (int i = 0; i < 8; i++) E::add(r, t);
+            break;
+        }
+        case 7: { typename E::aff o = E::to_affine(E::mul_scalar(Pl, s)); r = E::from_affine(o); if (!E::on_curve(o)) return -2; break; }
         default: return -1;
     }
     // return the projective result as 4 canonical coordinates (128 B): the caller normalises
@@ -139,6 +171,7 @@ template <class E> static int ec29_op_t(int op, const uint32_t* p, const uint32_
 extern "C" int hm_ec29_op(int curve, int op, const uint32_t* p, const uint32_t* q, const uint32_t* s, uint32_t* out) {
     switch (curve) {
         case 0: return ec29_op_t<SW<Secq256k1, Fp29<SecqFq>>>(op, p, q, s, out);
+        case 1: return ec29_op_t<SW<Zorro, Fp29<ZorroFq>>>(op, p, q, s, out);
         case 2: return ec29_op_t<TE<Curve25519, Fp29<Fp25519>>>(op, p, q, s, out);
     }
     return -1;

@@ -105,19 +105,23 @@ def test_curve_ops(lib, cid, cv):
 R261 = 1 << 261
 
 
-@pytest.mark.parametrize("field", [0, 1, 3])
+@pytest.mark.parametrize("field", [0, 1, 2, 3, 4])
 def test_fp29_ops(lib, field):
-    """csrc/fp29.cuh: 9 x 29-bit unsaturated limbs, Montgomery domain 2^261, lazy ("tight") reduction."""
+    """csrc/fp29.cuh: balanced 9 x 29-bit limbs, Montgomery domain 2^261, carry-free columns. Every multiplication in
+    the host build also checks the operand contract and the column bound (hm_fp29_violations)."""
     m = FIELDS[field]
     rnd = random.Random(4321 + field)
     rinv = pow(R261, -1, m)
+    lib.hm_fp29_violations.restype = ctypes.c_long
 
     def op(o, a, b=0):
         out = (ctypes.c_uint32 * 8)()
         rc = lib.hm_fp29_op(field, o, _b(a), _b(b), out)
         assert rc >= 0
         return int.from_bytes(bytes(out), "little"), rc
-    edge = [0, 1, 2, m - 1, m - 2, (1 << 255) % m, (1 << 232) - 1, (1 << 232), (m - 1) // 2, (1 << 145) - 1, m >> 1, (1 << 29) - 1]
+    half = sum(1 << (29 * k + 28) for k in range(8))          # every balanced digit at its extreme
+    edge = [0, 1, 2, m - 1, m - 2, (1 << 255) % m, (1 << 232) - 1, (1 << 232), (m - 1) // 2, (1 << 145) - 1, m >> 1, (1 << 29) - 1,
+            half % m, (half - 1) % m, (half + 1) % m, (m - half) % m, ((1 << 256) - 1) % m]
     vals = edge + [rnd.randrange(m) for _ in range(60)]
     for a in vals:
         for b in rnd.sample(vals, 6) + [m - 1, a, 0]:
@@ -128,18 +132,29 @@ def test_fp29_ops(lib, field):
             assert op(7, a, b)[0] == (((a - b) ** 2 * rinv - 3 * a) * (b - a)) * rinv % m
             d, e = op(9, a, b)
             assert d == (a - b) % m and e == (1 if a == b else 0)
+            assert op(14, a, b)[1] == 1
+            assert op(13, a, b)[0] == a * (b & 7) % m
+            v, z = op(15, a, b)
+            assert v == a and z == 1
         assert op(3, a)[0] == a * a * rinv % m
         assert op(4, a)[0] == (-a) % m
         assert op(5, a)[0] == 3 * a % m
         st, z = op(8, a)
         assert st == a * (1 << 256) * rinv % m and z == (1 if a == 0 else 0)
+        assert op(10, a)[0] == a * 32 % m
+        assert op(11, a)[0] == a
+    for a in vals[:8] + vals[-4:]:
+        inv = op(12, a)[0]
+        assert inv == (0 if a == 0 else pow(a * rinv, -1, m) * R261 % m)
+    assert lib.hm_fp29_violations() == 0
 
 
-@pytest.mark.parametrize("cid,cv", [(0, O.SECQ256K1), (2, O.CURVE25519)])
+@pytest.mark.parametrize("cid,cv", [(0, O.SECQ256K1), (1, O.ZORRO), (2, O.CURVE25519)])
 def test_curve_ops_fp29(lib, cid, cv):
     rnd = random.Random(199 + cid)
     q = cv.q
     rinv = pow(R261, -1, q)
+    lib.hm_fp29_violations.restype = ctypes.c_long
 
     def enc(P):
         if P is None:
@@ -173,6 +188,12 @@ def test_curve_ops_fp29(lib, cid, cv):
     assert run(4, P, neg(mul(2, P))) is None
     for s in [0, 1, 2, cv.r - 1, rnd.randrange(cv.r)]:
         assert run(3, P, None, s) == mul(s, P)
+        assert run(7, P, None, s) == mul(s, P)       # through to_affine (one inversion) and on_curve
+    # long chains keep the value bounds: P + 32(P + Q) doubled 8 times, times 9
+    Q = pts[1]
+    want = mul(9 * 256, add(P, mul(32, add(P, Q))))
+    assert run(6, P, Q) == want
+    assert lib.hm_fp29_violations() == 0
 
 
 def test_glv_split(lib):

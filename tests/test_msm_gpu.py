@@ -195,31 +195,3 @@ def test_msm_streamed_other_curves(curve):
     want = O.msm(cv, pts, sc)
     c.set_chunk(128)
     assert c.msm(pts, sc) == want
-
-
-@pytest.mark.parametrize("curve", ["secq256k1", "curve25519"])
-def test_msm_fp29_equals_fp32(curve):
-    """The 29-bit-limb accumulate kernel (csrc/fp29.cuh) and the 32-bit one give the same point, including the
-    exceptional cases of the group law (repeated points, P and -P, identity bases, all-equal scalars)."""
-    from ark_bulletproofs_b200 import Context
-    cv = O.CURVES[curve]
-    ctx = Context(curve, 0)
-    rnd = random.Random(2929)
-    n = 3000
-    pts = _points(cv, n, rnd)
-    for i in range(0, n, 11):
-        pts[i] = None
-    pts[1] = pts[2] = pts[3]
-    pts[4] = O.pt_neg(cv, pts[5])
-    cases = [[rnd.randrange(cv.r) for _ in range(n)], [7] * n, [cv.r - 1] * n, [0 if i % 3 else rnd.randrange(cv.r) for i in range(n)]]
-    cases[0][4] = cases[0][5]             # s*P + s*(-P) inside one bucket run
-    for sc in cases:
-        ctx.set_fp29(True)
-        a = ctx.msm(pts, sc)
-        ctx.set_fp29(False)
-        b = ctx.msm(pts, sc)
-        assert a == b
-    ctx.set_fp29(True)
-    assert ctx.msm(pts[:500], cases[0][:500]) == O.msm(cv, pts[:500], cases[0][:500])
-    same = [pts[7]] * 600                  # one bucket: first add is a doubling
-    assert ctx.msm(same, [5] * 600) == O.pt_mul(cv, 3000, pts[7])

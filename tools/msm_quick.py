@@ -11,7 +11,6 @@ sys.path.insert(0, ROOT)
 from ark_bulletproofs_b200 import Context  # noqa: E402
 
 ctx = Context("secq256k1", 0)
-ctx.set_fp29(os.environ.get("BP_FP29", "1") == "1")
 lo, hi = int(sys.argv[1]) if len(sys.argv) > 1 else 12, int(sys.argv[2]) if len(sys.argv) > 2 else 22
 nmax = 1 << hi
 pts = torch.empty(nmax * 64, dtype=torch.uint8, device="cuda")
