@@ -737,6 +737,12 @@ class InnerProductProof:
         return out + ser_scalar(cv, self.a) + ser_scalar(cv, self.b)
 
 
+def fold_generators(cv: Curve, L, R, sL, sR):
+    """inner_product_proof.rs:139-156 (first round, per-element factors) and :216-225: one 2-point msm + into_affine
+    per output, out[i] = sL[i]*L[i] + sR[i]*R[i]. (oracle/fast.py swaps in the C restatement for the large goldens.)"""
+    return [pt_add(cv, pt_mul(cv, a_, P), pt_mul(cv, b_, Q_)) for P, Q_, a_, b_ in zip(L, R, sL, sR)]
+
+
 def ipa_create(cv: Curve, t: Transcript, Q, G_factors, H_factors, G, H, a, b) -> InnerProductProof:
     """inner_product_proof.rs:37-239 — the reference's loop structure verbatim
     (per-element 2-point msm for the generator fold)."""
@@ -772,13 +778,15 @@ def ipa_create(cv: Curve, t: Transcript, Q, G_factors, H_factors, G, H, a, b) ->
         for i in range(n):
             a[i] = (aL[i] * u + ui * aR[i]) % r
             b[i] = (bL[i] * ui + u * bR[i]) % r
-            if first:
-                g0, g1 = ui * gf[i] % r, u * gf[n + i] % r
-                h0, h1 = u * hf[i] % r, ui * hf[n + i] % r
-            else:
-                g0, g1, h0, h1 = ui, u, u, ui
-            G[i] = pt_add(cv, pt_mul(cv, g0, GL[i]), pt_mul(cv, g1, GR[i]))
-            H[i] = pt_add(cv, pt_mul(cv, h0, HL[i]), pt_mul(cv, h1, HR[i]))
+        if first:
+            g0 = [ui * gf[i] % r for i in range(n)]
+            g1 = [u * gf[n + i] % r for i in range(n)]
+            h0 = [u * hf[i] % r for i in range(n)]
+            h1 = [ui * hf[n + i] % r for i in range(n)]
+        else:
+            g0, g1, h0, h1 = [ui] * n, [u] * n, [u] * n, [ui] * n
+        G[:n] = fold_generators(cv, GL, GR, g0, g1)
+        H[:n] = fold_generators(cv, HL, HR, h0, h1)
         a, b, G, H = a[:n], b[:n], G[:n], H[:n]
         first = False
     return InnerProductProof(L_vec, R_vec, a[0], b[0])

@@ -330,3 +330,101 @@ int ref_synth_points(int curve, const uint8_t* g_xy, uint8_t* out_xy, size_t n, 
     free(buf); free(pre);
     return 0;
 }
+
+/* ---- per-element generator fold with per-element scalars (first IPA round, src/inner_product_proof.rs:139-156):
+ *   out[i] = msm([L[i], R[i]], [sL[i], sR[i]]).into_affine() */
+int ref_fold_points_v(int curve, const uint8_t* L_xy, const uint8_t* R_xy, size_t h, const uint8_t* sL_mont, const uint8_t* sR_mont,
+                      uint8_t* out_xy, int threads) {
+    curves_init();
+    if (curve < 0 || curve > 1) return -1;
+    const curve_t* cv = &CURVES[curve];
+    const aff *L = (const aff*)L_xy, *R = (const aff*)R_xy;
+    aff* O = (aff*)out_xy;
+    if (threads < 1) threads = 1;
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (size_t i = 0; i < h; i++) {
+        aff b2[2] = {L[i], R[i]};
+        fe s2[2]; memcpy(&s2[0], sL_mont + 32 * i, 32); memcpy(&s2[1], sR_mont + 32 * i, 32);
+        jac r; msm_core(cv, b2, s2, 2, &r, 1);
+        jac_to_aff(cv, &O[i], &r);
+    }
+    return 0;
+}
+
+/* ---- merlin TranscriptRng draws (merlin 3.0 src/transcript.rs TranscriptRng::fill_bytes over strobe.rs; restated from the
+ * published crate, pinned by the public Merlin KAT through oracle/bp_oracle.py's Strobe128, against which
+ * tests/test_c_oracle.py checks this function): the prover's 2n blinding scalars are 8n dependent Keccak-f[1600]
+ * permutations, far too slow in pure Python at 2^16..2^20 multipliers. ------------------------------------------------ */
+static const uint64_t KRC[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL, 0x000000000000808BULL, 0x0000000080000001ULL,
+    0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008AULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000AULL,
+    0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+    0x000000000000800AULL, 0x800000008000000AULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+static inline uint64_t rol64(uint64_t x, int n) { return n ? (x << n) | (x >> (64 - n)) : x; }
+static void keccak_f(uint64_t a[25]) {
+    static const int rot[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    for (int rnd = 0; rnd < 24; rnd++) {
+        uint64_t c[5], d[5], b[25];
+        for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rol64(c[(x + 1) % 5], 1);
+        for (int i = 0; i < 25; i++) a[i] ^= d[i % 5];
+        for (int x = 0; x < 5; x++)
+            for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rol64(a[x + 5 * y], rot[x + 5 * y]);
+        for (int y = 0; y < 5; y++)
+            for (int x = 0; x < 5; x++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+        a[0] ^= KRC[rnd];
+    }
+}
+typedef struct { uint8_t st[200]; int pos, pos_begin, cur_flags; } strobe_t;
+enum { SR = 166, FI = 1, FA = 2, FC = 4, FT = 8, FM = 16, FK = 32 };
+static void strobe_run_f(strobe_t* s) {
+    s->st[s->pos] ^= (uint8_t)s->pos_begin;
+    s->st[s->pos + 1] ^= 0x04;
+    s->st[SR + 1] ^= 0x80;
+    uint64_t lanes[25];
+    memcpy(lanes, s->st, 200);          /* little-endian host */
+    keccak_f(lanes);
+    memcpy(s->st, lanes, 200);
+    s->pos = 0; s->pos_begin = 0;
+}
+static void strobe_absorb(strobe_t* s, const uint8_t* d, size_t n) {
+    for (size_t i = 0; i < n; i++) { s->st[s->pos++] ^= d[i]; if (s->pos == SR) strobe_run_f(s); }
+}
+static void strobe_squeeze(strobe_t* s, uint8_t* d, size_t n) {
+    for (size_t i = 0; i < n; i++) { d[i] = s->st[s->pos]; s->st[s->pos++] = 0; if (s->pos == SR) strobe_run_f(s); }
+}
+static void strobe_begin_op(strobe_t* s, int flags) {
+    uint8_t hdr[2] = {(uint8_t)s->pos_begin, (uint8_t)flags};
+    s->pos_begin = s->pos + 1;
+    s->cur_flags = flags;
+    strobe_absorb(s, hdr, 2);
+    if ((flags & (FC | FK)) && s->pos != 0) strobe_run_f(s);
+}
+static uint64_t trng_next_u64(strobe_t* s) {      /* fill_bytes(8): meta_ad(LE32(8), false); prf(8, false) */
+    const uint8_t len[4] = {8, 0, 0, 0};
+    strobe_begin_op(s, FM | FA);
+    strobe_absorb(s, len, 4);
+    strobe_begin_op(s, FI | FA | FC);
+    uint8_t out[8];
+    strobe_squeeze(s, out, 8);
+    uint64_t v; memcpy(&v, out, 8);
+    return v;
+}
+/* `count` draws of ark-ff Fp::rand (4 x next_u64, top bits shaved to the modulus' bit length, rejected unless < m);
+ * out = the accepted raw limbs, i.e. the Montgomery representation. state = strobe bytes, io = {pos, pos_begin, cur_flags}. */
+int ref_trng_scalars(uint8_t state[200], int io[3], const uint8_t modulus_le[32], size_t count, uint8_t* out_raw) {
+    strobe_t s;
+    memcpy(s.st, state, 200); s.pos = io[0]; s.pos_begin = io[1]; s.cur_flags = io[2];
+    uint64_t m[4]; memcpy(m, modulus_le, 32);
+    int bits = 256;
+    while (bits > 0 && !((m[(bits - 1) / 64] >> ((bits - 1) % 64)) & 1)) bits--;
+    const uint64_t mask = bits >= 256 ? ~0ULL : (~0ULL >> (256 - bits));
+    for (size_t i = 0; i < count;) {
+        uint64_t l[4];
+        for (int k = 0; k < 4; k++) l[k] = trng_next_u64(&s);
+        l[3] &= mask;
+        if (!geq(l, m)) { memcpy(out_raw + 32 * i, l, 32); i++; }
+    }
+    memcpy(state, s.st, 200); io[0] = s.pos; io[1] = s.pos_begin; io[2] = s.cur_flags;
+    return 0;
+}
