@@ -87,6 +87,20 @@ class Context:
         self.rank, self.world = rank, world
         self._check(self.lib.bp_ctx_set_collective(self.h, rank, world, ctypes.cast(self._coll_cb, ctypes.c_void_p), None))
 
+    def init_nccl(self, rank: int, world: int, group=None):
+        """Multi-GPU mode with the exchange owned by the library (bp_ctx_init_nccl): the 128-byte NCCL unique id is
+        made on rank 0 and broadcast through torch.distributed (host-side, once); afterwards every sharded MSM ends with
+        an ncclAllGather issued by the library on this context's stream. Call before creating generators."""
+        import torch.distributed as dist
+        box = [None]
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            self._check(self.lib.bp_nccl_unique_id(buf))
+            box[0] = buf.raw
+        dist.broadcast_object_list(box, src=0, group=group)
+        self._check(self.lib.bp_ctx_init_nccl(self.h, rank, world, box[0]))
+        self.rank, self.world = rank, world
+
     def set_device_gens(self, enable: bool):
         self._check(self.lib.bp_gens_set_device_generation(self.h, 1 if enable else 0))
 

@@ -54,6 +54,8 @@ def load():
         "bp_pedersen_set_table": (i32, [vp, i32]),
         "bp_gens_set_device_generation": (i32, [vp, i32]),
         "bp_ctx_set_collective": (i32, [vp, i32, i32, vp, vp]),
+        "bp_nccl_unique_id": (i32, [vp]),
+        "bp_ctx_init_nccl": (i32, [vp, i32, i32, vp]),
         "bp_ctx_set_timing": (i32, [vp, i32]),
         "bp_msm_last_phases": (i32, [vp, ctypes.POINTER(ctypes.c_float), pi32, pi32, pu64]),
         "bp_points_sum": (i32, [vp, vp, sz, vp, pi32]),

@@ -92,7 +92,17 @@ struct ApiImpl {
         return gens_upload(ctx, b, bb, G.data(), H.data(), cap, out);
     }
     static int gens_from_points(bp_ctx* ctx, const uint8_t* B, const uint8_t* Bb, const uint8_t* G, const uint8_t* H, size_t cap, GensDev** out) {
-        return gens_upload(ctx, ldp(B), ldp(Bb), reinterpret_cast<const affine*>(G), reinterpret_cast<const affine*>(H), cap, out);
+        if (!HC::point_valid(ldp(B)) || !HC::point_valid(ldp(Bb))) return BP_ERR_FORMAT;
+        GensDev* g = nullptr;
+        if (int rc = gens_upload(ctx, ldp(B), ldp(Bb), reinterpret_cast<const affine*>(G), reinterpret_cast<const affine*>(H), cap, &g)) return rc;
+        // the vectors are validated where they now live (canonical, on curve, prime-order subgroup), one thread per point
+        size_t lo = 0, lcap = cap;
+        if (ctx->world > 1) g->slice(0, cap, lo, lcap);
+        int rc = points_validate_device<C>(ctx, g->G.template as<affine>(), lcap);
+        if (rc == BP_OK) rc = points_validate_device<C>(ctx, g->H.template as<affine>(), lcap);
+        if (rc != BP_OK) { delete g; return rc; }
+        *out = g;
+        return BP_OK;
     }
     static int pedersen_commit(const GensDev* g, const uint8_t* v, const uint8_t* blind, uint8_t* out) {
         affine r = HC::add(HC::mul(g->B, ld(v)), HC::mul(g->B_blinding, ld(blind)));
@@ -154,7 +164,11 @@ struct ApiImpl {
     static void* verifier_new(bp_ctx* ctx, Transcript* t) { return new VerifierT<C>(ctx, t); }
     static void verifier_free(void* p) { delete static_cast<VerifierT<C>*>(p); }
     static ConstraintSystemBase* verifier_cs(void* p) { return static_cast<VerifierT<C>*>(p); }
-    static int verifier_commit(void* p, const uint8_t* V, Variable* var) { return static_cast<VerifierT<C>*>(p)->commit(ldp(V), *var); }
+    static int verifier_commit(void* p, const uint8_t* V, Variable* var) {
+        const affine c = ldp(V);
+        if (!HC::point_valid(c)) return BP_ERR_FORMAT;           // attacker-chosen public input: never reaches the transcript or the MSM unchecked
+        return static_cast<VerifierT<C>*>(p)->commit(c, *var);
+    }
     static int verifier_verify(void* p, const void* proof, const GensDev* g) {
         return static_cast<VerifierT<C>*>(p)->verify(*static_cast<const ProofT<C>*>(proof), *g);
     }
@@ -248,7 +262,12 @@ struct ApiImpl {
         else if (which >= 200 && which < 200 + (int)pr->R_vec.size()) a = &pr->R_vec[which - 200];
         else return BP_ERR_ARG;
         if (s) { if (set) memcpy(s->v, buf, 32); else memcpy(buf, s->v, 32); }
-        else { if (set) memcpy(a, buf, 64); else memcpy(buf, a, 64); }
+        else if (set) {
+            affine np;
+            memcpy(&np, buf, 64);
+            if (!HC::point_valid(np)) return BP_ERR_FORMAT;
+            *a = np;
+        } else memcpy(buf, a, 64);
         return BP_OK;
     }
     static size_t proof_rounds(const void* p) { return static_cast<const ProofT<C>*>(p)->L_vec.size(); }

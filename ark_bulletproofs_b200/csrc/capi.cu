@@ -6,6 +6,7 @@
 #include <cstring>
 #include <vector>
 #include "ctx.cuh"
+#include "host/nccl_dyn.hpp"
 #include <new>
 
 // No C++ exception unwinds across the C ABI: every multi-statement entry point is a function-try-block.
@@ -62,6 +63,8 @@ void bp_ctx_destroy(bp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->for_each_buf([](bp::DevBuf* b) { b->release(); });
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->h_coll) cudaFreeHost(ctx->h_coll);
+    if (ctx->nccl_comm && bp::nccl_api().ok()) bp::nccl_api().CommDestroy((ncclComm_t)ctx->nccl_comm);
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -118,10 +121,45 @@ int bp_ipa_set_nofold_threshold(bp_ctx* ctx, size_t n) try {
 
 int bp_ctx_set_collective(bp_ctx* ctx, int rank, int world, bp_allgather_fn fn, void* user) try {
     if (!ctx || world < 1 || rank < 0 || rank >= world || (world & (world - 1)) || (world > 1 && !fn)) return BP_ERR_ARG;
+    if (ctx->nccl_comm && bp::nccl_api().ok()) { bp::nccl_api().CommDestroy((ncclComm_t)ctx->nccl_comm); ctx->nccl_comm = nullptr; }
     ctx->rank = rank;
     ctx->world = world;
     ctx->coll = fn;
     ctx->coll_user = user;
+    return BP_OK;
+} BP_ABI_CATCH
+
+// ---- library-owned collective: NCCL ----
+int bp_nccl_unique_id(uint8_t out[128]) try {
+    if (!out) return BP_ERR_ARG;
+    const bp::NcclApi& n = bp::nccl_api();
+    if (!n.ok()) return BP_ERR_UNSUPPORTED;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId");
+    ncclUniqueId id;
+    if (n.GetUniqueId(&id) != ncclSuccess) return BP_ERR_CUDA;
+    memcpy(out, &id, 128);
+    return BP_OK;
+} BP_ABI_CATCH
+
+int bp_ctx_init_nccl(bp_ctx* ctx, int rank, int world, const uint8_t unique_id[128]) try {
+    if (!ctx || !unique_id || world < 1 || world > 64 || rank < 0 || rank >= world || (world & (world - 1))) return BP_ERR_ARG;
+    const bp::NcclApi& n = bp::nccl_api();
+    if (!n.ok()) { ctx->err = "libnccl.so.2 not found"; return BP_ERR_UNSUPPORTED; }
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->nccl_comm) { n.CommDestroy((ncclComm_t)ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(&id, unique_id, 128);
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = n.CommInitRank(&comm, world, id, rank);
+    if (r != ncclSuccess) { ctx->err = std::string("ncclCommInitRank: ") + n.GetErrorString(r); return BP_ERR_CUDA; }
+    if (!ctx->h_coll) BP_CUDA_TRY(ctx, cudaMallocHost(&ctx->h_coll, BP_HOST_COLL_BYTES));
+    BP_CUDA_TRY(ctx, ctx->coll_send.reserve(64 * 8));
+    BP_CUDA_TRY(ctx, ctx->coll_recv.reserve(BP_HOST_COLL_BYTES));
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->coll = nullptr;
+    ctx->coll_user = nullptr;
     return BP_OK;
 } BP_ABI_CATCH
 
@@ -521,7 +559,7 @@ int bp_verifier_commit_batch(bp_verifier* v, const uint8_t* commitments, size_t 
 } BP_ABI_CATCH
 int bp_verifier_verify(bp_verifier* v, const bp_proof* proof, const bp_gens* gens) try {
     if (!v || !proof || !gens) return BP_ERR_ARG;
-    if (proof->curve != v->curve || gens->curve != v->curve) return BP_ERR_ARG;
+    if (proof->curve != v->curve || gens->curve != v->curve || gens->g->ctx != v->ctx) return BP_ERR_ARG;
     BP_CUDA_TRY(v->ctx, cudaSetDevice(v->ctx->device));
     return bp::curve_api(v->curve)->verifier_verify(v->impl, proof->impl, gens->g);
 } BP_ABI_CATCH
@@ -532,9 +570,12 @@ int bp_batch_verify(bp_ctx* ctx, bp_rng* rng, bp_verifier* const* verifiers, con
     std::vector<const void*> ps(n);
     for (size_t i = 0; i < n; i++) {
         if (!verifiers[i] || !proofs[i] || verifiers[i]->curve != ctx->curve || proofs[i]->curve != ctx->curve) return BP_ERR_ARG;
+        // the verifiers' scalar vectors live in their context's buffers and are produced on its stream: one context per batch
+        if (verifiers[i]->ctx != ctx) return BP_ERR_ARG;
         vs[i] = verifiers[i]->impl;
         ps[i] = proofs[i]->impl;
     }
+    if (gens->curve != ctx->curve || gens->g->ctx != ctx) return BP_ERR_ARG;
     return bp::curve_api(ctx->curve)->batch_verify(ctx, rng->r.get(), vs.data(), ps.data(), n, gens->g);
 } BP_ABI_CATCH
 
@@ -546,9 +587,11 @@ int bp_batch_verify_partial(bp_ctx* ctx, const uint8_t* alphas, bp_verifier* con
     std::vector<const void*> ps(n);
     for (size_t i = 0; i < n; i++) {
         if (!verifiers[i] || !proofs[i] || verifiers[i]->curve != ctx->curve || proofs[i]->curve != ctx->curve) return BP_ERR_ARG;
+        if (verifiers[i]->ctx != ctx) return BP_ERR_ARG;
         vs[i] = verifiers[i]->impl;
         ps[i] = proofs[i]->impl;
     }
+    if (gens->curve != ctx->curve || gens->g->ctx != ctx) return BP_ERR_ARG;
     return bp::curve_api(ctx->curve)->batch_verify_partial(ctx, alphas, vs.data(), ps.data(), n, gens->g, out_xy, out_is_identity);
 } BP_ABI_CATCH
 

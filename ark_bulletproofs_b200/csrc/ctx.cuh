@@ -33,6 +33,7 @@ struct DevBuf {
 }  // namespace bp
 
 static constexpr size_t BP_HOST_RESULT_BYTES = 128 * 1024;
+static constexpr size_t BP_HOST_COLL_BYTES = 64 * 8 * 64;      // world <= 64 ranks x MSM_MAX_BATCH partial points
 
 struct bp_ctx {
     int curve = 0;
@@ -53,6 +54,11 @@ struct bp_ctx {
     bp_allgather_fn coll = nullptr;
     void* coll_user = nullptr;
     uint64_t coll_calls = 0, coll_bytes = 0;
+    // library-owned exchange (bp_ctx_init_nccl): ncclAllGather of the 64-byte partial points on `stream`, no callback into
+    // the host program. nccl_comm is an ncclComm_t (host/nccl_dyn.hpp keeps NCCL out of the link line).
+    void* nccl_comm = nullptr;
+    bp::DevBuf coll_send, coll_recv;
+    void* h_coll = nullptr;     // pinned, BP_HOST_COLL_BYTES
     bool gens_on_device = true;              // BulletproofGens chains on the GPU where the stream is seekable (bp_gens_set_device_generation)
     bool pedersen_table = true;              // batched Pedersen commitments through the fixed-base table (bp_pedersen_set_table)
     bool ipa_glv = true;                     // GLV split of the uniform fold scalar where the curve has the endomorphism (bp_ipa_set_glv)
@@ -68,7 +74,7 @@ struct bp_ctx {
     bp::DevBuf p_aL, p_aR, p_aO, p_sL, p_sR, p_wL, p_wR, p_wO, p_ypow, p_yinv, p_l, p_r, p_Gf, p_Hf, v_pts, v_sc, v_g, v_h, v_accg, v_acch, f_kind, f_idx, f_coeff, f_start, f_keys, f_keys2, f_perm, f_perm2, f_contrib, f_sorted, f_ukeys, f_sums, f_tmp, f_wv;
     template <class F> void for_each_buf(F f) {
         bp::DevBuf* all[] = {&keys_a, &keys_b, &vals_a, &vals_b, &cub_tmp, &buckets, &part_keys, &part_pts, &seg_out, &win_out, &result,
-                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &c_v, &c_b, &c_out, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
+                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &coll_send, &coll_recv, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &c_v, &c_b, &c_out, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
                              &p_wL, &p_wR, &p_wO, &p_ypow, &p_yinv, &p_l, &p_r, &p_Gf, &p_Hf, &v_pts, &v_sc, &v_g, &v_h, &v_accg, &v_acch, &f_kind, &f_idx, &f_coeff, &f_start, &f_keys, &f_keys2, &f_perm, &f_perm2, &f_contrib, &f_sorted,
                              &f_ukeys, &f_sums, &f_tmp, &f_wv};
         for (auto* b : all) f(b);

@@ -49,12 +49,14 @@ static __global__ void __launch_bounds__(256) flatten_gather_kernel(const fe* __
 template <class C>
 __global__ void __launch_bounds__(256) flatten_scatter_kernel(const uint32_t* __restrict__ ukeys, const fe* __restrict__ sums,
                                                               const int* __restrict__ nruns, fe* __restrict__ wL, fe* __restrict__ wR,
-                                                              fe* __restrict__ wO, fe* __restrict__ wV, fe* __restrict__ wc) {
+                                                              fe* __restrict__ wO, fe* __restrict__ wV, fe* __restrict__ wc, uint32_t n, uint32_t m) {
     using F = Fp<typename C::Fr>;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)*nruns) return;
     uint32_t k = ukeys[i], kd = k >> 29, ix = k & 0x1FFFFFFFu;
     fe s = ld_fe_rw(sums + i);
+    // defence in depth: the host rejects out-of-range variables when they are recorded (check_terms, r1cs.cuh)
+    if (kd >= 1 && kd <= 3 ? ix >= n : kd == 0 ? ix >= m : false) return;
     switch (kd) {
         case 0: st_fe(wV + ix, F::neg(s)); break;
         case 1: st_fe(wL + ix, s); break;

@@ -131,15 +131,14 @@ __global__ void __launch_bounds__(128) points_decompress_kernel(const uint8_t* _
     const uint32_t flags = b[32];
     affine p;
     p.x = F::zero(); p.y = F::zero();
-    bool good = (flags & 0x3Fu) == 0;
+    bool good = (flags & 0xC0u) != 0xC0u;                      // both SWFlags bits: UnexpectedFlags; the six low bits are padding
     bool geq = true;                                           // x >= q is not canonical
     for (int k = 7; k >= 0; k--) {
         uint32_t mk = C::Fq::m(k);
         if (x.v[k] != mk) { geq = x.v[k] > mk; break; }
     }
     good = good && !geq;
-    if (good && (flags & 0x40u)) {                             // infinity: no sign bit, x = 0
-        good = !(flags & 0x80u) && F::is_zero(x);
+    if (good && (flags & 0x40u)) {                             // infinity: the identity whatever x (< q) is, as ark-ec decides
     } else if (good) {
         fe xm = F::to_mont(x);
         fe rhs = F::add(F::mul(F::sqr(xm), xm), F::template curve_b<C>());
@@ -176,6 +175,51 @@ int points_decompress_device(bp_ctx* ctx, const uint8_t* comp, size_t n, const S
     BP_CUDA_TRY(ctx, cudaMemcpyAsync(ok, dk.p, n, cudaMemcpyDeviceToHost, ctx->stream));
     BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return BP_OK;
+}
+
+// Validation of caller-supplied generator vectors (bp_gens_from_points): canonical coordinates, on the curve, and -- on the
+// twisted Edwards curve (cofactor 8) -- r * P = O. Any failure sets *bad.
+template <class C>
+__global__ void __launch_bounds__(128) points_validate_kernel(const affine* __restrict__ pts, size_t n, int* __restrict__ bad) {
+    using E = GroupLaw<C>;
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    affine p = ld_affine(pts + j);
+    bool good = true;
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+        const fe& v = c ? p.y : p.x;
+        bool geq = true;
+        for (int k = 7; k >= 0; k--) {
+            uint32_t mk = C::Fq::m(k);
+            if (v.v[k] != mk) { geq = v.v[k] > mk; break; }
+        }
+        good = good && !geq;
+    }
+    if (good && !E::is_identity(p)) {
+        good = E::on_curve(p);
+        if (good && C::KIND == 1) {
+            uint32_t rl[8];
+            for (int i = 0; i < 8; i++) rl[i] = C::Fr::m(i);
+            good = E::is_identity(E::mul_scalar(p, rl));
+        }
+    }
+    if (!good) atomicOr(bad, 1);
+}
+
+template <class C>
+int points_validate_device(bp_ctx* ctx, const affine* d_pts, size_t n) {
+    if (n == 0) return BP_OK;
+    DevBuf flag;
+    struct Guard { DevBuf* b; ~Guard() { b->release(); } } guard{&flag};
+    BP_CUDA_TRY(ctx, flag.reserve(sizeof(int)));
+    BP_CUDA_TRY(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
+    points_validate_kernel<C><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_pts, n, flag.as<int>());
+    BP_LAUNCH_CHECK(ctx);
+    int bad = 0;
+    BP_CUDA_TRY(ctx, cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return bad ? BP_ERR_FORMAT : BP_OK;
 }
 
 // out[j] = in[j * stride + offset]  (this rank's cyclic shard of the chain)

@@ -216,6 +216,25 @@ struct HostCurve {
         }
     }
 
+    // What ark-serialize's validation guarantees for every `G` the reference ever holds, applied to points that enter the
+    // C ABI in the raw 64-byte form (statement commitments, caller-supplied generators, bp_proof_set_field): both
+    // coordinates canonical (Montgomery residues < q), on the curve, and in the prime-order subgroup (TE, cofactor 8).
+    static bool point_valid(const affine& p) {
+        uint64_t l[4];
+        memcpy(l, p.x.v, 32);
+        if (Fq::geq_m(l)) return false;
+        memcpy(l, p.y.v, 32);
+        if (Fq::geq_m(l)) return false;
+        if (E::is_identity(p)) return true;
+        if (!E::on_curve(p)) return false;
+        if constexpr (IS_TE) {
+            uint32_t rl[8];
+            for (int i = 0; i < 8; i++) rl[i] = C::Fr::m(i);
+            if (!E::is_identity(E::mul_scalar(p, rl))) return false;
+        }
+        return true;
+    }
+
     // deserialize_compressed with validation (on curve, and in the prime-order subgroup for TE)
     static bool point_from_compressed(const uint8_t* in, affine& out) {
         if constexpr (IS_TE) {
@@ -236,14 +255,16 @@ struct HostCurve {
             if (E::is_identity(out)) out = E::affine_identity();
             return true;
         } else {
+            // ark-ff 0.4 deserialize_with_flags: only the two SWFlags bits of byte 32 are interpreted (both set ->
+            // UnexpectedFlags), the integer comes from the first 32 bytes (its six padding bits are never read), and
+            // ark-ec returns the identity on the infinity flag without looking at x -- the same accept/reject decisions,
+            // including malleated encodings.
             uint8_t flags = in[32];
-            if (flags & 0x3F) return false;
+            if ((flags & 0xC0) == 0xC0) return false;
             uint64_t l[4];
             memcpy(l, in, 32);
             if (Fq::geq_m(l)) return false;
             if (flags & 0x40) {
-                if (flags & 0x80) return false;
-                if (l[0] | l[1] | l[2] | l[3]) return false;
                 out = E::affine_identity();
                 return true;
             }

@@ -26,6 +26,7 @@
 #include <thread>
 #include <vector>
 #include "ctx.cuh"
+#include "host/nccl_dyn.hpp"
 
 namespace bp {
 
@@ -641,8 +642,33 @@ int msm_run_job_sharded(bp_ctx* ctx, MsmJob& job, int nmsm, uint8_t (*out_xy)[64
     if (job.nmsm < nmsm) job.nmsm = nmsm;           // a rank may hold no term of some MSM
     if (int rc = msm_run_job<C>(ctx, job, out_xy, out_is_identity)) return rc;
     if (ctx->world <= 1) return BP_OK;
-    if (!ctx->coll) return BP_ERR_ARG;
     const size_t bytes = (size_t)nmsm * 64;
+    if (ctx->nccl_comm) {
+        // library-owned exchange: the partial points (identity = zeros) go through ncclAllGather on the context's stream --
+        // 64 B per MSM and rank over NVLink -- and come back in one pinned copy; no callback, no Python, no torch tensor.
+        if (bytes * ctx->world > BP_HOST_COLL_BYTES) return BP_ERR_LEN;
+        uint8_t* hs = (uint8_t*)ctx->h_coll;
+        for (int m = 0; m < nmsm; m++) {
+            if (out_is_identity[m]) memset(hs + (size_t)m * 64, 0, 64);
+            else memcpy(hs + (size_t)m * 64, out_xy[m], 64);
+        }
+        cudaStream_t st = ctx->stream;
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coll_send.p, hs, bytes, cudaMemcpyHostToDevice, st));
+        const NcclApi& nc = nccl_api();
+        ncclResult_t r = nc.AllGather(ctx->coll_send.p, ctx->coll_recv.p, bytes, ncclUint8, (ncclComm_t)ctx->nccl_comm, st);
+        if (r != ncclSuccess) { ctx->err = std::string("ncclAllGather: ") + nc.GetErrorString(r); return BP_ERR_CUDA; }
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(hs, ctx->coll_recv.p, bytes * ctx->world, cudaMemcpyDeviceToHost, st));
+        BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        ctx->coll_calls++;
+        ctx->coll_bytes += bytes * ctx->world;
+        uint8_t pts[64 * 64];
+        for (int m = 0; m < nmsm; m++) {
+            for (int r2 = 0; r2 < ctx->world; r2++) memcpy(pts + (size_t)r2 * 64, hs + (size_t)r2 * bytes + (size_t)m * 64, 64);
+            if (int rc = host_points_sum(ctx->curve, pts, ctx->world, out_xy[m], &out_is_identity[m])) return rc;
+        }
+        return BP_OK;
+    }
+    if (!ctx->coll) return BP_ERR_ARG;
     std::vector<uint8_t> send(bytes), recv(bytes * ctx->world), pts((size_t)ctx->world * 64);
     for (int m = 0; m < nmsm; m++) {
         if (out_is_identity[m]) memset(&send[(size_t)m * 64], 0, 64);

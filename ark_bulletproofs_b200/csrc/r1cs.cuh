@@ -423,6 +423,25 @@ struct ConstraintStore {
     size_t count() const { return start.size() - 1; }
 };
 
+// A Variable that did not come from this constraint system (another prover's, a stale phase-2 one, a forged bp_var)
+// panics on an index in the Rust reference; here it would index a_L / wL ... out of bounds. Every term that
+// crosses multiply / constrain is checked against the current number of multipliers and commitments.
+inline int check_terms(const Variable* v, size_t n, size_t multipliers, size_t commitments) {
+    for (size_t i = 0; i < n; i++) {
+        switch (v[i].kind) {
+            case VAR_MUL_LEFT: case VAR_MUL_RIGHT: case VAR_MUL_OUT:
+                if (v[i].idx >= multipliers) return BP_ERR_ARG;
+                break;
+            case VAR_COMMITTED:
+                if (v[i].idx >= commitments) return BP_ERR_ARG;
+                break;
+            case VAR_ONE: break;
+            default: return BP_ERR_ARG;
+        }
+    }
+    return BP_OK;
+}
+
 // Device flatten: d_wL/d_wR/d_wO (n each, device) are filled; wV (m) and wc come back to the host.
 template <class C>
 int flatten_device(bp_ctx* ctx, const ConstraintStore& cs, const fe& z, size_t n, size_t m, fe* d_wL, fe* d_wR, fe* d_wO,
@@ -472,7 +491,7 @@ int flatten_device(bp_ctx* ctx, const ConstraintStore& cs, const fe& z, size_t n
     BP_CUDA_TRY(ctx, cub::DeviceReduce::ReduceByKey(ctx->f_tmp.p, tmp2, keys2, ctx->f_ukeys.as<uint32_t>(), ctx->f_sorted.as<fe>(), ctx->f_sums.as<fe>(), d_nruns,
                                                     FeAddOp<C>(), (int)T, st));
     BP_CUDA_TRY(ctx, cudaMemsetAsync(d_wV, 0, (m + 1) * sizeof(fe), st));
-    flatten_scatter_kernel<C><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(ctx->f_ukeys.as<uint32_t>(), ctx->f_sums.as<fe>(), d_nruns, d_wL, d_wR, d_wO, d_wV, d_wc);
+    flatten_scatter_kernel<C><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(ctx->f_ukeys.as<uint32_t>(), ctx->f_sums.as<fe>(), d_nruns, d_wL, d_wR, d_wO, d_wV, d_wc, (uint32_t)n, (uint32_t)m);
     BP_LAUNCH_CHECK(ctx);
     std::vector<fe> back(m + 1);
     if (int rc = D::download(ctx, back.data(), d_wV, (m + 1) * sizeof(fe))) return rc;
@@ -498,6 +517,10 @@ struct ProverT : ConstraintSystemBase {
     bool has_pending = false, randomizing = false;
     size_t pending = 0;
 
+    ~ProverT() override {                                                                      // prover.rs:74-94 (Drop for Secrets)
+        for (auto* w : {&v, &v_blinding, &a_L, &a_R, &a_O})
+            if (!w->empty()) explicit_bzero(w->data(), w->size() * sizeof(fe));
+    }
     ProverT(bp_ctx* c, const GensDev* g, Transcript* t) : ctx(c), gens(g), transcript(t) {     // prover.rs:291-308
         t->append_message("dom-sep", (const uint8_t*)"r1cs v1", 7);
         cs.one = Fr::one();
@@ -520,6 +543,8 @@ struct ProverT : ConstraintSystemBase {
         return tot;
     }
     int multiply(const Variable* lv, const fe* lc, size_t ln, const Variable* rv, const fe* rc, size_t rn, Variable out[3]) override {   // :103-133
+        if (int rc_ = check_terms(lv, ln, a_L.size(), v.size())) return rc_;
+        if (int rc_ = check_terms(rv, rn, a_L.size(), v.size())) return rc_;
         fe l = eval(lv, lc, ln), r = eval(rv, rc, rn);
         fe o = Fr::mul(l, r);
         uint64_t i = a_L.size();
@@ -552,7 +577,11 @@ struct ProverT : ConstraintSystemBase {
         a_L.push_back(*l); a_R.push_back(*r); a_O.push_back(Fr::mul(*l, *r));
         return BP_OK;
     }
-    int constrain(const Variable* vv, const fe* c, size_t n) override { cs.push(vv, c, n); return BP_OK; }   // :189-193
+    int constrain(const Variable* vv, const fe* c, size_t n) override {                         // :189-193
+        if (int rc_ = check_terms(vv, n, a_L.size(), v.size())) return rc_;
+        cs.push(vv, c, n);
+        return BP_OK;
+    }
     size_t multipliers_len() const override { return a_L.size(); }
     int challenge_scalar(const char* label, fe* out) override {                                 // :262-267
         if (!randomizing) return BP_ERR_ARG;
@@ -605,7 +634,10 @@ struct ProverT : ConstraintSystemBase {
                                                                                            dout.as<affine>(), m);
         }
         BP_LAUNCH_CHECK(ctx);
-        if (int rc = D::download(ctx, V_out, dout.p, m * sizeof(affine))) return rc;
+        int rc_dl = D::download(ctx, V_out, dout.p, m * sizeof(affine));
+        cudaMemsetAsync(dv.p, 0, m * sizeof(fe), ctx->stream);        // values and blindings do not outlive the call on the device
+        cudaMemsetAsync(db.p, 0, m * sizeof(fe), ctx->stream);
+        if (rc_dl) return rc_dl;
         for (size_t i = 0; i < m; i++) {
             vars[i] = {VAR_COMMITTED, (uint64_t)v.size()};
             v.push_back(vals[i]);
@@ -674,9 +706,22 @@ struct ProverT : ConstraintSystemBase {
         TranscriptRng rng = t.make_rng("v_blinding", wit, prng);                                // :483-494
         size_t n1 = a_L.size();
         if (gens->capacity < n1) return BP_ERR_GENS;                                            // :499-501
-        fe bl1[3];
+        fe bl1[3], bl2[3] = {Fr::zero(), Fr::zero(), Fr::zero()}, tb[6];
         for (int k = 0; k < 3; k++) bl1[k] = HC::scalar_rand(rng);                              // :506-508
         std::vector<fe> s_L(n1), s_R(n1);
+        // Secrets (mirrors `impl Drop for Secrets` and the clearing at prover.rs:74-94,805-812): the blinding scalars and
+        // vectors on the host and every witness-derived device buffer are zeroed when prove() leaves, on the error
+        // paths too. Declared before the draw thread's joiner, so it runs after the thread has stopped writing.
+        struct Wiper {
+            bp_ctx* ctx; fe *bl1, *bl2, *tb; std::vector<fe>*sl, *sr;
+            ~Wiper() {
+                DevBuf* sec[] = {&ctx->p_aL, &ctx->p_aR, &ctx->p_aO, &ctx->p_sL, &ctx->p_sR, &ctx->p_l, &ctx->p_r, &ctx->ipa_s};
+                for (auto* b : sec) if (b->p) cudaMemsetAsync(b->p, 0, b->cap, ctx->stream);
+                explicit_bzero(bl1, 3 * sizeof(fe)); explicit_bzero(bl2, 3 * sizeof(fe)); explicit_bzero(tb, 6 * sizeof(fe));
+                if (!sl->empty()) explicit_bzero(sl->data(), sl->size() * sizeof(fe));   // one bulk clear the compiler may not elide
+                if (!sr->empty()) explicit_bzero(sr->data(), sr->size() * sizeof(fe));
+            }
+        } wiper{ctx, bl1, bl2, tb, &s_L, &s_R};
         // The 8*n1 dependent Keccak permutations behind s_L, s_R are the longest stage of a large proof and need only
         // the host: for large one-phase parts they run on a second host thread while this one uploads a_L, a_R, a_O and
         // commits A_I, A_O (which do not depend on them); S follows when the draws are done. Same draws, same order.
@@ -719,7 +764,6 @@ struct ProverT : ConstraintSystemBase {
         if (int rc = create_randomized_constraints()) return rc;                                // :567
         size_t n = a_L.size(), n2 = n - n1, padded_n = next_pow2(n), pad = padded_n - n;
         if (gens->capacity < padded_n) return BP_ERR_GENS;                                      // :577-579
-        fe bl2[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
         if (n2 > 0) for (int k = 0; k < 3; k++) bl2[k] = HC::scalar_rand(rng);                   // :585-597
         s_L.resize(n); s_R.resize(n);
         HC::scalar_rand_bulk(rng, s_L.data() + n1, n - n1);                                     // :599-602
@@ -776,7 +820,6 @@ struct ProverT : ConstraintSystemBase {
             if (int rc = D::download(ctx, tc, d_t, 6 * sizeof(fe))) return rc;
         }
         tm.lap(ST_VEC);
-        fe tb[6];
         tb[0] = HC::scalar_rand(rng);                                                           // t_1_blinding :705
         for (int k = 2; k < 6; k++) tb[k] = HC::scalar_rand(rng);                               // t_3..t_6   :706-709
         // T_i = t_i*B + tb_i*B_blinding for i in {1,3,4,5,6}: five 2-term MSMs in one batch (:711-715)
@@ -827,12 +870,7 @@ struct ProverT : ConstraintSystemBase {
                                ctx->p_l.as<fe>(), ctx->p_r.as<fe>(), padded_n, proof.L_vec, proof.R_vec, proof.a, proof.b,
                                geo ? &geo_rG : nullptr, geo ? &y_inv : nullptr, n1, &u);                                // :791-800
         tm.lap(ST_IPA);
-        // secrets: zero the device copies (mirrors prover.rs:74-94,805-812)
-        DevBuf* sec[] = {&ctx->p_aL, &ctx->p_aR, &ctx->p_aO, &ctx->p_sL, &ctx->p_sR, &ctx->p_l, &ctx->p_r};
-        for (auto* b : sec) if (b->p) cudaMemsetAsync(b->p, 0, b->cap, st);
-        if (!s_L.empty()) explicit_bzero(s_L.data(), s_L.size() * sizeof(fe));   // one bulk clear the compiler may not elide
-        if (!s_R.empty()) explicit_bzero(s_R.data(), s_R.size() * sizeof(fe));
-        tm.lap(ST_TAIL);
+        tm.lap(ST_TAIL);          // the wiper's clears are queued on the stream as prove() returns
         return rc;
     }
 };
@@ -858,6 +896,8 @@ struct VerifierT : ConstraintSystemBase {
         cs.minus_one = Fr::neg(Fr::one());
     }
     int multiply(const Variable* lv, const fe* lc, size_t ln, const Variable* rv, const fe* rc, size_t rn, Variable out[3]) override {   // :74-98
+        if (int rc_ = check_terms(lv, ln, num_vars, V.size())) return rc_;
+        if (int rc_ = check_terms(rv, rn, num_vars, V.size())) return rc_;
         uint64_t i = num_vars++;
         out[0] = {VAR_MUL_LEFT, i}; out[1] = {VAR_MUL_RIGHT, i}; out[2] = {VAR_MUL_OUT, i};
         fe minus_one = Fr::neg(Fr::one());
@@ -875,7 +915,11 @@ struct VerifierT : ConstraintSystemBase {
         out[0] = {VAR_MUL_LEFT, i}; out[1] = {VAR_MUL_RIGHT, i}; out[2] = {VAR_MUL_OUT, i};
         return BP_OK;
     }
-    int constrain(const Variable* vv, const fe* c, size_t n) override { cs.push(vv, c, n); return BP_OK; }
+    int constrain(const Variable* vv, const fe* c, size_t n) override {
+        if (int rc_ = check_terms(vv, n, num_vars, V.size())) return rc_;
+        cs.push(vv, c, n);
+        return BP_OK;
+    }
     size_t multipliers_len() const override { return num_vars; }
     int challenge_scalar(const char* label, fe* out) override {
         if (!randomizing) return BP_ERR_ARG;
@@ -1090,6 +1134,7 @@ int batch_verify_t(bp_ctx* ctx, Rng* prng, const fe* alphas, std::vector<Verifie
             // grow the accumulators, keeping what is already summed, zero-extending (:631-633)
             size_t want = np;
             DevBuf ng, nh;
+            struct Owner { DevBuf *a, *b; bool keep = false; ~Owner() { if (!keep) { a->release(); b->release(); } } } own{&ng, &nh};   // not leaked on the error paths
             BP_CUDA_TRY(ctx, ng.reserve((want + 1) * sizeof(fe)));
             BP_CUDA_TRY(ctx, nh.reserve((want + 1) * sizeof(fe)));
             BP_CUDA_TRY(ctx, cudaMemsetAsync(ng.p, 0, want * sizeof(fe), ctx->stream));
@@ -1101,6 +1146,7 @@ int batch_verify_t(bp_ctx* ctx, Rng* prng, const fe* alphas, std::vector<Verifie
             BP_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
             ctx->v_accg.release(); ctx->v_acch.release();
             ctx->v_accg = ng; ctx->v_acch = nh;
+            own.keep = true;
             acc_n = want;
         }
         fe alpha = alphas ? alphas[p] : HC::scalar_rand(*prng);                                 // :649 (same draw order)

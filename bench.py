@@ -100,7 +100,9 @@ def cpu_reference_run(lg_sample, steps, warmup, threads=None):
     from ark_bulletproofs_b200 import codec
     import bp_oracle as O
 
-    threads = threads or c_oracle.num_threads()
+    # os.cpu_count(), not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1, which made the N > 1 reference arm of
+    # round 1 single-threaded; the C code passes the count in a num_threads() clause, which overrides the environment
+    threads = threads or os.cpu_count() or 1
     n = 1 << lg_sample
     pts = c_oracle.synth_points(0, codec.enc_point(O.SECQ256K1.G, CURVE), n, 0)
     rng = np.random.default_rng(2)
@@ -132,7 +134,7 @@ def cpu_r1cs_baseline(lg_n, threads=None):
     from ark_bulletproofs_b200 import codec
     import bp_oracle as O
     N = 1 << lg_n
-    threads = threads or c_oracle.num_threads()
+    threads = threads or os.cpu_count() or 1
     g = codec.enc_point(O.SECQ256K1.G, CURVE)
     rng = np.random.default_rng(7)
 
@@ -140,6 +142,7 @@ def cpu_r1cs_baseline(lg_n, threads=None):
         sc = rng.integers(0, 256, size=k * 32, dtype=np.uint8)
         sc.reshape(k, 32)[:, 31] &= 0x7F
         return sc.tobytes()
+    threads = threads if threads else (os.cpu_count() or 1)
     out = {}
     for label, th in (("all_cores", threads), ("one_thread", 1)):
         h = 2048 if th > 1 else 256
@@ -249,6 +252,117 @@ def kshuffle_prove_verify(ctx, k):
             "prove_stages_ms": st_best, "prove_reps_ms": reps, "note": "prove_ms includes the 2k Pedersen commitments and the gadget, like the reference's bench"}
 
 
+def batch_verify_bench(ctx, local_rank, rank, world, lg_n, count, nctx, dist, torch):
+    """BASELINE config 5: batch verification (verifier.rs:604-691) of `count` chain-circuit proofs of 2^lg_n multipliers,
+    proofs sharded over the ranks (bp_batch_verify_partial) and, inside a rank, over `nctx` contexts on host threads so
+    that one context's verifier assembly overlaps another's kernels; partial points summed, NCCL all-gather for N > 1.
+    `distinct` different proofs are repeated to fill the batch (the verifier's work per instance is the same)."""
+    from ark_bulletproofs_b200 import Context, codec
+    from ark_bulletproofs_b200 import r1cs as R
+    from ark_bulletproofs_b200.dist import allgather_sum_points
+    N = 1 << lg_n
+    r = codec.MODULI[CURVE][1]
+    distinct = 4
+    ctxs = [ctx] + [Context(CURVE, local_rank) for _ in range(nctx - 1)]
+    gens_k = [R.Gens(c, N) for c in ctxs]
+    made = []
+    for d in range(distinct):
+        wit = R.ChaChaRng(bytes([(4 + d) % 256] * 32))
+        x0_raw = wit.scalars_raw(CURVE, 1)
+        ks_raw = wit.scalars_raw(CURVE, N)
+        rng = R.ChaChaRng(bytes(range(32)))
+        p = R.Prover(ctx, gens_k[0], R.Transcript(b"ChainCircuit"))
+        com, var = p.commit(codec.dec_fe(x0_raw, r), rng.scalar(CURVE))
+        p.chain_circuit_raw(var, N, ks_raw, x0_raw)
+        made.append((p.prove(rng), com, ks_raw))
+    mine = list(range(rank, count, world))
+    arng = R.ChaChaRng(bytes([5] * 32))
+    alphas = [arng.scalar(CURVE) for _ in range(count)]
+    shares = [mine[k::nctx] for k in range(nctx)]
+
+    def build(c, idx):
+        out = []
+        for i in idx:
+            proof, com, ks_raw = made[i % distinct]
+            v = R.Verifier(c, R.Transcript(b"ChainCircuit"))
+            vv = v.commit(com)
+            v.chain_circuit_raw(vv, N, ks_raw, None)
+            out.append((v, proof))
+        return out
+    best, best_total = None, None
+    for _ in range(2):
+        if world > 1:
+            dist.barrier()
+        t00 = time.perf_counter()
+        parts = [None] * nctx
+        t_verify = [0.0] * nctx
+
+        def work(k):
+            insts = build(ctxs[k], shares[k])          # verifier assembly (host) is part of the pipeline
+            t0 = time.perf_counter()
+            parts[k] = R.batch_verify_partial(ctxs[k], [alphas[i] for i in shares[k]], insts, gens_k[k])
+            t_verify[k] = time.perf_counter() - t0
+        th = [threading.Thread(target=work, args=(k,)) for k in range(nctx)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        part = ctx.points_sum(parts) if nctx > 1 else parts[0]
+        if world > 1:
+            _, idn = allgather_sum_points(CURVE, codec.enc_point(part, CURVE) if part is not None else bytes(64), part is None,
+                                          device=torch.device("cuda", local_rank))
+            assert idn, "batch rejected"
+        else:
+            assert part is None, "batch rejected"
+        total = time.perf_counter() - t00
+        if world > 1:
+            t = torch.tensor([total], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t[0])
+        if best_total is None or total < best_total:
+            best_total, best = total, max(t_verify)
+    return {"proofs": count, "multipliers": "2^%d" % lg_n, "n_gpus": world, "contexts_per_gpu": nctx, "ms": round(best_total * 1e3, 1),
+            "proofs_per_s": round(count / best_total, 1),
+            "note": "wall time of building the %d verifiers (constraint systems, commitments) and bp_batch_verify_partial on every context; "
+                    "%d distinct proofs repeated" % (count, distinct)}
+
+
+def other_curve_bench(curve, lg_n):
+    """BASELINE config 5, second half: zorro / curve25519 R1CS prove + verify of the chain circuit at 2^lg_n multipliers."""
+    from ark_bulletproofs_b200 import Context, codec
+    from ark_bulletproofs_b200 import r1cs as R
+    N = 1 << lg_n
+    c = Context(curve, 0)
+    t0 = time.perf_counter()
+    gens = R.Gens(c, N)
+    gens_s = time.perf_counter() - t0
+    r = codec.MODULI[curve][1]
+    wit = R.ChaChaRng(bytes([3] * 32))
+    x0_raw = wit.scalars_raw(curve, 1)
+    ks_raw = wit.scalars_raw(curve, N)
+    best_p, best_v = None, None
+    for _ in range(2):
+        rng = R.ChaChaRng(bytes(range(32)))
+        p = R.Prover(c, gens, R.Transcript(b"ChainCircuit"))
+        com, var = p.commit(codec.dec_fe(x0_raw, r), rng.scalar(curve))
+        p.chain_circuit_raw(var, N, ks_raw, x0_raw)
+        t0 = time.perf_counter()
+        proof = p.prove(rng)
+        tp = (time.perf_counter() - t0) * 1e3
+        st = {k: v for k, v in c.last_stage_ms().items() if v}
+        v = R.Verifier(c, R.Transcript(b"ChainCircuit"))
+        vv = v.commit(com)
+        v.chain_circuit_raw(vv, N, ks_raw, None)
+        t0 = time.perf_counter()
+        v.verify(proof, gens)
+        tv = (time.perf_counter() - t0) * 1e3
+        if best_p is None or tp < best_p[0]:
+            best_p = (tp, st)
+        best_v = tv if best_v is None or tv < best_v else best_v
+    return {"curve": curve, "multipliers": "2^%d" % lg_n, "prove_ms": round(best_p[0], 2), "verify_ms": round(best_v, 2),
+            "rng_ms": best_p[1].get("rng"), "ipa_ms": best_p[1].get("ipa"), "gens_s": round(gens_s, 2), "proof_bytes": len(proof.to_bytes())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,6 +373,9 @@ def main():
     ap.add_argument("--cpu-lg-n", type=int, default=0, help="log2 of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--r1cs-lg-n", default="16,20", help="log2 multipliers of the secondary R1CS prove/verify measurements, comma separated (0 = skip)")
+    ap.add_argument("--batch-verify", default="16,1024,4", help="lg multipliers, proofs, contexts per GPU of the batch-verification measurement (empty = skip)")
+    ap.add_argument("--other-curves", default="zorro,curve25519", help="curves of the 2^16 prove/verify measurement at N = 1 (empty = skip)")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--shuffle-k", type=int, default=1024, help="k of the reference's own k-shuffle bench, reported next to r1cs (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -270,17 +387,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ncores = os.cpu_count() or 1
-        lg = args.cpu_lg_n or (20 if ncores >= 16 else 18)
-        val, ms, threads = cpu_reference_run(lg, args.steps, warmup)
+        # the same workload as the b200 arm (2^lg_n points per step); every step is one full MSM on all host cores, so the
+        # number of timed steps is capped to keep the run within minutes (a step takes ~10 s at 2^24 on 16 cores)
+        lg = args.cpu_lg_n or args.lg_n
+        steps = max(1, min(args.steps, 2 if lg >= 22 else 5))
+        wu = 1 if lg < 22 else 0
+        val, ms, threads = cpu_reference_run(lg, steps, wu)
         line = {
-            "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": wu, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u256 (Montgomery, 4x64-bit limbs)", "data": "synthetic",
-            "config": {"workload": workload, "sample": "2^%d-point MSM per step (bounded sample of the workload)" % lg},
+            "config": {"workload": workload, "steps_requested": args.steps,
+                       "note": "CPU arm: same 2^%d-point MSM per step, steps capped at %d (one step is a whole MSM on every host core)" % (lg, steps)},
             "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "oracle/c/bp_ref.c ark-style wNAF Pippenger (windows over OpenMP threads, the analogue of "
-                                       "feature `parallel`), 2^%d points; the Rust crate cannot be built here (no cargo/rustc)" % lg},
+                             "sample": "oracle/c/bp_ref.c: ark-ec 0.4 msm_bigint_wnaf restated in portable C (windows over %d OpenMP threads, the "
+                                       "analogue of feature `parallel`; generic CIOS multiplication, roughly 2x slower per modmul than ark-ff's "
+                                       "x86-64 assembly), %d x 2^%d points; the Rust crate cannot be built here (no cargo/rustc)" % (threads, steps, lg)},
             "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
@@ -369,14 +491,51 @@ def main():
     assert res_e2e == ref, "host-buffer path disagrees with the device-resident path"
     e2e_val = world * n / (ms_e2e / args.steps * 1e-3) / 1e6
 
+    # BASELINE config 1: the MSM sweep 2^12 .. 2^24 on one GPU (device-resident inputs: prefixes of the same buffers)
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        sweep = []
+        peak_imad = imad_peak()[0]
+        for lg in range(12, args.lg_n + 1, 2):
+            m = 1 << lg
+            for _ in range(3):
+                ctx.msm_device(pts.data_ptr(), sc.data_ptr(), m)
+            reps = 20 if lg <= 18 else 5
+            ms_s, _, _, _ = timed(lambda: ctx.msm_device(pts.data_ptr(), sc.data_ptr(), m), reps)
+            ph = ctx.last_phases()
+            per = ms_s / reps
+            acc = ph["ms"].get("accumulate") or 0.0
+            sweep.append({"lg_n": lg, "ms": round(per, 4), "mpoints_per_s": round(m / per / 1e3, 2), "window_bits": ph["c"], "windows": ph["windows"],
+                          "accumulate_ms": round(acc, 4),
+                          "accumulate_frac_of_imad_peak": round(ph["entries"] * MADD_MODMUL * MODMUL_IMAD / (acc * 1e-3) / peak_imad, 4) if acc > 0 else None,
+                          "whole_msm_frac_of_imad_peak": round(ph["entries"] * MADD_MODMUL * MODMUL_IMAD / (per * 1e-3) / peak_imad, 4)})
+        ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n)      # leave the phase timers on the headline size
+        phases = ctx.last_phases()
+
+    # strong scaling (north star: "a 2^24-point MSM running on 1-8 B200"): the same 2^lg_n points in total, 2^lg_n / N per GPU
+    strong = None
+    if world > 1:
+        from ark_bulletproofs_b200.dist import shard_range
+        lo, hi = shard_range(n, rank, world)
+        cnt = hi - lo
+
+        def step_strong():
+            return combine(*ctx.msm_device(pts.data_ptr(), sc.data_ptr(), cnt))    # this rank's points are distinct multiples of G already
+        for _ in range(warmup):
+            step_strong()
+        ms_st, _, _, _ = timed(step_strong, args.steps)
+        per = ms_st / args.steps
+        strong = {"scaling": "strong", "total_points": n, "points_per_gpu": cnt, "ms_per_step": round(per, 4), "value": round(n / per / 1e3, 3), "unit": UNIT,
+                  "speedup_vs_1gpu_weak_step": round(ms_per_step / per, 3),
+                  "note": "same 2^%d points in total; per-GPU MSM of 2^%d/%d points + one 64-byte all-gather and a host point sum per step" % (args.lg_n, args.lg_n, world)}
+
     # secondary metric: R1CS prove / verify. With N > 1 the context switches to multi-GPU mode (cyclic generator
     # shards, partial points all-gathered over NCCL) and every rank takes part in the same proof.
     r1cs = None
     lgs = [int(x) for x in str(args.r1cs_lg_n).split(",") if int(x) > 0]
     if lgs:
         if world > 1:
-            from ark_bulletproofs_b200.dist import torch_allgather
-            ctx.set_collective(rank, world, torch_allgather(device=torch.device("cuda", local_rank)))
+            ctx.init_nccl(rank, world)          # library-owned ncclAllGather of the partial points (no Python on the data path)
         runs = []
         for lg in lgs:
             one = r1cs_prove_verify(ctx, lg)
@@ -389,11 +548,22 @@ def main():
         r1cs["sizes"] = {"2^%d" % lg: {"prove_ms": o["prove_ms"], "verify_ms": o["verify_ms"], "proof_bytes": o["proof_bytes"],
                                         "rng_ms": o["prove_stages_ms"].get("rng"), "ipa_ms": o["prove_stages_ms"].get("ipa")} for lg, o in zip(lgs, runs)}
         if world > 1:
-            r1cs["sharding"] = "generators cyclic over %d GPUs; every MSM's 64 B partial points all-gathered (NCCL); scalars, transcript and TranscriptRng replicated" % world
+            r1cs["sharding"] = ("generators cyclic over %d GPUs; every MSM's 64 B partial points all-gathered by the library (ncclAllGather on the "
+                                "context's stream, bp_ctx_init_nccl); scalars, transcript and TranscriptRng replicated" % world)
         elif args.shuffle_k > 1:
             r1cs["reference_bench_kshuffle"] = kshuffle_prove_verify(ctx, args.shuffle_k)
         if world == 1 and not args.no_cpu_baseline:
             r1cs["cpu_baseline"] = cpu_r1cs_baseline(lgs[0])
+
+    batch = None
+    if args.batch_verify:
+        # batch verification shards proofs, not generators: fresh single-GPU contexts when `ctx` is in multi-GPU mode
+        blg, bcount, bctx = [int(x) for x in args.batch_verify.split(",")]
+        batch = batch_verify_bench(ctx if world == 1 else Context(CURVE, local_rank), local_rank, rank, world, blg, bcount, bctx,
+                                   dist if world > 1 else None, torch)
+    others = None
+    if world == 1 and args.other_curves:
+        others = [other_curve_bench(c, 16) for c in args.other_curves.split(",") if c]
 
     if rank != 0:
         if world > 1:
@@ -440,6 +610,14 @@ def main():
             "msm_reduce_kernel+window_sum": {"bound": "imad", "frac": round(phases["windows"] * (1 << (phases["c"] - 1)) * 2 * 14 * MODMUL_IMAD / (phases["ms"]["reduce"] * 1e-3) / peak, 4)},
         },
     }
+    if sweep is not None:
+        line["sweep"] = sweep
+    if strong is not None:
+        line["strong_scaling"] = strong
+    if batch is not None:
+        line["batch_verify"] = batch
+    if others is not None:
+        line["other_curves"] = others
     if r1cs is not None:
         line["r1cs"] = r1cs
     if world == 1 and not args.no_cpu_baseline:

@@ -91,6 +91,15 @@ int bp_ctx_last_stage_ms(const bp_ctx* ctx, double out[16]);
  * world must be a power of two that divides every generator count used. */
 typedef int (*bp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes);
 int bp_ctx_set_collective(bp_ctx* ctx, int rank, int world, bp_allgather_fn fn, void* user);
+/* The same multi-GPU mode with the exchange owned by the library ("sum the per-GPU partial points with a
+ * tiny NCCL all-gather over NVLink"): rank 0 calls bp_nccl_unique_id and hands the 128 bytes to every rank (any
+ * out-of-band channel); every rank then calls bp_ctx_init_nccl (collective: it returns once all `world` ranks have
+ * joined). From then on each sharded MSM ends with one ncclAllGather of the 64-byte partial points on the context's
+ * stream -- no callback into the host program. NCCL is reached through dlopen("libnccl.so.2"), so inside a torch process
+ * it is the copy torch has loaded; BP_ERR_UNSUPPORTED when no NCCL can be found. Replaces rayon's in-process reduction of
+ * the reference's `parallel` feature (Cargo.toml:76) across GPUs. */
+int bp_nccl_unique_id(uint8_t out[128]);
+int bp_ctx_init_nccl(bp_ctx* ctx, int rank, int world, const uint8_t unique_id[128]);
 /* bp_msm over host buffers of more than 1.5x `points` points (default 2^22) is streamed: the input is copied chunk by
  * chunk (first chunk points/4, each next one 1.5x larger, at most 2x points) while the kernels of the chunks already
  * on the device run, all chunks adding into one bucket array. Exposed for tests and tuning. */

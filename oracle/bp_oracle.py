@@ -598,17 +598,17 @@ def de_point_compressed(cv: Curve, b: bytes):
     if cv.kind == "sw":
         if len(b) != 33:
             raise ValueError("len")
+        # ark-ff 0.4 deserialize_with_flags (restated from the published crate): the 33rd byte carries SWFlags in its top
+        # two bits (from_u8_remove_flags clears only those; both set -> UnexpectedFlags) and the integer is rebuilt from
+        # the first 32 bytes alone, so the six low bits of the flag byte are never looked at; x >= q -> InvalidData.
+        # ark-ec Affine::deserialize_with_mode returns the identity on the infinity flag without examining x.
         flags = b[32]
-        if flags & 0x3F:
-            raise ValueError("flag bits")
+        if (flags & 0xC0) == 0xC0:
+            raise ValueError("both flags")
         x = int.from_bytes(b[:32], "little")
         if x >= q:
             raise ValueError("x >= q")
         if flags & 0x40:
-            if flags & 0x80:
-                raise ValueError("both flags")
-            if x != 0:
-                raise ValueError("inf with x != 0")
             return None
         y = sqrt_mod((x * x * x + cv.a * x + cv.b) % q, q)
         if y is None:

@@ -82,8 +82,18 @@ def test_serialisation_roundtrip():
         if O.sqrt_mod((x ** 3 + 7) % cv.q, cv.q) is None:
             assert lib.bp_point_decompress(0, cand, ctypes.create_string_buffer(64)) == -8
             break
-    bad[32] = 0x01
-    assert lib.bp_point_decompress(0, bytes(bad), ctypes.create_string_buffer(64)) == -8
+    # ark-ff reads the integer from the first 32 bytes only: the six padding bits of the flag byte are ignored, both
+    # flag bits together are UnexpectedFlags, and the infinity flag gives the identity whatever x is
+    good = O.ser_point(cv, P, True)
+    for pad in (0x01, 0x3F):
+        back = ctypes.create_string_buffer(64)
+        enc = good[:32] + bytes([good[32] | pad])
+        assert lib.bp_point_decompress(0, enc, back) == 0
+        assert codec.dec_point(back.raw, "secq256k1") == P == O.de_point_compressed(cv, enc)
+    assert lib.bp_point_decompress(0, good[:32] + b"\xC0", ctypes.create_string_buffer(64)) == -8
+    back = ctypes.create_string_buffer(64)
+    assert lib.bp_point_decompress(0, good[:32] + b"\x40", back) == 0 and codec.dec_point(back.raw, "secq256k1") is None
+    assert O.de_point_compressed(cv, good[:32] + b"\x40") is None
     assert lib.bp_point_decompress(0, b"\xff" * 32 + b"\x00", ctypes.create_string_buffer(64)) == -8
     s = ctypes.create_string_buffer(32)
     assert lib.bp_scalar_from_bytes(0, (cv.r).to_bytes(32, "little"), s) == -8

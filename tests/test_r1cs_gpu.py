@@ -591,8 +591,9 @@ def test_proofs_from_bytes_batch(curve):
         bad.append(bytes(b))
     sign = bytearray(base); sign[pc - 1] ^= 0x80; bad.append(bytes(sign))
     if pc == 33:
-        fl = bytearray(base); fl[32] |= 0x01; bad.append(bytes(fl))            # unused flag bit
-        inf = bytearray(base); inf[32] = 0xC0; bad.append(bytes(inf))           # infinity + sign
+        fl = bytearray(base); fl[32] |= 0x01; bad.append(bytes(fl))            # padding bit: ark-ff never reads it -> accepted
+        inf = bytearray(base); inf[32] = 0xC0; bad.append(bytes(inf))           # infinity + sign: UnexpectedFlags
+        inx = bytearray(base); inx[pc * 3 + 32] = 0x40; bad.append(bytes(inx))  # A_I2 := infinity flag with x != 0: the identity for ark-ec
         big = bytearray(base); big[0:32] = b"\xff" * 32; bad.append(bytes(big))  # x >= q
     bad.append(base[:-5])
     sc = bytearray(base); sc[-32:] = b"\xff" * 32; bad.append(bytes(sc))        # scalar >= r
@@ -606,8 +607,110 @@ def test_proofs_from_bytes_batch(curve):
             want = None
         assert (pr is None) == (want is None)
         if pr is not None:
-            assert pr.to_bytes() == want.to_bytes() == blob
+            assert pr.to_bytes() == want.to_bytes()
+            malleated = pc == 33 and any(blob[33 * k + 32] & 0x3F or (blob[33 * k + 32] & 0x40 and any(blob[33 * k:33 * k + 32])) for k in range(11))
+            assert (pr.to_bytes() == blob) != malleated          # re-serialisation is canonical
+            cvo = O.CURVES[curve]
+            assert O.R1CSProof.from_bytes(cvo, blob).to_bytes(cvo) == pr.to_bytes()
         else:
             n_rej += 1
     assert n_rej >= 3 and all(p is not None for p in got[:len(blobs)])
     assert R.Proof.from_bytes_batch(ctx, []) == []
+
+
+# ---- ABI hardening: foreign variables, unchecked points, mixed contexts ----------------------------------------
+def test_foreign_variables_rejected(env):
+    """A Variable that does not belong to the constraint system (stale, forged kind, out-of-range index) is BP_ERR_ARG at
+    multiply / constrain instead of an out-of-bounds index in flatten (the Rust reference panics on the index)."""
+    from ark_bulletproofs_b200 import r1cs as R
+    curve = "secq256k1"
+    ctx, gens = env(curve, 8)
+    for make in (lambda: R.Prover(ctx, gens, R.Transcript(b"t")), lambda: R.Verifier(ctx, R.Transcript(b"t"))):
+        cs = make()
+        if isinstance(cs, R.Prover):
+            _, v0 = cs.commit(5, 7)
+            l, r_, o = cs.allocate_multiplier((3, 4))
+        else:
+            v0 = cs.commit(O.pt_mul(O.SECQ256K1, 9, O.SECQ256K1.G))
+            l, r_, o = cs.allocate_multiplier(None)
+        cs.constrain(R.LC.of(l) + v0 - o)                                        # fine
+        for bad in (R.Variable(1, 1), R.Variable(2, 1 << 20), R.Variable(3, (1 << 29) + 0), R.Variable(0, 1), R.Variable(5, 0), R.Variable(9, 0)):
+            with pytest.raises(R.BpError) as e:
+                cs.constrain(R.LC.of(bad) - l)
+            assert e.value.code == -1
+            with pytest.raises(R.BpError) as e:
+                cs.multiply(R.LC.of(bad), R.LC.of(l))
+            assert e.value.code == -1
+
+
+@pytest.mark.parametrize("curve", ["secq256k1", "zorro", "curve25519"])
+def test_invalid_points_rejected_at_the_boundary(env, curve):
+    """Statement commitments, caller-supplied generators and bp_proof_set_field take raw 64-byte points: off-curve,
+    non-canonical and (curve25519, cofactor 8) small-order points are BP_ERR_FORMAT, as ark-serialize's validation would
+    have rejected them before the reference ever held them as `G`."""
+    import ctypes as ct
+    from ark_bulletproofs_b200 import codec
+    from ark_bulletproofs_b200 import r1cs as R
+    cv = O.CURVES[curve]
+    ctx, gens = env(curve, 8)
+    q = cv.q
+    good = O.pt_mul(cv, 12345, cv.G)
+    off_curve = codec.enc_fe(good[0], q) + codec.enc_fe((good[1] + 1) % q, q)
+    # a Montgomery residue >= q (not canonical): x + q still fits 256 bits for all three base fields
+    raw_x = int.from_bytes(codec.enc_fe(good[0], q), "little")
+    bads = [off_curve]
+    if raw_x + q < 1 << 256:
+        bads.append((raw_x + q).to_bytes(32, "little") + codec.enc_fe(good[1], q))
+    if curve == "curve25519":
+        bads.append(codec.enc_fe(0, q) + codec.enc_fe(q - 1, q))                  # (0, -1): order 2
+        # an order-8 point times nothing: good + (0,-1) is on the curve but outside the prime-order subgroup
+        bads.append(codec.enc_point(O.pt_add(cv, good, (0, q - 1)), curve))
+    v = R.Verifier(ctx, R.Transcript(b"t"))
+    for b in bads:
+        var = R.BpVar()
+        assert v.lib.bp_verifier_commit(v.h, b, ct.byref(var)) == -8
+    v.commit(good)
+    v.commit(None)                                                               # the identity is a valid group element
+    # proof fields
+    proof, _ = gpu_prove_case(R, ctx, gens, "shuffle_fixed", {"inp": [5, 9, 2], "out": [2, 5, 9]}, curve)
+    for b in bads:
+        assert proof.lib.bp_proof_set_field(proof.h, 10, b) == -8
+    # generators
+    G = [O.pt_mul(cv, 100 + i, cv.G) for i in range(4)]
+    H = [O.pt_mul(cv, 200 + i, cv.G) for i in range(4)]
+    pc = O.PedersenGens(cv)
+    lib = ctx.lib
+    h = ct.c_void_p()
+    ok_args = [codec.enc_point(pc.B, curve), codec.enc_point(pc.B_blinding, curve), codec.enc_points(G, curve), codec.enc_points(H, curve)]
+    assert lib.bp_gens_from_points(ctx.h, *ok_args, 4, ct.byref(h)) == 0
+    lib.bp_gens_free(h)
+    for slot in range(4):
+        for b in bads:
+            args = list(ok_args)
+            args[slot] = b + args[slot][64:] if slot >= 2 else b
+            assert lib.bp_gens_from_points(ctx.h, *args, 4, ct.byref(h)) == -8
+
+
+def test_batch_verify_rejects_foreign_contexts(env):
+    """bp_batch_verify / bp_verifier_verify with a verifier or generators of another context: BP_ERR_ARG (their buffers live
+    on that context's stream)."""
+    from ark_bulletproofs_b200 import Context
+    from ark_bulletproofs_b200 import r1cs as R
+    curve = "secq256k1"
+    ctx, gens = env(curve, 8)
+    other = Context(curve, 0)
+    gens2 = R.Gens(other, 8)
+    kind, params = "shuffle_fixed", {"inp": [5, 9, 2], "out": [2, 5, 9]}
+    proof, coms = gpu_prove_case(R, ctx, gens, kind, params, curve)
+    v_other = gpu_verifier(R, other, kind, params, curve, coms)
+    with pytest.raises(R.BpError) as e:
+        R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), [(v_other, proof)], gens)
+    assert e.value.code == -1
+    with pytest.raises(R.BpError) as e:
+        R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), [(gpu_verifier(R, ctx, kind, params, curve, coms), proof)], gens2)
+    assert e.value.code == -1
+    with pytest.raises(R.BpError) as e:
+        gpu_verifier(R, ctx, kind, params, curve, coms).verify(proof, gens2)
+    assert e.value.code == -1
+    R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), [(gpu_verifier(R, ctx, kind, params, curve, coms), proof)], gens)
+    gpu_verifier(R, other, kind, params, curve, coms).verify(proof, gens2)
