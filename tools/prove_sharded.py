@@ -25,8 +25,14 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = Context(curve, local)
 ctx.set_timing(True)
+mode = os.environ.get("BP_COLL", "nccl")      # nccl: library-owned ncclAllGather (bp_ctx_init_nccl); callback: torch.distributed through bp_ctx_set_collective
 if world > 1:
-    ctx.set_collective(rank, world, torch_allgather(device=torch.device("cuda", local)))
+    if mode == "nccl":
+        ctx.init_nccl(rank, world)
+    else:
+        ctx.set_collective(rank, world, torch_allgather(device=torch.device("cuda", local)))
+_gold_path = os.path.join(ROOT, "tests", "golden", "large.json")
+GOLD = json.load(open(_gold_path)) if os.path.exists(_gold_path) else {}
 r = codec.MODULI[curve][1]
 for lg in lgs:
     N = 1 << lg
@@ -66,8 +72,11 @@ for lg in lgs:
         digs = [None] * world
         dist.all_gather_object(digs, digest)
         assert len(set(digs)) == 1, "ranks disagree on the proof bytes"
+    gold = GOLD.get("chain_2p%d" % lg)
+    if gold is not None:
+        assert digest == gold["sha256"], "proof differs from the oracle's golden bytes (tests/golden/large.json)"
     if rank == 0:
-        print(json.dumps({"lg_n": lg, "n_gpus": world, "prove_ms": round(float(t[0]), 2), "verify_ms": round(float(t[1]), 2), "gens_s": round(t_gens, 2),
+        print(json.dumps({"lg_n": lg, "n_gpus": world, "collective": mode if world > 1 else None, "golden": gold is not None, "prove_ms": round(float(t[0]), 2), "verify_ms": round(float(t[1]), 2), "gens_s": round(t_gens, 2),
                           "proof_sha256": digest, "prove_stages": {k: v_ for k, v_ in best[2].items() if v_},
                           "verify_stages": {k: v_ for k, v_ in best[3].items() if v_}}), flush=True)
     del gens
