@@ -141,6 +141,22 @@ class Context:
         self._check(self.lib.bp_msm_device(self.h, d_bases, d_scalars, n, out, ctypes.byref(ident)))
         return out.raw, bool(ident.value)
 
+    def bases_upload(self, bases_ptr_or_bytes, n: int):
+        """bp_bases_upload: returns an opaque handle (free with bases_free)."""
+        h = ctypes.c_void_p()
+        self._check(self.lib.bp_bases_upload(self.h, bases_ptr_or_bytes, n, ctypes.byref(h)))
+        return h
+
+    def bases_free(self, h):
+        self.lib.bp_bases_free(h)
+
+    def msm_bases(self, h, scalars_ptr_or_bytes, n: int, offset: int = 0):
+        """bp_msm_bases: bases resident on the GPU, scalars from host memory; returns (64-byte affine, is_identity)."""
+        out = ctypes.create_string_buffer(64)
+        ident = ctypes.c_int(0)
+        self._check(self.lib.bp_msm_bases(self.h, h, offset, scalars_ptr_or_bytes, n, out, ctypes.byref(ident)))
+        return out.raw, bool(ident.value)
+
     def points_sum(self, points):
         out = ctypes.create_string_buffer(64)
         ident = ctypes.c_int(0)

@@ -45,6 +45,10 @@ def load():
         "bp_ctx_launch_count": (u64, [vp]),
         "bp_msm": (i32, [vp, vp, vp, sz, vp, pi32]),
         "bp_msm_device": (i32, [vp, vp, vp, sz, vp, pi32]),
+        "bp_bases_upload": (i32, [vp, vp, sz, pvp]),
+        "bp_bases_free": (None, [vp]),
+        "bp_bases_device_ptr": (vp, [vp]),
+        "bp_msm_bases": (i32, [vp, vp, sz, vp, sz, vp, pi32]),
         "bp_msm_set_window": (i32, [vp, i32]),
         "bp_msm_set_tiny": (i32, [vp, i32]),
         "bp_msm_set_chunk": (i32, [vp, sz]),

@@ -8,6 +8,7 @@
 #include "ctx.cuh"
 #include "host/nccl_dyn.hpp"
 #include <new>
+#include <memory>
 
 // No C++ exception unwinds across the C ABI: every multi-statement entry point is a function-try-block.
 #define BP_ABI_CATCH catch (const std::bad_alloc&) { return BP_ERR_INTERNAL; } catch (...) { return BP_ERR_INTERNAL; }
@@ -17,7 +18,7 @@ int msm_dispatch(bp_ctx* ctx, const void* d_bases, const void* d_scalars, size_t
 int host_points_sum(int curve, const uint8_t* pts_xy, size_t n, uint8_t out_xy[64], int* out_is_identity);
 int synth_points_dispatch(bp_ctx* ctx, void* d_out, size_t n, uint64_t start);
 int msm_streamed_dispatch(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scalars, size_t n, const std::vector<size_t>& lo_of,
-                          const std::vector<size_t>& cnt_of, uint8_t out_xy[64], int* out_is_identity);
+                          const std::vector<size_t>& cnt_of, uint8_t out_xy[64], int* out_is_identity, const void* d_bases);
 }  // namespace bp
 
 extern "C" {
@@ -205,41 +206,79 @@ int bp_msm_device(bp_ctx* ctx, const void* d_bases_xy, const void* d_scalars, si
     return bp::msm_dispatch(ctx, d_bases_xy, d_scalars, n, out_xy, out_is_identity);
 } BP_ABI_CATCH
 
-int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) try {
-    if (!ctx || !out_xy || (n && (!bases_xy || !scalars))) return BP_ERR_ARG;
-    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+// bases_xy: host bases (d_bases == nullptr) or ignored when the bases are already on the device
+static int msm_host_scalars(bp_ctx* ctx, const uint8_t* bases_xy, const void* d_bases, const uint8_t* scalars, size_t n, uint8_t out_xy[64],
+                            int* out_is_identity) {
     // Large host-resident inputs are streamed in chunks: the H2D copy of chunk k+1 (copy stream) overlaps the kernels
     // of chunk k (compute stream), and every chunk adds into the one bucket array of the whole MSM
     // (bp::msm_run_streamed, msm_kernels.cuh). An MSM is a sum of independent terms, so chunking does not change the value.
     const size_t CHUNK = ctx->msm_chunk;
     if (n <= CHUNK + CHUNK / 2) {
         if (n) {
-            BP_CUDA_TRY(ctx, ctx->stage_bases.reserve(n * 64));
+            if (!d_bases) BP_CUDA_TRY(ctx, ctx->stage_bases.reserve(n * 64));
             BP_CUDA_TRY(ctx, ctx->stage_scalars.reserve(n * 32));
-            BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_bases.p, bases_xy, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+            if (!d_bases) BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_bases.p, bases_xy, n * 64, cudaMemcpyHostToDevice, ctx->stream));
             BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
         }
-        return bp::msm_dispatch(ctx, ctx->stage_bases.p, ctx->stage_scalars.p, n, out_xy, out_is_identity);
+        return bp::msm_dispatch(ctx, d_bases ? d_bases : ctx->stage_bases.p, ctx->stage_scalars.p, n, out_xy, out_is_identity);
     }
-    // Chunk schedule: the copy stream runs back to back (55 GB/s: 1.7 ms per 2^20 points), the kernels follow at ~2.4 ms
-    // per 2^20 points plus ~0.5 ms of slot levels per chunk. The first copy cannot be hidden, so the first chunk is small
-    // (CHUNK/4); large chunks are cheaper per point (longer runs per bucket, fewer slot levels), and chunk k+1 has arrived
-    // when chunk k is done as long as it is at most ~1.4x as large -- so the chunks grow by 1.5x, up to 2 CHUNK.
-    // 2^24 points with the default CHUNK = 2^22: 1M, 1.5M, 2.25M, 3.4M, 5.1M, 2.8M.
+    // Chunk schedule: the copy stream runs back to back (55 GB/s: 1.7 ms per 2^20 points, 0.6 ms when only the scalars
+    // move), the kernels follow at ~2.4 ms per 2^20 points plus ~0.5 ms of slot levels per chunk. The first copy cannot be
+    // hidden, so the first chunk is small (CHUNK/4); large chunks are cheaper per point (longer runs per bucket, fewer slot
+    // levels), and chunk k+1 has arrived when chunk k is done as long as it is at most ~1.4x as large (~4x with resident
+    // bases) -- so the chunks grow by 1.5x (3x), up to 2 CHUNK (4 CHUNK).
+    // 2^24 points with the default CHUNK = 2^22: 1M, 1.5M, 2.25M, 3.4M, 5.1M, 2.8M; with resident bases 1M, 3M, 9M, 3M.
     std::vector<size_t> lo_of, cnt_of;
     {
         size_t a = CHUNK / 4 ? CHUNK / 4 : 1, rem = n, lo = 0;
         if (const char* e = getenv("BP_MSM_FIRST_CHUNK")) { size_t v = strtoull(e, nullptr, 10); if (v) a = v; }
+        const size_t cap = d_bases ? 4 * CHUNK : 2 * CHUNK;
         while (rem > 0) {
             size_t take = a < rem ? a : rem;
             if (rem - take < a / 2) take = rem;
             lo_of.push_back(lo); cnt_of.push_back(take);
             lo += take; rem -= take;
-            a += a / 2 ? a / 2 : 1;
-            if (a > 2 * CHUNK) a = 2 * CHUNK;
+            a += d_bases ? 2 * a : (a / 2 ? a / 2 : 1);
+            if (a > cap) a = cap;
         }
     }
-    return bp::msm_streamed_dispatch(ctx, bases_xy, scalars, n, lo_of, cnt_of, out_xy, out_is_identity);
+    return bp::msm_streamed_dispatch(ctx, bases_xy, scalars, n, lo_of, cnt_of, out_xy, out_is_identity, d_bases);
+}
+
+int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) try {
+    if (!ctx || !out_xy || (n && (!bases_xy || !scalars))) return BP_ERR_ARG;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return msm_host_scalars(ctx, bases_xy, nullptr, scalars, n, out_xy, out_is_identity);
+} BP_ABI_CATCH
+
+// ---- bases resident on the device (every large MSM of the protocol is over fixed generators) ----
+struct bp_bases { bp_ctx* ctx; bp::DevBuf buf; size_t n; };
+int bp_bases_upload(bp_ctx* ctx, const uint8_t* bases_xy, size_t n, bp_bases** out) try {
+    if (!ctx || !out || (n && !bases_xy)) return BP_ERR_ARG;
+    *out = nullptr;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<bp_bases> b(new bp_bases{ctx, {}, n});
+    if (n) {
+        if (b->buf.reserve(n * 64) != cudaSuccess) { ctx->err = "bp_bases_upload: out of device memory"; return BP_ERR_CUDA; }
+        cudaError_t e = cudaMemcpyAsync(b->buf.p, bases_xy, n * 64, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { b->buf.release(); ctx->err = cudaGetErrorString(e); return BP_ERR_CUDA; }
+    }
+    *out = b.release();
+    return BP_OK;
+} BP_ABI_CATCH
+void bp_bases_free(bp_bases* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    b->buf.release();
+    delete b;
+}
+const void* bp_bases_device_ptr(const bp_bases* b) { return b ? b->buf.p : nullptr; }
+int bp_msm_bases(bp_ctx* ctx, const bp_bases* bases, size_t offset, const uint8_t* scalars, size_t n, uint8_t out_xy[64], int* out_is_identity) try {
+    if (!ctx || !bases || !out_xy || bases->ctx != ctx || (n && !scalars)) return BP_ERR_ARG;
+    if (offset > bases->n || n > bases->n - offset) return BP_ERR_LEN;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return msm_host_scalars(ctx, nullptr, n ? (const uint8_t*)bases->buf.p + offset * 64 : nullptr, scalars, n, out_xy, out_is_identity);
 } BP_ABI_CATCH
 
 int bp_points_sum(bp_ctx* ctx, const uint8_t* points_xy, size_t n, uint8_t out_xy[64], int* out_is_identity) try {

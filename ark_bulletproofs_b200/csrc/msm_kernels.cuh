@@ -706,7 +706,8 @@ int msm_run(bp_ctx* ctx, const affine* d_bases, const fe* d_scalars, size_t n, u
 // digits -> sort -> accumulate<ACC> -> slot levels<ACC> per chunk; reduce, window sums and the host Horner once.
 template <class C>
 int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scalars, size_t n, const std::vector<size_t>& lo_of,
-                     const std::vector<size_t>& cnt_of, uint8_t out_xy[64], int* out_is_identity) {
+                     const std::vector<size_t>& cnt_of, uint8_t out_xy[64], int* out_is_identity, const affine* d_bases = nullptr) {
+    // d_bases != nullptr: the bases already live on the device (bp_bases, e.g. generators) and only the scalars stream
     cudaStream_t st = ctx->stream;
     if (n > MSM_IDX_MASK) return BP_ERR_LEN;
     const size_t nchunks = lo_of.size();
@@ -716,7 +717,7 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
     const size_t max_entries = (maxc * (size_t)p.W + 63) & ~(size_t)63;   // 256-byte aligned halves of the double buffers
     // the whole input is staged (96 B per point: 1.6 GB at 2^24, 26 GB at the 2^28 limit of the pair format -- HBM has
     // 180 GB), so the copy stream runs back to back from the first byte to the last and never waits for a kernel
-    BP_CUDA_TRY(ctx, ctx->stage_bases.reserve(n * 64));
+    if (!d_bases) BP_CUDA_TRY(ctx, ctx->stage_bases.reserve(n * 64));
     BP_CUDA_TRY(ctx, ctx->stage_scalars.reserve(n * 32));
     BP_CUDA_TRY(ctx, ctx->keys_a.reserve(max_entries * 4));
     BP_CUDA_TRY(ctx, ctx->keys_b.reserve(2 * max_entries * 4));     // sorted pairs: one buffer per chunk parity
@@ -779,7 +780,8 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
     for (size_t k = 0; k < nchunks; k++) {
         BP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sc.copied[k], cudaEventDisableTiming));
         const size_t lo = lo_of[k], cnt = cnt_of[k];
-        BP_CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->stage_bases.p + lo * 64, h_bases + lo * 64, cnt * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (!d_bases)
+            BP_CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->stage_bases.p + lo * 64, h_bases + lo * 64, cnt * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
         BP_CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->stage_scalars.p + lo * 32, h_scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
         BP_CUDA_TRY(ctx, cudaEventRecord(sc.copied[k], ctx->copy_stream));
     }
@@ -790,7 +792,7 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
         uint32_t* skeys = ctx->keys_b.as<uint32_t>() + (size_t)s * max_entries;
         uint32_t* svals = ctx->vals_b.as<uint32_t>() + (size_t)s * max_entries;
         MsmJob job;
-        job.add(ctx->stage_bases.as<affine>() + lo, ctx->stage_scalars.as<fe>() + lo, cnt, 0);
+        job.add((d_bases ? d_bases : ctx->stage_bases.as<affine>()) + lo, ctx->stage_scalars.as<fe>() + lo, cnt, 0);
         MsmPlan q = make_plan(cnt, 1, p.c, ctx->sm_count);   // same c, W, nb, key_bits; L and T of this chunk
         // prep
         BP_CUDA_TRY(ctx, cudaStreamWaitEvent(sc.prep, sc.copied[k], 0));

@@ -25,6 +25,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL's own log lines (e.g. "NCCL version ..." when NCCL_DEBUG is set by the environment) must not share stdout with the
+# JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 CURVE = "secq256k1"
 METRIC = "secq256k1_msm_mpoints_per_s"
@@ -491,6 +494,20 @@ def main():
     assert res_e2e == ref, "host-buffer path disagrees with the device-resident path"
     e2e_val = world * n / (ms_e2e / args.steps * 1e-3) / 1e6
 
+    # the same MSM with the bases resident on the GPU (bp_bases_upload; the protocol's large MSMs are over fixed generators):
+    # only the 32-byte scalars cross PCIe inside the timed region
+    hb = ctx.bases_upload(h_pts.data_ptr(), n)
+
+    def step_resident():
+        return combine(*ctx.msm_bases(hb, h_sc.data_ptr(), n))
+    step_resident()
+    ms_res, res_res, _, _ = timed(step_resident, args.steps)
+    assert res_res == ref, "resident-bases path disagrees with the device-resident path"
+    ctx.bases_free(hb)
+    e2e_res = {"value": round(world * n / (ms_res / args.steps * 1e-3) / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": n * 32,
+               "d2h_bytes_per_step": 64 + phases["windows"] * 128, "ms_per_step": round(ms_res / args.steps, 4),
+               "api": "bp_msm_bases (C ABI; bases uploaded once with bp_bases_upload, scalars in pinned host memory)"}
+
     # BASELINE config 1: the MSM sweep 2^12 .. 2^24 on one GPU (device-resident inputs: prefixes of the same buffers)
     sweep = None
     if world == 1 and not args.no_sweep:
@@ -590,6 +607,7 @@ def main():
                    "parallelism": "msm-shard x%d + all-gather of 64 B partial points" % world},
         "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 64 + phases["windows"] * 128,
                 "ms_per_step": round(ms_e2e / args.steps, 4), "api": "bp_msm (C ABI, pinned host buffers)"},
+        "e2e_resident_bases": e2e_res,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": round(achieved / 1e12, 4), "peak": round(peak / 1e12, 4),

@@ -69,6 +69,16 @@ int bp_msm(bp_ctx* ctx, const uint8_t* bases_xy, const uint8_t* scalars, size_t 
 /* Same, with bases and scalars already resident in this context's GPU memory. */
 int bp_msm_device(bp_ctx* ctx, const void* d_bases_xy, const void* d_scalars, size_t n, uint8_t out_xy[64],
                   int* out_is_identity);
+/* Bases resident on the GPU, scalars in host memory: every large MSM of the protocol is over the fixed generator tables
+ * (src/generators.rs:150-183), so a caller uploads them once (bp_bases_upload) and each bp_msm_bases call moves only the
+ * 32-byte scalars -- streamed in growing chunks while the chunks already there are accumulated, like bp_msm. Computes
+ * sum_i scalars[i] * bases[offset + i]. */
+typedef struct bp_bases bp_bases;
+int bp_bases_upload(bp_ctx* ctx, const uint8_t* bases_xy, size_t n, bp_bases** out);
+void bp_bases_free(bp_bases* b);
+const void* bp_bases_device_ptr(const bp_bases* b);
+int bp_msm_bases(bp_ctx* ctx, const bp_bases* bases, size_t offset, const uint8_t* scalars, size_t n, uint8_t out_xy[64],
+                 int* out_is_identity);
 /* Per-phase device timing of the last MSM (cudaEvents on the context's stream), for the roofline
  * numbers in bench.py: phase_ms[0..4] = digits, sort, accumulate, partial reduction, bucket
  * reduction + window sums; *c / *windows / *entries describe the Pippenger plan that ran. */

@@ -92,6 +92,19 @@ def test_msm_closed_form(ctx, lg_n, kind):
     idn = ctypes.c_int(0)
     ctx._check(ctx.lib.bp_msm(ctx.h, h_pts.data_ptr(), h_sc.data_ptr(), n, out, ctypes.byref(idn)))
     assert _dec(out.raw, bool(idn.value)) == want, "bp_msm (host buffers) differs from the closed form (n = 2^%d, %s)" % (lg_n, kind)
+    # bases resident on the GPU (bp_bases_upload), scalars streamed from the host
+    hb = ctx.bases_upload(h_pts.data_ptr(), n)
+    try:
+        assert _dec(*ctx.msm_bases(hb, h_sc.data_ptr(), n)) == want, "bp_msm_bases differs from the closed form (n = 2^%d, %s)" % (lg_n, kind)
+        if kind == "uniform":
+            # a window of the resident table: points [off, off + m) with the first m scalars
+            off, m = n // 4 + 3, n // 2
+            w2 = _closed_form(sc[:m * 32], m, start + off)
+            assert _dec(*ctx.msm_bases(hb, h_sc.data_ptr(), m, offset=off)) == w2
+            with pytest.raises(Exception):
+                ctx.msm_bases(hb, h_sc.data_ptr(), n, offset=1)          # out of range: BP_ERR_LEN
+    finally:
+        ctx.bases_free(hb)
     if lg_n == 20 and kind in ("uniform", "all_equal"):
         # forced small chunks: many chunks adding into one bucket array
         ctx.set_chunk(1 << 17)
