@@ -330,6 +330,57 @@ def batch_verify_bench(ctx, local_rank, rank, world, lg_n, count, nctx, dist, to
                     "%d distinct proofs repeated" % (count, distinct)}
 
 
+def prover_throughput_bench(local_rank, lg_n, concurrencies, golden_sha=None):
+    """North star "absolute ms and proofs/s": one proof keeps the GPU idle most of the time (the serial TranscriptRng Keccak
+    chain runs on one host core), so throughput comes from several provers -- one context, stream and host thread each --
+    sharing the GPU: the Keccak chains of different proofs run on different cores while the GPU works on another proof's
+    MSMs and folds. Every prover proves the same SEED-A chain statement; all proofs must be byte-identical."""
+    import hashlib
+    from ark_bulletproofs_b200 import Context, codec
+    from ark_bulletproofs_b200 import r1cs as R
+    N = 1 << lg_n
+    r = codec.MODULI[CURVE][1]
+    wit = R.ChaChaRng(bytes([3] * 32))
+    x0_raw = wit.scalars_raw(CURVE, 1)
+    ks_raw = wit.scalars_raw(CURVE, N)
+    x0 = codec.dec_fe(x0_raw, r)
+    kmax = max(concurrencies)
+    ctxs = [Context(CURVE, local_rank) for _ in range(kmax)]
+    gens = [R.Gens(c, N) for c in ctxs]
+
+    def one(k):
+        rng = R.ChaChaRng(bytes(range(32)))
+        p = R.Prover(ctxs[k], gens[k], R.Transcript(b"ChainCircuit"))
+        _, var = p.commit(x0, rng.scalar(CURVE))
+        p.chain_circuit_raw(var, N, ks_raw, x0_raw)
+        return hashlib.sha256(p.prove(rng).to_bytes()).hexdigest()
+    ref = one(0)
+    if golden_sha is not None:
+        assert ref == golden_sha, "proof differs from the oracle's golden bytes"
+    out = []
+    for conc in concurrencies:
+        per = max(3, 24 // conc)
+        digs = [None] * conc
+
+        def work(k):
+            d = set()
+            for _ in range(per):
+                d.add(one(k))
+            digs[k] = d
+        th = [threading.Thread(target=work, args=(k,)) for k in range(conc)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        dt = time.perf_counter() - t0
+        assert all(d == {ref} for d in digs), "concurrent provers disagree on the proof bytes"
+        out.append({"provers": conc, "proofs": conc * per, "proofs_per_s": round(conc * per / dt, 2), "ms_per_proof": round(dt * 1e3 / (conc * per), 2)})
+    return {"multipliers": "2^%d" % lg_n, "host_cores": os.cpu_count(), "runs": out, "byte_identical": True,
+            "golden": golden_sha is not None,
+            "note": "wall time including circuit construction; one bp_ctx (stream, scratch, generator tables) and one host thread per prover"}
+
+
 def other_curve_bench(curve, lg_n):
     """BASELINE config 5, second half: zorro / curve25519 R1CS prove + verify of the chain circuit at 2^lg_n multipliers."""
     from ark_bulletproofs_b200 import Context, codec
@@ -379,6 +430,7 @@ def main():
     ap.add_argument("--batch-verify", default="16,1024,4", help="lg multipliers, proofs, contexts per GPU of the batch-verification measurement (empty = skip)")
     ap.add_argument("--other-curves", default="zorro,curve25519", help="curves of the 2^16 prove/verify measurement at N = 1 (empty = skip)")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--prover-throughput", default="16:1,4,8,16", help="lg multipliers : concurrent provers of the proofs/s measurement at N = 1 (empty = skip)")
     ap.add_argument("--shuffle-k", type=int, default=1024, help="k of the reference's own k-shuffle bench, reported next to r1cs (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -578,6 +630,12 @@ def main():
         blg, bcount, bctx = [int(x) for x in args.batch_verify.split(",")]
         batch = batch_verify_bench(ctx if world == 1 else Context(CURVE, local_rank), local_rank, rank, world, blg, bcount, bctx,
                                    dist if world > 1 else None, torch)
+    throughput = None
+    if world == 1 and args.prover_throughput:
+        tlg, tcs = args.prover_throughput.split(":")
+        gpath = os.path.join(ROOT, "tests", "golden", "large.json")
+        gold = json.load(open(gpath)).get("chain_2p%s" % tlg, {}).get("sha256") if os.path.exists(gpath) else None
+        throughput = prover_throughput_bench(local_rank, int(tlg), [int(x) for x in tcs.split(",")], gold)
     others = None
     if world == 1 and args.other_curves:
         others = [other_curve_bench(c, 16) for c in args.other_curves.split(",") if c]
@@ -636,6 +694,8 @@ def main():
         line["batch_verify"] = batch
     if others is not None:
         line["other_curves"] = others
+    if throughput is not None:
+        line["prover_throughput"] = throughput
     if r1cs is not None:
         line["r1cs"] = r1cs
     if world == 1 and not args.no_cpu_baseline:
