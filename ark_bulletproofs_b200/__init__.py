@@ -116,6 +116,9 @@ class Context:
     def set_chunk(self, points: int):
         self._check(self.lib.bp_msm_set_chunk(self.h, points))
 
+    def set_affine_rounds(self, rounds: int, min_entries: int = 0):
+        self._check(self.lib.bp_msm_set_affine_rounds(self.h, rounds, min_entries))
+
     def set_tiny(self, max_terms: int):
         self._check(self.lib.bp_msm_set_tiny(self.h, max_terms))
 

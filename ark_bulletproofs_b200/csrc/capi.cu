@@ -188,6 +188,13 @@ int bp_ipa_set_geometric(bp_ctx* ctx, int enable) try {
     return BP_OK;
 } BP_ABI_CATCH
 
+int bp_msm_set_affine_rounds(bp_ctx* ctx, int rounds, size_t min_entries) try {
+    if (!ctx || rounds < 0 || rounds > 6) return BP_ERR_ARG;
+    ctx->msm_affine_rounds = rounds;
+    if (min_entries) ctx->msm_affine_min_entries = min_entries;
+    return BP_OK;
+} BP_ABI_CATCH
+
 int bp_msm_set_tiny(bp_ctx* ctx, int max_terms) try {
     if (!ctx || max_terms < 0 || max_terms > 4096) return BP_ERR_ARG;
     ctx->msm_tiny_max = max_terms;

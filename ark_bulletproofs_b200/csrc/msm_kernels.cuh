@@ -235,6 +235,81 @@ __global__ void __launch_bounds__(128, BP_ACC_MIN_BLOCKS) msm_accumulate_kernel(
     }
 }
 
+// ---- 3a. batched-affine pre-addition ("pair rounds") ---------------------------------------------------------------
+// A mixed XYZZ addition costs 8M + 2S; an affine addition costs one inversion + 2M + 1S, and Montgomery's trick shares
+// the inversion: 3 more multiplications per addition plus one Fermat inversion (~450 modmul on secq256k1) per batch --
+// 6 + 450/K modmul per addition. Before the XYZZ accumulation, round r = 0, 1, ... adds the neighbours (i, i + 2^r) of
+// the *sorted* pair list that lie in the same bucket, K pairs per thread sharing one inversion:
+//   pass A  walks the thread's pairs forward:  dx_j = x_Q - x_P, prefix products into a coalesced scratch column;
+//   pass B  walks them backward: 1/dx_j from the running inverse, lambda, (x3, y3) -> pairpts[i / 2].
+// The list keeps its length and its keys: the left entry's value becomes a reference to pairpts (segment 7 of the job),
+// the right one a reference to a zero point, which the accumulate kernel's mixed addition skips on its identity test --
+// so msm_accumulate_kernel runs unchanged on a list whose real entries have halved per round. Pairs the affine law
+// cannot add (P = +-Q: dx = 0; an identity base; x = 0) are simply left for the XYZZ accumulation, which handles every
+// exceptional case. Short-Weierstrass curves only (the twisted Edwards law has no cheap affine form).
+// Pairs are dealt to the threads round-robin (pair p = j * T + t): neighbouring lanes read neighbouring pairs (coalesced
+// keys, values and prefix products), every thread gets the same number of pairs K = ceil(npairs / T), and T is a whole
+// number of resident waves -- the first version (contiguous 512-pair chunks per thread) ran 2.25 waves of long threads at
+// 2^24 points and left the multiplier 47 % busy (profiles/r2_ncu_pair_affine_lg22_v1.txt).
+template <class C>
+__global__ void __launch_bounds__(128, 5) msm_pair_affine_kernel(const uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, size_t M, uint32_t stride,
+                                                                 size_t npairs, int K, size_t T, const __grid_constant__ MsmJob job,
+                                                                 affine* __restrict__ pairpts, fe* __restrict__ pre, uint32_t hole_val) {
+    using F = Fp<typename C::Fq>;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    auto src = [&](uint32_t v) -> const affine* { return job.bases[(v >> 28) & 7u] + (v & MSM_IDX_MASK); };
+    // dx of pair j, or false when the pair is not added in this round (identical decisions in both passes)
+    auto pair_dx = [&](int j, size_t& left, uint32_t& v0, uint32_t& v1, fe& px, fe& qx, fe& dx) -> bool {
+        const size_t pidx = (size_t)j * T + t;
+        if (pidx >= npairs) return false;
+        left = pidx * 2 * stride;
+        const size_t right = left + stride;
+        if (right >= M) return false;
+        const uint32_t k0 = keys[left];
+        if (k0 == INVALID_KEY || k0 != keys[right]) return false;
+        v0 = vals[left];
+        v1 = vals[right];
+        if (v0 == hole_val || v1 == hole_val) return false;
+        px = ld_fe_rw(&src(v0)->x);
+        qx = ld_fe_rw(&src(v1)->x);
+        if (F::is_zero(px) || F::is_zero(qx)) return false;      // the identity (0,0), or a point with x = 0: left to the XYZZ path
+        dx = F::sub(qx, px);
+        return !F::is_zero(dx);                                  // P = +-Q
+    };
+    fe prod = F::one();
+#pragma unroll 1
+    for (int j = 0; j < K; j++) {
+        size_t left;
+        uint32_t v0, v1;
+        fe px, qx, dx;
+        if (!pair_dx(j, left, v0, v1, px, qx, dx)) continue;
+        st_fe(pre + (size_t)j * T + t, prod);
+        prod = F::mul(prod, dx);
+    }
+    fe inv = F::inv(prod);
+#pragma unroll 1
+    for (int j = K - 1; j >= 0; j--) {
+        size_t left;
+        uint32_t v0, v1;
+        fe px, qx, dx;
+        if (!pair_dx(j, left, v0, v1, px, qx, dx)) continue;
+        fe py = ld_fe_rw(&src(v0)->y), qy = ld_fe_rw(&src(v1)->y);
+        if (v0 >> 31) py = F::neg(py);
+        if (v1 >> 31) qy = F::neg(qy);
+        const fe invj = F::mul(inv, ld_fe_rw(pre + (size_t)j * T + t));
+        inv = F::mul(inv, dx);
+        const fe lam = F::mul(F::sub(qy, py), invj);
+        const fe x3 = F::sub(F::sub(F::sqr(lam), px), qx);
+        const fe y3 = F::sub(F::mul(lam, F::sub(px, x3)), py);
+        affine* o = pairpts + (left >> 1);
+        st_fe(&o->x, x3);
+        st_fe(&o->y, y3);
+        vals[left] = (7u << 28) | (uint32_t)(left >> 1);
+        vals[left + stride] = hole_val;
+    }
+}
+
 // level >= 2: dense sorted (key, XYZZ partial) slots -> run sums
 template <class C, bool ACC = false>
 __global__ void __launch_bounds__(128) msm_partials_level_kernel(const uint32_t* __restrict__ in_keys, const xyzz* __restrict__ in_pts,
@@ -514,6 +589,32 @@ int msm_fold_slots(bp_ctx* ctx, size_t slots1, cudaStream_t st) {
     return BP_OK;
 }
 
+// Batched-affine pair rounds over a sorted pair list (see msm_pair_affine_kernel); `job` gains segment 7 = the pair points.
+template <class C>
+int msm_pair_rounds(bp_ctx* ctx, MsmJob& job, const uint32_t* keys, uint32_t* vals, size_t entries, cudaStream_t st) {
+    if (C::KIND != 0 || ctx->msm_affine_rounds <= 0 || job.nseg > 7 || entries < ctx->msm_affine_min_entries) return BP_OK;
+    const size_t npairs = (entries + 1) / 2;
+    if (npairs + 1 > MSM_IDX_MASK) return BP_OK;
+    BP_CUDA_TRY(ctx, ctx->pairpts.reserve((npairs + 1) * sizeof(affine)));
+    BP_CUDA_TRY(ctx, ctx->pairpre.reserve(npairs * sizeof(fe)));
+    affine* pp = ctx->pairpts.as<affine>();
+    BP_CUDA_TRY(ctx, cudaMemsetAsync(pp + npairs, 0, sizeof(affine), st));       // the zero point every hole refers to
+    job.bases[7] = pp;
+    const uint32_t hole = (7u << 28) | (uint32_t)npairs;
+    for (int r = 0; r < ctx->msm_affine_rounds; r++) {
+        const uint32_t stride = 1u << r;
+        const size_t np = (entries + 2 * (size_t)stride - 1) / (2 * (size_t)stride);      // pairs (i, i + stride), i = 2 * stride * p
+        // whole resident waves (5 blocks of 128 threads per SM), at least ~256 pairs per thread to amortise the inversion
+        size_t T = (size_t)ctx->sm_count * 5 * 128;
+        while (T * 2 * 320 <= np) T *= 2;
+        if (T > np) T = np;
+        const int K = (int)((np + T - 1) / T);
+        msm_pair_affine_kernel<C><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(keys, vals, entries, stride, np, K, T, job, pp, ctx->pairpre.as<fe>(), hole);
+        BP_LAUNCH_CHECK(ctx);
+    }
+    return BP_OK;
+}
+
 // Runs the batch; out_xy / out_is_identity have job.nmsm entries.
 template <class C>
 int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_is_identity) {
@@ -556,6 +657,12 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
         }
     }
     MsmPlan p = make_plan(n, job.nmsm, ctx->force_c, ctx->sm_count);
+    if (C::KIND == 0 && ctx->msm_affine_rounds > 0 && job.nseg <= 7 && p.entries >= ctx->msm_affine_min_entries) {
+        // after r pair rounds only ~1/2^r of the entries are real additions: keep the work per accumulate thread
+        int L2 = p.L << ctx->msm_affine_rounds;
+        p.L = L2 > 512 ? 512 : L2;
+        p.T = (p.entries + p.L - 1) / p.L;
+    }
     const int NW = job.nmsm * p.W;   // windows over the whole batch
     BP_CUDA_TRY(ctx, ctx->keys_a.reserve(p.entries * 4));
     BP_CUDA_TRY(ctx, ctx->keys_b.reserve(p.entries * 4));
@@ -592,8 +699,10 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
     BP_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, nbuckets * sizeof(xyzz), st));
     uint32_t* pk = ctx->part_keys.as<uint32_t>();
     xyzz* pp = ctx->part_pts.as<xyzz>();
+    MsmJob ajob = job;
+    if (int rc = msm_pair_rounds<C>(ctx, ajob, ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, st)) return rc;
     msm_accumulate_kernel<C><<<(unsigned)((p.T + 127) / 128), 128, 0, st>>>(ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, p.L,
-                                                                            p.T, job, ctx->buckets.as<xyzz>(), pk, pp);
+                                                                            p.T, ajob, ctx->buckets.as<xyzz>(), pk, pp);
     BP_LAUNCH_CHECK(ctx);
     mark(2);
     if (int rc = msm_fold_slots<C, false>(ctx, slots1, st)) return rc;

@@ -195,3 +195,55 @@ def test_msm_streamed_other_curves(curve):
     want = O.msm(cv, pts, sc)
     c.set_chunk(128)
     assert c.msm(pts, sc) == want
+
+
+@pytest.mark.parametrize("rounds", [1, 2, 3, 5])
+def test_msm_affine_pair_rounds_edge_cases(_ctx, rounds):
+    """Batched-affine pair rounds (msm_pair_affine_kernel) forced on small inputs: every exceptional pair is left to the
+    XYZZ path -- a repeated point (P + P), P and -P (in one bucket run, all-equal scalars), identity bases, zero scalars --
+    and the result equals the oracle's."""
+    cv = O.SECQ256K1
+    rnd = random.Random(900 + rounds)
+    n = 1500
+    pts = _points(cv, n, rnd)
+    same = rnd.randrange(cv.r)
+    pm = [pts[i // 2] if i % 2 == 0 else O.pt_neg(cv, pts[i // 2]) for i in range(n)]
+    withid = list(pts)
+    for i in range(0, n, 5):
+        withid[i] = None
+    cases = [
+        (pts, [rnd.randrange(cv.r) for _ in range(n)]),
+        (pts, [same] * n),                                   # one bucket per window: long runs, sums collide with later bases
+        ([pts[3]] * n, [same] * n),                          # all pairs are P + P
+        (pm, [same] * n),                                    # neighbours are P and -P
+        (withid, [same] * n),
+        (pts, [0 if i % 2 else same for i in range(n)]),
+        (pts, [cv.r - 1] * n),
+        (pts[:7], [same] * 7),
+    ]
+    _ctx.set_tiny(0)
+    _ctx.set_affine_rounds(rounds, 1)
+    try:
+        for bases, sc in cases:
+            assert _ctx.msm(bases, sc) == O.msm(cv, bases, sc)
+            _ctx.set_window(5)
+            try:
+                assert _ctx.msm(bases, sc) == O.msm(cv, bases, sc)
+            finally:
+                _ctx.set_window(0)
+    finally:
+        _ctx.set_affine_rounds(0, 1 << 22)
+        _ctx.set_tiny(768)
+
+
+def test_msm_affine_pair_rounds_zorro():
+    from ark_bulletproofs_b200 import Context
+    cv = O.ZORRO
+    c = Context("zorro", 0)
+    rnd = random.Random(31)
+    n = 700
+    pts = _points(cv, n, rnd)
+    c.set_tiny(0)
+    c.set_affine_rounds(2, 1)
+    for sc in ([rnd.randrange(cv.r) for _ in range(n)], [12345] * n):
+        assert c.msm(pts, sc) == O.msm(cv, pts, sc)

@@ -120,6 +120,24 @@ def test_msm_closed_form(ctx, lg_n, kind):
         assert _dec(ref, ref == bytes(64)) == want, "oracle/c/bp_ref.c differs from the closed form"
 
 
+@pytest.mark.parametrize("lg_n,rounds", [(20, 1), (20, 3), (24, 2), (24, 4)])
+@pytest.mark.parametrize("kind", ["uniform", "all_equal", "half_zero"])
+def test_msm_closed_form_affine_rounds(ctx, lg_n, rounds, kind):
+    """The batched-affine pair rounds (bp_msm_set_affine_rounds) in front of the XYZZ accumulation, at the bench sizes."""
+    import torch
+    n, start = 1 << lg_n, 11
+    pts = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    ctx.synth_points_device(pts.data_ptr(), n, start)
+    sc = _scalar_bytes(kind, n, 500 + lg_n + rounds)
+    torch.cuda.synchronize()
+    want = _closed_form(sc, n, start)
+    ctx.set_affine_rounds(rounds, 1 << 16)
+    try:
+        assert _dec(*ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n)) == want
+    finally:
+        ctx.set_affine_rounds(0, 1 << 22)
+
+
 @pytest.mark.parametrize("c", [12, 16, 18])
 def test_msm_closed_form_forced_windows(ctx, c):
     """Other window widths at 2^18 points (segment sizes 4..32 of the bucket reduction, L < 64)."""
