@@ -20,6 +20,7 @@ using xyzz = xyzz_t<fe>;       // 128 B in HBM
 
 template <class C, class F_ = Fp<typename C::Fq>>
 struct SW {
+    static constexpr bool IS_TE = false;
     using F = F_;
     using el = typename F::el;
     using aff = affine_t<el>;
@@ -192,6 +193,7 @@ struct SW {
 // ABI: aff (x,y); the identity is (0,1) and, on input, also (0,0).
 template <class C, class F_ = Fp<typename C::Fq>>
 struct TE {
+    static constexpr bool IS_TE = true;
     using F = F_;
     using el = typename F::el;
     using aff = affine_t<el>;

@@ -181,6 +181,67 @@ struct ScalarBits { uint32_t w[8]; };   // canonical (non-Montgomery) little-end
 // (fG, fH) into the MSM scalars of the next round, so only one scalar multiplication per output
 // point remains. Threads [0,count) fold (L0,R0) with kappa0, threads [count,2*count) fold (L1,R1)
 // with kappa1 (G and H in one launch).
+// XYZZ / extended -> affine for a whole 128-thread block with ONE field inversion (Montgomery's trick across the block).
+// A fold output costs ~2 250 modmul of double-and-add and, with a private Fermat inversion, another ~450: one sixth of the
+// kernel. Here every thread contributes z_i = ZZ*ZZZ (Z on the twisted Edwards curve), the warps build
+// prefix and suffix products with shuffles (5 + 5 multiplications per thread), warp 0 inverts the product of the four
+// warp totals -- one inversion stream for 128 outputs; the other warps wait at the barrier and leave the multiplier to
+// the other resident blocks -- and 1/z_i = 1/total * (product of everything but z_i). Threads without an output, and
+// identity points, take part with z = 1. Must be reached by all 128 threads of the block.
+__device__ __forceinline__ fe shfl_fe(const fe& v, int src_lane) {
+    fe r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = __shfl_sync(0xFFFFFFFFu, v.v[k], src_lane);
+    return r;
+}
+template <class E>
+__device__ __forceinline__ affine block_to_affine_128(const xyzz& p, bool valid) {
+    using F = typename E::F;
+    __shared__ fe sh_tot[4];
+    __shared__ fe sh_inv[4];
+    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+    const bool live = valid && !E::is_identity(p);
+    const bool te = E::IS_TE;
+    const fe z = live ? (te ? p.zz : F::mul(p.zz, p.zzz)) : F::one();
+    fe pre = z, suf = z;                                  // inclusive prefix / suffix products inside the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const fe up = shfl_fe(pre, lane >= d ? lane - d : lane);
+        const fe dn = shfl_fe(suf, lane + d < 32 ? lane + d : lane);
+        if (lane >= d) pre = F::mul(pre, up);
+        if (lane + d < 32) suf = F::mul(suf, dn);
+    }
+    if (lane == 31) sh_tot[warp] = pre;
+    __syncthreads();
+    if (warp == 0) {
+        const fe t0 = sh_tot[0], t1 = sh_tot[1], t2 = sh_tot[2], t3 = sh_tot[3];
+        const fe t01 = F::mul(t0, t1), t23 = F::mul(t2, t3);
+        const fe inv = F::inv(F::mul(t01, t23));          // the one inversion of the block
+        if (lane < 4) {
+            // 1 / t_lane = inv * (product of the other three warp totals)
+            const fe others = lane == 0 ? F::mul(t1, t23) : lane == 1 ? F::mul(t0, t23) : lane == 2 ? F::mul(t01, t3) : F::mul(t01, t2);
+            sh_inv[lane] = F::mul(inv, others);
+        }
+    }
+    __syncthreads();
+    // everything in this warp but z_i: exclusive prefix (lane - 1) times exclusive suffix (lane + 1)
+    const fe pe = shfl_fe(pre, lane > 0 ? lane - 1 : 0), se = shfl_fe(suf, lane < 31 ? lane + 1 : 31);
+    fe w = sh_inv[warp];
+    if (lane > 0) w = F::mul(w, pe);
+    if (lane < 31) w = F::mul(w, se);
+    affine r = E::affine_identity();
+    if (live) {
+        if (te) {
+            r.x = F::mul(p.x, w);
+            r.y = F::mul(p.y, w);
+        } else {
+            r.x = F::mul(p.x, F::mul(w, p.zzz));          // 1/ZZ = ZZZ / (ZZ*ZZZ)
+            r.y = F::mul(p.y, F::mul(w, p.zz));
+        }
+    }
+    return r;
+}
+
 template <class C>
 __global__ void __launch_bounds__(128) ipa_fold_points_uniform_kernel(const affine* __restrict__ L0, const affine* __restrict__ R0,
                                                                       affine* __restrict__ out0, const affine* __restrict__ L1,
@@ -190,7 +251,8 @@ __global__ void __launch_bounds__(128) ipa_fold_points_uniform_kernel(const affi
                                                                       const __grid_constant__ ScalarBits k1x, size_t cross_lo, size_t cross_hi, ShardIdx sh) {
     using E = GroupLaw<C>;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * count) return;
+    const bool valid = t < 2 * count;
+    if (!valid) t = 0;                // keeps the block together for the shared inversion at the end
     const bool second = t >= count;   // count is a multiple of the block size or the block is split; either way correct
     size_t i = second ? t - count : t;
     const affine* L = second ? L1 : L0;
@@ -211,7 +273,8 @@ __global__ void __launch_bounds__(128) ipa_fold_points_uniform_kernel(const affi
     }
     affine pl = ld_affine(L + i);
     E::madd(acc, pl);
-    affine r = E::to_affine(acc);
+    affine r = block_to_affine_128<E>(acc, valid);
+    if (!valid) return;
     st_fe(&out[i].x, r.x);
     st_fe(&out[i].y, r.y);
 }
@@ -232,7 +295,8 @@ __global__ void __launch_bounds__(128) ipa_fold_points_glv_kernel(const affine* 
     using E = GroupLaw<C>;
     using F = Fp<typename C::Fq>;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * count) return;
+    const bool valid = t < 2 * count;
+    if (!valid) t = 0;
     const bool second = t >= count;
     size_t i = second ? t - count : t;
     const affine* L = second ? L1 : L0;
@@ -263,7 +327,8 @@ __global__ void __launch_bounds__(128) ipa_fold_points_glv_kernel(const affine* 
     }
     affine pl = ld_affine(L + i);
     E::madd(acc, pl);
-    affine r = E::to_affine(acc);
+    affine r = block_to_affine_128<E>(acc, valid);
+    if (!valid) return;
     st_fe(&out[i].x, r.x);
     st_fe(&out[i].y, r.y);
 }
@@ -281,7 +346,8 @@ __global__ void __launch_bounds__(128) ipa_fold_points_joint_kernel(const affine
     using Fr = Fp<typename C::Fr>;
     // h = global half length (factor vectors are replicated), hl = local half length (points are this rank's shard)
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * hl) return;
+    const bool valid = t < 2 * hl;
+    if (!valid) t = 0;
     const bool second = t >= hl;
     size_t i = second ? t - hl : t;
     const size_t gi = i * sh.P + sh.g;
@@ -306,7 +372,8 @@ __global__ void __launch_bounds__(128) ipa_fold_points_joint_kernel(const affine
             }
         }
     }
-    affine r = E::to_affine(acc);
+    affine r = block_to_affine_128<E>(acc, valid);
+    if (!valid) return;
     st_fe(&out[i].x, r.x);
     st_fe(&out[i].y, r.y);
 }
