@@ -58,10 +58,10 @@ struct ApiImpl {
     static int gens_create(bp_ctx* ctx, size_t cap, GensDev** out) {
         affine b, bb;
         GensHost<C>::pedersen_default(b, bb);
-        // secq256k1: every Affine::rand attempt reads 9 keystream words, so the chains are generated on the device
-        // (gens_kernels.cuh); other curves, tiny capacities and the 2^-128 irregular stream use the host generator
-        constexpr bool fixed_stride = C::KIND == 0 && C::Fq::m(7) == 0xFFFFFFFFu && C::Fq::m(6) == 0xFFFFFFFFu && C::Fq::m(5) == 0xFFFFFFFFu;
-        if constexpr (fixed_stride) {
+        // The chains are generated on the device (gens_kernels.cuh): every Affine::rand attempt of secq256k1 and
+        // curve25519 reads nine keystream words; zorro's x draw rejects, so the host walks the keystream and the device
+        // evaluates the accepted draws. Tiny capacities and the astronomically unlikely irregular stream use the host generator.
+        {
             if (ctx->gens_on_device && cap >= 256) {
                 std::unique_ptr<GensDev> g(new GensDev());
                 g->ctx = ctx; g->capacity = cap; g->B = b; g->B_blinding = bb; g->rank = ctx->rank; g->world = ctx->world;

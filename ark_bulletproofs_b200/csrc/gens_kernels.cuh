@@ -14,6 +14,8 @@
 #pragma once
 #include <cub/device/device_select.cuh>
 #include "ctx.cuh"
+#include "host/fp_host.hpp"
+#include "host/merlin.hpp"
 
 namespace bp {
 
@@ -71,14 +73,20 @@ __device__ bool fq_sqrt_dev(const fe& a, const SqrtParams& sp, fe& out) {
     return true;
 }
 
+// One `Affine::rand` attempt per thread. The attempt's nine keystream words start at word offsets[j] (curves whose x
+// draw rejects: the host parses the stream, see gens_chain_device) or at 9 * (attempt0 + j) (fixed stride).
+//   short Weierstrass: x = the 8 words, y = sqrt(x^3 + a x + b), root chosen by `greatest`;
+//   twisted Edwards:   y = the 8 words with the top bit shaved (255-bit field), x = sqrt((1 - y^2) / (a - d y^2)) chosen by
+//                      `greatest`, then mul_by_cofactor (three doublings) -- ark-ec's Affine::rand for both models.
 template <class C>
 __global__ void __launch_bounds__(128) gens_attempt_kernel(const __grid_constant__ ChaChaKey key, uint64_t attempt0, size_t count,
-                                                           const __grid_constant__ SqrtParams sp, affine* __restrict__ pts,
-                                                           uint8_t* __restrict__ ok, int* __restrict__ irregular) {
+                                                           const uint32_t* __restrict__ offsets, const __grid_constant__ SqrtParams sp,
+                                                           affine* __restrict__ pts, uint8_t* __restrict__ ok, int* __restrict__ irregular) {
     using F = Fp<typename C::Fq>;
+    using E = GroupLaw<C>;
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
-    const uint64_t w0 = (attempt0 + j) * 9u;
+    const uint64_t w0 = offsets ? (uint64_t)offsets[j] : (attempt0 + j) * 9u;
     const uint64_t blk = w0 / 16u;
     const int off = (int)(w0 % 16u);
     uint32_t buf[32];
@@ -87,27 +95,46 @@ __global__ void __launch_bounds__(128) gens_attempt_kernel(const __grid_constant
     fe x;
 #pragma unroll
     for (int k = 0; k < 8; k++) x.v[k] = buf[off + k];        // 4 x next_u64 = 8 little-endian words; raw = Montgomery repr
+    if (C::Fq::BITS < 256) x.v[7] &= 0xFFFFFFFFu >> (256 - C::Fq::BITS);   // Fp::rand shaves the bits above the modulus' length
     const bool greatest = (buf[off + 8] >> 31) & 1u;           // bool::rand = top bit of next_u32
-    // x >= q cannot be shaved (256-bit modulus): Fp::rand would redraw and shift the stream
+    // a raw value >= q makes Fp::rand redraw and shifts the stream: impossible here for pre-parsed offsets, astronomically
+    // unlikely for the fixed-stride curves (the caller falls back to the host generator)
     bool geq = true;
     for (int k = 7; k >= 0; k--) {
         uint32_t mk = C::Fq::m(k);
         if (x.v[k] != mk) { geq = x.v[k] > mk; break; }
     }
     if (geq) { atomicExch(irregular, 1); ok[j] = 0; return; }
-    fe rhs = F::add(F::mul(F::sqr(x), x), F::template curve_b<C>());
-    if (C::A_SMALL != 0) rhs = F::add(rhs, F::mul_small(x, C::A_SMALL));
-    fe y;
-    if (!fq_sqrt_dev<F>(rhs, sp, y)) { ok[j] = 0; return; }
-    // ark: pick the larger / smaller root as canonical integers
-    fe ny = F::neg(y);
-    fe yc = F::from_mont(y), nc = F::from_mont(ny);
-    bool y_larger = false;
-    for (int k = 7; k >= 0; k--)
-        if (yc.v[k] != nc.v[k]) { y_larger = yc.v[k] > nc.v[k]; break; }
+    auto larger = [](const fe& v) {                            // v > -v as canonical integers
+        fe nv = F::neg(v);
+        fe vc = F::from_mont(v), nc = F::from_mont(nv);
+        for (int k = 7; k >= 0; k--)
+            if (vc.v[k] != nc.v[k]) return vc.v[k] > nc.v[k];
+        return false;
+    };
     affine p;
-    p.x = x;
-    p.y = (greatest == y_larger) ? y : ny;
+    if (C::KIND == 1) {
+        const fe y = x;
+        const fe y2 = F::sqr(y);
+        const fe num = F::sub(F::one(), y2);
+        const fe den = F::sub(F::neg(F::one()), F::mul(F::template curve_b<C>(), y2));
+        if (F::is_zero(den)) { ok[j] = 0; return; }
+        fe xr;
+        if (!fq_sqrt_dev<F>(F::mul(num, F::inv(den)), sp, xr)) { ok[j] = 0; return; }
+        p.x = (greatest == larger(xr)) ? xr : F::neg(xr);
+        p.y = y;
+        xyzz acc = E::from_affine(p);
+        for (int k = 0; k < 3; k++) acc = E::dbl(acc);         // cofactor 8
+        p = E::to_affine(acc);
+        if (E::is_identity(p)) { p.x = F::zero(); p.y = F::one(); }
+    } else {
+        fe rhs = F::add(F::mul(F::sqr(x), x), F::template curve_b<C>());
+        if (C::A_SMALL != 0) rhs = F::add(rhs, F::mul_small(x, C::A_SMALL));
+        fe y;
+        if (!fq_sqrt_dev<F>(rhs, sp, y)) { ok[j] = 0; return; }
+        p.x = x;
+        p.y = (greatest == larger(y)) ? y : F::neg(y);
+    }
     st_fe(&pts[j].x, p.x);
     st_fe(&pts[j].y, p.y);
     ok[j] = 1;
@@ -248,13 +275,38 @@ int gens_chain_device(bp_ctx* ctx, const uint8_t seed[32], const SqrtParams& sp,
     BP_CUDA_TRY(ctx, cudaMemsetAsync(misc.p, 0, 64, st));
     size_t produced = 0;
     uint64_t attempt0 = 0;
+    // A 256-bit base field well below 2^256 (zorro: q ~ 2^255) rejects about half of the x draws, each rejected draw eating
+    // eight words: where an attempt starts depends on every draw before it. That scan is inherently serial and cheap (a
+    // ChaCha20 keystream and one 256-bit comparison per draw), so the host walks the stream and hands the device the word
+    // offset of every draw that Fp::rand accepts; the square roots -- all of the arithmetic -- stay on the device.
+    constexpr bool x_rejects = C::Fq::BITS == 256 && !(C::Fq::m(7) == 0xFFFFFFFFu && C::Fq::m(6) == 0xFFFFFFFFu && C::Fq::m(5) == 0xFFFFFFFFu);
+    ChaCha20Rng walker(seed);
+    std::vector<uint32_t> h_off;
+    DevBuf d_off;
+    struct OffGuard { DevBuf* b; ~OffGuard() { b->release(); } } off_guard{&d_off};
     while (produced < count) {
         size_t want = (count - produced) * 2 + 1024;
         if (want > ((size_t)1 << 30)) return BP_ERR_LEN;
         BP_CUDA_TRY(ctx, att.reserve(want * sizeof(affine)));
         BP_CUDA_TRY(ctx, sel.reserve(want * sizeof(affine)));
         BP_CUDA_TRY(ctx, okb.reserve(want));
-        gens_attempt_kernel<C><<<(unsigned)((want + 127) / 128), 128, 0, st>>>(key, attempt0, want, sp, att.as<affine>(), okb.as<uint8_t>(), d_irregular);
+        const uint32_t* offs = nullptr;
+        if (x_rejects) {
+            h_off.resize(want);
+            for (size_t k = 0; k < want;) {
+                const uint64_t at = walker.words_used;
+                if (at + 9 > 0xFFFFFFFFull) return BP_ERR_LEN;
+                uint64_t l[4];
+                for (int q = 0; q < 4; q++) l[q] = walker.next_u64();
+                if (HostFp<typename C::Fq>::geq_m(l)) continue;        // Fp::rand redraws: the next draw starts 8 words on
+                walker.next_u32();                                     // the `greatest` word of this attempt
+                h_off[k++] = (uint32_t)at;
+            }
+            BP_CUDA_TRY(ctx, d_off.reserve(want * sizeof(uint32_t)));
+            BP_CUDA_TRY(ctx, cudaMemcpyAsync(d_off.p, h_off.data(), want * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            offs = d_off.as<uint32_t>();
+        }
+        gens_attempt_kernel<C><<<(unsigned)((want + 127) / 128), 128, 0, st>>>(key, attempt0, want, offs, sp, att.as<affine>(), okb.as<uint8_t>(), d_irregular);
         BP_LAUNCH_CHECK(ctx);
         size_t tb = 0;
         BP_CUDA_TRY(ctx, cub::DeviceSelect::Flagged(nullptr, tb, att.as<affine>(), okb.as<uint8_t>(), sel.as<affine>(), d_nsel, (int)want, st));

@@ -169,17 +169,34 @@ def test_synth_points_are_multiples_of_g(ctx):
         assert codec.dec_point(raw[64 * i:64 * i + 64], CURVE) == O.pt_mul(cv, start + i + 1, cv.G)
 
 
-@pytest.mark.parametrize("cap", [256, 1000])
-def test_device_generators_match_oracle(cap):
-    """BulletproofGens chains generated on the GPU (csrc/gens_kernels.cuh; capacity >= 256 takes the device path)
-    against the oracle's restatement of src/generators.rs:71-121,196-221 -- not against the repo's own host generator."""
+@pytest.mark.parametrize("curve,cap", [("secq256k1", 256), ("secq256k1", 1000), ("zorro", 256), ("zorro", 700), ("curve25519", 256), ("curve25519", 600)])
+def test_device_generators_match_oracle(curve, cap):
+    """BulletproofGens chains generated on the GPU (csrc/gens_kernels.cuh; capacity >= 256 takes the device path) against
+    the oracle's restatement of src/generators.rs:71-121,196-221 -- not against the repo's own host generator. zorro: the x
+    draw rejects about every second time (the host walks the keystream, the device takes the square roots); curve25519:
+    point from y, then the cofactor."""
     from ark_bulletproofs_b200 import Context
     from ark_bulletproofs_b200 import r1cs as R
-    c = Context(CURVE, 0)
+    c = Context(curve, 0)
     g = R.Gens(c, cap)
-    bp = O.BulletproofGens(O.SECQ256K1, cap, 1)
+    bp = O.BulletproofGens(O.CURVES[curve], cap, 1)
     assert g.export(0, 0, cap) == bp.G(cap)
     assert g.export(1, 0, cap) == bp.H(cap)
+    c.set_device_gens(False)
+    g2 = R.Gens(c, cap)                       # the host generator gives the same tables
+    assert g2.export(0, 0, cap) == bp.G(cap) and g2.export(1, 0, cap) == bp.H(cap)
+
+
+@pytest.mark.parametrize("curve", ["zorro", "curve25519"])
+def test_device_generators_large_match_host(curve):
+    """2^14 generators per chain: device chain == threaded host chain (which tests/test_host_layer.py pins to the oracle)."""
+    from ark_bulletproofs_b200 import Context
+    from ark_bulletproofs_b200 import r1cs as R
+    cap = 1 << 14
+    c = Context(curve, 0)
+    g = R.Gens(c, cap)
+    _, _, G, H = R.generate_gens_host(curve, cap)
+    assert g.export(0, 0, cap) == G and g.export(1, 0, cap) == H
 
 
 # ---- byte-identical proofs at 2^16 / 2^20 multipliers (tests/golden/large.json, made by make_golden_large.py) ----------
