@@ -7,13 +7,14 @@
 //! ark-ff `Fp256<MontBackend<_, 4>>` is `[u64; 4]` little-endian limbs in Montgomery form (R = 2^256) -- exactly the
 //! 32-byte scalar / 2 x 32-byte affine point format of the C ABI, so marshalling is a copy of the limbs.
 pub mod ffi;
+pub mod r1cs;
 
 use ark_ec::{short_weierstrass::Affine, AffineRepr};
 use ark_ff::{BigInt, Fp256, MontBackend, MontConfig};
 use core::ffi::c_int;
 
 /// Raw Montgomery limbs of an ark-ff 256-bit field element.
-fn limbs<P: MontConfig<4>>(x: &Fp256<MontBackend<P, 4>>) -> [u8; 32] {
+pub(crate) fn limbs<P: MontConfig<4>>(x: &Fp256<MontBackend<P, 4>>) -> [u8; 32] {
     let BigInt(l) = x.0; // the in-memory (Montgomery) representation, not `into_bigint()`
     let mut out = [0u8; 32];
     for (i, w) in l.iter().enumerate() {
@@ -59,4 +60,28 @@ pub fn msm(
         ark_ff::Fp::<MontBackend<ark_secq256k1::FqConfig, 4>, 4>(BigInt(l), core::marker::PhantomData)
     };
     Ok(Affine::new_unchecked(fq(&out[..32]), fq(&out[32..])))
+}
+
+/// ark-ff field element from the 32 raw Montgomery bytes of the C ABI (no conversion: `Fp(BigInt(limbs))`).
+pub(crate) fn fp_from_limbs<P: MontConfig<4>>(raw: &[u8; 32]) -> Fp256<MontBackend<P, 4>> {
+    let mut l = [0u64; 4];
+    for i in 0..4 {
+        l[i] = u64::from_le_bytes(raw[8 * i..8 * i + 8].try_into().unwrap());
+    }
+    ark_ff::Fp::<MontBackend<P, 4>, 4>(BigInt(l), core::marker::PhantomData)
+}
+/// `x || y` as raw Montgomery limbs, identity = 64 zero bytes.
+pub(crate) fn affine_bytes(p: &ark_secq256k1::Affine) -> [u8; 64] {
+    let mut out = [0u8; 64];
+    if !p.is_zero() {
+        out[..32].copy_from_slice(&limbs(&p.x));
+        out[32..].copy_from_slice(&limbs(&p.y));
+    }
+    out
+}
+pub(crate) fn affine_from_bytes(b: &[u8; 64]) -> ark_secq256k1::Affine {
+    if b.iter().all(|&x| x == 0) {
+        return Affine::identity();
+    }
+    Affine::new_unchecked(fp_from_limbs(b[..32].try_into().unwrap()), fp_from_limbs(b[32..].try_into().unwrap()))
 }
