@@ -742,25 +742,15 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
     return BP_OK;
 }
 
-// Multi-GPU contexts (bp_ctx_set_collective): the job holds this rank's shard of each of the `nmsm` MSMs. The partial
-// points are all-gathered through the host program's collective (64 B per MSM and rank, identity = zeros) and added
-// on the host, so every rank returns the full sums. With world == 1 this is msm_run_job.
-int host_points_sum(int curve, const uint8_t* pts_xy, size_t n, uint8_t out_xy[64], int* out_is_identity);
-template <class C>
-int msm_run_job_sharded(bp_ctx* ctx, MsmJob& job, int nmsm, uint8_t (*out_xy)[64], int* out_is_identity) {
-    if (job.nmsm < nmsm) job.nmsm = nmsm;           // a rank may hold no term of some MSM
-    if (int rc = msm_run_job<C>(ctx, job, out_xy, out_is_identity)) return rc;
-    if (ctx->world <= 1) return BP_OK;
-    const size_t bytes = (size_t)nmsm * 64;
+// All-gather of `bytes` bytes per rank in a multi-GPU context: recv[r * bytes ...] = rank r's send. Library-owned when the
+// context has an NCCL communicator (bp_ctx_init_nccl): ncclAllGather on the context's stream over NVLink, staged through
+// one pinned buffer -- no callback, no Python, no torch tensor; otherwise the host program's callback (bp_ctx_set_collective).
+inline int ctx_allgather(bp_ctx* ctx, const uint8_t* send, size_t bytes, uint8_t* recv) {
+    if (ctx->world <= 1) { memcpy(recv, send, bytes); return BP_OK; }
     if (ctx->nccl_comm) {
-        // library-owned exchange: the partial points (identity = zeros) go through ncclAllGather on the context's stream --
-        // 64 B per MSM and rank over NVLink -- and come back in one pinned copy; no callback, no Python, no torch tensor.
-        if (bytes * ctx->world > BP_HOST_COLL_BYTES) return BP_ERR_LEN;
+        if (bytes * ctx->world > BP_HOST_COLL_BYTES || bytes > ctx->coll_send.cap) return BP_ERR_LEN;
         uint8_t* hs = (uint8_t*)ctx->h_coll;
-        for (int m = 0; m < nmsm; m++) {
-            if (out_is_identity[m]) memset(hs + (size_t)m * 64, 0, 64);
-            else memcpy(hs + (size_t)m * 64, out_xy[m], 64);
-        }
+        memcpy(hs, send, bytes);
         cudaStream_t st = ctx->stream;
         BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coll_send.p, hs, bytes, cudaMemcpyHostToDevice, st));
         const NcclApi& nc = nccl_api();
@@ -768,24 +758,32 @@ int msm_run_job_sharded(bp_ctx* ctx, MsmJob& job, int nmsm, uint8_t (*out_xy)[64
         if (r != ncclSuccess) { ctx->err = std::string("ncclAllGather: ") + nc.GetErrorString(r); return BP_ERR_CUDA; }
         BP_CUDA_TRY(ctx, cudaMemcpyAsync(hs, ctx->coll_recv.p, bytes * ctx->world, cudaMemcpyDeviceToHost, st));
         BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        ctx->coll_calls++;
-        ctx->coll_bytes += bytes * ctx->world;
-        uint8_t pts[64 * 64];
-        for (int m = 0; m < nmsm; m++) {
-            for (int r2 = 0; r2 < ctx->world; r2++) memcpy(pts + (size_t)r2 * 64, hs + (size_t)r2 * bytes + (size_t)m * 64, 64);
-            if (int rc = host_points_sum(ctx->curve, pts, ctx->world, out_xy[m], &out_is_identity[m])) return rc;
-        }
-        return BP_OK;
+        memcpy(recv, hs, bytes * ctx->world);
+    } else {
+        if (!ctx->coll) return BP_ERR_ARG;
+        if (ctx->coll(ctx->coll_user, send, recv, bytes)) { ctx->err = "collective all-gather failed"; return BP_ERR_CUDA; }
     }
-    if (!ctx->coll) return BP_ERR_ARG;
+    ctx->coll_calls++;
+    ctx->coll_bytes += bytes * ctx->world;
+    return BP_OK;
+}
+
+// Multi-GPU contexts: the job holds this rank's shard of each of the `nmsm` MSMs. The partial points (64 B per MSM and
+// rank, identity = zeros) are all-gathered and added on the host, so every rank returns the full sums. With world == 1
+// this is msm_run_job.
+int host_points_sum(int curve, const uint8_t* pts_xy, size_t n, uint8_t out_xy[64], int* out_is_identity);
+template <class C>
+int msm_run_job_sharded(bp_ctx* ctx, MsmJob& job, int nmsm, uint8_t (*out_xy)[64], int* out_is_identity) {
+    if (job.nmsm < nmsm) job.nmsm = nmsm;           // a rank may hold no term of some MSM
+    if (int rc = msm_run_job<C>(ctx, job, out_xy, out_is_identity)) return rc;
+    if (ctx->world <= 1) return BP_OK;
+    const size_t bytes = (size_t)nmsm * 64;
     std::vector<uint8_t> send(bytes), recv(bytes * ctx->world), pts((size_t)ctx->world * 64);
     for (int m = 0; m < nmsm; m++) {
         if (out_is_identity[m]) memset(&send[(size_t)m * 64], 0, 64);
         else memcpy(&send[(size_t)m * 64], out_xy[m], 64);
     }
-    if (ctx->coll(ctx->coll_user, send.data(), recv.data(), bytes)) { ctx->err = "collective all-gather failed"; return BP_ERR_CUDA; }
-    ctx->coll_calls++;
-    ctx->coll_bytes += bytes * ctx->world;
+    if (int rc = ctx_allgather(ctx, send.data(), bytes, recv.data())) return rc;
     for (int m = 0; m < nmsm; m++) {
         for (int r = 0; r < ctx->world; r++) memcpy(&pts[(size_t)r * 64], &recv[(size_t)r * bytes + (size_t)m * 64], 64);
         if (int rc = host_points_sum(ctx->curve, pts.data(), ctx->world, out_xy[m], &out_is_identity[m])) return rc;

@@ -407,8 +407,14 @@ struct ConstraintStore {
     std::vector<uint32_t> start;      // constraint q covers terms [start[q], start[q+1])
     fe one, minus_one;
     bool overflow = false;            // an index >= 2^29 or more than 2^32 - 3 terms: reported by flatten_device
+    // Multi-GPU verifier: rank r only ever needs w_L, w_R, w_O at the generator indices it holds
+    // (i = r mod world), so its store keeps only those multiplier terms -- 1/world of the upload, sort and reduce of
+    // flatten_device. Committed and constant terms (w_V, w_c) are kept everywhere. The prover keeps everything (its l(x),
+    // r(x) vectors are replicated).
+    uint32_t shard_rank = 0, shard_world = 1;
     ConstraintStore() { start.push_back(0); }
     void push_term(const Variable& v, const fe& c) {
+        if (shard_world > 1 && v.kind >= VAR_MUL_LEFT && v.kind <= VAR_MUL_OUT && (v.idx % shard_world) != shard_rank) return;
         if (v.idx >= (1ull << 29) || key.size() >= 0xFFFFFFF0ull) overflow = true;
         key.push_back(((uint32_t)v.kind << 29) | (uint32_t)(v.idx & 0x1FFFFFFFu));
         if (memcmp(c.v, one.v, 32) == 0) cref.push_back(0u);
@@ -894,6 +900,8 @@ struct VerifierT : ConstraintSystemBase {
         t->append_message("dom-sep", (const uint8_t*)"r1cs v1", 7);
         cs.one = Fr::one();
         cs.minus_one = Fr::neg(Fr::one());
+        cs.shard_rank = (uint32_t)c->rank;
+        cs.shard_world = (uint32_t)c->world;
     }
     int multiply(const Variable* lv, const fe* lc, size_t ln, const Variable* rv, const fe* rc, size_t rn, Variable out[3]) override {   // :74-98
         if (int rc_ = check_terms(lv, ln, num_vars, V.size())) return rc_;
@@ -1034,6 +1042,17 @@ struct VerifierT : ConstraintSystemBase {
         BP_LAUNCH_CHECK(ctx);
         fe delta;
         if (int rc = D::download(ctx, &delta, d_delta, sizeof(fe))) return rc;
+        if (ctx->world > 1) {
+            // delta = <y^-n o w_R, w_L> runs over all multipliers; every rank has summed the indices it holds
+            std::vector<uint8_t> all((size_t)ctx->world * sizeof(fe));
+            if (int rc = ctx_allgather(ctx, (const uint8_t*)&delta, sizeof(fe), all.data())) return rc;
+            delta = Fr::zero();
+            for (int r2 = 0; r2 < ctx->world; r2++) {
+                fe part;
+                memcpy(&part, &all[(size_t)r2 * sizeof(fe)], sizeof(fe));
+                delta = Fr::add(delta, part);
+            }
+        }
         // r: challenge on a CLONE of the transcript (verifier.rs:516-519)
         Transcript tc = t;
         fe r = TP<C>::challenge_scalar(tc, "r");
