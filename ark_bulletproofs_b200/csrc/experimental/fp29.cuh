@@ -1,15 +1,16 @@
-// Balanced 9 x 29-bit field elements with carry-free column accumulation -- the multiplier of every IMAD-bound kernel
-// (bucket accumulation, bucket reduction, generator folds).
+// Balanced 9 x 29-bit field elements with carry-free column accumulation.
 //
-// Why (profiles/r2_microbench3.json): on B200 an IMAD.WIDE that produces or consumes a carry
-// predicate occupies the fmaheavy pipe for two passes (31/clk/SM), a plain IMAD.WIDE Rd = a*b + Rc (64-bit
-// accumulate, no flags) issues at the full IMAD rate (59/clk/SM). The 8 x 32-bit CIOS of fp.cuh is therefore pinned
-// at ~580 pipe cycles per warp modmul, half of the IMAD peak. Here a product is 81 plain IMAD.WIDE into 18 signed
-// 64-bit columns, the Montgomery reduction is 9 x (1 IMAD + one IMAD.WIDE per non-zero limb of m), and *carries move
-// with IMAD.WIDE too* (column += carry * 1), so there is not a single carry-flag instruction in a multiplication:
-// 161 pipe instructions for secq256k1's base field (125 for a squaring) against 136 two-pass ones.
+// EXPERIMENT, not linked into the product (profiles/r2_microbench3_fp29_vs_cios.json). The premise
+// -- round 1's reading that only a *carry-chained* IMAD.WIDE is a two-pass instruction -- turned out to be wrong: a plain
+// IMAD.WIDE Rd = a*b + Rc also holds the multiplier for two issue slots (4 clk per warp instruction). This layer has not
+// a single flag instruction in a multiplication (81 plain IMAD.WIDE into 18 signed 64-bit columns, a Montgomery reduction
+// of 9 x (1 IMAD + one IMAD.WIDE per non-zero limb of m), carries moved with IMAD.WIDE too: 152 + 9 pipe instructions for
+// secq256k1's base field, 116 + 9 for a squaring) and runs at 56.9 G modmul/s against 66.2 for the 8 x 32 CIOS of fp.cuh
+// (128 + 8 products); only its squaring wins (72.3). It stays as a verified reference point: host-tested against the
+// oracle on all five moduli and three curves (tests/test_hostmath.py), bit-identical to the CIOS on the device
+// (tools/microbench3.cu).
 //
-// What makes that possible is the **balanced** digit set: limbs 0..7 lie in [-2^28, 2^28], so |a_i * b_j| <= 2^56
+// What makes the flag-free form possible is the **balanced** digit set: limbs 0..7 lie in [-2^28, 2^28], so |a_i * b_j| <= 2^56
 // and a column (9 products + <= 6 reduction terms + a carry) stays below 2^60 -- its carry (column >> 29) fits the
 // 32-bit multiplicand of IMAD.WIDE. With unsigned 29-bit limbs the same column reaches 2^61.5 and the carry needs
 // 33 bits (round 1's fp29 resolved carries with IADD3/IADD3.X pairs and lost to the ALU traffic; ptxas moreover

@@ -10,9 +10,10 @@
 // IMAD.WIDE.U32(.X) with predicate carries -- 128 wide multiplies + 8 for the quotients per
 // modmul (checked with cuobjdump; see profiles/).
 //
-// A 9 x 29-bit unsaturated variant (carry-free IMAD.WIDE into 64-bit columns, 135 multiplies) was
-// built and measured in round 1: 46 G modmul/s vs 66.5 for this one -- its ~250 ALU ops per
-// modmul saturate the ALU pipe, which on B200 is as narrow as the IMAD pipe.
+// Two unsaturated variants were built and measured against it: round 1's 9 x 29-bit columns with ALU
+// carries (46 G modmul/s vs 66.5), and round 2's balanced 9 x 29-bit layer without a single flag instruction
+// (experimental/fp29.cuh: 56.9 vs 66.2). Both lose for one reason: an IMAD.WIDE costs two multiplier passes with or without
+// carry predicates, and this CIOS has the fewest 32x32->64 products (128 + 8) of any 8-limb formulation.
 //
 // Every value handed between functions is fully reduced (< m): the secq256k1
 // moduli are within 2^129 of 2^256, so there are no spare bits for lazy reduction.

@@ -671,7 +671,12 @@ def main():
         "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": round(achieved / 1e12, 4), "peak": round(peak / 1e12, 4),
                      "unit": "TIMAD/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                      "algorithmic": "%d bucket additions x 10 modmul x 136 IMAD" % phases["entries"], "peak_source": peak_src,
-                     "launch_ms": round(acc_ms, 4)},
+                     "launch_ms": round(acc_ms, 4),
+                     # every 32x32->64 product (IMAD.WIDE with or without carry, IMAD.HI) holds the multiplier for two issue
+                     # slots: 31.7 IMAD.HI/clk/SM against 63.3 IMAD.lo/clk/SM (profiles/r1_microbench.json), 4 clk per warp
+                     # IMAD.WIDE in both multipliers of profiles/r2_microbench3_fp29_vs_cios.json -- so a formulation built
+                     # on 64-bit products tops out at 0.5 of `peak`
+                     "frac_of_wide_product_ceiling": round(achieved / peak / 0.5, 4)},
         "roofline_hbm": {"bound": "hbm", "kernel": "cub radix sort of (bucket, point) pairs", "achieved": round(sort_bytes / (phases["ms"]["sort"] * 1e-3) / 1e9, 1),
                          "peak": hbm, "unit": "GB/s", "frac": round(sort_bytes / (phases["ms"]["sort"] * 1e-3) / 1e9 / hbm, 4),
                          "peak_source": hbm_src, "launch_ms": round(phases["ms"]["sort"], 4)},
@@ -700,10 +705,11 @@ def main():
         line["r1cs"] = r1cs
     if world == 1 and not args.no_cpu_baseline:
         ncores = os.cpu_count() or 1
-        lg = args.cpu_lg_n or (20 if ncores >= 16 else 18)
+        lg = args.cpu_lg_n or (22 if ncores >= 16 else 18)      # bounded sample; `--impl reference` runs the full 2^24 workload
         val, cms, threads = cpu_reference_run(lg, 1, 0)
         line["cpu_baseline"] = {"value": round(val, 4), "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "one 2^%d-point MSM, oracle/c/bp_ref.c (ark-style wNAF Pippenger), %.1f s" % (lg, cms / 1e3)}
+                                "sample": "one 2^%d-point MSM, oracle/c/bp_ref.c (ark-ec 0.4 msm_bigint_wnaf restated in portable C, windows over "
+                                          "%d OpenMP threads; roughly 2x slower per modmul than ark-ff's x86-64 assembly), %.1f s" % (lg, threads, cms / 1e3)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
