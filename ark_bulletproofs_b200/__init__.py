@@ -116,6 +116,9 @@ class Context:
     def set_chunk(self, points: int):
         self._check(self.lib.bp_msm_set_chunk(self.h, points))
 
+    def set_device_transcript(self, min_proofs: int):
+        self._check(self.lib.bp_batch_verify_set_device_transcript(self.h, min_proofs))
+
     def set_affine_rounds(self, rounds: int, min_entries: int = 0):
         self._check(self.lib.bp_msm_set_affine_rounds(self.h, rounds, min_entries))
 

@@ -59,6 +59,8 @@ def load():
         "bp_pedersen_set_table": (i32, [vp, i32]),
         "bp_gens_set_device_generation": (i32, [vp, i32]),
         "bp_ctx_set_collective": (i32, [vp, i32, i32, vp, vp]),
+        "bp_batch_verify_set_device_transcript": (i32, [vp, i32]),
+        "bp_transcript_ipa_challenges_device": (i32, [vp, vp, u64, vp, vp, sz, vp, vp, vp, pi32]),
         "bp_nccl_unique_id": (i32, [vp]),
         "bp_ctx_init_nccl": (i32, [vp, i32, i32, vp]),
         "bp_ctx_set_timing": (i32, [vp, i32]),

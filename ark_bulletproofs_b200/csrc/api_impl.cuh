@@ -272,6 +272,37 @@ struct ApiImpl {
     }
     static size_t proof_rounds(const void* p) { return static_cast<const ProofT<C>*>(p)->L_vec.size(); }
 
+    // The device transcript on one transcript (test hook of transcript_dev.cuh): u_j, u_j^-1 for j < lg_n and r, from
+    // the state of `t` (which is not advanced), the domain separator for `padded_n` and the points L, R.
+    static int ipa_challenges_device(bp_ctx* ctx, const Transcript* t, uint64_t padded_n, const uint8_t* L, const uint8_t* R, size_t lg_n,
+                                     uint8_t* out_u, uint8_t* out_uinv, uint8_t* out_r, int* status) {
+        if (lg_n > 32) return BP_ERR_LEN;
+        DevTranscriptIn in;
+        memset(&in, 0, sizeof(in));
+        memcpy(in.st, t->strobe.state, 200);
+        in.pos = t->strobe.pos; in.pos_begin = t->strobe.pos_begin;
+        in.lg_n = (uint32_t)lg_n; in.padded_n = padded_n; in.pt_off = 0;
+        std::vector<affine> pts(2 * lg_n + 1);
+        for (size_t j = 0; j < lg_n; j++) { pts[j] = ldp(L + 64 * j); pts[lg_n + j] = ldp(R + 64 * j); }
+        cudaStream_t st = ctx->stream;
+        BP_CUDA_TRY(ctx, ctx->tr_in.reserve(sizeof(in)));
+        BP_CUDA_TRY(ctx, ctx->tr_pts.reserve(pts.size() * sizeof(affine)));
+        BP_CUDA_TRY(ctx, ctx->tr_out.reserve(65 * sizeof(fe) + 16));
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tr_in.p, &in, sizeof(in), cudaMemcpyHostToDevice, st));
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tr_pts.p, pts.data(), pts.size() * sizeof(affine), cudaMemcpyHostToDevice, st));
+        fe* d_u = ctx->tr_out.template as<fe>();
+        verifier_ipa_challenges_kernel<C><<<1, 64, 0, st>>>(ctx->tr_in.template as<DevTranscriptIn>(), ctx->tr_pts.template as<affine>(), 1, d_u, d_u + 32, d_u + 64,
+                                                           reinterpret_cast<uint8_t*>(d_u + 65));
+        BP_LAUNCH_CHECK(ctx);
+        std::vector<uint8_t> back(65 * sizeof(fe) + 16);
+        BP_CUDA_TRY(ctx, cudaMemcpyAsync(back.data(), ctx->tr_out.p, back.size(), cudaMemcpyDeviceToHost, st));
+        BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        memcpy(out_u, back.data(), lg_n * 32);
+        memcpy(out_uinv, back.data() + 32 * 32, lg_n * 32);
+        memcpy(out_r, back.data() + 64 * 32, 32);
+        *status = back[65 * 32];
+        return BP_OK;
+    }
     static int chain_circuit(ConstraintSystemBase* cs, const Variable* v0, size_t n, const uint8_t* ks, const uint8_t* x0) {
         fe x = Fr::zero();
         if (x0) x = ld(x0);
@@ -390,7 +421,8 @@ struct ApiImpl {
             gens_generate_host, gens_create, gens_from_points, pedersen_commit, challenge_scalar, rng_scalar, scalar_to_bytes, scalar_from_bytes,
             point_compress, point_uncompressed, point_decompress, prover_new, prover_free, prover_cs, prover_commit, prover_commit_batch, prover_prove, verifier_new,
             verifier_free, verifier_cs, verifier_commit, verifier_verify, batch_verify, batch_verify_partial, proof_free, proof_to_bytes, proof_from_bytes, proof_clone,
-            proof_field, proof_rounds, chain_circuit, ipa_create_host, ipa_verify_host, rng_scalars, shuffle_gadget, proofs_from_bytes_batch};
+            proof_field, proof_rounds, chain_circuit, ipa_create_host, ipa_verify_host, rng_scalars, shuffle_gadget, proofs_from_bytes_batch,
+            ipa_challenges_device};
         return &api;
     }
 };

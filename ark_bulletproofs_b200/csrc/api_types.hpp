@@ -52,6 +52,8 @@ struct CurveApi {
     int (*rng_scalars)(Rng*, size_t n, uint8_t* out);
     int (*shuffle_gadget)(ConstraintSystemBase*, const Variable* x, const Variable* y, size_t k);
     int (*proofs_from_bytes_batch)(bp_ctx*, const uint8_t* const* bufs, const size_t* lens, size_t n, void** out, int* status);
+    int (*ipa_challenges_device)(bp_ctx*, const Transcript*, uint64_t padded_n, const uint8_t* L, const uint8_t* R, size_t lg_n, uint8_t* out_u,
+                                 uint8_t* out_uinv, uint8_t* out_r, int* status);
 };
 
 const CurveApi* curve_api_secq();

@@ -641,6 +641,18 @@ int bp_batch_verify_partial(bp_ctx* ctx, const uint8_t* alphas, bp_verifier* con
     return bp::curve_api(ctx->curve)->batch_verify_partial(ctx, alphas, vs.data(), ps.data(), n, gens->g, out_xy, out_is_identity);
 } BP_ABI_CATCH
 
+int bp_batch_verify_set_device_transcript(bp_ctx* ctx, int min_proofs) try {
+    if (!ctx || min_proofs < 0) return BP_ERR_ARG;
+    ctx->dev_transcript_min = min_proofs;
+    return BP_OK;
+} BP_ABI_CATCH
+int bp_transcript_ipa_challenges_device(bp_ctx* ctx, const bp_transcript* t, uint64_t padded_n, const uint8_t* L_xy, const uint8_t* R_xy, size_t lg_n,
+                                        uint8_t* out_u, uint8_t* out_u_inv, uint8_t out_r[32], int* out_identity_seen) try {
+    if (!ctx || !t || !out_u || !out_u_inv || !out_r || !out_identity_seen || (lg_n && (!L_xy || !R_xy))) return BP_ERR_ARG;
+    BP_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return bp::curve_api(ctx->curve)->ipa_challenges_device(ctx, &t->t, padded_n, L_xy, R_xy, lg_n, out_u, out_u_inv, out_r, out_identity_seen);
+} BP_ABI_CATCH
+
 // ---- proofs ----
 void bp_proof_free(bp_proof* p) { if (p) { bp::curve_api(p->curve)->proof_free(p->impl); delete p; } }
 int bp_proof_to_bytes(const bp_proof* p, uint8_t* out, size_t cap, size_t* len) try {

@@ -70,13 +70,14 @@ struct bp_ctx {
     size_t msm_warp_partials_below = (size_t)1 << 17;   // partial-slot lists shorter than this are reduced by warp-segmented scans
     // MSM scratch
     bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;
-    bp::DevBuf stage_bases, stage_scalars, pairpts, pairpre;
+    bp::DevBuf stage_bases, stage_scalars, pairpts, pairpre, tr_in, tr_pts, tr_out;
+    int dev_transcript_min = 32;             // batches of at least this many proofs derive their IPA challenges on the device (0 = never)
     // IPA / prover / verifier work buffers (r1cs.cuh)
     bp::DevBuf ipa_G, ipa_H, ipa_s, ipa_parts, small, c_v, c_b, c_out;
     bp::DevBuf p_aL, p_aR, p_aO, p_sL, p_sR, p_wL, p_wR, p_wO, p_ypow, p_yinv, p_l, p_r, p_Gf, p_Hf, v_pts, v_sc, v_g, v_h, v_accg, v_acch, f_kind, f_idx, f_coeff, f_start, f_keys, f_keys2, f_perm, f_perm2, f_contrib, f_sorted, f_ukeys, f_sums, f_tmp, f_wv;
     template <class F> void for_each_buf(F f) {
         bp::DevBuf* all[] = {&keys_a, &keys_b, &vals_a, &vals_b, &cub_tmp, &buckets, &part_keys, &part_pts, &seg_out, &win_out, &result,
-                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &coll_send, &coll_recv, &pairpts, &pairpre, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &c_v, &c_b, &c_out, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
+                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &coll_send, &coll_recv, &pairpts, &pairpre, &tr_in, &tr_pts, &tr_out, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &c_v, &c_b, &c_out, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
                              &p_wL, &p_wR, &p_wO, &p_ypow, &p_yinv, &p_l, &p_r, &p_Gf, &p_Hf, &v_pts, &v_sc, &v_g, &v_h, &v_accg, &v_acch, &f_kind, &f_idx, &f_coeff, &f_start, &f_keys, &f_keys2, &f_perm, &f_perm2, &f_contrib, &f_sorted,
                              &f_ukeys, &f_sums, &f_tmp, &f_wv};
         for (auto* b : all) f(b);

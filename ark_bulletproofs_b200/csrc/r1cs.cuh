@@ -22,6 +22,7 @@
 #include "r1cs_types.hpp"
 #include "msm_kernels.cuh"
 #include "flatten.cuh"
+#include "transcript_dev.cuh"
 #include "host/glv_host.hpp"
 #include "vec_kernels.cuh"
 
@@ -978,65 +979,99 @@ struct VerifierT : ConstraintSystemBase {
         fe *g = nullptr, *h = nullptr;   // context-owned device buffers (valid until the next verification_scalars)
     };
 
-    int verification_scalars(const ProofT<C>& proof, const GensDev& gens, Scalars& out) {
+    // verification_scalars (verifier.rs:394-541) in three steps, so that a batch can derive the inner-product challenges
+    // of all its proofs in one launch (transcript_dev.cuh) between the first and the last:
+    //   vs_head        the transcript through the challenge `w` (host; runs the randomised-phase callbacks)
+    //   vs_challenges  the IPA challenges u_j, their inverses and `r` (host here; device for batches)
+    //   vs_tail        flatten, the g / h scalar kernel, the tail scalars
+    struct Head {
+        fe y, z, u, x, w, r;
+        size_t n1 = 0, n = 0, padded_n = 0, lg_n = 0;
+        std::vector<fe> ch, ch_inv;      // u_j and u_j^-1 (zeros stay zeros)
+    };
+    int vs_head(const ProofT<C>& proof, const GensDev& gens, Head& h) {
         Transcript& t = *transcript;
-        cudaStream_t st = ctx->stream;
         t.append_u64("m", V.size());                                                            // :404
-        size_t n1 = num_vars;
+        h.n1 = num_vars;
         if (TP<C>::validate_and_append_point(t, "A_I1", proof.A_I1)) return BP_ERR_VERIFY;      // :407-409
         if (TP<C>::validate_and_append_point(t, "A_O1", proof.A_O1)) return BP_ERR_VERIFY;
         if (TP<C>::validate_and_append_point(t, "S1", proof.S1)) return BP_ERR_VERIFY;
         if (int rc = create_randomized_constraints()) return rc;                                // :412
-        size_t n = num_vars, padded_n = next_pow2(n);
-        if (gens.capacity < padded_n) return BP_ERR_GENS;                                       // :425-427
+        h.n = num_vars;
+        h.padded_n = next_pow2(h.n);
+        if (gens.capacity < h.padded_n) return BP_ERR_GENS;                                     // :425-427
         TP<C>::append_point(t, "A_I2", proof.A_I2);                                             // :430-432
         TP<C>::append_point(t, "A_O2", proof.A_O2);
         TP<C>::append_point(t, "S2", proof.S2);
-        fe y = TP<C>::challenge_scalar(t, "y"), z = TP<C>::challenge_scalar(t, "z");            // :434-436
+        h.y = TP<C>::challenge_scalar(t, "y");                                                  // :434-436
+        h.z = TP<C>::challenge_scalar(t, "z");
         if (TP<C>::validate_and_append_point(t, "T_1", proof.T_1)) return BP_ERR_VERIFY;        // :438-442
         if (TP<C>::validate_and_append_point(t, "T_3", proof.T_3)) return BP_ERR_VERIFY;
         if (TP<C>::validate_and_append_point(t, "T_4", proof.T_4)) return BP_ERR_VERIFY;
         if (TP<C>::validate_and_append_point(t, "T_5", proof.T_5)) return BP_ERR_VERIFY;
         if (TP<C>::validate_and_append_point(t, "T_6", proof.T_6)) return BP_ERR_VERIFY;
-        fe u = TP<C>::challenge_scalar(t, "u"), x = TP<C>::challenge_scalar(t, "x");            // :444-445
+        h.u = TP<C>::challenge_scalar(t, "u");                                                  // :444-445
+        h.x = TP<C>::challenge_scalar(t, "x");
         TP<C>::append_scalar(t, "t_x", proof.t_x);                                              // :447-457
         TP<C>::append_scalar(t, "t_x_blinding", proof.t_x_blinding);
         TP<C>::append_scalar(t, "e_blinding", proof.e_blinding);
-        fe w = TP<C>::challenge_scalar(t, "w");                                                 // :459
+        h.w = TP<C>::challenge_scalar(t, "w");                                                  // :459
+        // InnerProductProof::verification_scalars (inner_product_proof.rs:244-314): shape checks
+        h.lg_n = proof.L_vec.size();
+        if (h.lg_n >= 32 || proof.R_vec.size() != h.lg_n || h.padded_n != ((size_t)1 << h.lg_n)) return BP_ERR_VERIFY;   // :256-264
+        return BP_OK;
+    }
+    int vs_challenges_host(const ProofT<C>& proof, Head& h) {
+        Transcript& t = *transcript;
+        const size_t lg_n = h.lg_n;
+        t.append_message("dom-sep", (const uint8_t*)"ipp v1", 6);
+        t.append_u64("n", h.padded_n);
+        h.ch.assign(lg_n, Fr::zero());
+        h.ch_inv.assign(lg_n, Fr::zero());
+        for (size_t j = 0; j < lg_n; j++) {                                                     // :271-277
+            if (TP<C>::validate_and_append_point(t, "L", proof.L_vec[j])) return BP_ERR_VERIFY;
+            if (TP<C>::validate_and_append_point(t, "R", proof.R_vec[j])) return BP_ERR_VERIFY;
+            h.ch[j] = TP<C>::challenge_scalar(t, "u");
+        }
+        // ark_ff::batch_inversion (:283-288): Montgomery's trick, zeros stay zeros -- one field inversion for all rounds
+        // (sixteen separate Fermat inversions were 0.2 ms of a 2.1 ms verification at 2^16 multipliers)
+        std::vector<fe> pre(lg_n);
+        fe run = Fr::one();
+        for (size_t j = 0; j < lg_n; j++) {
+            pre[j] = run;
+            if (!Fr::is_zero(h.ch[j])) run = Fr::mul(run, h.ch[j]);
+        }
+        fe inv = Fr::inv(run);
+        for (size_t j = lg_n; j-- > 0;) {
+            if (Fr::is_zero(h.ch[j])) { h.ch_inv[j] = h.ch[j]; continue; }
+            h.ch_inv[j] = Fr::mul(inv, pre[j]);
+            inv = Fr::mul(inv, h.ch[j]);
+        }
+        // r: challenge on a CLONE of the transcript (verifier.rs:516-519)
+        Transcript tc = t;
+        h.r = TP<C>::challenge_scalar(tc, "r");
+        return BP_OK;
+    }
+    int verification_scalars(const ProofT<C>& proof, const GensDev& gens, Scalars& out) {
+        Head h;
+        if (int rc = vs_head(proof, gens, h)) return rc;
+        if (int rc = vs_challenges_host(proof, h)) return rc;
+        return vs_tail(proof, gens, h, out);
+    }
+    int vs_tail(const ProofT<C>& proof, const GensDev& gens, Head& hd, Scalars& out) {
+        cudaStream_t st = ctx->stream;
+        const fe &y = hd.y, &z = hd.z, &u = hd.u, &x = hd.x, &w = hd.w, &r = hd.r;
+        const size_t n1 = hd.n1, n = hd.n, padded_n = hd.padded_n, lg_n = hd.lg_n;
+        (void)gens;
         std::vector<fe> wV;
         fe wc;
         DevBuf* wb0[] = {&ctx->p_wL, &ctx->p_wR, &ctx->p_wO};
         for (auto* bf : wb0) BP_CUDA_TRY(ctx, bf->reserve((n + 1) * sizeof(fe)));
         if (int rc = flatten_device<C>(ctx, cs, z, n, V.size(), ctx->p_wL.as<fe>(), ctx->p_wR.as<fe>(), ctx->p_wO.as<fe>(), wV, &wc)) return rc;   // :462
-        // InnerProductProof::verification_scalars (inner_product_proof.rs:244-314), host part
-        size_t lg_n = proof.L_vec.size();
-        if (lg_n >= 32 || proof.R_vec.size() != lg_n || padded_n != ((size_t)1 << lg_n)) return BP_ERR_VERIFY;   // :256-264
-        t.append_message("dom-sep", (const uint8_t*)"ipp v1", 6);
-        t.append_u64("n", padded_n);
-        std::vector<fe> ch(lg_n), ch_inv(lg_n);
-        for (size_t j = 0; j < lg_n; j++) {                                                     // :271-277
-            if (TP<C>::validate_and_append_point(t, "L", proof.L_vec[j])) return BP_ERR_VERIFY;
-            if (TP<C>::validate_and_append_point(t, "R", proof.R_vec[j])) return BP_ERR_VERIFY;
-            ch[j] = TP<C>::challenge_scalar(t, "u");
-        }
-        // ark_ff::batch_inversion (:283-288): Montgomery's trick, zeros stay zeros -- one field inversion for all rounds
-        // (sixteen separate Fermat inversions were 0.2 ms of a 2.1 ms verification at 2^16 multipliers)
-        fe allinv = Fr::one();
-        {
-            std::vector<fe> pre(lg_n);
-            fe run = Fr::one();
-            for (size_t j = 0; j < lg_n; j++) {
-                pre[j] = run;
-                if (!Fr::is_zero(ch[j])) run = Fr::mul(run, ch[j]);
-            }
-            fe inv = Fr::inv(run);
-            allinv = inv;                                                                       // product of the inverses of the non-zero challenges
-            for (size_t j = lg_n; j-- > 0;) {
-                if (Fr::is_zero(ch[j])) { ch_inv[j] = ch[j]; continue; }
-                ch_inv[j] = Fr::mul(inv, pre[j]);
-                inv = Fr::mul(inv, ch[j]);
-            }
-        }
+        std::vector<fe> ch = hd.ch, ch_inv = hd.ch_inv;
+        fe allinv = Fr::one();                                                                  // product of the inverses of the non-zero challenges
+        for (size_t j = 0; j < lg_n; j++)
+            if (!Fr::is_zero(ch_inv[j])) allinv = Fr::mul(allinv, ch_inv[j]);
         VerifyInputs vin;
         for (size_t j = 0; j < lg_n; j++) { ch[j] = Fr::sqr(ch[j]); ch_inv[j] = Fr::sqr(ch_inv[j]); vin.usq[j] = ch[j]; }   // :292-296
         const fe& a = proof.a;
@@ -1076,9 +1111,6 @@ struct VerifierT : ConstraintSystemBase {
                 delta = Fr::add(delta, part);
             }
         }
-        // r: challenge on a CLONE of the transcript (verifier.rs:516-519)
-        Transcript tc = t;
-        fe r = TP<C>::challenge_scalar(tc, "r");
         fe xx = Fr::sqr(x), rxx = Fr::mul(r, xx), xxx = Fr::mul(x, xx);
         out.padded_n = padded_n;
         // scalars[0], scalars[1]  (:529-530)
@@ -1151,6 +1183,59 @@ struct VerifierT : ConstraintSystemBase {
     }
 };
 
+// IPA challenges of many verifier transcripts in one launch (transcript_dev.cuh). heads[p] must come from vs_head;
+// proofs whose head failed are skipped; an identity L_j / R_j sets head_rc[p] = BP_ERR_VERIFY.
+template <class C>
+int device_ipa_challenges(bp_ctx* ctx, std::vector<VerifierT<C>*>& verifiers, std::vector<const ProofT<C>*>& proofs,
+                          std::vector<typename VerifierT<C>::Head>& heads, std::vector<int>& head_rc) {
+    const size_t k = verifiers.size();
+    std::vector<DevTranscriptIn> in(k);
+    std::vector<affine> pts;
+    for (size_t p = 0; p < k; p++) {
+        DevTranscriptIn& d = in[p];
+        memset(&d, 0, sizeof(d));
+        if (head_rc[p]) continue;                                  // lg_n = 0: the thread only draws an (unused) r
+        const Strobe128& s = verifiers[p]->transcript->strobe;
+        memcpy(d.st, s.state, 200);
+        d.pos = s.pos; d.pos_begin = s.pos_begin;
+        d.lg_n = (uint32_t)heads[p].lg_n;
+        d.padded_n = heads[p].padded_n;
+        if (pts.size() > 0xFFFFFFFFull - 64) return BP_ERR_LEN;
+        d.pt_off = (uint32_t)pts.size();
+        pts.insert(pts.end(), proofs[p]->L_vec.begin(), proofs[p]->L_vec.end());
+        pts.insert(pts.end(), proofs[p]->R_vec.begin(), proofs[p]->R_vec.end());
+    }
+    cudaStream_t st = ctx->stream;
+    const size_t out_fe = k * 32 * 2 + k;                          // u, u^-1 (32 slots per proof), r
+    BP_CUDA_TRY(ctx, ctx->tr_in.reserve(k * sizeof(DevTranscriptIn)));
+    BP_CUDA_TRY(ctx, ctx->tr_pts.reserve((pts.size() + 1) * sizeof(affine)));
+    BP_CUDA_TRY(ctx, ctx->tr_out.reserve(out_fe * sizeof(fe) + k));
+    BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tr_in.p, in.data(), k * sizeof(DevTranscriptIn), cudaMemcpyHostToDevice, st));
+    if (!pts.empty()) BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tr_pts.p, pts.data(), pts.size() * sizeof(affine), cudaMemcpyHostToDevice, st));
+    fe* d_u = ctx->tr_out.as<fe>();
+    fe* d_ui = d_u + k * 32;
+    fe* d_r = d_ui + k * 32;
+    uint8_t* d_status = reinterpret_cast<uint8_t*>(d_r + k);
+    verifier_ipa_challenges_kernel<C><<<(unsigned)((k + 63) / 64), 64, 0, st>>>(ctx->tr_in.as<DevTranscriptIn>(), ctx->tr_pts.as<affine>(), k, d_u, d_ui, d_r, d_status);
+    BP_LAUNCH_CHECK(ctx);
+    std::vector<uint8_t> back(out_fe * sizeof(fe) + k);
+    BP_CUDA_TRY(ctx, cudaMemcpyAsync(back.data(), ctx->tr_out.p, back.size(), cudaMemcpyDeviceToHost, st));
+    BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    const fe* h_u = reinterpret_cast<const fe*>(back.data());
+    const fe* h_ui = h_u + k * 32;
+    const fe* h_r = h_ui + k * 32;
+    const uint8_t* h_status = reinterpret_cast<const uint8_t*>(h_r + k);
+    for (size_t p = 0; p < k; p++) {
+        if (head_rc[p]) continue;
+        if (h_status[p]) { head_rc[p] = BP_ERR_VERIFY; continue; }  // validate_and_append_point (transcript.rs:81-93)
+        const size_t lg = heads[p].lg_n;
+        heads[p].ch.assign(h_u + p * 32, h_u + p * 32 + lg);
+        heads[p].ch_inv.assign(h_ui + p * 32, h_ui + p * 32 + lg);
+        heads[p].r = h_r[p];
+    }
+    return BP_OK;
+}
+
 // ---- batch_verify (src/r1cs/verifier.rs:604-691) -------------------------------------------------
 template <class C>
 int batch_verify_t(bp_ctx* ctx, Rng* prng, const fe* alphas, std::vector<VerifierT<C>*>& verifiers, std::vector<const ProofT<C>*>& proofs,
@@ -1167,9 +1252,22 @@ int batch_verify_t(bp_ctx* ctx, Rng* prng, const fe* alphas, std::vector<Verifie
     std::vector<affine> pts;
     std::vector<fe> tail;
     size_t max_n = 0, acc_n = 0;
+    // Large batches derive the inner-product challenges of all proofs in one launch (transcript_dev.cuh): every proof's
+    // host transcript runs through `w` first, the device appends the (L_j, R_j) and draws u_j, u_j^-1 and r for all of
+    // them, and the per-proof tails follow. Errors are still reported in proof order, like the reference's loop.
+    const bool dev_tr = ctx->dev_transcript_min > 0 && k >= (size_t)ctx->dev_transcript_min;
+    std::vector<typename VerifierT<C>::Head> heads(dev_tr ? k : 0);
+    std::vector<int> head_rc(dev_tr ? k : 0, BP_OK);
+    if (dev_tr) {
+        for (size_t p = 0; p < k; p++) head_rc[p] = verifiers[p]->vs_head(*proofs[p], gens, heads[p]);
+        if (int rc = device_ipa_challenges<C>(ctx, verifiers, proofs, heads, head_rc)) return rc;
+    }
     for (size_t p = 0; p < k; p++) {
         typename VerifierT<C>::Scalars sc;
-        if (int rc = verifiers[p]->verification_scalars(*proofs[p], gens, sc)) return rc;           // :619
+        if (dev_tr) {
+            if (head_rc[p]) return head_rc[p];
+            if (int rc = verifiers[p]->vs_tail(*proofs[p], gens, heads[p], sc)) return rc;
+        } else if (int rc = verifiers[p]->verification_scalars(*proofs[p], gens, sc)) return rc;           // :619
         size_t np = sc.padded_n;
         if (np > max_n) max_n = np;
         if (np > acc_n) {

@@ -278,6 +278,16 @@ int bp_batch_verify_partial(bp_ctx* ctx, const uint8_t* alphas, bp_verifier* con
                             const bp_gens* gens, uint8_t out_xy[64], int* out_is_identity);
 
 /* ---- R1CSProof::{to_bytes, from_bytes} (src/r1cs/proof.rs:74-91). With out == NULL only *len is set. */
+/* Device-side transcript (csrc/transcript_dev.cuh): batches of at least `min_proofs` proofs
+ * (default 32; 0 = never) derive the inner-product challenges u_j (src/inner_product_proof.rs:266-277), their inverses and
+ * the challenge `r` (src/r1cs/verifier.rs:516-519) of all their transcripts in one launch -- Keccak-f / STROBE / Merlin /
+ * ChaCha20 / ScalarField::rand, one transcript per thread -- instead of serially on the host. Same values, same decisions. */
+int bp_batch_verify_set_device_transcript(bp_ctx* ctx, int min_proofs);
+/* The device transcript on one transcript, for parity tests: continues from the state of `t` (not advanced) with
+ * innerproduct_domain_sep(padded_n) and the lg_n (L_j, R_j) pairs; out_u / out_u_inv = lg_n Montgomery scalars each,
+ * out_r = the challenge drawn from the clone; *out_identity_seen = 1 if an L_j or R_j is the identity. */
+int bp_transcript_ipa_challenges_device(bp_ctx* ctx, const bp_transcript* t, uint64_t padded_n, const uint8_t* L_xy, const uint8_t* R_xy, size_t lg_n,
+                                        uint8_t* out_u, uint8_t* out_u_inv, uint8_t out_r[32], int* out_identity_seen);
 void bp_proof_free(bp_proof* p);
 int bp_proof_to_bytes(const bp_proof* p, uint8_t* out, size_t cap, size_t* len);
 int bp_proof_from_bytes(int curve, const uint8_t* data, size_t len, bp_proof** out);

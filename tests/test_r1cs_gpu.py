@@ -714,3 +714,92 @@ def test_batch_verify_rejects_foreign_contexts(env):
     assert e.value.code == -1
     R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), [(gpu_verifier(R, ctx, kind, params, curve, coms), proof)], gens)
     gpu_verifier(R, other, kind, params, curve, coms).verify(proof, gens2)
+
+
+# ---- device-side transcript (csrc/transcript_dev.cuh) ------------------------------------------------
+@pytest.mark.parametrize("curve", ["secq256k1", "zorro", "curve25519"])
+def test_device_transcript_challenges_match_oracle(curve):
+    """Keccak-f / STROBE / Merlin / ChaCha20 / ScalarField::rand on the GPU: every inner-product challenge u_j, its
+    inverse, and the cloned-transcript challenge r equal the oracle's, for transcripts in different STROBE positions,
+    1..20 rounds (each round crosses the 166-byte rate at a different offset) and all three curves (curve25519's scalar
+    field rejects half of the ChaCha draws; its points serialise without a flag byte)."""
+    import ctypes as ct
+    from ark_bulletproofs_b200 import Context, codec
+    from ark_bulletproofs_b200 import r1cs as R
+    cv = O.CURVES[curve]
+    ctx = Context(curve, 0)
+    rnd = random.Random(4242)
+    r = cv.r
+    for lg_n, prefix in [(1, 0), (2, 3), (5, 17), (8, 40), (16, 101), (20, 7)]:
+        pts = [O.pt_mul(cv, rnd.randrange(1, r), cv.G) for _ in range(2 * lg_n)]
+        L, Rp = pts[:lg_n], pts[lg_n:]
+        n = 1 << lg_n
+        # same prefix on both sides, so the IPA part starts at different byte positions of the sponge
+        ot, gt = O.Transcript(b"devtr"), R.Transcript(b"devtr")
+        msg = bytes(range(prefix))
+        ot.append_message(b"pad", msg)
+        gt.append_message(b"pad", msg)
+        assert O.challenge_scalar(cv, ot, b"w") == gt.challenge_scalar(curve, b"w")
+        # oracle: inner_product_proof.rs:266-277, then verifier.rs:516-519
+        ot.append_message(b"dom-sep", b"ipp v1")
+        ot.append_u64(b"n", n)
+        want_u = []
+        for j in range(lg_n):
+            O.validate_and_append_point(cv, ot, b"L", L[j])
+            O.validate_and_append_point(cv, ot, b"R", Rp[j])
+            want_u.append(O.challenge_scalar(cv, ot, b"u"))
+        want_r = O.challenge_scalar(cv, ot.clone(), b"r")
+        out_u, out_ui, out_r = ct.create_string_buffer(32 * lg_n), ct.create_string_buffer(32 * lg_n), ct.create_string_buffer(32)
+        bad = ct.c_int(0)
+        rc = ctx.lib.bp_transcript_ipa_challenges_device(ctx.h, gt.h, n, codec.enc_points(L, curve), codec.enc_points(Rp, curve), lg_n,
+                                                         out_u, out_ui, out_r, ct.byref(bad))
+        assert rc == 0 and bad.value == 0
+        got_u = [codec.dec_fe(out_u.raw[32 * j:32 * j + 32], r) for j in range(lg_n)]
+        got_ui = [codec.dec_fe(out_ui.raw[32 * j:32 * j + 32], r) for j in range(lg_n)]
+        assert got_u == want_u
+        assert got_ui == [pow(u, -1, r) for u in want_u]
+        assert codec.dec_fe(out_r.raw, r) == want_r
+        # the host transcript was not advanced: the next host challenge is what the oracle gets before the IPA part
+        # an identity point is reported (validate_and_append_point -> VerificationError)
+        Lbad = list(L)
+        Lbad[lg_n // 2] = None
+        rc = ctx.lib.bp_transcript_ipa_challenges_device(ctx.h, gt.h, n, codec.enc_points(Lbad, curve), codec.enc_points(Rp, curve), lg_n,
+                                                         out_u, out_ui, out_r, ct.byref(bad))
+        assert rc == 0 and bad.value == 1
+
+
+@pytest.mark.parametrize("curve", ["secq256k1", "curve25519"])
+def test_batch_verify_device_transcript(env, curve):
+    """batch_verify with the IPA challenges of all proofs derived on the device (forced: threshold 1) makes the same
+    decisions as with the host transcript: accepts the golden proofs, rejects a batch with one tampered proof, and
+    reports an identity L_j as a verification error."""
+    from ark_bulletproofs_b200 import r1cs as R
+    ctx, gens = env(curve, 128)
+    cases = [("shuffle_fixed", {"inp": [5, 9, 2], "out": [2, 5, 9]}), ("chain", {"N": 20}), ("range", {"value": 0xA5, "bits": 8}), ("example", {})]
+    made = [(k, p) + gpu_prove_case(R, ctx, gens, k, p, curve) for k, p in cases]
+
+    def instances(tamper=None):
+        out = []
+        for i, (k, p, proof, coms) in enumerate(made):
+            pr = proof
+            if tamper is not None and i == tamper[0]:
+                pr = proof.clone()
+                tamper[1](pr)
+            out.append((gpu_verifier(R, ctx, k, p, curve, coms), pr))
+        return out
+    for thresh in (1, 0):
+        ctx.set_device_transcript(thresh)
+        try:
+            R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), instances(), gens)
+            with pytest.raises(R.BpError) as e:
+                R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), instances((1, lambda pr: pr.set_scalar(3, (pr.get_scalar(3) + 1) % O.CURVES[curve].r))), gens)
+            assert e.value.code == -7
+            with pytest.raises(R.BpError) as e:
+                R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), instances((2, lambda pr: pr.set_point(100, None))), gens)
+            assert e.value.code == -7
+            other = O.pt_mul(O.CURVES[curve], 999, O.CURVES[curve].G)
+            with pytest.raises(R.BpError) as e:
+                R.batch_verify(ctx, R.ChaChaRng(bytes([5] * 32)), instances((0, lambda pr: pr.set_point(200, other))), gens)
+            assert e.value.code == -7
+        finally:
+            ctx.set_device_transcript(32)
