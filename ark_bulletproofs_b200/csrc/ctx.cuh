@@ -32,6 +32,13 @@ struct DevBuf {
 
 }  // namespace bp
 
+#include <vector>
+// host copy of the constraint store whose flattening inputs (and sorted keys / permutation) are resident in the f_* buffers
+struct FlattenCache {
+    bool valid = false;
+    std::vector<uint32_t> key, cref, start, coeff;
+};
+
 static constexpr size_t BP_HOST_RESULT_BYTES = 128 * 1024;
 static constexpr size_t BP_HOST_COLL_BYTES = 64 * 8 * 64;      // world <= 64 ranks x MSM_MAX_BATCH partial points
 
@@ -71,6 +78,7 @@ struct bp_ctx {
     // MSM scratch
     bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;
     bp::DevBuf stage_bases, stage_scalars, pairpts, pairpre, tr_in, tr_pts, tr_out;
+    FlattenCache flatten_cache;
     int dev_transcript_min = 32;             // batches of at least this many proofs derive their IPA challenges on the device (0 = never)
     // IPA / prover / verifier work buffers (r1cs.cuh)
     bp::DevBuf ipa_G, ipa_H, ipa_s, ipa_parts, small, c_v, c_b, c_out;

@@ -460,9 +460,13 @@ inline int check_terms(const Variable* v, size_t n, size_t multipliers, size_t c
 }
 
 // Device flatten: d_wL/d_wR/d_wO (n each, device) are filled; wV (m) and wc come back to the host.
+// `reuse`: batch verification flattens many constraint systems that are usually the same circuit (same terms, same
+// coefficients; only z differs). The context remembers the store it uploaded last (an exact host copy, compared with
+// memcmp -- no hashing, no false hits) and, on a match, skips the four pageable uploads (4.4 MB at 2^16 multipliers:
+// ~0.45 ms, which is what bound bp_batch_verify) and the radix sort, whose result depends on the keys only.
 template <class C>
 int flatten_device(bp_ctx* ctx, const ConstraintStore& cs, const fe& z, size_t n, size_t m, fe* d_wL, fe* d_wR, fe* d_wO,
-                   std::vector<fe>& wV, fe* wc) {
+                   std::vector<fe>& wV, fe* wc, bool reuse = false) {
     using Fr = HostFp<typename C::Fr>;
     using D = Dev<C>;
     cudaStream_t st = ctx->stream;
@@ -486,10 +490,22 @@ int flatten_device(bp_ctx* ctx, const ConstraintStore& cs, const fe& z, size_t n
     BP_CUDA_TRY(ctx, ctx->f_ukeys.reserve(T * 4));
     BP_CUDA_TRY(ctx, ctx->f_sums.reserve(T * sizeof(fe)));
     BP_CUDA_TRY(ctx, ctx->f_wv.reserve((m + 2) * sizeof(fe) + 16));
-    D::upload(ctx, ctx->f_keys.p, cs.key.data(), T * 4);
-    D::upload(ctx, ctx->f_idx.p, cs.cref.data(), T * 4);
-    D::upload(ctx, ctx->f_coeff.p, cs.coeff_ex.data(), E * sizeof(fe));
-    if (int rc = D::upload(ctx, ctx->f_start.p, cs.start.data(), (Q + 1) * 4)) return rc;
+    FlattenCache& fc = ctx->flatten_cache;
+    const bool hit = reuse && fc.valid && fc.key.size() == T && fc.start.size() == Q + 1 && fc.coeff.size() == E * 8 &&
+                     memcmp(fc.key.data(), cs.key.data(), T * 4) == 0 && memcmp(fc.cref.data(), cs.cref.data(), T * 4) == 0 &&
+                     memcmp(fc.start.data(), cs.start.data(), (Q + 1) * 4) == 0 &&
+                     (E == 0 || memcmp(fc.coeff.data(), cs.coeff_ex.data(), E * sizeof(fe)) == 0);
+    fc.valid = false;                                   // the device buffers are about to change (or are confirmed below)
+    if (!hit) {
+        D::upload(ctx, ctx->f_keys.p, cs.key.data(), T * 4);
+        D::upload(ctx, ctx->f_idx.p, cs.cref.data(), T * 4);
+        D::upload(ctx, ctx->f_coeff.p, cs.coeff_ex.data(), E * sizeof(fe));
+        if (int rc = D::upload(ctx, ctx->f_start.p, cs.start.data(), (Q + 1) * 4)) return rc;
+        if (reuse) {
+            fc.key = cs.key; fc.cref = cs.cref; fc.start = cs.start;
+            fc.coeff.assign(reinterpret_cast<const uint32_t*>(cs.coeff_ex.data()), reinterpret_cast<const uint32_t*>(cs.coeff_ex.data()) + E * 8);
+        }
+    }
     uint32_t *keys = ctx->f_keys.as<uint32_t>(), *keys2 = ctx->f_keys2.as<uint32_t>(), *perm = ctx->f_perm.as<uint32_t>(), *perm2 = ctx->f_perm2.as<uint32_t>();
     flatten_contrib_kernel<C><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(ctx->f_idx.as<uint32_t>(), ctx->f_coeff.as<fe>(), ctx->f_start.as<uint32_t>(), Q,
                                                                           D::pow_table(z), perm, ctx->f_contrib.as<fe>());
@@ -502,7 +518,7 @@ int flatten_device(bp_ctx* ctx, const ConstraintStore& cs, const fe& z, size_t n
     BP_CUDA_TRY(ctx, cub::DeviceReduce::ReduceByKey(nullptr, tmp2, keys2, ctx->f_ukeys.as<uint32_t>(), ctx->f_sorted.as<fe>(), ctx->f_sums.as<fe>(), d_nruns,
                                                     FeAddOp<C>(), (int)T, st));
     BP_CUDA_TRY(ctx, ctx->f_tmp.reserve(tmp1 > tmp2 ? tmp1 : tmp2));
-    BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->f_tmp.p, tmp1, keys, keys2, perm, perm2, T, 0, 32, st));
+    if (!hit) BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->f_tmp.p, tmp1, keys, keys2, perm, perm2, T, 0, 32, st));
     flatten_gather_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(ctx->f_contrib.as<fe>(), perm2, T, ctx->f_sorted.as<fe>());
     BP_LAUNCH_CHECK(ctx);
     BP_CUDA_TRY(ctx, cub::DeviceReduce::ReduceByKey(ctx->f_tmp.p, tmp2, keys2, ctx->f_ukeys.as<uint32_t>(), ctx->f_sorted.as<fe>(), ctx->f_sums.as<fe>(), d_nruns,
@@ -514,6 +530,7 @@ int flatten_device(bp_ctx* ctx, const ConstraintStore& cs, const fe& z, size_t n
     if (int rc = D::download(ctx, back.data(), d_wV, (m + 1) * sizeof(fe))) return rc;
     for (size_t i = 0; i < m; i++) wV[i] = back[i];
     if (wc) *wc = back[m];
+    fc.valid = reuse;                                   // keys, coefficients, starts, sorted keys and permutation are resident
     return BP_OK;
 }
 
@@ -1052,13 +1069,13 @@ struct VerifierT : ConstraintSystemBase {
         h.r = TP<C>::challenge_scalar(tc, "r");
         return BP_OK;
     }
-    int verification_scalars(const ProofT<C>& proof, const GensDev& gens, Scalars& out) {
+    int verification_scalars(const ProofT<C>& proof, const GensDev& gens, Scalars& out, bool reuse_store = false) {
         Head h;
         if (int rc = vs_head(proof, gens, h)) return rc;
         if (int rc = vs_challenges_host(proof, h)) return rc;
-        return vs_tail(proof, gens, h, out);
+        return vs_tail(proof, gens, h, out, reuse_store);
     }
-    int vs_tail(const ProofT<C>& proof, const GensDev& gens, Head& hd, Scalars& out) {
+    int vs_tail(const ProofT<C>& proof, const GensDev& gens, Head& hd, Scalars& out, bool reuse_store = false) {
         cudaStream_t st = ctx->stream;
         const fe &y = hd.y, &z = hd.z, &u = hd.u, &x = hd.x, &w = hd.w, &r = hd.r;
         const size_t n1 = hd.n1, n = hd.n, padded_n = hd.padded_n, lg_n = hd.lg_n;
@@ -1067,7 +1084,7 @@ struct VerifierT : ConstraintSystemBase {
         fe wc;
         DevBuf* wb0[] = {&ctx->p_wL, &ctx->p_wR, &ctx->p_wO};
         for (auto* bf : wb0) BP_CUDA_TRY(ctx, bf->reserve((n + 1) * sizeof(fe)));
-        if (int rc = flatten_device<C>(ctx, cs, z, n, V.size(), ctx->p_wL.as<fe>(), ctx->p_wR.as<fe>(), ctx->p_wO.as<fe>(), wV, &wc)) return rc;   // :462
+        if (int rc = flatten_device<C>(ctx, cs, z, n, V.size(), ctx->p_wL.as<fe>(), ctx->p_wR.as<fe>(), ctx->p_wO.as<fe>(), wV, &wc, reuse_store)) return rc;   // :462
         std::vector<fe> ch = hd.ch, ch_inv = hd.ch_inv;
         fe allinv = Fr::one();                                                                  // product of the inverses of the non-zero challenges
         for (size_t j = 0; j < lg_n; j++)
@@ -1266,8 +1283,8 @@ int batch_verify_t(bp_ctx* ctx, Rng* prng, const fe* alphas, std::vector<Verifie
         typename VerifierT<C>::Scalars sc;
         if (dev_tr) {
             if (head_rc[p]) return head_rc[p];
-            if (int rc = verifiers[p]->vs_tail(*proofs[p], gens, heads[p], sc)) return rc;
-        } else if (int rc = verifiers[p]->verification_scalars(*proofs[p], gens, sc)) return rc;           // :619
+            if (int rc = verifiers[p]->vs_tail(*proofs[p], gens, heads[p], sc, k > 1)) return rc;
+        } else if (int rc = verifiers[p]->verification_scalars(*proofs[p], gens, sc, k > 1)) return rc;           // :619
         size_t np = sc.padded_n;
         if (np > max_n) max_n = np;
         if (np > acc_n) {
