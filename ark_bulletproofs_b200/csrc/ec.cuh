@@ -67,7 +67,7 @@ struct SW {
         el M = F::mul3(F::sqr(p.x));
         if (C::A_SMALL != 0) M = F::add(M, F::from_u32(C::A_SMALL));
         r.x = F::sub(F::sqr(M), F::dbl_l(S));
-        r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+        r.y = F::mul_sub(M, F::sub(S, r.x), W, p.y);
         r.zz = V;
         r.zzz = W;
         return r;
@@ -84,7 +84,7 @@ struct SW {
         el M = F::mul3(F::sqr(p.x));
         if (C::A_SMALL != 0) M = F::add(M, mul_a(F::sqr(p.zz)));
         r.x = F::sub(F::sqr(M), F::dbl_l(S));
-        r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+        r.y = F::mul_sub(M, F::sub(S, r.x), W, p.y);
         r.zz = F::mul(V, p.zz);
         r.zzz = F::mul(W, p.zzz);
         return r;
@@ -107,7 +107,7 @@ struct SW {
         el PPP = F::mul(P, PP);
         el Q = F::mul(acc.x, PP);
         el X3 = F::sub(F::sub_l(F::sqr(R), PPP), F::dbl_l(Q));
-        el Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(acc.y, PPP));
+        el Y3 = F::mul_sub(R, F::sub(Q, X3), acc.y, PPP);
         acc.x = X3;
         acc.y = Y3;
         acc.zz = F::mul(acc.zz, PP);
@@ -133,7 +133,7 @@ struct SW {
         el PPP = F::mul(P, PP);
         el Q = F::mul(U1, PP);
         el X3 = F::sub(F::sub_l(F::sqr(R), PPP), F::dbl_l(Q));
-        el Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(S1, PPP));
+        el Y3 = F::mul_sub(R, F::sub(Q, X3), S1, PPP);
         acc.x = X3;
         acc.y = Y3;
         acc.zz = F::mul(F::mul(acc.zz, q.zz), PP);

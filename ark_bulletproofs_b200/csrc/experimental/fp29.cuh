@@ -165,6 +165,7 @@ struct Fp29 {
     BP_HD static fl dbl_l(const fl& a) { fl r; for (int k = 0; k < 9; k++) r.v[k] = a.v[k] * 2; return r; }
     BP_HD static fl add(const fl& a, const fl& b) { return norm(add_l(a, b)); }
     BP_HD static fl sub(const fl& a, const fl& b) { return norm(sub_l(a, b)); }
+    BP_HD static fl mul_sub(const fl& a, const fl& b, const fl& c, const fl& d) { return sub(mul(a, b), mul(c, d)); }
     BP_HD static fl dbl(const fl& a) { return norm(dbl_l(a)); }
     BP_HD static fl mul3(const fl& a) { fl r; for (int k = 0; k < 9; k++) r.v[k] = a.v[k] * 3; return norm(r); }
     BP_HD static fl neg(const fl& a) { fl r; for (int k = 0; k < 9; k++) r.v[k] = -a.v[k]; return r; }

@@ -316,7 +316,208 @@ struct Fp {
         return o;
     }
 
-    BP_HD static fe sqr(const fe& a) { return mul(a, a); }
+    // r = t - m if t >= m for a 9-limb t < 3m: the result keeps its 9th limb (t9 < 2m afterwards)
+    BP_HD static void cond_sub9(uint32_t* t) {
+        uint32_t s[9];
+        s[0] = sub_cc(t[0], M::m(0));
+#pragma unroll
+        for (int i = 1; i < 8; i++) s[i] = subc_cc(t[i], M::m(i));
+        s[8] = subc_cc(t[8], 0u);
+        uint32_t borrow = subc(0u, 0u);    // 0xFFFFFFFF iff t < m
+#pragma unroll
+        for (int i = 0; i < 9; i++) t[i] = borrow ? t[i] : s[i];
+    }
+
+    // a*b + c*d (SUB = false) or a*b - c*d (SUB = true), times 2^-256 mod m: two products, ONE Montgomery reduction.
+    // The same even/odd-column CIOS as mul_generic with a second pair of product chains per round: 128 + 64 wide
+    // multiplies + 8 quotients instead of 2 x (128 + 8). Every XYZZ addition and doubling ends in one of these
+    // (Y3 = R*(Q - X3) - Y1*PPP). The difference is formed as a*b + c*(m - d), so all addends stay non-negative:
+    // T' <= (T + 3*(2^32 - 1)*m) / 2^32 keeps T < 3m, i.e. X, Y < 2^260 (9 limbs each), and the result needs two
+    // conditional subtractions instead of one.
+    template <bool SUB>
+    BP_HD static fe mul2(const fe& a, const fe& b, const fe& c, const fe& d_in) {
+        fe d = d_in;
+        if (SUB) {                                   // d <- m - d  (in (0, m]; d = 0 gives m = 0 mod m)
+            d.v[0] = sub_cc(M::m(0), d_in.v[0]);
+#pragma unroll
+            for (int i = 1; i < 7; i++) d.v[i] = subc_cc(M::m(i), d_in.v[i]);
+            d.v[7] = subc(M::m(7), d_in.v[7]);
+        }
+        uint32_t X[10], Y[10];
+#pragma unroll
+        for (int i = 0; i < 10; i++) { X[i] = 0; Y[i] = 0; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t bk = b.v[k], dk = d.v[k];
+            uint32_t Xn[10], Yn[10];
+            Xn[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+            for (int j = 1; j < 9; j++) Xn[j] = Y[j];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) wmadc_to_cc(Yn[j], Yn[j + 1], a.v[j + 1], bk, X[j + 2], X[j + 3]);
+            Yn[8] = addc(0u, 0u);
+            wmad_cc(Xn[0], Xn[1], a.v[0], bk);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Xn[j], Xn[j + 1], a.v[j], bk);
+            Xn[8] = addc(Xn[8], 0u);
+            wmad_cc(Yn[0], Yn[1], c.v[1], dk);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Yn[j], Yn[j + 1], c.v[j + 1], dk);
+            Yn[8] = addc(Yn[8], 0u);
+            wmad_cc(Xn[0], Xn[1], c.v[0], dk);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Xn[j], Xn[j + 1], c.v[j], dk);
+            Xn[8] = addc(Xn[8], 0u);
+            const uint32_t q = Xn[0] * M::INV32;
+            wmad_cc(Yn[0], Yn[1], q, M::m(1));
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Yn[j], Yn[j + 1], q, M::m(j + 1));
+            Yn[8] = addc(Yn[8], 0u);
+            wmad_cc(Xn[0], Xn[1], q, M::m(0));
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Xn[j], Xn[j + 1], q, M::m(j));
+            Xn[8] = addc(Xn[8], 0u);
+#pragma unroll
+            for (int j = 0; j < 9; j++) { X[j] = Xn[j]; Y[j] = Yn[j]; }
+            X[9] = 0; Y[9] = 0;
+        }
+        uint32_t r[9];
+        r[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+        for (int j = 1; j < 8; j++) r[j] = addc_cc(Y[j], X[j + 1]);
+        r[8] = addc(Y[8], 0u);
+        cond_sub9(r);
+        fe o;
+        final_sub(o, r, r[8]);
+        return o;
+    }
+#if defined(BP_NO_MUL2)
+    BP_HD static fe mul_add(const fe& a, const fe& b, const fe& c, const fe& d) { return add(mul(a, b), mul(c, d)); }
+    BP_HD static fe mul_sub(const fe& a, const fe& b, const fe& c, const fe& d) { return sub(mul(a, b), mul(c, d)); }
+#else
+    BP_HD static fe mul_add(const fe& a, const fe& b, const fe& c, const fe& d) { return mul2<false>(a, b, c, d); }
+    BP_HD static fe mul_sub(const fe& a, const fe& b, const fe& c, const fe& d) { return mul2<true>(a, b, c, d); }
+#endif
+
+    // a^2 * 2^-256 mod m with 36 + 64 wide multiplies instead of 128: the 28 off-diagonal products a_i*a_j (i < j) are
+    // summed once (even/odd columns as above, one row per a_i), doubled by a one-bit funnel shift, the 8 squares a_i^2
+    // are added on one chain, and the 512-bit square is reduced by the quotient rounds of the CIOS alone (the high half
+    // joins at the end: (L + Q*m)/2^256 + H < 2m).
+    BP_HD static fe sqr_sos(const fe& a) {
+        // off-diagonal sum S = sum_{i<j} a_i a_j 2^(32(i+j)) < 2^511: aligned columns E[p], offset columns O[p] (value 2^32 * O)
+        uint32_t E[16], O[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { E[i] = 0; O[i] = 0; }
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            // row i: products at positions p = i + j, j = i+1..7. Odd p go to O[p-1], O[p]; even p to E[p], E[p+1].
+            // Each parity is one carry chain over contiguous limbs; its carry-out lands on the limb above the last product,
+            // which earlier rows have touched at most as their own carry limb -- by S < 2^511 the ripple ends there.
+            const uint32_t ai = a.v[i];
+            // first position of the row, i + (i+1) = 2i+1, is odd
+            {
+                bool first = true;
+                int last = -1;
+#pragma unroll
+                for (int j = i + 1; j < 8; j += 2) {           // odd positions p = i + j (j - i odd)
+                    const int p = i + j;
+                    if (first) { wmad_cc(O[p - 1], O[p], ai, a.v[j]); first = false; }
+                    else wmadc_cc(O[p - 1], O[p], ai, a.v[j]);
+                    last = p;
+                }
+                if (last >= 0) {
+                    O[last + 1] = addc_cc(O[last + 1], 0u);
+                    O[last + 2] = addc(O[last + 2], 0u);
+                }
+            }
+            {
+                bool first = true;
+                int last = -1;
+#pragma unroll
+                for (int j = i + 2; j < 8; j += 2) {           // even positions
+                    const int p = i + j;
+                    if (first) { wmad_cc(E[p], E[p + 1], ai, a.v[j]); first = false; }
+                    else wmadc_cc(E[p], E[p + 1], ai, a.v[j]);
+                    last = p;
+                }
+                if (last >= 0) {
+                    E[last + 2] = addc_cc(E[last + 2], 0u);
+                    if (last + 3 < 16) E[last + 3] = addc(E[last + 3], 0u);
+                }
+            }
+        }
+        // S = E + 2^32 * O ; T = 2*S + sum a_i^2 2^(64 i)
+        uint32_t S[16];
+        S[0] = E[0];
+        S[1] = add_cc(E[1], O[0]);
+#pragma unroll
+        for (int i = 2; i < 15; i++) S[i] = addc_cc(E[i], O[i - 1]);
+        S[15] = addc(E[15], O[14]);
+        uint32_t T[16];
+        T[0] = S[0] << 1;
+#pragma unroll
+        for (int i = 1; i < 16; i++) T[i] = (S[i] << 1) | (S[i - 1] >> 31);
+        wmad_cc(T[0], T[1], a.v[0], a.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) wmadc_cc(T[2 * i], T[2 * i + 1], a.v[i], a.v[i]);
+        // Montgomery-reduce the low half: eight quotient rounds (X aligned, Y offset by one limb, as in mul_generic)
+        uint32_t X[10], Y[10];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { X[i] = T[i]; Y[i] = 0; }
+        X[8] = 0; X[9] = 0; Y[8] = 0; Y[9] = 0;
+        // round 0 has nothing to shift in yet: q from X[0]
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t Xn[10], Yn[10];
+            if (k == 0) {
+#pragma unroll
+                for (int j = 0; j < 9; j++) { Xn[j] = X[j]; Yn[j] = 0; }
+            } else {
+                Xn[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+                for (int j = 1; j < 9; j++) Xn[j] = Y[j];
+            }
+            const uint32_t q = Xn[0] * M::INV32;
+            if (k == 0) {
+                wmad_cc(Yn[0], Yn[1], q, M::m(1));
+#pragma unroll
+                for (int j = 2; j < 8; j += 2) wmadc_cc(Yn[j], Yn[j + 1], q, M::m(j + 1));
+                Yn[8] = addc(0u, 0u);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) wmadc_to_cc(Yn[j], Yn[j + 1], q, M::m(j + 1), X[j + 2], X[j + 3]);
+                Yn[8] = addc(0u, 0u);
+            }
+            wmad_cc(Xn[0], Xn[1], q, M::m(0));
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Xn[j], Xn[j + 1], q, M::m(j));
+            Xn[8] = addc(Xn[8], 0u);
+#pragma unroll
+            for (int j = 0; j < 9; j++) { X[j] = Xn[j]; Y[j] = Yn[j]; }
+            X[9] = 0; Y[9] = 0;
+        }
+        // (L + Q*m) / 2^256 = Y + (X >> 32), plus the high half H = T[8..15]
+        uint32_t r[9];
+        r[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+        for (int j = 1; j < 8; j++) r[j] = addc_cc(Y[j], X[j + 1]);
+        r[8] = addc(Y[8], 0u);
+        r[0] = add_cc(r[0], T[8]);
+#pragma unroll
+        for (int j = 1; j < 8; j++) r[j] = addc_cc(r[j], T[8 + j]);
+        r[8] = addc(r[8], 0u);
+        fe o;
+        final_sub(o, r, r[8]);
+        return o;
+    }
+
+    BP_HD static fe sqr(const fe& a) {
+#if defined(BP_NO_SQR)
+        return mul(a, a);
+#else
+        return sqr_sos(a);
+#endif
+    }
 
     BP_HD static fe one() {
         fe r;

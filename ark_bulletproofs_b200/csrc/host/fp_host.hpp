@@ -121,6 +121,8 @@ struct HostFp {
         return put(t);
     }
     static inline fe sqr(const fe& a) { return mul(a, a); }
+    static inline fe mul_sub(const fe& a, const fe& b, const fe& c, const fe& d) { return sub(mul(a, b), mul(c, d)); }
+    static inline fe mul_add(const fe& a, const fe& b, const fe& c, const fe& d) { return add(mul(a, b), mul(c, d)); }
     static inline fe one() { fe r; for (int i = 0; i < 8; i++) r.v[i] = M::one(i); return r; }
     static inline fe r2() { fe r; for (int i = 0; i < 8; i++) r.v[i] = M::r2(i); return r; }
     static inline fe to_mont(const fe& a) { return mul(a, r2()); }

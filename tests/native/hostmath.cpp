@@ -48,6 +48,34 @@ extern "C" int hm_fp_op(int field, int op, const uint32_t* a, const uint32_t* b,
     return -1;
 }
 
+// four-operand field operations: a*b - c*d and a*b + c*d with one reduction (Fp::mul2)
+template <class F> static int fp_op4_t(int op, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out) {
+    fe x, y, z, w, r;
+    memcpy(x.v, a, 32); memcpy(y.v, b, 32); memcpy(z.v, c, 32); memcpy(w.v, d, 32);
+    switch (op) {
+        case 0: r = F::mul_sub(x, y, z, w); break;
+        case 1: r = F::mul_add(x, y, z, w); break;
+        default: return -1;
+    }
+    memcpy(out, r.v, 32);
+    return 0;
+}
+extern "C" int hm_fp_op4(int field, int op, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out) {
+    switch (field) {
+        case 0: return fp_op4_t<Fp<SecqFq>>(op, a, b, c, d, out);
+        case 1: return fp_op4_t<Fp<SecqFr>>(op, a, b, c, d, out);
+        case 2: return fp_op4_t<Fp<ZorroFq>>(op, a, b, c, d, out);
+        case 3: return fp_op4_t<Fp<Fp25519>>(op, a, b, c, d, out);
+        case 4: return fp_op4_t<Fp<Fr25519>>(op, a, b, c, d, out);
+        case 10: return fp_op4_t<HostFp<SecqFq>>(op, a, b, c, d, out);
+        case 11: return fp_op4_t<HostFp<SecqFr>>(op, a, b, c, d, out);
+        case 12: return fp_op4_t<HostFp<ZorroFq>>(op, a, b, c, d, out);
+        case 13: return fp_op4_t<HostFp<Fp25519>>(op, a, b, c, d, out);
+        case 14: return fp_op4_t<HostFp<Fr25519>>(op, a, b, c, d, out);
+    }
+    return -1;
+}
+
 // points cross as affine (x,y) Montgomery, (0,0) = identity
 template <class E> static int ec_op_t(int op, const uint32_t* p, const uint32_t* q, const uint32_t* s, uint32_t* out) {
     affine P, Q;

@@ -58,6 +58,36 @@ def test_field_ops(lib, field):
             assert inv == pow(a, -1, m) * R % m
 
 
+@pytest.mark.parametrize("field", list(range(5)) + list(range(10, 15)))
+def test_field_fused_products_and_square(lib, field):
+    """Fp::mul2 (a*b -/+ c*d with one Montgomery reduction) and the dedicated squaring against big-integer
+    arithmetic: edge values that maximise every column (all-ones limbs, m - 1, top-bit patterns) and random ones."""
+    m = FIELDS[field % 10]
+    rnd = random.Random(99 + field)
+    rinv = pow(R, -1, m)
+    edge = [0, 1, 2, m - 1, m - 2, (m - 1) // 2, (1 << 255) % m, ((1 << 256) - 1) % m, 0xFFFFFFFF, (1 << 224) - 1,
+            int("ffffffff00000000" * 4, 16) % m, int("00000000ffffffff" * 4, 16) % m, int("80000000" * 8, 16) % m,
+            int("7fffffff" * 8, 16) % m, m - 0xFFFFFFFF, m - (1 << 128)]
+    vals = edge + [rnd.randrange(m) for _ in range(60)]
+
+    def op4(op, a, b, c, d):
+        out = (ctypes.c_uint32 * 8)()
+        assert lib.hm_fp_op4(field, op, _b(a), _b(b), _b(c), _b(d), out) == 0
+        return int.from_bytes(bytes(out), "little")
+
+    for a in vals:
+        assert _fp(lib, field, 7, a) == a * a * rinv % m
+    for a in edge:
+        for b in edge:
+            for c, d in [(m - 1, m - 1), (m - 1, 0), (0, m - 1), (a, b), (b, a), (m - 1, 1)]:
+                assert op4(0, a, b, c, d) == (a * b - c * d) * rinv % m
+                assert op4(1, a, b, c, d) == (a * b + c * d) * rinv % m
+    for _ in range(400):
+        a, b, c, d = (rnd.choice(vals) for _ in range(4))
+        assert op4(0, a, b, c, d) == (a * b - c * d) * rinv % m
+        assert op4(1, a, b, c, d) == (a * b + c * d) * rinv % m
+
+
 def _pt(cv, P):
     if P is None:
         return (ctypes.c_uint32 * 16)()
