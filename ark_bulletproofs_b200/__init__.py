@@ -107,8 +107,9 @@ class Context:
     def set_pedersen_table(self, enable: bool):
         self._check(self.lib.bp_pedersen_set_table(self.h, 1 if enable else 0))
 
-    def set_ipa_glv(self, enable: bool):
-        self._check(self.lib.bp_ipa_set_glv(self.h, 1 if enable else 0))
+    def set_ipa_glv(self, enable):
+        """0 = plain 256-step fold, 1 / True = GLV with joint-sparse-form digits (default), 2 = GLV with binary digits"""
+        self._check(self.lib.bp_ipa_set_glv(self.h, int(enable)))
 
     def set_ipa_geometric(self, enable: bool):
         self._check(self.lib.bp_ipa_set_geometric(self.h, 1 if enable else 0))
@@ -121,6 +122,9 @@ class Context:
 
     def set_affine_rounds(self, rounds: int, min_entries: int = 0):
         self._check(self.lib.bp_msm_set_affine_rounds(self.h, rounds, min_entries))
+
+    def set_two_level_reduce(self, enable: bool):
+        self._check(self.lib.bp_msm_set_two_level_reduce(self.h, int(enable)))
 
     def set_tiny(self, max_terms: int):
         self._check(self.lib.bp_msm_set_tiny(self.h, max_terms))

@@ -179,6 +179,7 @@ int bp_pedersen_set_table(bp_ctx* ctx, int enable) try {
 int bp_ipa_set_glv(bp_ctx* ctx, int enable) try {
     if (!ctx) return BP_ERR_ARG;
     ctx->ipa_glv = enable != 0;
+    ctx->ipa_jsf = enable != 2;
     return BP_OK;
 } BP_ABI_CATCH
 
@@ -192,6 +193,12 @@ int bp_msm_set_affine_rounds(bp_ctx* ctx, int rounds, size_t min_entries) try {
     if (!ctx || rounds < 0 || rounds > 6) return BP_ERR_ARG;
     ctx->msm_affine_rounds = rounds;
     if (min_entries) ctx->msm_affine_min_entries = min_entries;
+    return BP_OK;
+} BP_ABI_CATCH
+
+int bp_msm_set_two_level_reduce(bp_ctx* ctx, int enable) try {
+    if (!ctx) return BP_ERR_ARG;
+    ctx->msm_pair_reduce = enable != 0;
     return BP_OK;
 } BP_ABI_CATCH
 

@@ -68,11 +68,13 @@ struct bp_ctx {
     void* h_coll = nullptr;     // pinned, BP_HOST_COLL_BYTES
     bool gens_on_device = true;              // BulletproofGens chains on the GPU where the stream is seekable (bp_gens_set_device_generation)
     bool pedersen_table = true;              // batched Pedersen commitments through the fixed-base table (bp_pedersen_set_table)
+    bool ipa_jsf = true;                     // joint-sparse-form digits for the GLV fold (bp_ipa_set_glv(ctx, 2) = binary digits)
     bool ipa_glv = true;                     // GLV split of the uniform fold scalar where the curve has the endomorphism (bp_ipa_set_glv)
     bool ipa_geo = true;                     // use the uniform-scalar fold for geometric factor vectors (bp_ipa_set_geometric)
     int sm_count = 148;
     int msm_affine_rounds = 0;               // batched-affine pair rounds before the XYZZ accumulation (bp_msm_set_affine_rounds)
     size_t msm_affine_min_entries = (size_t)1 << 22;
+    bool msm_pair_reduce = true;             // two-level bucket reduction for large windows (msm_reduce_windows; bp_msm_set_two_level_reduce)
     int msm_tiny_max = 768;                  // MSMs of a batch with at most this many terms each take the single-launch path (0 = never; bp_msm_set_tiny)
     size_t msm_warp_partials_below = (size_t)1 << 17;   // partial-slot lists shorter than this are reduced by warp-segmented scans
     // MSM scratch

@@ -16,6 +16,57 @@ struct GlvSplit {
     int top;                 // index of the highest set bit over both magnitudes (-1 if both are zero)
 };
 
+// Joint sparse form (Solinas) of two non-negative magnitudes < 2^160: digits u1[j], u2[j] in {-1, 0, 1} with
+// sum u_i[j] 2^j = k_i and at most one zero column... precisely: of any two consecutive columns at least one is (0, 0),
+// so a joint double-and-add over {p1, p2, p1 + p2, p1 - p2} adds in about half of its steps (3/4 for plain binary
+// digits). Step j is the 4-bit code (u1 + 1) | (u2 + 1) << 2 at bits 4*(j & 7) of code[j >> 3]; top = last step.
+struct JsfDigits {
+    uint32_t code[21];
+    int top;
+};
+inline bool jsf_digits(const uint32_t k1[5], const uint32_t k2[5], JsfDigits& out) {
+    uint32_t a[6] = {k1[0], k1[1], k1[2], k1[3], k1[4], 0}, b[6] = {k2[0], k2[1], k2[2], k2[3], k2[4], 0};
+    auto nz = [](const uint32_t* x) { return (x[0] | x[1] | x[2] | x[3] | x[4] | x[5]) != 0; };
+    auto shr1 = [](uint32_t* x) {
+        for (int i = 0; i < 5; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+        x[5] >>= 1;
+    };
+    memset(out.code, 0, sizeof(out.code));
+    int d1 = 0, d2 = 0, j = 0;
+    while (nz(a) || nz(b) || d1 || d2) {
+        if (j >= 168) return false;
+        const int l1 = (int)((a[0] & 7u) + (uint32_t)d1) & 7, l2 = (int)((b[0] & 7u) + (uint32_t)d2) & 7;
+        int u1 = 0, u2 = 0;
+        if (l1 & 1) { u1 = 2 - (l1 & 3); if ((l1 == 3 || l1 == 5) && (l2 & 3) == 2) u1 = -u1; }
+        if (l2 & 1) { u2 = 2 - (l2 & 3); if ((l2 == 3 || l2 == 5) && (l1 & 3) == 2) u2 = -u2; }
+        if (2 * d1 == 1 + u1) d1 = 1 - d1;
+        if (2 * d2 == 1 + u2) d2 = 1 - d2;
+        shr1(a);
+        shr1(b);
+        out.code[j >> 3] |= (uint32_t)((u1 + 1) | ((u2 + 1) << 2)) << (4 * (j & 7));
+        j++;
+    }
+    out.top = j - 1;
+    // check: the digits reproduce both magnitudes (signed accumulation, MSB first)
+    for (int which = 0; which < 2; which++) {
+        __int128 hi = 0;            // value >> 64 would overflow 128 bits at 160-bit magnitudes: track two halves
+        uint64_t acc[3] = {0, 0, 0};   // 192-bit two's complement
+        for (int s = out.top; s >= 0; s--) {
+            // acc = 2*acc + u
+            uint64_t c = 0;
+            for (int i = 0; i < 3; i++) { uint64_t n = (acc[i] << 1) | c; c = acc[i] >> 63; acc[i] = n; }
+            const int u = (int)((out.code[s >> 3] >> (4 * (s & 7) + 2 * which)) & 3u) - 1;
+            if (u == 1) { for (int i = 0; i < 3; i++) { if (++acc[i] != 0) break; } }
+            else if (u == -1) { for (int i = 0; i < 3; i++) { if (acc[i]-- != 0) break; } }
+        }
+        (void)hi;
+        const uint32_t* k = which ? k2 : k1;
+        const uint64_t w0 = (uint64_t)k[0] | ((uint64_t)k[1] << 32), w1 = (uint64_t)k[2] | ((uint64_t)k[3] << 32), w2 = k[4];
+        if (acc[0] != w0 || acc[1] != w1 || acc[2] != w2) return false;
+    }
+    return true;
+}
+
 template <class C>
 struct GlvHost {
     using Fr = HostFp<typename C::Fr>;

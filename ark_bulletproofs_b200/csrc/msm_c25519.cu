@@ -1,4 +1,5 @@
 // curve25519 (twisted Edwards; tests/r1cs_curve25519.rs) instantiation of the MSM kernels.
+#define BP_MSM_INSTANTIATE
 #include "msm_kernels.cuh"
 namespace bp {
 template int msm_run<Curve25519>(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);

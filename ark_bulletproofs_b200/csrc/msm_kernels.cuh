@@ -426,9 +426,13 @@ __global__ void __launch_bounds__(128) msm_partials_final_kernel(const uint32_t*
 }
 
 // ---- 5. bucket reduction ---------------------------------------------------------------------
-template <class C>
+// PAIR = false: seg_out[t] = sum over the segment of (b + 1) * B_b (the segment offset lo * run by double-and-add).
+// PAIR = true (large windows): the offset is left to the next level -- seg_out[t] = sum (b - lo + 1) * B_b and
+// seg_run[t] = sum B_b; msm_window_partial_kernel adds seg * sum_s s * run_s, a weighted sum over nseg values instead of a
+// 13-bit double-and-add in every one of the nseg threads (11 % of this kernel's modmul at 64-bucket segments).
+template <class C, bool PAIR = false>
 __global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz* __restrict__ buckets, uint32_t nb, uint32_t seg, uint32_t nseg,
-                                                         int W, xyzz* __restrict__ seg_out) {
+                                                         int W, xyzz* __restrict__ seg_out, xyzz* __restrict__ seg_run = nullptr) {
     using E = GroupLaw<C>;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)W * nseg) return;
@@ -445,12 +449,56 @@ __global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz* __restrict_
         E::add(acc, run);
         v = nxt;
     }
-    // acc = sum (b - lo + 1) B_b ; weights are b + 1  ->  add lo * run
-    if (lo != 0 && !E::is_identity(run)) {
+    if (PAIR) {
+        st_xyzz(seg_run + t, run);
+    } else if (lo != 0 && !E::is_identity(run)) {
+        // acc = sum (b - lo + 1) B_b ; weights are b + 1  ->  add lo * run
         xyzz m = E::mul_u32(run, lo);
         E::add(acc, m);
     }
     st_xyzz(seg_out + t, acc);
+}
+
+// Second level of the PAIR reduction: block (slice, w) takes a contiguous range of window w's segments, every thread `per`
+// consecutive ones: sum_s acc_s + seg * sum_s s * run_s over the range (running sums inside the thread, one short
+// double-and-add for the thread's first segment index), tree-summed over the block into part_out[w * slices + slice].
+template <class C>
+__global__ void __launch_bounds__(128) msm_window_partial_kernel(const xyzz* __restrict__ seg_acc, const xyzz* __restrict__ seg_run, uint32_t nseg,
+                                                                 uint32_t seg, uint32_t per, xyzz* __restrict__ part_out) {
+    using E = GroupLaw<C>;
+    __shared__ xyzz sh[128];
+    const uint32_t w = blockIdx.y, slices = gridDim.x;
+    const uint32_t s0 = (blockIdx.x * blockDim.x + threadIdx.x) * per;
+    xyzz val = E::identity();
+    if (s0 < nseg) {
+        const uint32_t s1 = s0 + per < nseg ? s0 + per : nseg;
+        const xyzz* A = seg_acc + (size_t)w * nseg;
+        const xyzz* R = seg_run + (size_t)w * nseg;
+        xyzz r = E::identity(), a = E::identity();
+        for (uint32_t sidx = s1; sidx-- > s0;) {
+            xyzz rv = ld_xyzz(R + sidx);
+            E::add(r, rv);
+            E::add(a, r);                                  // a = sum (sidx - s0 + 1) * run
+            xyzz av = ld_xyzz(A + sidx);
+            E::add(val, av);
+        }
+        // sum sidx * run = a + (s0 - 1) * r
+        if (s0 == 0) { xyzz nr = E::neg(r); E::add(a, nr); }
+        else if (s0 > 1 && !E::is_identity(r)) { xyzz m = E::mul_u32(r, s0 - 1); E::add(a, m); }
+        if (!E::is_identity(a)) { xyzz m = E::mul_u32(a, seg); E::add(val, m); }
+    }
+    sh[threadIdx.x] = val;
+    __syncthreads();
+    for (int stride = 64; stride > 0; stride >>= 1) {
+        if ((int)threadIdx.x < stride) {
+            xyzz x = sh[threadIdx.x];
+            xyzz y = sh[threadIdx.x + stride];
+            E::add(x, y);
+            sh[threadIdx.x] = x;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_xyzz(part_out + (size_t)w * slices + blockIdx.x, sh[0]);
 }
 
 // ---- 6. window sums --------------------------------------------------------------------------
@@ -557,11 +605,10 @@ int host_combine(int curve, const void* win, int W, int c, uint8_t out_xy[64], i
 // the levels ping-pong between that region and the one behind it). Long lists: serial 16-slot chunks (throughput);
 // short lists: warp-segmented scans (latency).
 static constexpr int MSM_PL = 16;
+// pk / pp: a region of slots1 + 2 * ceil(slots1 / PL) + 64 slots whose first slots1 entries hold the level-1 list
 template <class C, bool ACC>
-int msm_fold_slots(bp_ctx* ctx, size_t slots1, cudaStream_t st) {
+int msm_fold_slots_at(bp_ctx* ctx, uint32_t* pk, xyzz* pp, size_t slots1, cudaStream_t st) {
     const int PL = MSM_PL;
-    uint32_t* pk = ctx->part_keys.as<uint32_t>();
-    xyzz* pp = ctx->part_pts.as<xyzz>();
     size_t nslots = slots1;
     uint32_t* in_k = pk;
     xyzz* in_p = pp;
@@ -585,6 +632,40 @@ int msm_fold_slots(bp_ctx* ctx, size_t slots1, cudaStream_t st) {
         xyzz* tp = in_p; in_p = out_p; out_p = tp;
     }
     msm_partials_warp_kernel<C, ACC><<<1, 32, 0, st>>>(in_k, in_p, nslots, 1, ctx->buckets.as<xyzz>(), out_k, out_p);
+    BP_LAUNCH_CHECK(ctx);
+    return BP_OK;
+}
+template <class C, bool ACC>
+int msm_fold_slots(bp_ctx* ctx, size_t slots1, cudaStream_t st) {
+    return msm_fold_slots_at<C, ACC>(ctx, ctx->part_keys.as<uint32_t>(), ctx->part_pts.as<xyzz>(), slots1, st);
+}
+static inline size_t msm_fold_region(size_t slots1) { return slots1 + 2 * ((slots1 + MSM_PL - 1) / MSM_PL) + 64; }
+
+// Bucket reduction + window sums of NW windows into ctx->win_out. Large windows (>= MSM_PAIR_MIN_NSEG segments) take the
+// two-level PAIR path: reduce (acc, run) per segment -> per-slice partial sums with the segment offsets -> window sums.
+static constexpr uint32_t MSM_PAIR_MIN_NSEG = 1024;
+static constexpr uint32_t MSM_PAIR_SLICES = 16;
+template <class C>
+int msm_reduce_windows(bp_ctx* ctx, const MsmPlan& p, int NW, cudaStream_t st) {
+    const size_t rt = (size_t)NW * p.nseg;
+    if (ctx->msm_pair_reduce && p.nseg >= MSM_PAIR_MIN_NSEG) {
+        BP_CUDA_TRY(ctx, ctx->seg_out.reserve((2 * rt + (size_t)NW * MSM_PAIR_SLICES) * sizeof(xyzz)));
+        xyzz* seg_acc = ctx->seg_out.as<xyzz>();
+        xyzz* seg_run = seg_acc + rt;
+        xyzz* part = seg_run + rt;
+        msm_reduce_kernel<C, true><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, NW, seg_acc, seg_run);
+        BP_LAUNCH_CHECK(ctx);
+        const uint32_t per = (p.nseg + MSM_PAIR_SLICES * 128 - 1) / (MSM_PAIR_SLICES * 128);
+        msm_window_partial_kernel<C><<<dim3(MSM_PAIR_SLICES, NW), 128, 0, st>>>(seg_acc, seg_run, p.nseg, p.seg, per, part);
+        BP_LAUNCH_CHECK(ctx);
+        msm_window_sum_kernel<C><<<NW, 128, 0, st>>>(part, MSM_PAIR_SLICES, ctx->win_out.as<xyzz>());
+        BP_LAUNCH_CHECK(ctx);
+        return BP_OK;
+    }
+    msm_reduce_kernel<C, false><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, NW,
+                                                                             ctx->seg_out.as<xyzz>());
+    BP_LAUNCH_CHECK(ctx);
+    msm_window_sum_kernel<C><<<NW, 128, 0, st>>>(ctx->seg_out.as<xyzz>(), p.nseg, ctx->win_out.as<xyzz>());
     BP_LAUNCH_CHECK(ctx);
     return BP_OK;
 }
@@ -676,7 +757,7 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
     size_t slots2 = 2 * ((slots1 + PL - 1) / PL);
     BP_CUDA_TRY(ctx, ctx->part_keys.reserve((slots1 + slots2 + 64) * 4));
     BP_CUDA_TRY(ctx, ctx->part_pts.reserve((slots1 + slots2 + 64) * sizeof(xyzz)));
-    BP_CUDA_TRY(ctx, ctx->seg_out.reserve((size_t)NW * p.nseg * sizeof(xyzz)));
+    BP_CUDA_TRY(ctx, ctx->seg_out.reserve((2 * (size_t)NW * p.nseg + (size_t)NW * MSM_PAIR_SLICES) * sizeof(xyzz)));
     BP_CUDA_TRY(ctx, ctx->win_out.reserve((size_t)NW * sizeof(xyzz)));
     if ((size_t)NW * sizeof(xyzz) > BP_HOST_RESULT_BYTES) return BP_ERR_LEN;
     size_t tmp_bytes = 0;
@@ -707,12 +788,7 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
     mark(2);
     if (int rc = msm_fold_slots<C, false>(ctx, slots1, st)) return rc;
     mark(3);
-    size_t rt = (size_t)NW * p.nseg;
-    msm_reduce_kernel<C><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, NW,
-                                                                       ctx->seg_out.as<xyzz>());
-    BP_LAUNCH_CHECK(ctx);
-    msm_window_sum_kernel<C><<<NW, 128, 0, st>>>(ctx->seg_out.as<xyzz>(), p.nseg, ctx->win_out.as<xyzz>());
-    BP_LAUNCH_CHECK(ctx);
+    if (int rc = msm_reduce_windows<C>(ctx, p, NW, st)) return rc;
     mark(4);
     // The Horner combination over windows is 256 dependent doublings: 1.35 ms on one GPU
     // thread (measured), ~0.1 ms on a host core. The W window sums (W*128 B) go to the host.
@@ -842,7 +918,7 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
         BP_CUDA_TRY(ctx, ctx->part_keys.reserve((worst1 + slots2 + 64) * 4));
         BP_CUDA_TRY(ctx, ctx->part_pts.reserve((worst1 + slots2 + 64) * sizeof(xyzz)));
     }
-    BP_CUDA_TRY(ctx, ctx->seg_out.reserve((size_t)p.W * p.nseg * sizeof(xyzz)));
+    BP_CUDA_TRY(ctx, ctx->seg_out.reserve((2 * (size_t)p.W * p.nseg + (size_t)p.W * MSM_PAIR_SLICES) * sizeof(xyzz)));
     BP_CUDA_TRY(ctx, ctx->win_out.reserve((size_t)p.W * sizeof(xyzz)));
     if ((size_t)p.W * sizeof(xyzz) > BP_HOST_RESULT_BYTES) return BP_ERR_LEN;
     size_t tmp_bytes = 0;
@@ -925,12 +1001,7 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
         BP_CUDA_TRY(ctx, cudaEventRecord(sc.fold_done, sc.fold));
     }
     BP_CUDA_TRY(ctx, cudaStreamWaitEvent(st, sc.fold_done, 0));
-    size_t rt = (size_t)p.W * p.nseg;
-    msm_reduce_kernel<C><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, p.W,
-                                                                       ctx->seg_out.as<xyzz>());
-    BP_LAUNCH_CHECK(ctx);
-    msm_window_sum_kernel<C><<<p.W, 128, 0, st>>>(ctx->seg_out.as<xyzz>(), p.nseg, ctx->win_out.as<xyzz>());
-    BP_LAUNCH_CHECK(ctx);
+    if (int rc = msm_reduce_windows<C>(ctx, p, p.W, st)) return rc;
     BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_result, ctx->win_out.p, (size_t)p.W * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
     BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return host_combine(ctx->curve, (const xyzz*)ctx->h_result, p.W, p.c, out_xy, out_is_identity);
@@ -943,5 +1014,17 @@ int synth_points_run(bp_ctx* ctx, void* d_out, size_t n, uint64_t start) {
     BP_LAUNCH_CHECK(ctx);
     return BP_OK;
 }
+
+// The kernels are instantiated once per curve, in msm_<curve>.cu (which define BP_MSM_INSTANTIATE); every other
+// translation unit that includes this header (the prover / verifier layer) links against those instances.
+#if !defined(BP_MSM_INSTANTIATE)
+#define BP_MSM_EXTERN(C)                                                                          \
+    extern template int msm_run<C>(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);    \
+    extern template int msm_run_job<C>(bp_ctx*, const MsmJob&, uint8_t (*)[64], int*);
+BP_MSM_EXTERN(Secq256k1)
+BP_MSM_EXTERN(Zorro)
+BP_MSM_EXTERN(Curve25519)
+#undef BP_MSM_EXTERN
+#endif
 
 }  // namespace bp

@@ -1,4 +1,5 @@
 // secq256k1 instantiation of the MSM kernels (one curve per translation unit keeps nvcc parallel).
+#define BP_MSM_INSTANTIATE
 #include "msm_kernels.cuh"
 namespace bp {
 template int msm_run<Secq256k1>(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);

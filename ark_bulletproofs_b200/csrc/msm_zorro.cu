@@ -1,4 +1,5 @@
 // zorro (src/curve/zorro/g1.rs) instantiation of the MSM kernels.
+#define BP_MSM_INSTANTIATE
 #include "msm_kernels.cuh"
 namespace bp {
 template int msm_run<Zorro>(bp_ctx*, const affine*, const fe*, size_t, uint8_t*, int*);

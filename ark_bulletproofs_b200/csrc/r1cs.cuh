@@ -212,6 +212,19 @@ int ipa_create(bp_ctx* ctx, Transcript& t, const affine& Q, const fe* d_Gf, cons
             const fe* ks[4] = {&kG, &kH, &kGx, &kHx};
             bool ok = ctx->ipa_glv;
             for (int q = 0; q < 4 && ok; q++) ok = GlvHost<C>::split(*ks[q], sp[q]);
+            JsfDigits jd[4];
+            bool jsf = ok && ctx->ipa_jsf;
+            for (int q = 0; q < 4 && jsf; q++) jsf = jsf_digits(sp[q].k1, sp[q].k2, jd[q]);
+            if (jsf) {
+                JsfBits b[4];
+                for (int q = 0; q < 4; q++) {
+                    memcpy(b[q].code, jd[q].code, sizeof(jd[q].code));
+                    b[q].neg1 = sp[q].neg1; b[q].neg2 = sp[q].neg2; b[q].top = jd[q].top;
+                }
+                ipa_fold_points_jsf_kernel<C><<<grid, 128, 0, st>>>(GL, GR, Gout, HL, HR, Hout, cnt, b[0], b[1], b[2], b[3], cross_lo, cross_hi, sh);
+                BP_LAUNCH_CHECK(ctx);
+                return BP_OK;
+            }
             if (ok) {
                 GlvBits b[4];
                 for (int q = 0; q < 4; q++) {

@@ -333,6 +333,125 @@ __global__ void __launch_bounds__(128) ipa_fold_points_glv_kernel(const affine* 
     st_fe(&out[i].y, r.y);
 }
 
+// The GLV fold with joint-sparse-form digits (host/glv_host.hpp: jsf_digits): the chain adds one of
+// {+-p1, +-p2, +-(p1 + p2), +-(p1 - p2)} in about half of its ~130 steps (the binary joint chain above adds in three
+// quarters of them, a quarter of those as full XYZZ additions of the un-normalised p1 + p2). p1 + p2 and p1 - p2 are
+// made affine for the whole block with one shared inversion, so every addition of the chain is a mixed one:
+// ~130 * (dbl + madd / 2) instead of ~130 * (dbl + madd / 2 + add / 4) modmul per output. Uniform control flow as before.
+struct JsfBits { uint32_t code[21]; int neg1, neg2, top; };
+
+// two XYZZ points -> affine with one field inversion per 128-thread block (see block_to_affine_128)
+template <class E>
+__device__ __forceinline__ void block_to_affine_128_x2(const xyzz& p, const xyzz& q, bool valid, affine& rp, affine& rq) {
+    using F = typename E::F;
+    static_assert(!E::IS_TE, "short Weierstrass only");
+    __shared__ fe sh_tot2[4];
+    __shared__ fe sh_inv2[4];
+    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+    const bool lp = valid && !E::is_identity(p), lq = valid && !E::is_identity(q);
+    const fe zp = lp ? F::mul(p.zz, p.zzz) : F::one();
+    const fe zq = lq ? F::mul(q.zz, q.zzz) : F::one();
+    const fe z = F::mul(zp, zq);
+    fe pre = z, suf = z;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const fe up = shfl_fe(pre, lane >= d ? lane - d : lane);
+        const fe dn = shfl_fe(suf, lane + d < 32 ? lane + d : lane);
+        if (lane >= d) pre = F::mul(pre, up);
+        if (lane + d < 32) suf = F::mul(suf, dn);
+    }
+    if (lane == 31) sh_tot2[warp] = pre;
+    __syncthreads();
+    if (warp == 0) {
+        const fe t0 = sh_tot2[0], t1 = sh_tot2[1], t2 = sh_tot2[2], t3 = sh_tot2[3];
+        const fe t01 = F::mul(t0, t1), t23 = F::mul(t2, t3);
+        const fe inv = F::inv(F::mul(t01, t23));
+        if (lane < 4) {
+            const fe others = lane == 0 ? F::mul(t1, t23) : lane == 1 ? F::mul(t0, t23) : lane == 2 ? F::mul(t01, t3) : F::mul(t01, t2);
+            sh_inv2[lane] = F::mul(inv, others);
+        }
+    }
+    __syncthreads();
+    const fe pe = shfl_fe(pre, lane > 0 ? lane - 1 : 0), se = shfl_fe(suf, lane < 31 ? lane + 1 : 31);
+    fe w = sh_inv2[warp];
+    if (lane > 0) w = F::mul(w, pe);
+    if (lane < 31) w = F::mul(w, se);              // w = 1 / (zp * zq)
+    rp = E::affine_identity();
+    rq = E::affine_identity();
+    if (lp) {
+        const fe wp = F::mul(w, zq);               // 1 / zp
+        rp.x = F::mul(p.x, F::mul(wp, p.zzz));
+        rp.y = F::mul(p.y, F::mul(wp, p.zz));
+    }
+    if (lq) {
+        const fe wq = F::mul(w, zp);
+        rq.x = F::mul(q.x, F::mul(wq, q.zzz));
+        rq.y = F::mul(q.y, F::mul(wq, q.zz));
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) ipa_fold_points_jsf_kernel(const affine* __restrict__ L0, const affine* __restrict__ R0,
+                                                                  affine* __restrict__ out0, const affine* __restrict__ L1,
+                                                                  const affine* __restrict__ R1, affine* __restrict__ out1,
+                                                                  size_t count, const __grid_constant__ JsfBits g0,
+                                                                  const __grid_constant__ JsfBits g1, const __grid_constant__ JsfBits g0x,
+                                                                  const __grid_constant__ JsfBits g1x, size_t cross_lo, size_t cross_hi, ShardIdx sh) {
+    using E = GroupLaw<C>;
+    using F = Fp<typename C::Fq>;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < 2 * count;
+    if (!valid) t = 0;
+    const bool second = t >= count;
+    size_t i = second ? t - count : t;
+    const affine* L = second ? L1 : L0;
+    const affine* R = second ? R1 : R0;
+    affine* out = second ? out1 : out0;
+    const size_t gi = i * sh.P + sh.g;
+    const bool cross = gi >= cross_lo && gi < cross_hi;     // see ipa_fold_points_uniform_kernel
+    const JsfBits& g = second ? (cross ? g1x : g1) : (cross ? g0x : g0);
+    affine p1 = ld_affine(R + i);
+    affine p2;
+    fe beta;
+#pragma unroll
+    for (int k = 0; k < 8; k++) beta.v[k] = C::glv_beta(k);
+    p2.x = F::mul(p1.x, beta);
+    p2.y = p1.y;
+    if (E::is_identity(p1)) p2 = p1;
+    if (g.neg1) p1 = E::neg(p1);
+    if (g.neg2) p2 = E::neg(p2);
+    affine ps, pd;
+    {
+        xyzz s = E::from_affine(p1), d = E::from_affine(p1);
+        E::madd(s, p2);
+        E::madd(d, E::neg(p2));
+        block_to_affine_128_x2<E>(s, d, valid, ps, pd);
+    }
+    xyzz acc = E::identity();
+#pragma unroll 1
+    for (int step = g.top; step >= 0; step--) {
+        acc = E::dbl(acc);
+        const uint32_t code = (g.code[step >> 3] >> (4 * (step & 7))) & 15u;
+        if (code == 5u) continue;                            // (0, 0)
+        const int u1 = (int)(code & 3u) - 1, u2 = (int)(code >> 2) - 1;
+        // u1*p1 + u2*p2 = +-p1, +-p2, +-(p1 + p2) or +-(p1 - p2)
+        affine q;
+        bool ng;
+        if (u2 == 0) { q = p1; ng = u1 < 0; }
+        else if (u1 == 0) { q = p2; ng = u2 < 0; }
+        else if (u1 == u2) { q = ps; ng = u1 < 0; }
+        else { q = pd; ng = u1 < 0; }
+        if (ng) q = E::neg(q);
+        E::madd(acc, q);
+    }
+    affine pl = ld_affine(L + i);
+    E::madd(acc, pl);
+    affine r = block_to_affine_128<E>(acc, valid);
+    if (!valid) return;
+    st_fe(&out[i].x, r.x);
+    st_fe(&out[i].y, r.y);
+}
+
 // First-round fold with per-element factors (inner_product_proof.rs:143-155):
 //   out[i] = (cL*f[i]) * P[i] + (cR*f[h+i]) * P[h+i]      (joint double-and-add)
 // Threads [0,h) handle (P0,f0,cL0,cR0) = (G, G_factors, u^-1, u); threads [h,2h) handle H with

@@ -216,3 +216,11 @@ extern "C" int hm_glv_split(const uint32_t* kappa_mont, uint32_t* out) {
     out[10] = (uint32_t)s.neg1; out[11] = (uint32_t)s.neg2; out[12] = (uint32_t)s.top;
     return 1;
 }
+
+// joint sparse form of two 160-bit magnitudes (host/glv_host.hpp); returns top, -1000 on failure
+extern "C" int hm_jsf(const uint32_t* k1, const uint32_t* k2, uint32_t* code21) {
+    JsfDigits d;
+    if (!jsf_digits(k1, k2, d)) return -1000;
+    memcpy(code21, d.code, sizeof(d.code));
+    return d.top;
+}

@@ -249,3 +249,29 @@ def test_glv_split(lib):
         assert abs(k1) < 1 << 130 and abs(k2) < 1 << 130
         top = max(abs(k1).bit_length(), abs(k2).bit_length()) - 1
         assert ctypes.c_int32(out[12]).value == top
+
+
+def test_joint_sparse_form(lib):
+    """jsf_digits (host/glv_host.hpp): the signed digits reproduce both magnitudes, no two consecutive columns are both
+    non-zero, and the joint weight is about half of the length (Solinas)."""
+    rnd = random.Random(7)
+    cases = [(0, 0), (1, 0), (0, 1), (1, 1), (3, 5), ((1 << 130) - 1, (1 << 130) - 1), ((1 << 159) + 1, 1), (11, (1 << 160) - 1)]
+    cases += [(rnd.getrandbits(130), rnd.getrandbits(130)) for _ in range(300)]
+    cases += [(rnd.getrandbits(rnd.randrange(1, 160)), rnd.getrandbits(rnd.randrange(1, 160))) for _ in range(300)]
+    weight = steps = 0
+    for k1, k2 in cases:
+        a = (ctypes.c_uint32 * 5).from_buffer_copy(k1.to_bytes(20, "little"))
+        b = (ctypes.c_uint32 * 5).from_buffer_copy(k2.to_bytes(20, "little"))
+        code = (ctypes.c_uint32 * 21)()
+        top = lib.hm_jsf(a, b, code)
+        assert top >= -1
+        u = [((code[j >> 3] >> (4 * (j & 7))) & 3) - 1 for j in range(top + 1)]
+        v = [((code[j >> 3] >> (4 * (j & 7) + 2)) & 3) - 1 for j in range(top + 1)]
+        assert all(x in (-1, 0, 1) for x in u + v)
+        assert sum(x << j for j, x in enumerate(u)) == k1
+        assert sum(x << j for j, x in enumerate(v)) == k2
+        nzc = [bool(x or y) for x, y in zip(u, v)]
+        if k1.bit_length() > 100 and k2.bit_length() > 100:
+            weight += sum(nzc)
+            steps += top + 1
+    assert 0.45 < weight / steps < 0.55

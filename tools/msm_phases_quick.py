@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from ark_bulletproofs_b200 import Context, codec  # noqa: E402
 import bp_oracle as O  # noqa: E402
 
+MODES = [int(x) for x in os.environ.get("BP_MODES", "1").split(",")]
 lgs = [int(x) for x in sys.argv[1:]] or [24]
 ctx = Context("secq256k1", 0)
 ctx.set_timing(True)
@@ -27,6 +28,7 @@ torch.cuda.synchronize()
 cv = O.SECQ256K1
 R256 = 1 << 256
 for lg in lgs:
+  if True:
     n = 1 << lg
     w = torch.arange(1, n + 1, dtype=torch.int64, device="cuda")
     b = sc[: n * 32].view(n, 32)
@@ -35,6 +37,8 @@ for lg in lgs:
         total += int((b[:, l].to(torch.int64) * w).sum().item()) << (8 * l)
     s = total % cv.r * pow(R256, -1, cv.r) % cv.r
     want = O.pt_mul(cv, s, cv.G) if s else None
+  for mode in MODES:
+    ctx.set_two_level_reduce(bool(mode))
     for _ in range(3):
         res = ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -47,5 +51,5 @@ for lg in lgs:
     raw, ident = res
     got = None if ident else codec.dec_point(raw, "secq256k1")
     ph = ctx.last_phases()
-    print(json.dumps({"lg_n": lg, "ms": round(e0.elapsed_time(e1) / reps, 3), "closed_form_ok": got == want,
+    print(json.dumps({"lg_n": lg, "two_level_reduce": mode, "ms": round(e0.elapsed_time(e1) / reps, 3), "closed_form_ok": got == want,
                       "phases_ms": {k: round(v, 3) for k, v in ph["ms"].items()}}), flush=True)

@@ -15,6 +15,8 @@ timing = len(sys.argv) > 2 and sys.argv[2] == "timing"
 curve = sys.argv[3] if len(sys.argv) > 3 else "secq256k1"
 ctx = Context(curve, 0)
 ctx.set_timing(timing)
+if os.environ.get("BP_GLV"):
+    ctx.set_ipa_glv(int(os.environ["BP_GLV"]))
 if os.environ.get("BP_NOFOLD"):
     ctx.set_ipa_nofold_threshold(int(os.environ["BP_NOFOLD"]))
 r = codec.MODULI[curve][1]
