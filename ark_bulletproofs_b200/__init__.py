@@ -123,6 +123,10 @@ class Context:
     def set_affine_rounds(self, rounds: int, min_entries: int = 0):
         self._check(self.lib.bp_msm_set_affine_rounds(self.h, rounds, min_entries))
 
+    def set_sort(self, mode: int, min_entries: int = 0):
+        """1 = the pipeline's own two-pass bucket sort (default), 0 = cub::DeviceRadixSort"""
+        self._check(self.lib.bp_msm_set_sort(self.h, mode, min_entries))
+
     def set_two_level_reduce(self, enable: bool):
         self._check(self.lib.bp_msm_set_two_level_reduce(self.h, int(enable)))
 

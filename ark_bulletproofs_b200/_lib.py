@@ -52,6 +52,7 @@ def load():
         "bp_msm_set_window": (i32, [vp, i32]),
         "bp_msm_set_tiny": (i32, [vp, i32]),
         "bp_msm_set_two_level_reduce": (i32, [vp, i32]),
+        "bp_msm_set_sort": (i32, [vp, i32, sz]),
         "bp_msm_set_affine_rounds": (i32, [vp, i32, sz]),
         "bp_msm_set_chunk": (i32, [vp, sz]),
         "bp_ipa_set_nofold_threshold": (i32, [vp, sz]),

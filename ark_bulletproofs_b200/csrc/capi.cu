@@ -196,6 +196,13 @@ int bp_msm_set_affine_rounds(bp_ctx* ctx, int rounds, size_t min_entries) try {
     return BP_OK;
 } BP_ABI_CATCH
 
+int bp_msm_set_sort(bp_ctx* ctx, int mode, size_t min_entries) try {
+    if (!ctx || mode < 0 || mode > 1) return BP_ERR_ARG;
+    ctx->msm_sort_mode = mode;
+    if (min_entries) ctx->msm_sort_min_entries = min_entries;
+    return BP_OK;
+} BP_ABI_CATCH
+
 int bp_msm_set_two_level_reduce(bp_ctx* ctx, int enable) try {
     if (!ctx) return BP_ERR_ARG;
     ctx->msm_pair_reduce = enable != 0;

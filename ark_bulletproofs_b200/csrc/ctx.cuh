@@ -74,12 +74,16 @@ struct bp_ctx {
     int sm_count = 148;
     int msm_affine_rounds = 0;               // batched-affine pair rounds before the XYZZ accumulation (bp_msm_set_affine_rounds)
     size_t msm_affine_min_entries = (size_t)1 << 22;
+    // pairs of single large MSMs are ordered by the two-pass bucket sort of msm_sort.cuh instead of cub::DeviceRadixSort
+    // (bp_msm_set_sort); below msm_sort_min_entries (point, window) pairs, and for batched MSMs, the library sort stays
+    int msm_sort_mode = 1;
+    size_t msm_sort_min_entries = (size_t)1 << 22;
     bool msm_pair_reduce = true;             // two-level bucket reduction for large windows (msm_reduce_windows; bp_msm_set_two_level_reduce)
     int msm_tiny_max = 768;                  // MSMs of a batch with at most this many terms each take the single-launch path (0 = never; bp_msm_set_tiny)
     size_t msm_warp_partials_below = (size_t)1 << 17;   // partial-slot lists shorter than this are reduced by warp-segmented scans
     // MSM scratch
     bp::DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_keys, part_pts, seg_out, win_out, result;
-    bp::DevBuf stage_bases, stage_scalars, pairpts, pairpre, tr_in, tr_pts, tr_out;
+    bp::DevBuf stage_bases, stage_scalars, pairpts, pairpre, tr_in, tr_pts, tr_out, sort_scratch;
     FlattenCache flatten_cache;
     int dev_transcript_min = 32;             // batches of at least this many proofs derive their IPA challenges on the device (0 = never)
     // IPA / prover / verifier work buffers (r1cs.cuh)
@@ -87,7 +91,7 @@ struct bp_ctx {
     bp::DevBuf p_aL, p_aR, p_aO, p_sL, p_sR, p_wL, p_wR, p_wO, p_ypow, p_yinv, p_l, p_r, p_Gf, p_Hf, v_pts, v_sc, v_g, v_h, v_accg, v_acch, f_kind, f_idx, f_coeff, f_start, f_keys, f_keys2, f_perm, f_perm2, f_contrib, f_sorted, f_ukeys, f_sums, f_tmp, f_wv;
     template <class F> void for_each_buf(F f) {
         bp::DevBuf* all[] = {&keys_a, &keys_b, &vals_a, &vals_b, &cub_tmp, &buckets, &part_keys, &part_pts, &seg_out, &win_out, &result,
-                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &coll_send, &coll_recv, &pairpts, &pairpre, &tr_in, &tr_pts, &tr_out, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &c_v, &c_b, &c_out, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
+                             &stage_bases, &stage_scalars, &stage2_bases, &stage2_scalars, &coll_send, &coll_recv, &pairpts, &pairpre, &tr_in, &tr_pts, &tr_out, &sort_scratch, &ipa_G, &ipa_H, &ipa_s, &ipa_parts, &small, &c_v, &c_b, &c_out, &p_aL, &p_aR, &p_aO, &p_sL, &p_sR,
                              &p_wL, &p_wR, &p_wO, &p_ypow, &p_yinv, &p_l, &p_r, &p_Gf, &p_Hf, &v_pts, &v_sc, &v_g, &v_h, &v_accg, &v_acch, &f_kind, &f_idx, &f_coeff, &f_start, &f_keys, &f_keys2, &f_perm, &f_perm2, &f_contrib, &f_sorted,
                              &f_ukeys, &f_sums, &f_tmp, &f_wv};
         for (auto* b : all) f(b);

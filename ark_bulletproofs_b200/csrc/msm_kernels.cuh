@@ -27,6 +27,7 @@
 #include <vector>
 #include "ctx.cuh"
 #include "host/nccl_dyn.hpp"
+#include "msm_sort.cuh"
 
 namespace bp {
 
@@ -766,6 +767,11 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
                                                      p.key_bits, st));
     BP_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
 
+    SortPlan splan;
+    if (ctx->msm_sort_mode == 1 && job.nmsm == 1 && p.entries >= ctx->msm_sort_min_entries && !(C::KIND == 0 && ctx->msm_affine_rounds > 0)) {
+        splan = make_sort_plan(n, p.W, p.c - 1);
+        if (splan.ok) BP_CUDA_TRY(ctx, ctx->sort_scratch.reserve(sort_scratch_bytes(splan)));
+    }
     ctx->last_c = p.c; ctx->last_W = p.W; ctx->last_entries = p.entries;
     auto mark = [&](int i) { if (ctx->timing) cudaEventRecord(ctx->ev[i], st); };
     mark(0);
@@ -773,9 +779,16 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
                                                                      ctx->vals_a.as<uint32_t>());
     BP_LAUNCH_CHECK(ctx);
     mark(7);
-    BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->keys_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(),
-                                                     ctx->vals_a.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, 0,
-                                                     p.key_bits, st));
+    if (splan.ok) {
+        int nl = 0;
+        BP_CUDA_TRY(ctx, sort_pairs_run(splan, ctx->keys_a.as<uint32_t>(), ctx->vals_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(),
+                                        ctx->sort_scratch.p, st, &nl));
+        ctx->launches += nl;
+    } else {
+        BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->keys_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(),
+                                                         ctx->vals_a.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), p.entries, 0,
+                                                         p.key_bits, st));
+    }
     mark(1);
     BP_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, nbuckets * sizeof(xyzz), st));
     uint32_t* pk = ctx->part_keys.as<uint32_t>();
@@ -926,6 +939,14 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
                                                      ctx->vals_a.as<uint32_t>(), ctx->vals_b.as<uint32_t>(), max_entries, 0,
                                                      p.key_bits, st));
     BP_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
+    if (ctx->msm_sort_mode == 1) {
+        size_t worst = 0;
+        for (size_t c : cnt_of) {
+            SortPlan sp = make_sort_plan(c, p.W, p.c - 1);
+            if (sp.ok && sort_scratch_bytes(sp) > worst) worst = sort_scratch_bytes(sp);
+        }
+        if (worst) BP_CUDA_TRY(ctx, ctx->sort_scratch.reserve(worst));
+    }
     ctx->last_c = p.c; ctx->last_W = p.W; ctx->last_entries = n * (size_t)p.W;
     if (ctx->timing) for (int i = 0; i < 5; i++) ctx->phase_ms[i] = 0;
 
@@ -983,8 +1004,16 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
         msm_digits_kernel<C><<<(unsigned)((cnt + 255) / 256), 256, 0, sc.prep>>>(job, cnt, q.c, q.W, ctx->keys_a.as<uint32_t>(),
                                                                                 ctx->vals_a.as<uint32_t>());
         BP_LAUNCH_CHECK(ctx);
-        BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->keys_a.as<uint32_t>(), skeys,
-                                                         ctx->vals_a.as<uint32_t>(), svals, q.entries, 0, q.key_bits, sc.prep));
+        SortPlan splan;
+        if (ctx->msm_sort_mode == 1 && q.entries >= ctx->msm_sort_min_entries) splan = make_sort_plan(cnt, q.W, q.c - 1);
+        if (splan.ok && sort_scratch_bytes(splan) <= ctx->sort_scratch.cap) {
+            int nl = 0;
+            BP_CUDA_TRY(ctx, sort_pairs_run(splan, ctx->keys_a.as<uint32_t>(), ctx->vals_a.as<uint32_t>(), skeys, svals, ctx->sort_scratch.p, sc.prep, &nl));
+            ctx->launches += nl;
+        } else {
+            BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->keys_a.as<uint32_t>(), skeys,
+                                                             ctx->vals_a.as<uint32_t>(), svals, q.entries, 0, q.key_bits, sc.prep));
+        }
         BP_CUDA_TRY(ctx, cudaEventRecord(sc.sorted[s], sc.prep));
         // main
         BP_CUDA_TRY(ctx, cudaStreamWaitEvent(st, sc.sorted[s], 0));

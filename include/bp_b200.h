@@ -143,6 +143,12 @@ int bp_gens_set_device_generation(bp_ctx* ctx, int enable);
  * thread sharing one field inversion (~7 instead of 10 modmul per addition). Applies to short-Weierstrass MSMs with at
  * least `min_entries` (point, window) pairs (0 keeps the current threshold, default 2^22). 0 rounds = off. */
 int bp_msm_set_affine_rounds(bp_ctx* ctx, int rounds, size_t min_entries);
+/* Ordering of the (bucket, point) pairs of a single large MSM (csrc/msm_sort.cuh): mode 1 (default) = the two-pass bucket
+ * sort written for this pipeline (coarse bins by the top bucket bits, then one thread block per bin ranks the low bits
+ * with shared-memory atomics; the order inside a bucket is free); mode 0 = cub::DeviceRadixSort. Applies to MSMs with at
+ * least `min_entries` (point, window) pairs (0 keeps the current threshold, default 2^22); batched MSMs always take the
+ * library sort. Same results. */
+int bp_msm_set_sort(bp_ctx* ctx, int mode, size_t min_entries);
 /* Two-level bucket reduction of large windows (csrc/msm_kernels.cuh, msm_reduce_windows): every 64-bucket segment
  * yields its (weighted sum, plain sum) pair and the segment offsets are applied once per slice of segments instead of by
  * a double-and-add in every segment thread (2^24 points: 4.9 -> 3.7 ms). Default on; same results. */

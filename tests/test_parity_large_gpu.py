@@ -295,3 +295,46 @@ def test_large_golden_sharded(world):
         return hashlib.sha256(raw).hexdigest()
     for digest in _sharded(world, g["curve"], run):
         assert digest == g["sha256"]
+
+
+@pytest.mark.parametrize("lg_n", [14, 16, 20])
+@pytest.mark.parametrize("kind", ["uniform", "all_equal", "half_zero", "r_minus_1"])
+def test_msm_bucket_sort_closed_form(ctx, lg_n, kind):
+    """csrc/msm_sort.cuh at sizes below its default threshold: the pipeline's own two-pass bucket sort against the closed
+    form and against the library sort, for every adversarial scalar set (all_equal / r_minus_1 put a whole window into one
+    bucket: the global-memory path of the bins kernel; half_zero: the zero-digit tail)."""
+    import torch
+    n, start = 1 << lg_n, 5 * (1 << lg_n) + 7
+    pts = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    ctx.synth_points_device(pts.data_ptr(), n, start)
+    ctx.sync()
+    sc = _scalar_bytes(kind, n, 4000 + lg_n)
+    torch.cuda.synchronize()
+    want = _closed_form(sc, n, start)
+    try:
+        ctx.set_sort(1, 1)
+        got1 = ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n)
+        ctx.set_sort(0, 1)
+        got0 = ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n)
+    finally:
+        ctx.set_sort(1, 1 << 22)
+    assert _dec(*got1) == want
+    assert got0 == got1
+
+
+def test_msm_bucket_sort_ragged_sizes(ctx):
+    """sizes that are no multiple of the tile or the bin size, through both sorts"""
+    import torch
+    for n in (32768 + 1, 40000 + 17, (1 << 17) - 3):
+        pts = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+        ctx.synth_points_device(pts.data_ptr(), n, 11)
+        ctx.sync()
+        sc = _scalar_bytes("uniform", n, 77 + n)
+        torch.cuda.synchronize()
+        want = _closed_form(sc, n, 11)
+        try:
+            ctx.set_sort(1, 1)
+            got1 = ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n)
+        finally:
+            ctx.set_sort(1, 1 << 22)
+        assert _dec(*got1) == want

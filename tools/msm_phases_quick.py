@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from ark_bulletproofs_b200 import Context, codec  # noqa: E402
 import bp_oracle as O  # noqa: E402
 
-MODES = [int(x) for x in os.environ.get("BP_MODES", "1").split(",")]
+MODES = [int(x) for x in os.environ.get("BP_MODES", "0,1").split(",")]
 lgs = [int(x) for x in sys.argv[1:]] or [24]
 ctx = Context("secq256k1", 0)
 ctx.set_timing(True)
@@ -38,7 +38,7 @@ for lg in lgs:
     s = total % cv.r * pow(R256, -1, cv.r) % cv.r
     want = O.pt_mul(cv, s, cv.G) if s else None
   for mode in MODES:
-    ctx.set_two_level_reduce(bool(mode))
+    ctx.set_sort(mode, 1 << 18)
     for _ in range(3):
         res = ctx.msm_device(pts.data_ptr(), sc.data_ptr(), n)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -51,5 +51,5 @@ for lg in lgs:
     raw, ident = res
     got = None if ident else codec.dec_point(raw, "secq256k1")
     ph = ctx.last_phases()
-    print(json.dumps({"lg_n": lg, "two_level_reduce": mode, "ms": round(e0.elapsed_time(e1) / reps, 3), "closed_form_ok": got == want,
+    print(json.dumps({"lg_n": lg, "sort(1=bucket sort,0=cub)": mode, "ms": round(e0.elapsed_time(e1) / reps, 3), "closed_form_ok": got == want,
                       "phases_ms": {k: round(v, 3) for k, v in ph["ms"].items()}}), flush=True)
