@@ -54,7 +54,8 @@ class Context:
         c, w, e = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_uint64(0)
         self._check(self.lib.bp_msm_last_phases(self.h, ph, ctypes.byref(c), ctypes.byref(w), ctypes.byref(e)))
         names = ["digits", "sort", "accumulate", "partials", "reduce"]
-        return {"ms": {n: ph[i] for i, n in enumerate(names)}, "c": c.value, "windows": w.value, "entries": e.value}
+        return {"ms": {n: ph[i] for i, n in enumerate(names)}, "c": c.value, "windows": w.value, "entries": e.value,
+                "bucket_sort": ph[5] == 1.0}
 
     STAGES = ["rng", "commit", "flatten", "vec", "t_commit", "ipa", "ipa_msm", "ipa_fold", "ipa_host", "verify_scalars", "verify_msm", "upload", "tail"]
 

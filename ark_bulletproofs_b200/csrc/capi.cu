@@ -244,11 +244,13 @@ static int msm_host_scalars(bp_ctx* ctx, const uint8_t* bases_xy, const void* d_
         return bp::msm_dispatch(ctx, d_bases ? d_bases : ctx->stage_bases.p, ctx->stage_scalars.p, n, out_xy, out_is_identity);
     }
     // Chunk schedule: the copy stream runs back to back (55 GB/s: 1.7 ms per 2^20 points, 0.6 ms when only the scalars
-    // move), the kernels follow at ~2.4 ms per 2^20 points plus ~0.5 ms of slot levels per chunk. The first copy cannot be
-    // hidden, so the first chunk is small (CHUNK/4); large chunks are cheaper per point (longer runs per bucket, fewer slot
-    // levels), and chunk k+1 has arrived when chunk k is done as long as it is at most ~1.4x as large (~4x with resident
-    // bases) -- so the chunks grow by 1.5x (3x), up to 2 CHUNK (4 CHUNK).
-    // 2^24 points with the default CHUNK = 2^22: 1M, 1.5M, 2.25M, 3.4M, 5.1M, 2.8M; with resident bases 1M, 3M, 9M, 3M.
+    // move), the kernels follow at ~2.4 ms per 2^20 points. The first copy cannot be hidden, so the first chunk is small
+    // (CHUNK/4); every further chunk costs one extra mixed addition per non-empty bucket (its runs start from the bucket's
+    // value instead of from their first point: 6.8 M additions ~ 1 ms at 2^24), so chunks should be few, and chunk k+1 has
+    // arrived when chunk k is done as long as it is at most ~1.4x as large (~4x with resident bases) -- so the chunks grow
+    // by 1.5x (3x), up to 2 CHUNK (4 CHUNK). Swept at 2^24 (tools/msm_e2e_sweep.py, round 2 kernels): CHUNK = 2^20 / 2^21 /
+    // 2^22 / 2^23 -> 49.2 / 47.2 / 48.4 / 49.4 ms against 40.2 ms device-resident.
+    // 2^24 points with the default CHUNK = 2^21: 0.5M, 0.75M, 1.1M, 1.7M, 2.5M, 3.8M, 4M, 1.9M.
     std::vector<size_t> lo_of, cnt_of;
     {
         size_t a = CHUNK / 4 ? CHUNK / 4 : 1, rem = n, lo = 0;

@@ -52,7 +52,7 @@ struct bp_ctx {
     std::string err;
     uint64_t launches = 0;
     int force_c = 0;
-    size_t msm_chunk = (size_t)1 << 22;
+    size_t msm_chunk = (size_t)1 << 21;
     size_t ipa_nofold_n = (size_t)1 << 13;   // IPA rounds with n <= this use MSMs over the stage generators instead of folding them   // host-buffer MSMs above 1.5x this are chunked (copy/compute overlap)
     // Multi-GPU: one bp_ctx per process/GPU; generators are sharded cyclically by index
     // (rank g holds i = g mod world), every MSM over them yields a partial point per rank, and the partials are

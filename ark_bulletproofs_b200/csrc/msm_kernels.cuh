@@ -814,6 +814,7 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
         cudaEventElapsedTime(&ctx->phase_ms[2], ctx->ev[1], ctx->ev[2]);
         cudaEventElapsedTime(&ctx->phase_ms[3], ctx->ev[2], ctx->ev[3]);
         cudaEventElapsedTime(&ctx->phase_ms[4], ctx->ev[3], ctx->ev[4]);
+        ctx->phase_ms[5] = splan.ok ? 1.0f : 0.0f;
     }
     // one Horner chain (~256 dependent doublings, ~0.1 ms) per MSM of the batch: independent, so the extra ones run on
     // their own host threads (L and R of an IPA round, the three vector commitments, the five T commitments)

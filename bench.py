@@ -681,7 +681,21 @@ def main():
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch_lg%d" % args.lg_n)
     hbm, hbm_src = hbm_peak()
-    sort_bytes = phases["entries"] * 8 * 2 * ((phases["c"] - 1 + max(1, (phases["windows"] - 1).bit_length()) + 7) // 8)
+    # pair ordering: the pipeline's bucket sort reads the keys once (histogram) and moves every 8-byte pair twice (36 B per
+    # pair); the library radix sort reads the keys once and moves every pair once per 8-bit pass
+    if phases.get("bucket_sort"):
+        sort_bytes = phases["entries"] * 36
+        sort_kernel = "bucket sort of (bucket, point) pairs (csrc/msm_sort.cuh: hist, colscan, binscan, scatter, bins)"
+    else:
+        sort_bytes = phases["entries"] * (4 + 8 * 2 * ((phases["c"] - 1 + max(1, (phases["windows"] - 1).bit_length()) + 7) // 8))
+        sort_kernel = "cub radix sort of (bucket, point) pairs"
+    # multiplier issue slots the mixed addition really executes (cuobjdump counts, tools/microbench7.cu): a wide product
+    # (IMAD.WIDE / IMAD.HI) holds the multiplier for two slots, a 32-bit IMAD for one. Product: 128 wide + 8 = 264;
+    # squaring (Fp::sqr_sos): 90 wide + 10 hi + 22 = 222; fused a*b - c*d with one reduction (Fp::mul2): 184 wide + 8 hi + 8 = 392.
+    # madd = 6 products + 2 squarings + 1 fused = 2420 slots (round 1: 10 products = 2640). The first addition into an
+    # empty bucket is a copy.
+    real_adds = phases["entries"] - phases["windows"] * (1 << (phases["c"] - 1))
+    pipe_frac = real_adds * 2420 / (acc_ms * 1e-3) / peak
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -698,12 +712,12 @@ def main():
                      "unit": "TIMAD/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                      "algorithmic": "%d bucket additions x 10 modmul x 136 IMAD" % phases["entries"], "peak_source": peak_src,
                      "launch_ms": round(acc_ms, 4),
-                     # every 32x32->64 product (IMAD.WIDE with or without carry, IMAD.HI) holds the multiplier for two issue
-                     # slots: 31.7 IMAD.HI/clk/SM against 63.3 IMAD.lo/clk/SM (profiles/r1_microbench.json), 4 clk per warp
-                     # IMAD.WIDE in both multipliers of profiles/r2_microbench3_fp29_vs_cios.json -- so a formulation built
-                     # on 64-bit products tops out at 0.5 of `peak`
-                     "frac_of_wide_product_ceiling": round(achieved / peak / 0.5, 4)},
-        "roofline_hbm": {"bound": "hbm", "kernel": "cub radix sort of (bucket, point) pairs", "achieved": round(sort_bytes / (phases["ms"]["sort"] * 1e-3) / 1e9, 1),
+                     # `frac` counts the reference formulation (10 modmul x 136 multiply-adds per addition) against the
+                     # 32-bit IMAD peak; a 32x32->64 product holds the multiplier for two issue slots, so a formulation of
+                     # 10 plain products tops out at 0.5 (round 1: 0.448). `multiplier_pipe_busy` is what the kernel really
+                     # issues (2420 slots per addition after the fused product and the dedicated squaring) over the same peak.
+                     "multiplier_pipe_busy": round(pipe_frac, 4)},
+        "roofline_hbm": {"bound": "hbm", "kernel": sort_kernel, "achieved": round(sort_bytes / (phases["ms"]["sort"] * 1e-3) / 1e9, 1),
                          "peak": hbm, "unit": "GB/s", "frac": round(sort_bytes / (phases["ms"]["sort"] * 1e-3) / 1e9 / hbm, 4),
                          "peak_source": hbm_src, "launch_ms": round(phases["ms"]["sort"], 4)},
         "phases_ms": {k: round(v, 4) for k, v in phases["ms"].items()},
@@ -712,7 +726,7 @@ def main():
         #   partials / reduce: XYZZ additions of 14 modmul x 136 IMAD        -> IMAD (reduce: 2 per bucket)
         "kernels": {
             "msm_digits_kernel": {"bound": "hbm", "frac": round(n * (32 + 8 * phases["windows"]) / (phases["ms"]["digits"] * 1e-3) / 1e9 / hbm, 4)},
-            "cub_radix_sort": {"bound": "hbm", "frac": round(sort_bytes / (phases["ms"]["sort"] * 1e-3) / 1e9 / hbm, 4)},
+            "pair_sort": {"bound": "hbm", "frac": round(sort_bytes / (phases["ms"]["sort"] * 1e-3) / 1e9 / hbm, 4)},
             "msm_accumulate_kernel": {"bound": "imad", "frac": round(achieved / peak, 4)},
             "msm_reduce_kernel+window_sum": {"bound": "imad", "frac": round(phases["windows"] * (1 << (phases["c"] - 1)) * 2 * 14 * MODMUL_IMAD / (phases["ms"]["reduce"] * 1e-3) / peak, 4)},
         },

@@ -81,7 +81,8 @@ int bp_msm_bases(bp_ctx* ctx, const bp_bases* bases, size_t offset, const uint8_
                  int* out_is_identity);
 /* Per-phase device timing of the last MSM (cudaEvents on the context's stream), for the roofline
  * numbers in bench.py: phase_ms[0..4] = digits, sort, accumulate, partial reduction, bucket
- * reduction + window sums; *c / *windows / *entries describe the Pippenger plan that ran. */
+ * reduction + window sums; phase_ms[5] = 1 if the pairs were ordered by the pipeline's own bucket sort (msm_sort.cuh),
+ * 0 for the library radix sort; *c / *windows / *entries describe the Pippenger plan that ran. */
 int bp_ctx_set_timing(bp_ctx* ctx, int enable);
 int bp_msm_last_phases(const bp_ctx* ctx, float phase_ms[8], int* c, int* windows, uint64_t* entries);
 /* Host wall-clock split (ms) of the last bp_prover_prove / bp_verifier_verify on this context:
@@ -110,7 +111,7 @@ int bp_ctx_set_collective(bp_ctx* ctx, int rank, int world, bp_allgather_fn fn, 
  * the reference's `parallel` feature (Cargo.toml:76) across GPUs. */
 int bp_nccl_unique_id(uint8_t out[128]);
 int bp_ctx_init_nccl(bp_ctx* ctx, int rank, int world, const uint8_t unique_id[128]);
-/* bp_msm over host buffers of more than 1.5x `points` points (default 2^22) is streamed: the input is copied chunk by
+/* bp_msm over host buffers of more than 1.5x `points` points (default 2^21) is streamed: the input is copied chunk by
  * chunk (first chunk points/4, each next one 1.5x larger, at most 2x points) while the kernels of the chunks already
  * on the device run, all chunks adding into one bucket array. Exposed for tests and tuning. */
 int bp_msm_set_chunk(bp_ctx* ctx, size_t points);

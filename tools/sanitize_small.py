@@ -32,6 +32,29 @@ for lg in (10, 15):
     d_sc.view(-1, 32)[:, 31] &= 0x7F
     torch.cuda.synchronize()
     ctx.msm_device(d_pts.data_ptr(), d_sc.data_ptr(), n)
+# round 2: the pipeline's own bucket sort (staged and oversize-bin paths, zero-digit tail) and the two-level bucket reduction
+for kind in ("uniform", "all_equal", "half_zero"):
+    n = 1 << 16
+    d_pts = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    ctx.synth_points_device(d_pts.data_ptr(), n, 0)
+    d_sc = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda")
+    d_sc[:, 31] &= 0x7F
+    if kind == "all_equal":
+        d_sc[:] = d_sc[0].clone()
+    if kind == "half_zero":
+        d_sc[1::2] = 0
+    torch.cuda.synchronize()
+    ctx.set_sort(1, 1)
+    a = ctx.msm_device(d_pts.data_ptr(), d_sc.data_ptr(), n)
+    ctx.set_sort(0, 1)
+    assert ctx.msm_device(d_pts.data_ptr(), d_sc.data_ptr(), n) == a
+ctx.set_sort(1, 1 << 22)
+ctx.set_window(17)                          # 2^16 buckets per window: 1024 reduce segments -> msm_reduce_kernel<PAIR>, msm_window_partial_kernel
+a = ctx.msm_device(d_pts.data_ptr(), d_sc.data_ptr(), 1 << 12)
+ctx.set_two_level_reduce(False)
+assert ctx.msm_device(d_pts.data_ptr(), d_sc.data_ptr(), 1 << 12) == a
+ctx.set_two_level_reduce(True)
+ctx.set_window(0)
 r = codec.MODULI[curve][1]
 
 
