@@ -90,6 +90,10 @@ struct SW {
         return r;
     }
 
+    // The doubling branches of madd / add (P == Q) are taken for adversarial inputs only. Moving them out of line
+    // (__noinline__) was measured: +3 % / +17 % on dependent chains of madd / add (tools/microbench7.cu), but the MSM kernels
+    // got slower (accumulate 31.95 -> 32.8 ms, reduce 3.77 -> 4.07 ms at 2^24: call ABI, stack frames, spills at the
+    // 128-register cap), so they stay inline.
     // acc += (x2,y2)   [madd-2008-s], all special cases handled
     BP_HD static void madd(ext& acc, const aff& q) {
         if (is_identity(q)) return;

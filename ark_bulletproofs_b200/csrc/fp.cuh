@@ -543,15 +543,25 @@ struct Fp {
         return to_mont(o);
     }
 
-    // a^e, e as 8 little-endian limbs (square-and-multiply, MSB first)
+    // a^e, e as 8 little-endian limbs: fixed 4-bit windows, MSB first -- 14 multiplications for the table, then four
+    // squarings and at most one multiplication per nibble (252 S + <= 77 M; plain square-and-multiply needs a
+    // multiplication per set bit: ~190 for the Fermat exponents of the secq256k1 fields, 250 for 2^255 - 19).
+    // The table lives in local memory (dynamic index); the chain is latency, not bandwidth.
     BP_HD_NOINL static fe pow(const fe& a, const uint32_t* e) {
+        fe tbl[16];
+        tbl[0] = one();
+        tbl[1] = a;
+        for (int i = 2; i < 16; i++) tbl[i] = mul(tbl[i - 1], a);
         fe r = one();
         bool started = false;
         for (int i = 7; i >= 0; i--) {
-            for (int bit = 31; bit >= 0; bit--) {
-                if (started) r = sqr(r);
-                if ((e[i] >> bit) & 1u) {
-                    r = started ? mul(r, a) : a;
+            for (int nib = 7; nib >= 0; nib--) {
+                const uint32_t d = (e[i] >> (4 * nib)) & 15u;
+                if (started) {
+                    r = sqr(sqr(sqr(sqr(r))));
+                    if (d) r = mul(r, tbl[d]);
+                } else if (d) {
+                    r = tbl[d];
                     started = true;
                 }
             }
