@@ -656,10 +656,16 @@ int msm_reduce_windows(bp_ctx* ctx, const MsmPlan& p, int NW, cudaStream_t st) {
         xyzz* part = seg_run + rt;
         msm_reduce_kernel<C, true><<<(unsigned)((rt + 127) / 128), 128, 0, st>>>(ctx->buckets.as<xyzz>(), p.nb, p.seg, p.nseg, NW, seg_acc, seg_run);
         BP_LAUNCH_CHECK(ctx);
-        const uint32_t per = (p.nseg + MSM_PAIR_SLICES * 128 - 1) / (MSM_PAIR_SLICES * 128);
-        msm_window_partial_kernel<C><<<dim3(MSM_PAIR_SLICES, NW), 128, 0, st>>>(seg_acc, seg_run, p.nseg, p.seg, per, part);
+        // The second level is a chain of ~50 dependent additions per thread: pure latency, and a warp that has its
+        // scheduler to itself runs it twice as fast as two sharing one -- so at most one 4-warp block per SM
+        // (2^24 points: 13 windows x 11 slices = 143 blocks on 148 SMs).
+        uint32_t slices = (uint32_t)(ctx->sm_count / NW);
+        if (slices < 1) slices = 1;
+        if (slices > MSM_PAIR_SLICES) slices = MSM_PAIR_SLICES;
+        const uint32_t per = (p.nseg + slices * 128 - 1) / (slices * 128);
+        msm_window_partial_kernel<C><<<dim3(slices, NW), 128, 0, st>>>(seg_acc, seg_run, p.nseg, p.seg, per, part);
         BP_LAUNCH_CHECK(ctx);
-        msm_window_sum_kernel<C><<<NW, 128, 0, st>>>(part, MSM_PAIR_SLICES, ctx->win_out.as<xyzz>());
+        msm_window_sum_kernel<C><<<NW, 128, 0, st>>>(part, slices, ctx->win_out.as<xyzz>());
         BP_LAUNCH_CHECK(ctx);
         return BP_OK;
     }
