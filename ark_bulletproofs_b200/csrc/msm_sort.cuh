@@ -16,8 +16,14 @@
 // stage (adversarial scalar sets: all scalars equal puts a whole window into one bucket) is ranked from global memory by
 // the same block, slower but correct.
 #pragma once
+#include <cstddef>
 #include <cstdint>
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#define BP_SORT_HD __host__ __device__
+#else
+#define BP_SORT_HD
+#endif
 
 namespace bp {
 
@@ -39,7 +45,7 @@ struct SortPlan {
     uint32_t tiles = 0;     // tiles per window
     size_t hist_elems() const { return (size_t)W * tiles * (nb1 + 1); }
     size_t bins_total() const { return (size_t)W * nb1; }
-    __host__ __device__ int low_of(uint32_t w) const { return w + 1 == W ? low_top : low_bits; }
+    BP_SORT_HD int low_of(uint32_t w) const { return w + 1 == W ? low_top : low_bits; }
 };
 
 // One MSM (nmsm == 1) of n terms, W windows of cb bucket bits. Returns ok = false where the library sort stays.
@@ -65,6 +71,7 @@ static inline SortPlan make_sort_plan(size_t n, int W, int cb, int scalar_bits =
     return s;
 }
 
+#if defined(__CUDACC__)
 // ---- hist: tile_hist[w][tile][b] for b in [0, nb1] (b = nb1 counts the zero digits) ------------------------------------
 static __global__ void __launch_bounds__(512) sort_hist_kernel(const uint32_t* __restrict__ keys, const __grid_constant__ SortPlan sp,
                                                         uint16_t* __restrict__ tile_hist) {
@@ -358,5 +365,7 @@ static inline cudaError_t sort_pairs_run(const SortPlan& sp, const uint32_t* key
     *launches += 5;
     return cudaGetLastError();
 }
+
+#endif  // __CUDACC__
 
 }  // namespace bp

@@ -7,6 +7,7 @@
 #include "../../ark_bulletproofs_b200/csrc/host/fp_host.hpp"
 #include "../../ark_bulletproofs_b200/csrc/experimental/fp29.cuh"
 #include "../../ark_bulletproofs_b200/csrc/host/glv_host.hpp"
+#include "../../ark_bulletproofs_b200/csrc/msm_sort.cuh"
 using namespace bp;
 
 // Fp<M>::mul_sparse where it exists (the device templates), the ordinary product for the host reference class
@@ -223,4 +224,11 @@ extern "C" int hm_jsf(const uint32_t* k1, const uint32_t* k2, uint32_t* code21) 
     if (!jsf_digits(k1, k2, d)) return -1000;
     memcpy(code21, d.code, sizeof(d.code));
     return d.top;
+}
+
+// planner of the MSM's bucket sort (csrc/msm_sort.cuh): out = {ok, low_bits, low_top, nb1, tiles, cap, tile}
+extern "C" void hm_sort_plan(uint64_t n, int W, int cb, uint32_t* out) {
+    SortPlan p = make_sort_plan((size_t)n, W, cb);
+    out[0] = p.ok; out[1] = (uint32_t)p.low_bits; out[2] = (uint32_t)p.low_top; out[3] = p.nb1; out[4] = p.tiles;
+    out[5] = SORT_BIN_CAP; out[6] = SORT_TS;
 }

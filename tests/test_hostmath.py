@@ -275,3 +275,32 @@ def test_joint_sparse_form(lib):
             weight += sum(nzc)
             steps += top + 1
     assert 0.45 < weight / steps < 0.55
+
+
+def test_bucket_sort_plan(lib):
+    """make_sort_plan (csrc/msm_sort.cuh) for every window width the MSM planner can choose and sizes from 2^12 to 2^26:
+    at most 1024 coarse bins and 1024 low-bit counters, bins that fit the shared-memory stage with a margin, the last
+    window's bins scaled to the range its digits really span, and a refusal (library sort) everywhere else."""
+    out = (ctypes.c_uint32 * 8)()
+    accepted = 0
+    for c in range(4, 21):
+        W, cb = 256 // c + 1, c - 1
+        for n in [1 << k for k in range(12, 27)] + [(1 << 20) + 12345, 3 * (1 << 20), (1 << 24) - 1, (1 << 24) + 1]:
+            lib.hm_sort_plan(ctypes.c_uint64(n), W, cb, out)
+            ok, low, low_top, nb1, tiles, cap, ts = out[0], out[1], out[2], out[3], out[4], out[5], out[6]
+            if not ok:
+                continue
+            accepted += 1
+            assert nb1 & (nb1 - 1) == 0 and 1 <= nb1 <= 1024
+            assert 0 <= low <= 10 and nb1 << low == 1 << cb
+            assert tiles == -(-n // ts)
+            assert n // nb1 <= cap * 4 // 5                    # average bin fits the stage with 25 % to spare
+            top_bits = max(0, min(cb, 256 - (W - 1) * c))      # the last window's buckets are < 2^top_bits
+            assert low_top <= low and (nb1 << low_top) >= (1 << top_bits)   # its coarse bin index stays below nb1
+            if top_bits > low_top:                             # ... and it uses as many of them as its range allows
+                assert (1 << (top_bits - low_top)) == min(nb1, 1 << top_bits)
+    lib.hm_sort_plan(ctypes.c_uint64(1 << 24), 13, 19, out)
+    assert list(out)[:5] == [1, 9, 6, 1024, 1024]                # the headline plan: 1024 bins of 16384 pairs, 512 low-bit counters
+    lib.hm_sort_plan(ctypes.c_uint64(1 << 25), 13, 19, out)
+    assert out[0] == 0                                         # bins would overflow the stage: library sort
+    assert accepted > 100
