@@ -63,6 +63,7 @@ void bp_ctx_destroy(bp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->for_each_buf([](bp::DevBuf* b) { b->release(); });
+    delete ctx->workers;
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->h_coll) cudaFreeHost(ctx->h_coll);
     if (ctx->nccl_comm && bp::nccl_api().ok()) bp::nccl_api().CommDestroy((ncclComm_t)ctx->nccl_comm);

@@ -6,6 +6,7 @@
 #include <string>
 #include "../../include/bp_b200.h"
 #include "ec.cuh"
+#include "host/workers.hpp"
 
 namespace bp {
 
@@ -96,6 +97,7 @@ struct bp_ctx {
                              &f_ukeys, &f_sums, &f_tmp, &f_wv};
         for (auto* b : all) f(b);
     }
+    bp::HostWorkers* workers = nullptr;      // persistent host threads for parallel Horner chains (created on first use)
     void* h_result = nullptr;   // pinned, BP_HOST_RESULT_BYTES
     // optional per-phase timing of the last MSM (cudaEvents on `stream`)
     bool timing = false;

@@ -23,7 +23,7 @@
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cstring>
-#include <thread>
+#include <functional>
 #include <vector>
 #include "ctx.cuh"
 #include "host/nccl_dyn.hpp"
@@ -705,6 +705,14 @@ int msm_pair_rounds(bp_ctx* ctx, MsmJob& job, const uint32_t* keys, uint32_t* va
     return BP_OK;
 }
 
+// fn(0) ... fn(n - 1) in parallel on the context's persistent host workers (host/workers.hpp); fn(0) on the caller
+template <class Fn>
+static inline void host_parallel(bp_ctx* ctx, int n, Fn&& fn) {
+    if (n <= 1) { if (n == 1) fn(0); return; }
+    if (!ctx->workers) ctx->workers = new HostWorkers(MSM_MAX_BATCH - 1);
+    ctx->workers->run(n, std::function<void(int)>(fn));
+}
+
 // Runs the batch; out_xy / out_is_identity have job.nmsm entries.
 template <class C>
 int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_is_identity) {
@@ -737,10 +745,7 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
                 rcs[m] = host_combine(ctx->curve, (const xyzz*)ctx->h_result + (size_t)m * MSM_TINY_W, MSM_TINY_W, MSM_TINY_C, out_xy[m],
                                       out_is_identity ? &out_is_identity[m] : nullptr);
             };
-            std::thread extra[MSM_MAX_BATCH];
-            for (int m = 1; m < job.nmsm; m++) extra[m] = std::thread(combine, m);
-            combine(0);
-            for (int m = 1; m < job.nmsm; m++) extra[m].join();
+            host_parallel(ctx, job.nmsm, combine);
             for (int m = 0; m < job.nmsm; m++)
                 if (rcs[m] != BP_OK) return rcs[m];
             return BP_OK;
@@ -831,10 +836,7 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
         rcs[m] = host_combine(ctx->curve, (const xyzz*)ctx->h_result + (size_t)m * p.W, p.W, p.c, out_xy[m],
                               out_is_identity ? &out_is_identity[m] : nullptr);
     };
-    std::thread extra[MSM_MAX_BATCH];
-    for (int m = 1; m < job.nmsm; m++) extra[m] = std::thread(combine, m);
-    combine(0);
-    for (int m = 1; m < job.nmsm; m++) extra[m].join();
+    host_parallel(ctx, job.nmsm, combine);
     for (int m = 0; m < job.nmsm; m++)
         if (rcs[m] != BP_OK) return rcs[m];
     return BP_OK;
