@@ -104,12 +104,12 @@ static __global__ void __launch_bounds__(256) sort_colscan_kernel(const uint16_t
     uint32_t* r = rel + (size_t)w * sp.tiles * nbp + b;
     uint32_t run = 0;
     uint32_t t = 0;
-    for (; t + 4 <= sp.tiles; t += 4) {            // the loads do not depend on the running sum: keep four in flight
-        const uint32_t v0 = h[(size_t)t * nbp], v1 = h[(size_t)(t + 1) * nbp], v2 = h[(size_t)(t + 2) * nbp], v3 = h[(size_t)(t + 3) * nbp];
-        r[(size_t)t * nbp] = run; run += v0;
-        r[(size_t)(t + 1) * nbp] = run; run += v1;
-        r[(size_t)(t + 2) * nbp] = run; run += v2;
-        r[(size_t)(t + 3) * nbp] = run; run += v3;
+    for (; t + 16 <= sp.tiles; t += 16) {          // the loads do not depend on the running sum: keep sixteen in flight
+        uint32_t v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = h[(size_t)(t + j) * nbp];
+#pragma unroll
+        for (int j = 0; j < 16; j++) { r[(size_t)(t + j) * nbp] = run; run += v[j]; }
     }
     for (; t < sp.tiles; t++) { const uint32_t v = h[(size_t)t * nbp]; r[(size_t)t * nbp] = run; run += v; }
     col_total[col] = run;
