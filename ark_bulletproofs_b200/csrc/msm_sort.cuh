@@ -28,7 +28,7 @@
 namespace bp {
 
 static constexpr uint32_t SORT_INVALID_KEY = 0xFFFFFFFFu;
-static constexpr int SORT_TS = 16384;          // pairs per tile (hist / scatter): 128 KB of shared-memory stage
+static constexpr int SORT_TS = 8192;           // pairs per tile (hist / scatter): 64 KB of stage + 16 KB of index, two blocks per SM
 static constexpr int SORT_BIN_TARGET = 8192;   // coarse bins hold between this many and twice as many pairs on average
 static constexpr int SORT_BIN_CAP = 20480;     // pairs staged in shared memory by the bins kernel (160 KB + 40 KB of index)
 
@@ -94,25 +94,49 @@ static __global__ void __launch_bounds__(512) sort_hist_kernel(const uint32_t* _
 }
 
 // ---- colscan: rel[w][tile][b] = pairs of column (w, b) in earlier tiles; col_total[w][b] -------------------------------
-static __global__ void __launch_bounds__(256) sort_colscan_kernel(const uint16_t* __restrict__ tile_hist, const __grid_constant__ SortPlan sp,
+// One thread per (column, group of tiles): 32 columns x 32 groups per block. A thread sums the counts of its tiles, the
+// groups of a column are combined through shared memory, and a second sweep over the same tiles (L2 hits) writes the
+// offsets -- a serial walk over all 2048 tiles of a column per thread was 0.15-0.2 ms of pure load latency at 2^24 points.
+static __global__ void __launch_bounds__(1024) sort_colscan_kernel(const uint16_t* __restrict__ tile_hist, const __grid_constant__ SortPlan sp,
                                                            uint32_t* __restrict__ rel, uint32_t* __restrict__ col_total) {
+    __shared__ uint32_t sh_sum[32][33];
     const uint32_t nbp = sp.nb1 + 1;
-    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= (size_t)sp.W * nbp) return;
-    const uint32_t w = (uint32_t)(col / nbp), b = (uint32_t)(col % nbp);
+    const uint32_t c = threadIdx.x & 31u, g = threadIdx.x >> 5;
+    const size_t col = (size_t)blockIdx.x * 32 + c;
+    const bool live = col < (size_t)sp.W * nbp;
+    const uint32_t w = live ? (uint32_t)(col / nbp) : 0u, b = live ? (uint32_t)(col % nbp) : 0u;
+    const uint32_t tpg = (sp.tiles + 31) / 32;
+    const uint32_t t0 = g * tpg < sp.tiles ? g * tpg : sp.tiles, t1 = t0 + tpg < sp.tiles ? t0 + tpg : sp.tiles;
     const uint16_t* h = tile_hist + (size_t)w * sp.tiles * nbp + b;
     uint32_t* r = rel + (size_t)w * sp.tiles * nbp + b;
-    uint32_t run = 0;
-    uint32_t t = 0;
-    for (; t + 16 <= sp.tiles; t += 16) {          // the loads do not depend on the running sum: keep sixteen in flight
-        uint32_t v[16];
+    uint32_t sum = 0;
+    if (live) {
+        uint32_t t = t0;
+        for (; t + 8 <= t1; t += 8) {
+            uint32_t v[8];
 #pragma unroll
-        for (int j = 0; j < 16; j++) v[j] = h[(size_t)(t + j) * nbp];
+            for (int j = 0; j < 8; j++) v[j] = h[(size_t)(t + j) * nbp];
 #pragma unroll
-        for (int j = 0; j < 16; j++) { r[(size_t)(t + j) * nbp] = run; run += v[j]; }
+            for (int j = 0; j < 8; j++) sum += v[j];
+        }
+        for (; t < t1; t++) sum += h[(size_t)t * nbp];
     }
-    for (; t < sp.tiles; t++) { const uint32_t v = h[(size_t)t * nbp]; r[(size_t)t * nbp] = run; run += v; }
-    col_total[col] = run;
+    sh_sum[g][c] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (uint32_t gg = 0; gg < g; gg++) run += sh_sum[gg][c];
+    if (live) {
+        if (g == 31) col_total[col] = run + sum;
+        uint32_t t = t0;
+        for (; t + 8 <= t1; t += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = h[(size_t)(t + j) * nbp];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { r[(size_t)(t + j) * nbp] = run; run += v[j]; }
+        }
+        for (; t < t1; t++) { const uint32_t v = h[(size_t)t * nbp]; r[(size_t)t * nbp] = run; run += v; }
+    }
 }
 
 // ---- binscan: bin_start[w * nb1 + b] (valid bins in key order), then the zero-digit regions of the windows; one block ----
@@ -189,7 +213,9 @@ __device__ __forceinline__ uint32_t sort_block_excl_scan_1024(uint32_t v, uint32
 // partially written sectors: measured at 2^24 points, 3.3x write and read amplification in DRAM (L2 evicts them before they
 // fill; ncu: 5.7 GB written for 1.7 GB of pairs, 5.9 ms). So the tile is ordered by coarse bin inside shared memory first
 // (counting sort with an inverse index: stage[] keeps the pairs, inv[] says which pair comes i-th) and written out
-// linearly: every (tile, bin) run of ~16 pairs is one contiguous 128-byte store stream.
+// linearly: every (tile, bin) run of ~8 pairs is one contiguous 64-byte store stream, completed to whole sectors in L2 by
+// the neighbouring tiles' runs (ncu: DRAM bytes written = bytes of pairs). Tiles of 8192 pairs keep the stage at 92 KB, so
+// two blocks share an SM and one block's loads overlap the other's stores (1.18 -> 1.01 ms at 2^24 against 16384-pair tiles).
 static constexpr int SORT_TILE_SMEM = SORT_TS * 8 + SORT_TS * 2 + 3 * 1028 * 4 + 32 * 4;
 static __global__ void __launch_bounds__(1024) sort_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                            const __grid_constant__ SortPlan sp, const uint32_t* __restrict__ rel,
@@ -358,7 +384,7 @@ static inline cudaError_t sort_pairs_run(const SortPlan& sp, const uint32_t* key
     const uint32_t nbp = sp.nb1 + 1;
     sort_hist_kernel<<<dim3(sp.tiles, sp.W), 512, nbp * 4, st>>>(keys_in, sp, s.tile_hist);
     const size_t cols = (size_t)sp.W * nbp;
-    sort_colscan_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(s.tile_hist, sp, s.rel, s.col_total);
+    sort_colscan_kernel<<<(unsigned)((cols + 31) / 32), 1024, 0, st>>>(s.tile_hist, sp, s.rel, s.col_total);
     sort_binscan_kernel<<<1, 1024, 0, st>>>(s.col_total, sp, s.bin_start);
     sort_scatter_kernel<<<dim3(sp.tiles, sp.W), 1024, SORT_TILE_SMEM, st>>>(keys_in, vals_in, sp, s.rel, s.bin_start, s.pairs, keys_out, vals_out);
     sort_bins_kernel<<<(unsigned)sp.bins_total(), 1024, SORT_BINS_SMEM, st>>>(s.pairs, s.bin_start, sp, keys_out, vals_out);
