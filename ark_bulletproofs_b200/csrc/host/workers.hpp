@@ -13,9 +13,7 @@ namespace bp {
 
 class HostWorkers {
 public:
-    explicit HostWorkers(int n) {
-        for (int i = 0; i < n; i++) threads_.emplace_back([this] { loop(); });
-    }
+    explicit HostWorkers(int max_workers) : max_(max_workers) {}
     ~HostWorkers() {
         {
             std::lock_guard<std::mutex> lk(m_);
@@ -25,12 +23,15 @@ public:
         for (auto& t : threads_) t.join();
     }
     int size() const { return (int)threads_.size(); }
-    // runs fn(0), ..., fn(njobs - 1); fn(0) on the calling thread, the rest on the workers (njobs - 1 <= size())
+    // runs fn(0), ..., fn(njobs - 1); fn(0) on the calling thread, the rest on the workers (njobs - 1 <= max_workers)
     void run(int njobs, const std::function<void(int)>& fn) {
         if (njobs <= 1) {
             if (njobs == 1) fn(0);
             return;
         }
+        // as many workers as this batch needs (at most max_), woken one per job: a context that only ever runs L/R pairs
+        // keeps a single helper thread, and nobody is woken for nothing on a host whose cores are busy with other provers
+        while ((int)threads_.size() < njobs - 1 && (int)threads_.size() < max_) threads_.emplace_back([this] { loop(); });
         {
             std::lock_guard<std::mutex> lk(m_);
             fn_ = &fn;
@@ -38,7 +39,7 @@ public:
             end_ = njobs;
             pending_ = njobs - 1;
         }
-        cv_work_.notify_all();
+        for (int j = 1; j < njobs; j++) cv_work_.notify_one();
         fn(0);
         std::unique_lock<std::mutex> lk(m_);
         cv_done_.wait(lk, [this] { return pending_ == 0; });
@@ -65,6 +66,7 @@ private:
     const std::function<void(int)>* fn_ = nullptr;
     int next_ = 0, end_ = 0, pending_ = 0;
     bool stop_ = false;
+    int max_ = 0;
 };
 
 }  // namespace bp

@@ -385,7 +385,7 @@ def prover_throughput_bench(local_rank, lg_n, concurrencies, golden_sha=None):
         assert ref == golden_sha, "proof differs from the oracle's golden bytes"
     out = []
     for conc in concurrencies:
-        per = max(3, 24 // conc)
+        per = max(6, 24 // conc)      # at least six proofs per prover: three were a burst whose rate varied 2x between runs
         digs = [None] * conc
 
         def work(k):

@@ -8,6 +8,8 @@
 #include "../../ark_bulletproofs_b200/csrc/experimental/fp29.cuh"
 #include "../../ark_bulletproofs_b200/csrc/host/glv_host.hpp"
 #include "../../ark_bulletproofs_b200/csrc/msm_sort.cuh"
+#include "../../ark_bulletproofs_b200/csrc/host/workers.hpp"
+#include <atomic>
 using namespace bp;
 
 // Fp<M>::mul_sparse where it exists (the device templates), the ordinary product for the host reference class
@@ -231,4 +233,19 @@ extern "C" void hm_sort_plan(uint64_t n, int W, int cb, uint32_t* out) {
     SortPlan p = make_sort_plan((size_t)n, W, cb);
     out[0] = p.ok; out[1] = (uint32_t)p.low_bits; out[2] = (uint32_t)p.low_top; out[3] = p.nb1; out[4] = p.tiles;
     out[5] = SORT_BIN_CAP; out[6] = SORT_TS;
+}
+
+// persistent host workers (host/workers.hpp): `iters` batches of 1..8 jobs; returns 0 when every job ran exactly once
+extern "C" int hm_workers_stress(int iters) {
+    HostWorkers w(7);
+    std::atomic<long> sum{0};
+    long want = 0;
+    for (int it = 0; it < iters; it++) {
+        const int n = 1 + it % 8;
+        std::function<void(int)> fn = [&](int j) { sum += (long)(j + 1) * (it + 1); };
+        w.run(n, fn);
+        want += (long)n * (n + 1) / 2 * (it + 1);
+        if (sum.load() != want) return 1;              // run() returns only when the whole batch is done
+    }
+    return w.size() == 7 ? 0 : 2;
 }

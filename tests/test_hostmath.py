@@ -304,3 +304,9 @@ def test_bucket_sort_plan(lib):
     lib.hm_sort_plan(ctypes.c_uint64(1 << 25), 13, 19, out)
     assert out[0] == 0                                         # bins would overflow the stage: library sort
     assert accepted > 100
+
+
+def test_host_workers(lib):
+    """host/workers.hpp: batches of 1..8 jobs on the persistent workers; every job runs exactly once and run() returns only
+    after the last one (the Horner chains of a batch of MSMs write into the caller's stack)."""
+    assert lib.hm_workers_stress(5000) == 0
