@@ -108,8 +108,18 @@ struct MsmJob {
     size_t total() const { return nseg ? start[nseg] : 0; }
 };
 
+static inline SortSegs sort_segs_of(const MsmJob& job) {
+    SortSegs g;
+    g.nseg = job.nseg;
+    for (int k = 0; k <= MSM_MAX_SEGS; k++) g.start[k] = k <= job.nseg ? job.start[k] : 0xFFFFFFFFu;
+    return g;
+}
+
 // ---- 1. digits -------------------------------------------------------------------------------
-template <class C>
+// KEYS_ONLY (the bucket-sort path): the sign rides in bit 31 of the key and no value array is written -- the value of
+// pair i is sign | segment | index, which the scatter kernel rebuilds from i (msm_sort.cuh); saves 4 of the 8 bytes per pair
+// that this kernel writes and the scatter kernel reads.
+template <class C, bool KEYS_ONLY = false>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const __grid_constant__ MsmJob job, size_t n, int c, int W,
                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,8 +145,12 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const __grid_constant__
         uint32_t neg = 0;
         if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else carry = 0;
         uint32_t key = d ? (((wbase + (uint32_t)w) << (c - 1)) | (d - 1u)) : INVALID_KEY;
-        keys[(size_t)w * n + i] = key;
-        vals[(size_t)w * n + i] = vbase | (neg << 31);
+        if (KEYS_ONLY) {
+            keys[(size_t)w * n + i] = d ? (key | (neg << 31)) : INVALID_KEY;
+        } else {
+            keys[(size_t)w * n + i] = key;
+            vals[(size_t)w * n + i] = vbase | (neg << 31);
+        }
     }
 }
 
@@ -788,13 +802,16 @@ int msm_run_job(bp_ctx* ctx, const MsmJob& job, uint8_t (*out_xy)[64], int* out_
     ctx->last_c = p.c; ctx->last_W = p.W; ctx->last_entries = p.entries;
     auto mark = [&](int i) { if (ctx->timing) cudaEventRecord(ctx->ev[i], st); };
     mark(0);
-    msm_digits_kernel<C><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(job, n, p.c, p.W, ctx->keys_a.as<uint32_t>(),
-                                                                     ctx->vals_a.as<uint32_t>());
+    if (splan.ok)
+        msm_digits_kernel<C, true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(job, n, p.c, p.W, ctx->keys_a.as<uint32_t>(), nullptr);
+    else
+        msm_digits_kernel<C><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(job, n, p.c, p.W, ctx->keys_a.as<uint32_t>(),
+                                                                         ctx->vals_a.as<uint32_t>());
     BP_LAUNCH_CHECK(ctx);
     mark(7);
     if (splan.ok) {
         int nl = 0;
-        BP_CUDA_TRY(ctx, sort_pairs_run(splan, ctx->keys_a.as<uint32_t>(), ctx->vals_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(),
+        BP_CUDA_TRY(ctx, sort_pairs_run(splan, sort_segs_of(job), ctx->keys_a.as<uint32_t>(), ctx->keys_b.as<uint32_t>(), ctx->vals_b.as<uint32_t>(),
                                         ctx->sort_scratch.p, st, &nl));
         ctx->launches += nl;
     } else {
@@ -1012,14 +1029,18 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
         // prep
         BP_CUDA_TRY(ctx, cudaStreamWaitEvent(sc.prep, sc.copied[k], 0));
         if (k >= 2) BP_CUDA_TRY(ctx, cudaStreamWaitEvent(sc.prep, sc.used[s], 0));   // chunk k-2 has consumed its sorted pairs
-        msm_digits_kernel<C><<<(unsigned)((cnt + 255) / 256), 256, 0, sc.prep>>>(job, cnt, q.c, q.W, ctx->keys_a.as<uint32_t>(),
-                                                                                ctx->vals_a.as<uint32_t>());
-        BP_LAUNCH_CHECK(ctx);
         SortPlan splan;
         if (ctx->msm_sort_mode == 1 && q.entries >= ctx->msm_sort_min_entries) splan = make_sort_plan(cnt, q.W, q.c - 1);
-        if (splan.ok && sort_scratch_bytes(splan) <= ctx->sort_scratch.cap) {
+        if (splan.ok && sort_scratch_bytes(splan) > ctx->sort_scratch.cap) splan.ok = false;
+        if (splan.ok)
+            msm_digits_kernel<C, true><<<(unsigned)((cnt + 255) / 256), 256, 0, sc.prep>>>(job, cnt, q.c, q.W, ctx->keys_a.as<uint32_t>(), nullptr);
+        else
+            msm_digits_kernel<C><<<(unsigned)((cnt + 255) / 256), 256, 0, sc.prep>>>(job, cnt, q.c, q.W, ctx->keys_a.as<uint32_t>(),
+                                                                                    ctx->vals_a.as<uint32_t>());
+        BP_LAUNCH_CHECK(ctx);
+        if (splan.ok) {
             int nl = 0;
-            BP_CUDA_TRY(ctx, sort_pairs_run(splan, ctx->keys_a.as<uint32_t>(), ctx->vals_a.as<uint32_t>(), skeys, svals, ctx->sort_scratch.p, sc.prep, &nl));
+            BP_CUDA_TRY(ctx, sort_pairs_run(splan, sort_segs_of(job), ctx->keys_a.as<uint32_t>(), skeys, svals, ctx->sort_scratch.p, sc.prep, &nl));
             ctx->launches += nl;
         } else {
             BP_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, ctx->keys_a.as<uint32_t>(), skeys,

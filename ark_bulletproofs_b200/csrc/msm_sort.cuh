@@ -48,6 +48,13 @@ struct SortPlan {
     BP_SORT_HD int low_of(uint32_t w) const { return w + 1 == W ? low_top : low_bits; }
 };
 
+// segments of the MSM job (msm_kernels.cuh: MsmJob): term i of a window belongs to segment sg with start[sg] <= i < start[sg + 1];
+// its value is sign << 31 | sg << 28 | (i - start[sg])
+struct SortSegs {
+    int nseg = 0;
+    uint32_t start[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+};
+
 // One MSM (nmsm == 1) of n terms, W windows of cb bucket bits. Returns ok = false where the library sort stays.
 static inline SortPlan make_sort_plan(size_t n, int W, int cb, int scalar_bits = 256) {
     SortPlan s;
@@ -84,7 +91,7 @@ static __global__ void __launch_bounds__(512) sort_hist_kernel(const uint32_t* _
     const uint32_t mask = sp.nb1 - 1;
     const int low = sp.low_of(w);
     for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const uint32_t k = __ldg(K + i);
+        const uint32_t k = __ldg(K + i);                 // bit 31 = sign of the digit; the mask drops it
         const uint32_t b = k == SORT_INVALID_KEY ? sp.nb1 : ((k >> low) & mask);
         atomicAdd(&sh_cnt[b], 1u);
     }
@@ -217,7 +224,7 @@ __device__ __forceinline__ uint32_t sort_block_excl_scan_1024(uint32_t v, uint32
 // the neighbouring tiles' runs (ncu: DRAM bytes written = bytes of pairs). Tiles of 8192 pairs keep the stage at 92 KB, so
 // two blocks share an SM and one block's loads overlap the other's stores (1.18 -> 1.01 ms at 2^24 against 16384-pair tiles).
 static constexpr int SORT_TILE_SMEM = SORT_TS * 8 + SORT_TS * 2 + 3 * 1028 * 4 + 32 * 4;
-static __global__ void __launch_bounds__(1024) sort_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+static __global__ void __launch_bounds__(1024) sort_scatter_kernel(const uint32_t* __restrict__ keys, const __grid_constant__ SortSegs segs,
                                                            const __grid_constant__ SortPlan sp, const uint32_t* __restrict__ rel,
                                                            const uint32_t* __restrict__ bin_start, uint2* __restrict__ pairs,
                                                            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
@@ -238,13 +245,20 @@ static __global__ void __launch_bounds__(1024) sort_scatter_kernel(const uint32_
     __syncthreads();
     const uint32_t lo = tile * SORT_TS, hi = lo + SORT_TS < sp.n ? lo + SORT_TS : sp.n, m = hi - lo;
     const uint32_t* K = keys + (size_t)w * sp.n + lo;
-    const uint32_t* V = vals + (size_t)w * sp.n + lo;
     const uint32_t mask = sp.nb1 - 1;
     const int low = sp.low_of(w);
     auto bin_of = [&](uint32_t k) -> uint32_t { return k == SORT_INVALID_KEY ? sp.nb1 : ((k >> low) & mask); };
 #pragma unroll 4
     for (uint32_t i = threadIdx.x; i < m; i += 1024) {
-        const uint32_t k = __ldg(K + i), v = __ldg(V + i);
+        // keys carry the sign in bit 31 (msm_digits_kernel<KEYS_ONLY>); the value is rebuilt from the term index
+        const uint32_t kr = __ldg(K + i);
+        const uint32_t gi = lo + i;
+        int sg = 0;
+#pragma unroll
+        for (int q = 1; q < 8; q++)
+            if (q < segs.nseg && gi >= segs.start[q]) sg = q;
+        const uint32_t v = (kr & 0x80000000u) | ((uint32_t)sg << 28) | (gi - segs.start[sg]);
+        const uint32_t k = kr == SORT_INVALID_KEY ? kr : (kr & 0x7FFFFFFFu);
         stage[i] = make_uint2(k, v);
         atomicAdd(&cnt[bin_of(k)], 1u);
     }
@@ -372,8 +386,8 @@ static inline SortScratch sort_scratch_at(void* base, const SortPlan& sp) {
     return s;
 }
 
-// keys_in / vals_in: window-major pairs (W * n); keys_out / vals_out: sorted, zero digits last. Returns the launch count.
-static inline cudaError_t sort_pairs_run(const SortPlan& sp, const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+// keys_in: window-major keys (W * n) with the digit's sign in bit 31; keys_out / vals_out: sorted pairs, zero digits last.
+static inline cudaError_t sort_pairs_run(const SortPlan& sp, const SortSegs& segs, const uint32_t* keys_in, uint32_t* keys_out, uint32_t* vals_out,
                                          void* scratch, cudaStream_t st, int* launches) {
     {   // per device; cheap driver calls
         cudaError_t e = cudaFuncSetAttribute(sort_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_BINS_SMEM);
@@ -386,7 +400,7 @@ static inline cudaError_t sort_pairs_run(const SortPlan& sp, const uint32_t* key
     const size_t cols = (size_t)sp.W * nbp;
     sort_colscan_kernel<<<(unsigned)((cols + 31) / 32), 1024, 0, st>>>(s.tile_hist, sp, s.rel, s.col_total);
     sort_binscan_kernel<<<1, 1024, 0, st>>>(s.col_total, sp, s.bin_start);
-    sort_scatter_kernel<<<dim3(sp.tiles, sp.W), 1024, SORT_TILE_SMEM, st>>>(keys_in, vals_in, sp, s.rel, s.bin_start, s.pairs, keys_out, vals_out);
+    sort_scatter_kernel<<<dim3(sp.tiles, sp.W), 1024, SORT_TILE_SMEM, st>>>(keys_in, segs, sp, s.rel, s.bin_start, s.pairs, keys_out, vals_out);
     sort_bins_kernel<<<(unsigned)sp.bins_total(), 1024, SORT_BINS_SMEM, st>>>(s.pairs, s.bin_start, sp, keys_out, vals_out);
     *launches += 5;
     return cudaGetLastError();
