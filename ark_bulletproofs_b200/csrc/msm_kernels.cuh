@@ -135,13 +135,12 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const __grid_constant__
     const uint32_t wbase = job.msm[sg] * (uint32_t)W;
     const uint32_t vbase = ((uint32_t)sg << 28) | local;
     uint32_t carry = 0;
-    for (int w = 0; w < W; w++) {
-        int bit = w * c;
-        int limb = bit >> 5, sh = bit & 31;
-        uint32_t lo = limb < 8 ? s.v[limb] : 0u;
-        uint32_t hi = (limb + 1) < 8 ? s.v[limb + 1] : 0u;
-        uint32_t d = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & mask;
-        d += carry;
+    // the scalar streams through a 64-bit bit buffer, one limb at a time (static limb indices: indexing s.v[] by the window's
+    // bit position costs two 8-way select chains per window); c <= 20, so the buffer never holds more than 51 bits
+    uint64_t buf = 0;
+    int have = 0, w = 0;
+    auto emit = [&](uint32_t raw) {
+        uint32_t d = raw + carry;
         uint32_t neg = 0;
         if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else carry = 0;
         uint32_t key = d ? (((wbase + (uint32_t)w) << (c - 1)) | (d - 1u)) : INVALID_KEY;
@@ -151,6 +150,21 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const __grid_constant__
             keys[(size_t)w * n + i] = key;
             vals[(size_t)w * n + i] = vbase | (neg << 31);
         }
+        w++;
+    };
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        buf |= (uint64_t)s.v[l] << have;
+        have += 32;
+        while (have >= c && w < W) {
+            emit((uint32_t)buf & mask);
+            buf >>= c;
+            have -= c;
+        }
+    }
+    while (w < W) {                                  // the bits left over (256 is no multiple of c), then zeros
+        emit((uint32_t)buf & mask);
+        buf >>= c;
     }
 }
 
