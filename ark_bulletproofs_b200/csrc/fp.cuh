@@ -399,6 +399,49 @@ struct Fp {
     BP_HD static fe mul_sub(const fe& a, const fe& b, const fe& c, const fe& d) { return mul2<true>(a, b, c, d); }
 #endif
 
+    // r (9 limbs) = (L + Q*m) / 2^256 for the 8-limb L: the eight quotient rounds of the CIOS alone (X aligned, Y offset by
+    // one limb, as in mul_generic); r <= m. 64 wide + 8 quotient multiplies.
+    BP_HD static void redc8(const uint32_t* L, uint32_t* r) {
+        uint32_t X[10], Y[10];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { X[i] = L[i]; Y[i] = 0; }
+        X[8] = 0; X[9] = 0; Y[8] = 0; Y[9] = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t Xn[10], Yn[10];
+            if (k == 0) {                            // nothing to shift in yet: q from X[0]
+#pragma unroll
+                for (int j = 0; j < 9; j++) { Xn[j] = X[j]; Yn[j] = 0; }
+            } else {
+                Xn[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+                for (int j = 1; j < 9; j++) Xn[j] = Y[j];
+            }
+            const uint32_t q = Xn[0] * M::INV32;
+            if (k == 0) {
+                wmad_cc(Yn[0], Yn[1], q, M::m(1));
+#pragma unroll
+                for (int j = 2; j < 8; j += 2) wmadc_cc(Yn[j], Yn[j + 1], q, M::m(j + 1));
+                Yn[8] = addc(0u, 0u);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) wmadc_to_cc(Yn[j], Yn[j + 1], q, M::m(j + 1), X[j + 2], X[j + 3]);
+                Yn[8] = addc(0u, 0u);
+            }
+            wmad_cc(Xn[0], Xn[1], q, M::m(0));
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) wmadc_cc(Xn[j], Xn[j + 1], q, M::m(j));
+            Xn[8] = addc(Xn[8], 0u);
+#pragma unroll
+            for (int j = 0; j < 9; j++) { X[j] = Xn[j]; Y[j] = Yn[j]; }
+            X[9] = 0; Y[9] = 0;
+        }
+        r[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+        for (int j = 1; j < 8; j++) r[j] = addc_cc(Y[j], X[j + 1]);
+        r[8] = addc(Y[8], 0u);
+    }
+
     // a^2 * 2^-256 mod m with 36 + 64 wide multiplies instead of 128: the 28 off-diagonal products a_i*a_j (i < j) are
     // summed once (even/odd columns as above, one row per a_i), doubled by a one-bit funnel shift, the 8 squares a_i^2
     // are added on one chain, and the 512-bit square is reduced by the quotient rounds of the CIOS alone (the high half
@@ -460,48 +503,9 @@ struct Fp {
         wmad_cc(T[0], T[1], a.v[0], a.v[0]);
 #pragma unroll
         for (int i = 1; i < 8; i++) wmadc_cc(T[2 * i], T[2 * i + 1], a.v[i], a.v[i]);
-        // Montgomery-reduce the low half: eight quotient rounds (X aligned, Y offset by one limb, as in mul_generic)
-        uint32_t X[10], Y[10];
-#pragma unroll
-        for (int i = 0; i < 8; i++) { X[i] = T[i]; Y[i] = 0; }
-        X[8] = 0; X[9] = 0; Y[8] = 0; Y[9] = 0;
-        // round 0 has nothing to shift in yet: q from X[0]
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            uint32_t Xn[10], Yn[10];
-            if (k == 0) {
-#pragma unroll
-                for (int j = 0; j < 9; j++) { Xn[j] = X[j]; Yn[j] = 0; }
-            } else {
-                Xn[0] = add_cc(Y[0], X[1]);
-#pragma unroll
-                for (int j = 1; j < 9; j++) Xn[j] = Y[j];
-            }
-            const uint32_t q = Xn[0] * M::INV32;
-            if (k == 0) {
-                wmad_cc(Yn[0], Yn[1], q, M::m(1));
-#pragma unroll
-                for (int j = 2; j < 8; j += 2) wmadc_cc(Yn[j], Yn[j + 1], q, M::m(j + 1));
-                Yn[8] = addc(0u, 0u);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) wmadc_to_cc(Yn[j], Yn[j + 1], q, M::m(j + 1), X[j + 2], X[j + 3]);
-                Yn[8] = addc(0u, 0u);
-            }
-            wmad_cc(Xn[0], Xn[1], q, M::m(0));
-#pragma unroll
-            for (int j = 2; j < 8; j += 2) wmadc_cc(Xn[j], Xn[j + 1], q, M::m(j));
-            Xn[8] = addc(Xn[8], 0u);
-#pragma unroll
-            for (int j = 0; j < 9; j++) { X[j] = Xn[j]; Y[j] = Yn[j]; }
-            X[9] = 0; Y[9] = 0;
-        }
-        // (L + Q*m) / 2^256 = Y + (X >> 32), plus the high half H = T[8..15]
+        // Montgomery-reduce the low half (redc8), then the high half H = T[8..15] joins
         uint32_t r[9];
-        r[0] = add_cc(Y[0], X[1]);
-#pragma unroll
-        for (int j = 1; j < 8; j++) r[j] = addc_cc(Y[j], X[j + 1]);
-        r[8] = addc(Y[8], 0u);
+        redc8(T, r);
         r[0] = add_cc(r[0], T[8]);
 #pragma unroll
         for (int j = 1; j < 8; j++) r[j] = addc_cc(r[j], T[8 + j]);
@@ -532,10 +536,12 @@ struct Fp {
         return r;
     }
     BP_HD static fe to_mont(const fe& a) { return mul(a, r2()); }
-    BP_HD static fe from_mont(const fe& a) {
-        fe o = zero();
-        o.v[0] = 1;
-        return mul(a, o);
+    BP_HD static fe from_mont(const fe& a) {         // a * 2^-256: the reduction without a product
+        uint32_t r[9];
+        redc8(a.v, r);
+        fe o;
+        final_sub(o, r, r[8]);
+        return o;
     }
     BP_HD static fe from_u32(uint32_t x) {
         fe o = zero();
