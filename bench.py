@@ -681,10 +681,10 @@ def main():
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch_lg%d" % args.lg_n)
     hbm, hbm_src = hbm_peak()
-    # pair ordering: the pipeline's bucket sort reads the keys once (histogram) and moves every 8-byte pair twice (36 B per
-    # pair); the library radix sort reads the keys once and moves every pair once per 8-bit pass
+    # pair ordering: the pipeline's bucket sort reads the 4-byte keys twice (histogram, scatter) and then moves every 8-byte
+    # pair once out of the scatter and once through the bins kernel (4 + 4 + 8 + 8 + 8 = 32 B per pair); the library radix sort reads the keys once and moves every pair once per 8-bit pass
     if phases.get("bucket_sort"):
-        sort_bytes = phases["entries"] * 36
+        sort_bytes = phases["entries"] * 32
         sort_kernel = "bucket sort of (bucket, point) pairs (csrc/msm_sort.cuh: hist, colscan, binscan, scatter, bins)"
     else:
         sort_bytes = phases["entries"] * (4 + 8 * 2 * ((phases["c"] - 1 + max(1, (phases["windows"] - 1).bit_length()) + 7) // 8))
@@ -725,7 +725,7 @@ def main():
         #   digits: 32 B scalar in, 8 B (key, value) out per window          -> HBM
         #   partials / reduce: XYZZ additions of 14 modmul x 136 IMAD        -> IMAD (reduce: 2 per bucket)
         "kernels": {
-            "msm_digits_kernel": {"bound": "hbm", "frac": round(n * (32 + 8 * phases["windows"]) / (phases["ms"]["digits"] * 1e-3) / 1e9 / hbm, 4)},
+            "msm_digits_kernel": {"bound": "hbm", "frac": round(n * (32 + (4 if phases.get("bucket_sort") else 8) * phases["windows"]) / (phases["ms"]["digits"] * 1e-3) / 1e9 / hbm, 4)},
             "pair_sort": {"bound": "hbm", "frac": round(sort_bytes / (phases["ms"]["sort"] * 1e-3) / 1e9 / hbm, 4)},
             "msm_accumulate_kernel": {"bound": "imad", "frac": round(achieved / peak, 4)},
             "msm_reduce_kernel+window_sum": {"bound": "imad", "frac": round(phases["windows"] * (1 << (phases["c"] - 1)) * 2 * 14 * MODMUL_IMAD / (phases["ms"]["reduce"] * 1e-3) / peak, 4)},
