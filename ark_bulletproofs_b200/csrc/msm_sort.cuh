@@ -8,8 +8,10 @@
 //   hist    : per tile of TS pairs of one window, counts per coarse bin (the top bits of the bucket id)        [reads keys]
 //   colscan : per (window, bin) column, exclusive running sum over the tiles; column totals
 //   binscan : exclusive scan of the column totals -> where every coarse bin starts in the output; zero digits last
-//   scatter : every pair goes to its coarse bin (cursor = bin start + tile offset, bumped by a shared atomic)  [reads keys, 1 write]
-//   bins    : one block per coarse bin (~4096 pairs): ranks by the remaining low bits with shared atomics, places the
+//   scatter : the tile is ordered by coarse bin in shared memory (counting sort, shared atomics) and every (tile, bin) run
+//             is written to its place: bin start + offset of the tile; the value of a pair (sign, segment, index) is
+//             rebuilt from its position -- the digits kernel writes keys only, sign in bit 31          [reads keys, 1 write]
+//   bins    : one block per coarse bin (8-16 K pairs): ranks by the remaining low bits with shared atomics, places the
 //             pairs in shared memory in their final order and writes them out linearly                         [1 read, 1 write]
 // Keys are read twice (4 B), pairs written once and moved once (8 B each way): 32 B of HBM traffic per pair against ~52 B for three
 // onesweep passes plus their histogram. Any key distribution is handled: a coarse bin that does not fit the shared-memory
