@@ -62,9 +62,14 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            # nvidia-smi needs a few hundred ms before its first row: wait for it here, outside the timed region, so that a
+            # short region (5 steps x 40 ms) still holds samples
+            t_end = time.time() + 5.0
+            while not self.rows and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
@@ -78,13 +83,15 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
+        if not any(t0 <= ts <= t1 + 0.06 for ts, _ in self.rows):      # region shorter than one sampling period
+            t0, t1 = t0 - 0.1, t1 + 0.1
         for ts, line in self.rows:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 6:
                 continue
             try:
                 mx = float(f[1])
-                if t0 - 0.05 <= ts <= t1 + 0.15:
+                if t0 <= ts <= t1 + 0.06:
                     sm.append(float(f[0]))
                     for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
                         if v.lower().startswith("active"):
