@@ -246,23 +246,31 @@ static int msm_host_scalars(bp_ctx* ctx, const uint8_t* bases_xy, const void* d_
     }
     // Chunk schedule: the copy stream runs back to back (55 GB/s: 1.7 ms per 2^20 points, 0.6 ms when only the scalars
     // move), the kernels follow at ~2.4 ms per 2^20 points. The first copy cannot be hidden, so the first chunk is small
-    // (CHUNK/4); every further chunk costs one extra mixed addition per non-empty bucket (its runs start from the bucket's
-    // value instead of from their first point: 6.8 M additions ~ 1 ms at 2^24), so chunks should be few, and chunk k+1 has
-    // arrived when chunk k is done as long as it is at most ~1.4x as large (~4x with resident bases) -- so the chunks grow
-    // by 1.5x (3x), up to 2 CHUNK (4 CHUNK). Swept at 2^24 (tools/msm_e2e_sweep.py, round 2 kernels): CHUNK = 2^20 / 2^21 /
-    // 2^22 / 2^23 -> 49.2 / 47.2 / 48.4 / 49.4 ms against 40.2 ms device-resident.
-    // 2^24 points with the default CHUNK = 2^21: 0.5M, 0.75M, 1.1M, 1.7M, 2.5M, 3.8M, 4M, 1.9M.
+    // (CHUNK/8; CHUNK/4 when only scalars move); every further chunk costs ~0.6 ms (a partly filled last wave of the
+    // accumulate kernel, its slot levels, and every run starting from its bucket's value instead of from its first point),
+    // so chunks should be few, and chunk k+1 has arrived when chunk k is done as long as it is at most ~1.3x as large (~4x
+    // with resident bases) -- so the chunks grow by 1.5x (3x), up to 2 CHUNK (4 CHUNK): waiting ~2 ms for copies in total is
+    // cheaper than the four extra chunks a growth of 1.3x needs. Swept at 2^24 with the bucket prefetch of the accumulate
+    // kernel (tools/msm_chunk_matrix.py, profiles/r2_msm_chunk_matrix.jsonl): first chunk 2^19 / 2^18 / 2^17 -> 46.4 /
+    // 45.1 / 45.4 ms; growth 1.2 / 1.25 / 1.3 / 1.4 / 1.5 -> 48.2 / 47.2 / 47.8 / 45.0 / 45.1 ms; CHUNK 2^20 / 2^22 -> 45.9 /
+    // 46.3 ms; against 39.6 ms device-resident. Resident bases: 42.7-43.3 ms for every setting tried.
+    // 2^24 points with the default CHUNK = 2^21: 0.26M, 0.39M, 0.59M, 0.88M, 1.3M, 2.0M, 3.0M, 4M, 4.3M.
+    // BP_MSM_FIRST_CHUNK / BP_MSM_GROWTH_PCT / BP_MSM_CHUNK_CAP (points, percent, points) override the schedule for sweeps.
     std::vector<size_t> lo_of, cnt_of;
     {
-        size_t a = CHUNK / 4 ? CHUNK / 4 : 1, rem = n, lo = 0;
+        size_t a = d_bases ? CHUNK / 4 : CHUNK / 8, rem = n, lo = 0;
+        if (a == 0) a = 1;
         if (const char* e = getenv("BP_MSM_FIRST_CHUNK")) { size_t v = strtoull(e, nullptr, 10); if (v) a = v; }
-        const size_t cap = d_bases ? 4 * CHUNK : 2 * CHUNK;
+        size_t cap = d_bases ? 4 * CHUNK : 2 * CHUNK;
+        if (const char* e = getenv("BP_MSM_CHUNK_CAP")) { size_t v = strtoull(e, nullptr, 10); if (v) cap = v; }
         while (rem > 0) {
             size_t take = a < rem ? a : rem;
             if (rem - take < a / 2) take = rem;
             lo_of.push_back(lo); cnt_of.push_back(take);
             lo += take; rem -= take;
-            a += d_bases ? 2 * a : (a / 2 ? a / 2 : 1);
+            size_t g = d_bases ? 300 : 150;
+            if (const char* e = getenv("BP_MSM_GROWTH_PCT")) { size_t v = strtoull(e, nullptr, 10); if (v > 100) g = v; }
+            a = a * g / 100 + 1;
             if (a > cap) a = cap;
         }
     }

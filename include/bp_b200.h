@@ -112,7 +112,7 @@ int bp_ctx_set_collective(bp_ctx* ctx, int rank, int world, bp_allgather_fn fn, 
 int bp_nccl_unique_id(uint8_t out[128]);
 int bp_ctx_init_nccl(bp_ctx* ctx, int rank, int world, const uint8_t unique_id[128]);
 /* bp_msm over host buffers of more than 1.5x `points` points (default 2^21) is streamed: the input is copied chunk by
- * chunk (first chunk points/4, each next one 1.5x larger, at most 2x points) while the kernels of the chunks already
+ * chunk (first chunk points/8, each next one 1.5x larger, at most 2x points) while the kernels of the chunks already
  * on the device run, all chunks adding into one bucket array. Exposed for tests and tuning. */
 int bp_msm_set_chunk(bp_ctx* ctx, size_t points);
 /* IPA rounds of length n <= this threshold do not fold the generators; their L/R are MSMs over the last
