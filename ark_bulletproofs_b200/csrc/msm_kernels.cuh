@@ -1003,6 +1003,13 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
     //   main : accumulate of chunk k, after its pairs are sorted and the slots of chunk k-1 are folded
     //   fold : the slot levels of chunk k -- a handful of latency-bound launches -- next to the prep of chunk k+1
     // prep and fold have the higher priority, so their blocks take the SM slots the long accumulate blocks free.
+    // Measured and not kept (profiles/r2_msm_stream_timeline.txt): the timeline (BP_MSM_TIMELINE=1) shows accumulate k+1
+    // starting exactly when the slot levels of chunk k are done, 0.2-1.3 ms after accumulate k (5.6 ms over nine chunks).
+    // Letting the slot levels add into a second bucket array with double-buffered slot lists, so that they run next to
+    // accumulate k+1, and copying the scalars of a chunk before its bases so that its sort starts earlier, closes every gap
+    // -- and the accumulate kernels get slower by the same amount (206-register slot-level blocks take the place of 1.6
+    // accumulate blocks each and last 3x longer themselves), plus 1.3 ms for merging the second array: 46.95 ms against
+    // 45.1 ms; with the fold stream at the accumulate kernel's priority 48.9 ms.
     // Sorted-pair buffer k&1 is free again once the accumulate kernel of chunk k has run.
     struct Scoped {
         cudaEvent_t used[2] = {nullptr, nullptr}, sorted[2] = {nullptr, nullptr};
@@ -1028,6 +1035,15 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
     BP_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&sc.fold, cudaStreamNonBlocking, prio_hi));
     BP_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&sc.prep, cudaStreamNonBlocking, prio_hi));
     sc.copied.assign(nchunks, nullptr);
+    // BP_MSM_TIMELINE=1: per-chunk timestamps (copy done, pairs sorted, accumulate start / end, slots folded) on stderr
+    const bool timeline = getenv("BP_MSM_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> tl;
+    struct TlFree { std::vector<cudaEvent_t>& v; ~TlFree() { for (auto x : v) if (x) cudaEventDestroy(x); } } tl_free{tl};
+    if (timeline) {
+        tl.assign(1 + 5 * nchunks + 1, nullptr);
+        for (auto& x : tl) BP_CUDA_TRY(ctx, cudaEventCreate(&x));
+        BP_CUDA_TRY(ctx, cudaEventRecord(tl[0], ctx->copy_stream));
+    }
     for (size_t k = 0; k < nchunks; k++) {
         BP_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sc.copied[k], cudaEventDisableTiming));
         const size_t lo = lo_of[k], cnt = cnt_of[k];
@@ -1035,6 +1051,7 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
             BP_CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->stage_bases.p + lo * 64, h_bases + lo * 64, cnt * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
         BP_CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->stage_scalars.p + lo * 32, h_scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
         BP_CUDA_TRY(ctx, cudaEventRecord(sc.copied[k], ctx->copy_stream));
+        if (timeline) BP_CUDA_TRY(ctx, cudaEventRecord(tl[1 + 5 * k], ctx->copy_stream));
     }
     BP_CUDA_TRY(ctx, cudaMemsetAsync(ctx->buckets.p, 0, nbuckets * sizeof(xyzz), st));
     for (size_t k = 0; k < nchunks; k++) {
@@ -1066,24 +1083,36 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
                                                              ctx->vals_a.as<uint32_t>(), svals, q.entries, 0, q.key_bits, sc.prep));
         }
         BP_CUDA_TRY(ctx, cudaEventRecord(sc.sorted[s], sc.prep));
+        if (timeline) BP_CUDA_TRY(ctx, cudaEventRecord(tl[2 + 5 * k], sc.prep));
         // main
         BP_CUDA_TRY(ctx, cudaStreamWaitEvent(st, sc.sorted[s], 0));
         if (k >= 1) BP_CUDA_TRY(ctx, cudaStreamWaitEvent(st, sc.fold_done, 0));      // slots of chunk k-1 folded into the buckets
+        if (timeline) BP_CUDA_TRY(ctx, cudaEventRecord(tl[3 + 5 * k], st));
         msm_accumulate_kernel<C, true><<<(unsigned)((q.T + 127) / 128), 128, 0, st>>>(skeys, svals, q.entries, q.L, q.T, job,
                                                                                       ctx->buckets.as<xyzz>(), ctx->part_keys.as<uint32_t>(),
                                                                                       ctx->part_pts.as<xyzz>());
         BP_LAUNCH_CHECK(ctx);
         BP_CUDA_TRY(ctx, cudaEventRecord(sc.used[s], st));
         BP_CUDA_TRY(ctx, cudaEventRecord(sc.acc_done, st));
+        if (timeline) BP_CUDA_TRY(ctx, cudaEventRecord(tl[4 + 5 * k], st));
         // fold
         BP_CUDA_TRY(ctx, cudaStreamWaitEvent(sc.fold, sc.acc_done, 0));
         if (int rc = msm_fold_slots<C, true>(ctx, 2 * q.T, sc.fold)) return rc;
         BP_CUDA_TRY(ctx, cudaEventRecord(sc.fold_done, sc.fold));
+        if (timeline) BP_CUDA_TRY(ctx, cudaEventRecord(tl[5 + 5 * k], sc.fold));
     }
     BP_CUDA_TRY(ctx, cudaStreamWaitEvent(st, sc.fold_done, 0));
     if (int rc = msm_reduce_windows<C>(ctx, p, p.W, st)) return rc;
     BP_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_result, ctx->win_out.p, (size_t)p.W * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
+    if (timeline) BP_CUDA_TRY(ctx, cudaEventRecord(tl[1 + 5 * nchunks], st));
     BP_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (timeline) {
+        auto at = [&](size_t i) { float ms = 0; cudaEventElapsedTime(&ms, tl[0], tl[i]); return ms; };
+        for (size_t k = 0; k < nchunks; k++)
+            fprintf(stderr, "[bp_msm timeline] chunk %zu: %8zu points  copied %7.3f  sorted %7.3f  accumulate %7.3f .. %7.3f  folded %7.3f ms\n", k,
+                    cnt_of[k], at(1 + 5 * k), at(2 + 5 * k), at(3 + 5 * k), at(4 + 5 * k), at(5 + 5 * k));
+        fprintf(stderr, "[bp_msm timeline] window sums on the host at %7.3f ms\n", at(1 + 5 * nchunks));
+    }
     return host_combine(ctx->curve, (const xyzz*)ctx->h_result, p.W, p.c, out_xy, out_is_identity);
 }
 
