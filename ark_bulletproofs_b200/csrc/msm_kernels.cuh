@@ -650,7 +650,11 @@ int msm_fold_slots_at(bp_ctx* ctx, uint32_t* pk, xyzz* pp, size_t slots1, cudaSt
     xyzz* in_p = pp;
     uint32_t* out_k = pk + slots1;
     xyzz* out_p = pp + slots1;
-    while (nslots > ctx->msm_warp_partials_below) {
+    size_t warp_below = ctx->msm_warp_partials_below;
+    // sweep knob of the streamed MSM's per-chunk slot levels (2^24-point bp_msm: 45.2 / 45.1 / 45.2 / 45.1 ms for 2^16 / 2^17 /
+    // 2^18 / 2^19, 45.9 ms for 2^15: flat, the default stays)
+    if (ACC) { if (const char* e = getenv("BP_MSM_STREAM_WARP_BELOW")) { size_t v = strtoull(e, nullptr, 10); if (v) warp_below = v; } }
+    while (nslots > warp_below) {
         size_t T2 = (nslots + PL - 1) / PL;
         msm_partials_level_kernel<C, ACC><<<(unsigned)((T2 + 127) / 128), 128, 0, st>>>(in_k, in_p, nslots, PL, T2, ctx->buckets.as<xyzz>(),
                                                                                         out_k, out_p);
