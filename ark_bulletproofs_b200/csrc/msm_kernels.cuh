@@ -1013,7 +1013,9 @@ int msm_run_streamed(bp_ctx* ctx, const uint8_t* h_bases, const uint8_t* h_scala
     // accumulate k+1, and copying the scalars of a chunk before its bases so that its sort starts earlier, closes every gap
     // -- and the accumulate kernels get slower by the same amount (206-register slot-level blocks take the place of 1.6
     // accumulate blocks each and last 3x longer themselves), plus 1.3 ms for merging the second array: 46.95 ms against
-    // 45.1 ms; with the fold stream at the accumulate kernel's priority 48.9 ms.
+    // 45.1 ms; with the fold stream at the accumulate kernel's priority 48.9 ms. The scalars-first copy order alone (the
+    // sort of chunk k+1 then runs next to accumulate k instead of next to the slot levels of chunk k): 46.3 ms -- whatever
+    // runs next to the accumulate kernel costs it more than the gap it would have filled.
     // Sorted-pair buffer k&1 is free again once the accumulate kernel of chunk k has run.
     struct Scoped {
         cudaEvent_t used[2] = {nullptr, nullptr}, sorted[2] = {nullptr, nullptr};
